@@ -1,0 +1,102 @@
+// extern "C" surface of libcrs_b200.so (declared in include/crs_b200.h).
+#include <cstdio>
+#include <cstring>
+#include "crs_common.cuh"
+
+namespace crs {
+static thread_local char g_cuda_err[256] = "";
+void set_cuda_error(cudaError_t e, const char* where) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+}  // namespace crs
+
+using namespace crs;
+
+extern "C" {
+
+CRS_API int crs_abi_version(void) { return CRS_ABI_VERSION; }
+
+CRS_API const char* crs_status_string(int status) {
+  switch (status) {
+    case CRS_OK: return "ok";
+    case CRS_ERR_INVALID_ARG: return "invalid argument";
+    case CRS_ERR_UNSUPPORTED: return "unsupported size (d > 16, n_obs > limit, K too large)";
+    case CRS_ERR_CUDA: return "CUDA runtime error";
+    case CRS_ERR_NOT_PSD: return "kernel matrix not positive definite";
+    case CRS_TIES_PENDING: return "tied minimisers pending host randomisation";
+  }
+  return "unknown status";
+}
+
+CRS_API const char* crs_last_cuda_error(void) { return g_cuda_err; }
+
+CRS_API int64_t crs_scan_workspace_bytes(void) { return scan_workspace_bytes(); }
+
+CRS_API int crs_gp_prepare(const crs_gp_state* st, int32_t arm_begin, int32_t arm_end, void* stream) {
+  return launch_gp_prepare(st, arm_begin, arm_end, (cudaStream_t)stream);
+}
+
+CRS_API int crs_posterior_grid(const crs_gp_state* st, const void* ctx, int64_t n_c, int32_t arm_begin,
+                       int32_t arm_end, void* mean, void* var, int64_t ld, int32_t col_offset,
+                       void* stream) {
+  return launch_posterior_grid(st, ctx, n_c, arm_begin, arm_end, mean, var, ld, col_offset, (cudaStream_t)stream);
+}
+
+CRS_API int crs_ocba_scan(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                  int32_t dtype, int32_t arm_offset, const int32_t* ext_best_arm,
+                  const void* ext_best_mean, const void* ext_best_var, int32_t* best_arm,
+                  void* min_zeta, int32_t* min_arm, int32_t* tie_cnt, crs_decision* decision,
+                  void* workspace, void* stream) {
+  return launch_ocba_scan(mean, var, n_c, K, ld, dtype, arm_offset, ext_best_arm, ext_best_mean,
+                          ext_best_var, best_arm, min_zeta, min_arm, tie_cnt, decision, workspace,
+                          (cudaStream_t)stream);
+}
+
+CRS_API int crs_ocba_resolve_tie(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                         int32_t dtype, const int32_t* best_arm, const void* min_zeta,
+                         const int32_t* tie_cnt, int64_t r, crs_decision* decision, void* stream) {
+  return launch_ocba_resolve_tie(mean, var, n_c, K, ld, dtype, best_arm, min_zeta, tie_cnt, r, decision, (cudaStream_t)stream);
+}
+
+CRS_API int crs_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
+                    int64_t ld, int32_t arm_offset, int32_t p_mode, double kernel_scale,
+                    crs_decision* decision, void* stream) {
+  return launch_ocba_select(st, ctx, mean, var, ld, arm_offset, p_mode, kernel_scale, decision, (cudaStream_t)stream);
+}
+
+CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                   int32_t dtype, int64_t num_samples, uint64_t seed, uint32_t offset,
+                   int32_t arm_offset, int64_t ctx_offset, uint32_t* counts, uint64_t* stats,
+                   void* stream) {
+  return launch_pcs_counts(mean, var, n_c, K, ld, dtype, num_samples, seed, offset, arm_offset, ctx_offset, counts, stats, (cudaStream_t)stream);
+}
+
+CRS_API int crs_philox_words(const uint32_t* ctr, int64_t n, uint32_t key0, uint32_t key1, uint32_t* out,
+                     void* stream) {
+  return launch_philox_words(ctr, n, key0, key1, out, (cudaStream_t)stream);
+}
+
+CRS_API int crs_gao_decide_host(const crs_gp_state* st, const void* ctx_host, int64_t n_c,
+                        int32_t prep_begin, int32_t prep_end, int32_t p_mode, double kernel_scale,
+                        int32_t randomize_ties, const crs_decide_ws* ws,
+                        crs_decision* decision_host, void* stream) {
+  if (!st || !ctx_host || !ws || !decision_host || n_c < 1) return CRS_ERR_INVALID_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t w = st->dtype == CRS_F64 ? 8 : 4;
+  const int K = st->num_arms;
+  CRS_CUDA_TRY(cudaMemcpyAsync(ws->ctx, ctx_host, (size_t)n_c * st->dim * w, cudaMemcpyHostToDevice, s), "ctx H2D");
+  int rc;
+  if (prep_end > prep_begin && (rc = launch_gp_prepare(st, prep_begin, prep_end, s)) != CRS_OK) return rc;
+  if ((rc = launch_posterior_grid(st, ws->ctx, n_c, 0, K, ws->mean, ws->var, K, 0, s)) != CRS_OK) return rc;
+  if ((rc = launch_ocba_scan(ws->mean, ws->var, n_c, K, K, st->dtype, 0, nullptr, nullptr, nullptr,
+                             ws->best_arm, ws->min_zeta, ws->min_arm, ws->tie_cnt, ws->decision,
+                             ws->scan_ws, s)) != CRS_OK) return rc;
+  if ((rc = launch_ocba_select(st, ws->ctx, ws->mean, ws->var, K, 0, p_mode, kernel_scale, ws->decision, s)) != CRS_OK) return rc;
+  CRS_CUDA_TRY(cudaMemcpyAsync(decision_host, ws->decision, sizeof(crs_decision), cudaMemcpyDeviceToHost, s), "decision D2H");
+  CRS_CUDA_TRY(cudaStreamSynchronize(s), "decide sync");
+  if (decision_host->reserved[0] != 0) return CRS_ERR_NOT_PSD;
+  if (randomize_ties && decision_host->tie_count > 1) return CRS_TIES_PENDING;
+  return CRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+// Shared device helpers for libcrs_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/crs_b200.h"
+
+namespace crs {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// gpytorch.settings.min_variance: 1e-10 for double, 1e-6 for float.
+template <typename T> __host__ __device__ inline T variance_floor();
+template <> __host__ __device__ inline double variance_floor<double>() { return 1e-10; }
+template <> __host__ __device__ inline float variance_floor<float>() { return 1e-6f; }
+
+// Stationary ARD correlation c(r) from the squared scaled distance r2 (outputscale folded into
+// alpha / linv_t by crs_gp_prepare).  Matern-5/2: (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r); RBF: exp(-r2/2).
+template <typename T> __device__ __forceinline__ T corr_matern52(T r2);
+template <> __device__ __forceinline__ double corr_matern52<double>(double r2) {
+  const double s5r = 2.23606797749978969641 * sqrt(r2);
+  const double poly = (s5r + 1.0) + (5.0 / 3.0) * r2;
+  return poly * exp(-s5r);
+}
+template <> __device__ __forceinline__ float corr_matern52<float>(float r2) {
+  const float s5r = 2.2360679775f * sqrtf(r2);
+  const float poly = (s5r + 1.0f) + (5.0f / 3.0f) * r2;
+  return poly * expf(-s5r);
+}
+template <typename T> __device__ __forceinline__ T corr_rbf(T r2);
+template <> __device__ __forceinline__ double corr_rbf<double>(double r2) { return exp(-0.5 * r2); }
+template <> __device__ __forceinline__ float corr_rbf<float>(float r2) { return expf(-0.5f * r2); }
+
+template <typename T> __device__ __forceinline__ T correlation(T r2, int kernel) {
+  return kernel == CRS_MATERN52 ? corr_matern52<T>(r2) : corr_rbf<T>(r2);
+}
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+inline int dim_pad_of(int d) {
+  int p = 1;
+  while (p < d) p <<= 1;
+  return p;
+}
+
+// Host-side error plumbing shared by the C ABI.
+void set_cuda_error(cudaError_t e, const char* where);
+#define CRS_CUDA_TRY(expr, where)                 \
+  do {                                            \
+    cudaError_t _e = (expr);                      \
+    if (_e != cudaSuccess) {                      \
+      crs::set_cuda_error(_e, where);             \
+      return CRS_ERR_CUDA;                        \
+    }                                             \
+  } while (0)
+
+// Kernel launchers (one translation unit each).
+int launch_gp_prepare(const crs_gp_state* st, int arm_begin, int arm_end, cudaStream_t s);
+int launch_posterior_grid(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm_begin,
+                          int arm_end, void* mean, void* var, int64_t ld, int col_offset,
+                          cudaStream_t s);
+int launch_ocba_scan(const void* mean, const void* var, int64_t n_c, int K, int64_t ld, int dtype,
+                     int arm_offset, const int32_t* ext_best_arm, const void* ext_best_mean,
+                     const void* ext_best_var, int32_t* best_arm, void* min_zeta, int32_t* min_arm,
+                     int32_t* tie_cnt, crs_decision* decision, void* workspace, cudaStream_t s);
+int launch_ocba_resolve_tie(const void* mean, const void* var, int64_t n_c, int K, int64_t ld,
+                            int dtype, const int32_t* best_arm, const void* min_zeta,
+                            const int32_t* tie_cnt, int64_t r, crs_decision* decision,
+                            cudaStream_t s);
+int launch_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
+                       int64_t ld, int arm_offset, int p_mode, double kernel_scale,
+                       crs_decision* decision, cudaStream_t s);
+int64_t scan_workspace_bytes();
+int launch_pcs_counts(const void* mean, const void* var, int64_t n_c, int K, int64_t ld, int dtype,
+                      int64_t num_samples, uint64_t seed, uint32_t offset, int arm_offset,
+                      int64_t ctx_offset, uint32_t* counts, uint64_t* stats, cudaStream_t s);
+int launch_philox_words(const uint32_t* ctr, int64_t n, uint32_t k0, uint32_t k1, uint32_t* out,
+                        cudaStream_t s);
+
+}  // namespace crs

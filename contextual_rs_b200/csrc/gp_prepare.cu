@@ -1,0 +1,252 @@
+// crs_gp_prepare: per-arm exact-GP state (transforms, K^ = o*c(X~,X~) + noise*I, Cholesky, alpha,
+// explicit L^-1) — the work GPyTorch caches after the first eval-mode `model.posterior` call
+// (model family of contextual_rs/experiment_utils.py:29-40).
+//
+// One CTA per arm, everything in fp64 in shared memory, results cast to the compute dtype T.
+// The grid kernel wants a multiply-only inner loop, so instead of L we store
+//     linv_t[j][i] = o * (L^-1)[i][j]   (row j = column j of L^-1, zero above the diagonal)
+//     alpha[i]     = o * (K^^-1 (y~ - m))[i]
+// which give  mu~ = m + c* . alpha  and  ||L^-1 k*||^2 = || sum_j linv_t[j][:] c*_j ||^2  for the
+// unscaled correlation vector c* = c(x~*, X~).
+#include "crs_common.cuh"
+
+namespace crs {
+namespace {
+
+constexpr int kPrepThreads = 256;
+constexpr double kMinRange = 1e-8;  // botorch Normalize(min_range)
+constexpr double kMinStdv = 1e-8;   // botorch Standardize(min_stdv)
+
+__device__ __forceinline__ double block_sum(double v, double* red, int tid, int nt) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (nt >> 5); ++w) t += red[w];
+  return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPrepThreads) gp_prepare_kernel(crs_gp_state st, int arm_begin) {
+  extern __shared__ double smem[];
+  const int k = arm_begin + blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int d = st.dim, dp = st.dim_pad, ncap = st.n_cap;
+  int n = st.n_obs[k];
+  if (n > ncap) n = ncap;
+  const int lda = ncap + 1;
+  double* A = smem;                     // [ncap][lda] lower triangle
+  double* xs = A + (size_t)ncap * lda;  // [ncap][dp]  normalised / lengthscale
+  double* rhs = xs + (size_t)ncap * dp; // [ncap]
+  double* red = rhs + ncap;             // [8] reduction scratch
+  double* tr = red + 8;                 // [2*CRS_MAX_DIM] mins, ranges
+  __shared__ int fail;
+  if (tid == 0) fail = 0;
+
+  const double* X = st.train_x + (size_t)k * ncap * d;
+  const double* Y = st.train_y + (size_t)k * ncap;
+
+  // ---- Normalize bounds ------------------------------------------------------------------
+  if (tid < d) {
+    double mn, rg;
+    if (st.flags & CRS_LEARN_NORMALIZE) {
+      if (n > 0) {
+        mn = X[tid];
+        double mx = mn;
+        for (int i = 1; i < n; ++i) {
+          const double v = X[(size_t)i * d + tid];
+          mn = fmin(mn, v);
+          mx = fmax(mx, v);
+        }
+        rg = mx - mn;
+        if (rg < kMinRange) rg = 1.0;
+      } else {
+        mn = 0.0;
+        rg = 1.0;
+      }
+      st.norm_mins[(size_t)k * d + tid] = mn;
+      st.norm_ranges[(size_t)k * d + tid] = rg;
+    } else {
+      mn = st.norm_mins[(size_t)k * d + tid];
+      rg = st.norm_ranges[(size_t)k * d + tid];
+    }
+    tr[tid] = mn;
+    tr[CRS_MAX_DIM + tid] = rg;
+  }
+  __syncthreads();
+
+  // ---- transformed inputs ----------------------------------------------------------------
+  T* xn_out = reinterpret_cast<T*>(st.xn) + (size_t)k * ncap * d;
+  T* xs_out = reinterpret_cast<T*>(st.xs) + (size_t)k * ncap * dp;
+  for (int idx = tid; idx < ncap * dp; idx += nt) {
+    const int i = idx / dp, dd = idx - i * dp;
+    double v = 0.0;
+    if (i < n && dd < d) {
+      const double x = X[(size_t)i * d + dd];
+      const double xn = (x - tr[dd]) / tr[CRS_MAX_DIM + dd];
+      v = xn / st.lengthscale[(size_t)k * d + dd];
+      // eval-mode model.train_inputs: normalised in the model dtype's own arithmetic
+      xn_out[(size_t)i * d + dd] = (T(x) - T(tr[dd])) / T(tr[CRS_MAX_DIM + dd]);
+    } else if (dd < d) {
+      xn_out[(size_t)i * d + dd] = T(0);
+    }
+    xs[idx] = v;
+    xs_out[idx] = T(v);
+  }
+
+  // ---- Standardize ------------------------------------------------------------------------
+  double ybar, ysd;
+  if (st.flags & CRS_LEARN_STANDARDIZE) {
+    double s = 0.0;
+    for (int i = tid; i < n; i += nt) s += Y[i];
+    s = block_sum(s, red, tid, nt);
+    ybar = n > 0 ? s / n : 0.0;
+    double ss = 0.0;
+    for (int i = tid; i < n; i += nt) {
+      const double dv = Y[i] - ybar;
+      ss += dv * dv;
+    }
+    ss = block_sum(ss, red, tid, nt);
+    ysd = n > 1 ? sqrt(ss / (n - 1)) : 1.0;
+    if (!(ysd >= kMinStdv)) ysd = 1.0;
+    if (tid == 0) {
+      st.y_mean[k] = ybar;
+      st.y_std[k] = ysd;
+    }
+  } else {
+    ybar = st.y_mean[k];
+    ysd = st.y_std[k];
+  }
+  const double o = st.outputscale[k], noise = st.noise[k], m = st.mean_const[k];
+  for (int i = tid; i < n; i += nt) rhs[i] = (Y[i] - ybar) / ysd - m;
+  __syncthreads();
+
+  // ---- K^ (lower triangle) -----------------------------------------------------------------
+  for (int idx = tid; idx < n * n; idx += nt) {
+    const int i = idx / n, j = idx - i * n;
+    if (j <= i) {
+      double r2 = 0.0;
+      for (int dd = 0; dd < d; ++dd) {
+        const double df = xs[i * dp + dd] - xs[j * dp + dd];
+        r2 += df * df;
+      }
+      double v = o * correlation<double>(r2, st.kernel);
+      if (i == j) v += noise;
+      A[i * lda + j] = v;
+    }
+  }
+
+  // ---- Cholesky, right-looking, in place ---------------------------------------------------
+  for (int j = 0; j < n; ++j) {
+    __syncthreads();
+    const double ajj = A[j * lda + j];
+    if (!(ajj > 0.0)) {
+      if (tid == 0) fail = j + 1;
+      break;  // uniform: every thread read the same ajj
+    }
+    const double ljj = sqrt(ajj);
+    __syncthreads();
+    if (tid == 0) A[j * lda + j] = ljj;
+    for (int i = j + 1 + tid; i < n; i += nt) A[i * lda + j] /= ljj;
+    __syncthreads();
+    const int mrem = n - j - 1;
+    for (int idx = tid; idx < mrem * mrem; idx += nt) {
+      const int i = j + 1 + idx / mrem, c = j + 1 + idx % mrem;
+      if (c <= i) A[i * lda + c] -= A[i * lda + j] * A[c * lda + j];
+    }
+  }
+  __syncthreads();
+  if (fail) {
+    if (tid == 0) st.status[k] = fail;
+    return;
+  }
+
+  // ---- alpha = K^^-1 rhs: L z = rhs, L^T a = z ----------------------------------------------
+  for (int j = 0; j < n; ++j) {
+    __syncthreads();
+    const double zj = rhs[j] / A[j * lda + j];
+    __syncthreads();
+    if (tid == 0) rhs[j] = zj;
+    for (int i = j + 1 + tid; i < n; i += nt) rhs[i] -= A[i * lda + j] * zj;
+  }
+  for (int j = n - 1; j >= 0; --j) {
+    __syncthreads();
+    const double aj = rhs[j] / A[j * lda + j];
+    __syncthreads();
+    if (tid == 0) rhs[j] = aj;
+    for (int i = tid; i < j; i += nt) rhs[i] -= A[j * lda + i] * aj;
+  }
+  __syncthreads();
+
+  // ---- L <- L^-1 in place (column sweep from the right) -------------------------------------
+  //   X[i][j] = -(sum_{c=j+1..i} X[i][c] L[c][j]) / L[j][j],  X[j][j] = 1 / L[j][j]
+  for (int j = n - 1; j >= 0; --j) {
+    const double inv = 1.0 / A[j * lda + j];
+    double acc[(CRS_MAX_OBS + kPrepThreads - 1) / kPrepThreads];
+    int cnt = 0;
+    for (int i = j + 1 + tid; i < n; i += nt, ++cnt) {
+      double a = 0.0;
+      for (int c = j + 1; c <= i; ++c) a += A[i * lda + c] * A[c * lda + j];
+      acc[cnt] = a;
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int i = j + 1 + tid; i < n; i += nt, ++cnt) A[i * lda + j] = -acc[cnt] * inv;
+    if (tid == 0) A[j * lda + j] = inv;
+    __syncthreads();
+  }
+
+  // ---- write the prepared state --------------------------------------------------------------
+  T* alpha = reinterpret_cast<T*>(st.alpha) + (size_t)k * ncap;
+  for (int i = tid; i < ncap; i += nt) alpha[i] = i < n ? T(o * rhs[i]) : T(0);
+  T* lt = reinterpret_cast<T*>(st.linv_t) + (size_t)k * ncap * ncap;
+  for (int idx = tid; idx < ncap * ncap; idx += nt) {
+    const int j = idx / ncap, i = idx - j * ncap;
+    lt[idx] = (i >= j && i < n) ? T(o * A[i * lda + j]) : T(0);
+  }
+  if (tid < dp) {
+    T* sub = reinterpret_cast<T*>(st.ctx_sub) + (size_t)k * dp;
+    T* mul = reinterpret_cast<T*>(st.ctx_mul) + (size_t)k * dp;
+    if (tid < d) {
+      sub[tid] = T(tr[tid]);
+      mul[tid] = T(1.0 / (tr[CRS_MAX_DIM + tid] * st.lengthscale[(size_t)k * d + tid]));
+    } else {
+      sub[tid] = T(0);
+      mul[tid] = T(0);
+    }
+  }
+  if (tid == 0) {
+    T* sc = reinterpret_cast<T*>(st.arm_scal) + (size_t)k * 4;
+    sc[0] = T(o);
+    sc[1] = T(m);
+    sc[2] = T(ybar);
+    sc[3] = T(ysd);
+    st.status[k] = 0;
+  }
+}
+
+}  // namespace
+
+int launch_gp_prepare(const crs_gp_state* st, int arm_begin, int arm_end, cudaStream_t s) {
+  if (!st || arm_begin < 0 || arm_end > st->num_arms || arm_begin > arm_end) return CRS_ERR_INVALID_ARG;
+  if (st->dim < 1 || st->dim > CRS_MAX_DIM || st->dim_pad != dim_pad_of(st->dim)) return CRS_ERR_UNSUPPORTED;
+  if (st->n_cap < 1 || st->n_cap > CRS_MAX_OBS) return CRS_ERR_UNSUPPORTED;
+  if (arm_begin == arm_end) return CRS_OK;
+  const size_t ncap = st->n_cap;
+  const size_t smem = (ncap * (ncap + 1) + ncap * st->dim_pad + ncap + 8 + 2 * CRS_MAX_DIM) * sizeof(double);
+  const int grid = arm_end - arm_begin;
+  if (st->dtype == CRS_F64) {
+    CRS_CUDA_TRY(cudaFuncSetAttribute(gp_prepare_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "prepare attr");
+    gp_prepare_kernel<double><<<grid, kPrepThreads, smem, s>>>(*st, arm_begin);
+  } else if (st->dtype == CRS_F32) {
+    CRS_CUDA_TRY(cudaFuncSetAttribute(gp_prepare_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "prepare attr");
+    gp_prepare_kernel<float><<<grid, kPrepThreads, smem, s>>>(*st, arm_begin);
+  } else {
+    return CRS_ERR_INVALID_ARG;
+  }
+  CRS_CUDA_TRY(cudaGetLastError(), "gp_prepare launch");
+  return CRS_OK;
+}
+
+}  // namespace crs

@@ -1,0 +1,225 @@
+/*
+ * crs_b200.h — C ABI of libcrs_b200.so: the B200 (sm_100a) implementation of contextual_rs's
+ * per-iteration decision hot path.
+ *
+ * The reference (saitcakmak/contextual_rs) is pure Python and has no FFI layer; its boundary for
+ * this path is the Python function signature plus a duck-typed BoTorch model.
+ * Each entry point below names the reference interface it replaces; INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, enums; no C++/torch types cross the boundary;
+ *   - every pointer is DEVICE memory owned by the caller unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every launch
+ *     goes to that stream and no entry point synchronises unless documented;
+ *   - return value: 0 (CRS_OK) or a crs_status code, never an exception;
+ *   - tables are row-major `[n_c, ld]` with the ARM index fastest, i.e. exactly the layout of the
+ *     reference's `posterior.mean` / `posterior.variance` (`n_c x K`).
+ */
+#ifndef CRS_B200_H
+#define CRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CRS_API __attribute__((visibility("default")))
+#else
+#define CRS_API
+#endif
+
+#define CRS_ABI_VERSION 1
+#define CRS_MAX_DIM 16   /* context dimension d <= 16 */
+#define CRS_MAX_OBS 160  /* observations per arm handled by the shared-memory Cholesky */
+
+typedef enum crs_status {
+  CRS_OK = 0,
+  CRS_ERR_INVALID_ARG = 1,
+  CRS_ERR_UNSUPPORTED = 2,   /* d > CRS_MAX_DIM, n_obs > CRS_MAX_OBS, ... */
+  CRS_ERR_CUDA = 3,          /* a CUDA runtime call failed; see crs_last_cuda_error() */
+  CRS_ERR_NOT_PSD = 4,       /* Cholesky pivot <= 0 for some arm (see state.status) */
+  CRS_TIES_PENDING = 5       /* crs_gao_decide_host: >1 exact minimisers; caller must resolve */
+} crs_status;
+
+typedef enum crs_dtype { CRS_F64 = 0, CRS_F32 = 1 } crs_dtype;
+typedef enum crs_kernel { CRS_MATERN52 = 0, CRS_RBF = 1 } crs_kernel;
+
+/* flags for crs_gp_state.flags */
+#define CRS_LEARN_NORMALIZE 1   /* learn Normalize bounds from each arm's train_x (else use norm_*) */
+#define CRS_LEARN_STANDARDIZE 2 /* learn Standardize mean/std from each arm's train_y (else use y_*) */
+
+/* p-surrogate of OCBA step 2(b): contextual_rs/contextual_rs_strategies.py:158-193 */
+typedef enum crs_p_mode {
+  CRS_P_COUNT = 0,   /* exact-match training counts   (:187-193) */
+  CRS_P_KDE = 1,     /* sum exp(-scale * ||x - c*||)  (:168-186; continuous_context.py:112-122) */
+  CRS_P_INFER = 2    /* prior / posterior variance    (:158-167) */
+} crs_p_mode;
+
+/*
+ * One ModelListGP of K independent SingleTaskGP arms
+ * (contextual_rs/experiment_utils.py:29-40: Standardize(m=1) + Normalize(d) + ScaleKernel(ARD
+ * Matern-5/2 | RBF) + ConstantMean + homoskedastic noise).  "Fitted description" arrays are inputs
+ * (always fp64); "prepared" arrays are written by crs_gp_prepare in the compute dtype T.
+ * `dim_pad` is d rounded up to {1,2,4,8,16}; padded coordinates are zero.
+ */
+typedef struct crs_gp_state {
+  int32_t num_arms;   /* K */
+  int32_t n_cap;      /* row capacity per arm, >= max n_obs, multiple of 8 */
+  int32_t dim;        /* d */
+  int32_t dim_pad;    /* padded d used by the prepared arrays */
+  int32_t kernel;     /* crs_kernel */
+  int32_t dtype;      /* crs_dtype of the prepared arrays and of all tables */
+  int32_t flags;      /* CRS_LEARN_* */
+  int32_t reserved;
+  /* fitted description */
+  const double* train_x;      /* [K, n_cap, d]  raw inputs */
+  const double* train_y;      /* [K, n_cap]     raw targets */
+  const int32_t* n_obs;       /* [K] */
+  const double* lengthscale;  /* [K, d] */
+  const double* outputscale;  /* [K] */
+  const double* noise;        /* [K] */
+  const double* mean_const;   /* [K] */
+  double* norm_mins;          /* [K, d]  in (frozen) or out (learnt) */
+  double* norm_ranges;        /* [K, d] */
+  double* y_mean;             /* [K] */
+  double* y_std;              /* [K] */
+  /* prepared */
+  void* xn;        /* [K, n_cap, d]        T  normalised inputs == eval-mode model.train_inputs */
+  void* xs;        /* [K, n_cap, dim_pad]  T  normalised / lengthscale */
+  void* alpha;     /* [K, n_cap]           T  o * K^-1 (y~ - m) */
+  void* linv_t;    /* [K, n_cap, n_cap]    T  row j = o * (column j of L^-1), zero above diagonal */
+  void* ctx_sub;   /* [K, dim_pad]         T  Normalize mins */
+  void* ctx_mul;   /* [K, dim_pad]         T  1 / (range * lengthscale), 0 in padded dims */
+  void* arm_scal;  /* [K, 4]               T  (outputscale, mean_const, y_mean, y_std) */
+  int32_t* status; /* [K]  0 = ok, j+1 = non-positive Cholesky pivot at column j */
+} crs_gp_state;
+
+/* Result of the allocation scan + step 2(b); lives in device memory, 64 bytes. */
+typedef struct crs_decision {
+  double min_zeta;     /* global min of zeta_{c,j}                 (strategies.py:145) */
+  double psi_best;     /* y_s_1                                     (strategies.py:195) */
+  double psi_rest;     /* y_s_2                                     (strategies.py:196) */
+  int64_t tie_count;   /* # of (context, arm) entries equal to min_zeta (strategies.py:147-149) */
+  int32_t context;     /* min_context                               (strategies.py:155) */
+  int32_t zeta_arm;    /* arm id attaining min_zeta at that context (strategies.py:157,201) */
+  int32_t best_arm;    /* predicted best arm at that context */
+  int32_t next_arm;    /* the decision                              (strategies.py:199-201) */
+  int32_t reserved[4];
+} crs_decision;
+
+CRS_API int crs_abi_version(void);
+CRS_API const char* crs_status_string(int status);
+CRS_API const char* crs_last_cuda_error(void);
+
+/* Bytes of workspace crs_ocba_scan needs; zero it once, the kernel leaves it zeroed. */
+CRS_API int64_t crs_scan_workspace_bytes(void);
+
+/*
+ * Replaces the one-off work of `ModelListGP.posterior` that GPyTorch caches after the first
+ * eval-mode call: input/outcome transforms, K^ = K(X,X) + noise*I, its Cholesky factor and
+ * alpha.  Arms [arm_begin, arm_end); one CTA per arm, fp64 throughout,
+ * results cast to T.  Re-run it for one arm after appending an observation to get the
+ * `condition_on_observations` update of experiments/wsc_experiments/main.py:356-362.
+ */
+CRS_API int crs_gp_prepare(const crs_gp_state* st, int32_t arm_begin, int32_t arm_end, void* stream);
+
+/*
+ * Replaces `model.posterior(context_set)` -> (.mean, .variance)
+ * (contextual_rs/contextual_rs_strategies.py:133-136, generalized_pcs.py:443-444,
+ * continuous_context.py:68,96, experiments/wsc_experiments/main.py:460).
+ * ctx: [n_c, d] T.  Writes columns [col_offset + arm - arm_begin] of mean/var ([n_c, ld], T) for
+ * arms [arm_begin, arm_end).  Variance is clamped at gpytorch's min_variance (1e-10 / 1e-6).
+ */
+CRS_API int crs_posterior_grid(const crs_gp_state* st, const void* ctx, int64_t n_c,
+                       int32_t arm_begin, int32_t arm_end,
+                       void* mean, void* var, int64_t ld, int32_t col_offset, void* stream);
+
+/*
+ * Replaces sort + gather + zeta + global argmin of gao_modellist
+ * (contextual_rs/contextual_rs_strategies.py:137-157), `_get_hat_Z` / `MinZeta.forward`
+ * (contextual_rs/continuous_context.py:21-36, 57-74; min_zeta[c] == -MinZeta(c)) and the best-arm
+ * readout `posterior.mean.argmax` (experiments/wsc_experiments/main.py:459-468).
+ * mean/var: [n_c, ld] T, K valid columns.  Per-context outputs (any may be NULL):
+ *   best_arm[n_c] int32, min_zeta[n_c] T, min_arm[n_c] int32, tie_cnt[n_c] int32.
+ * If ext_best_* are non-NULL the predicted best of every context is taken from them (global arm
+ * id, mean, variance — the all-gathered best of an arm-sharded run) instead of the local row.
+ * arm_offset is added to local column indices to form arm ids.  `decision` (may be NULL) receives
+ * min_zeta/context/zeta_arm/best_arm/tie_count.  workspace: crs_scan_workspace_bytes() bytes, zeroed.
+ * Tie rule (the reference's is implementation-defined): lowest arm id wins the
+ * arg-max; among equal zeta the larger mean then the lower arm id; among contexts the lowest.
+ */
+CRS_API int crs_ocba_scan(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                  int32_t dtype, int32_t arm_offset,
+                  const int32_t* ext_best_arm, const void* ext_best_mean, const void* ext_best_var,
+                  int32_t* best_arm, void* min_zeta, int32_t* min_arm, int32_t* tie_cnt,
+                  crs_decision* decision, void* workspace, void* stream);
+
+/*
+ * Replaces the tie randomisation of contextual_rs/contextual_rs_strategies.py:147-154: given the
+ * caller's draw r = torch.randint(tie_count, (1,)) rewrites decision->{context, zeta_arm, best_arm}
+ * to the r-th tied entry in flat (context-major) order.
+ */
+CRS_API int crs_ocba_resolve_tie(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                         int32_t dtype, const int32_t* best_arm, const void* min_zeta,
+                         const int32_t* tie_cnt, int64_t r, crs_decision* decision, void* stream);
+
+/*
+ * Replaces OCBA step 2(b) (contextual_rs/contextual_rs_strategies.py:158-202,
+ * contextual_rs/continuous_context.py:110-132): y_i = p_i / var_i at the selected context, psi of
+ * the best arm vs the sum over the others, and the final arm.  Reads decision->context/zeta_arm/
+ * best_arm from device memory (no host round-trip) and writes psi_best, psi_rest, next_arm.
+ * ctx: [n_c, d] T; var: [n_c, ld] T with st->num_arms valid columns; arm_offset maps local columns
+ * to arm ids (arm-sharded runs: psi_* are then partial sums the host all-reduces).  decision->
+ * reserved[0] receives (first arm with a failed Cholesky)+1, or 0.
+ */
+CRS_API int crs_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
+                    int64_t ld, int32_t arm_offset, int32_t p_mode, double kernel_scale,
+                    crs_decision* decision, void* stream);
+
+/*
+ * Replaces the sampling half of estimate_current_generalized_pcs for a ModelListGP
+ * (contextual_rs/generalized_pcs.py:441-475): for every context, the number of the S posterior
+ * draws in which the predicted-best arm beats every other arm (func_I = strict indicator).  Draws
+ * are per-(context, arm) marginals from a Philox4x32-10 stream keyed by
+ * (seed; sample/4, context + ctx_offset, arm + arm_offset, offset); nothing S-sized touches HBM.
+ * counts: [n_c] uint32.  stats (may be NULL): [2] uint64 = {draws executed, draws skipped by the
+ * exact |z| <= 5.7683 screen}.
+ */
+CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                   int32_t dtype, int64_t num_samples, uint64_t seed, uint32_t offset,
+                   int32_t arm_offset, int64_t ctx_offset, uint32_t* counts, uint64_t* stats,
+                   void* stream);
+
+/* Raw Philox4x32-10 words for known-answer tests: out[4*i..4*i+3] = philox(ctr[4*i..], key). */
+CRS_API int crs_philox_words(const uint32_t* ctr, int64_t n, uint32_t key0, uint32_t key1, uint32_t* out,
+                     void* stream);
+
+/*
+ * Whole decision through one call with HOST context buffers — the reference-facing entry that
+ * stands in for `gao_modellist(model, context_set, ...)` when context_set lives on the CPU, as it
+ * does in the reference's driver (experiments/wsc_experiments/main.py:226-228).
+ * Copies ctx_host (pinned or pageable, [n_c, d] T) to ws_ctx, optionally re-prepares arms
+ * [prep_begin, prep_end), runs grid -> scan -> select on `stream`, copies the decision back to
+ * decision_host and synchronises the stream.  Returns CRS_TIES_PENDING if randomize_ties and
+ * tie_count > 1 (the caller then draws r, calls crs_ocba_resolve_tie + crs_ocba_select).
+ * ws_* are caller-owned device buffers: ctx [n_c,d] T, mean/var [n_c,K] T, best_arm/min_arm/
+ * tie_cnt [n_c] int32, min_zeta [n_c] T, decision (device), scan workspace.
+ */
+typedef struct crs_decide_ws {
+  void* ctx; void* mean; void* var;
+  int32_t* best_arm; void* min_zeta; int32_t* min_arm; int32_t* tie_cnt;
+  crs_decision* decision; void* scan_ws;
+} crs_decide_ws;
+
+CRS_API int crs_gao_decide_host(const crs_gp_state* st, const void* ctx_host, int64_t n_c,
+                        int32_t prep_begin, int32_t prep_end, int32_t p_mode, double kernel_scale,
+                        int32_t randomize_ties, const crs_decide_ws* ws,
+                        crs_decision* decision_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRS_B200_H */
