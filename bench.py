@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — the GP-C-OCBA decision benchmark on BASELINE.json config 2 (default workload).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
+
+A *step* is one whole GP-C-OCBA decision on a model whose caches are cold: per-arm Cholesky
+state (crs_gp_prepare, all arms), ModelListGP posterior over the arm x context grid
+(crs_posterior_grid), zeta scan + global argmin (crs_ocba_scan) and OCBA step 2(b)
+(crs_ocba_select) — what `gao_modellist(model, context_set)` does in the reference
+(contextual_rs/contextual_rs_strategies.py:100-202) on a freshly fitted model.
+
+  value : decisions/s with every input already resident in HBM (device timed, CUDA events).
+  e2e   : decisions/s through the public drop-in `contextual_rs_b200.gao_modellist(model,
+          context_set)` with the context set in pinned HOST memory: host->device copy of the
+          contexts and device->host read of the decision inside every timed step.
+  N > 1 : the context set is sharded over the ranks (one process per GPU, NCCL); every decision
+          ends in one 64-byte-per-rank all-gather.  Fixed total work -> "strong" scaling.
+
+The L2 is flushed (256 MiB write) between timed steps; each step is bracketed by its own pair of
+CUDA events on the launching stream and the per-step durations are summed.
+`--impl reference` times the CPU restatement of the reference (oracle/, PyTorch on the host
+cores; BoTorch/GPyTorch are not installable here) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    "c2": "c2: GP-C-OCBA decision, 100 arms x 1,024 contexts, 4-D, 20 obs/arm, Matern-5/2",
+    "c3": "c3: GP-C-OCBA decision, 256 arms x 8,192 contexts, 4-D, 20 obs/arm, Matern-5/2",
+    "c4": "c4: GP-C-OCBA decision, 1,000 arms x 65,536 Sobol contexts, 8-D, 18 obs/arm, Matern-5/2",
+    "c5": "c5: GP-C-OCBA decision, 1,000 arms x 16,384 contexts, 4-D, 20 obs/arm, Matern-5/2",
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_flops(K, n_c, n, d):
+    """distance + kernel eval + mean dot + triangular solve + squared norm."""
+    return K * n_c * (n * (3 * d + 10) + 2 * n + n * n)
+
+
+# ------------------------------------------------------------------------------------------- CPU
+class _TableModel:
+    def __init__(self, mean, var, train_inputs, K):
+        self._p = type("P", (), {"mean": mean, "variance": var})()
+        self.models = [None] * K
+        self.train_inputs = train_inputs
+
+    def posterior(self, X):
+        return self._p
+
+
+def cpu_decision_step(desc, ctx, variant):
+    """One decision with the oracle on the host cores (cold model caches, like the GPU step)."""
+    from oracle import gp_oracle, ocba_oracle
+    if variant == "batched":
+        mean, var = gp_oracle.posterior_grid_batched(desc, ctx)
+        K = len(desc["train_X"])
+        TX = torch.stack(desc["train_X"])
+        mins = TX.min(dim=1, keepdim=True).values
+        rng = TX.max(dim=1, keepdim=True).values - mins
+        rng = torch.where(rng < 1e-8, torch.ones_like(rng), rng)
+        xn = (TX - mins) / rng
+        model = _TableModel(mean, var, [(xn[k],) for k in range(K)], K)
+    else:
+        model = gp_oracle.model_from_description(desc)
+    arm, x = ocba_oracle.gao_modellist_ref(model, ctx)
+    return int(arm)
+
+
+def time_cpu(desc, ctx, budget_s, max_steps):
+    torch.set_num_threads(os.cpu_count() or 1)
+    best = None
+    for variant in ("batched", "modellist"):
+        t0 = time.perf_counter()
+        cpu_decision_step(desc, ctx, variant)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[1]:
+            best = (variant, dt)
+    variant, est = best
+    steps = int(max(2, min(max_steps, budget_s / max(est, 1e-6))))
+    cpu_decision_step(desc, ctx, variant)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_decision_step(desc, ctx, variant)
+    dt = (time.perf_counter() - t0) / steps
+    return variant, steps, dt
+
+
+def run_reference(args, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from contextual_rs_b200.synthetic import make_config
+    desc, ctx = make_config(name)
+    K, n_c = len(desc["train_X"]), ctx.shape[0]
+    full = name == "c2"
+    if not full:  # bounded sample: a slice of the contexts, scaled linearly
+        sub = max(256, n_c // 64)
+        ctx_s = ctx[:sub]
+    else:
+        sub, ctx_s = n_c, ctx
+    variant, steps, dt = time_cpu(desc, ctx_s, budget_s=min(60.0, 4.0 * max(args.steps, 1)), max_steps=max(args.steps, 2))
+    dt_full = dt * (n_c / sub)
+    cores = torch.get_num_threads()
+    sample = (f"{steps} decisions on {sub}/{n_c} contexts x {K} arms, oracle '{variant}' variant "
+              f"(PyTorch CPU, {cores} threads), time scaled x{n_c / sub:.0f}")
+    val = 1.0 / dt_full
+    print(json.dumps({
+        "impl": "reference", "metric": "gp_c_ocba_decisions_per_sec", "value": val, "unit": "decisions/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt_full * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[name]},
+        "cpu_baseline": {"value": val, "unit": "decisions/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------- GPU
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (profiling only)")
+    args = ap.parse_args()
+    name = args.workload
+    if args.impl == "reference":
+        return run_reference(args, name)
+
+    import torch.distributed as dist
+    import contextual_rs_b200 as crs
+    from contextual_rs_b200 import _lib
+    from contextual_rs_b200.contextual_rs_strategies import _scan
+    from contextual_rs_b200.sharded import ContextShardedDecider, REC_CONTEXT, REC_NEXT_ARM, shard_bounds
+    from contextual_rs_b200.synthetic import make_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: contextual_rs_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K_steps = max(args.warmup, 3), args.steps
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    w = 8 if dtype == torch.float64 else 4
+
+    desc, ctx = make_config(name)
+    K, n_c, d = len(desc["train_X"]), ctx.shape[0], ctx.shape[1]
+    n_obs = desc["train_X"][0].shape[0]
+    model = crs.B200ModelListGP(desc, device=dev, dtype=dtype)
+    model.check_status()
+    lib = _lib.get()
+    peaks, peak_src = load_peaks()
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def flush():
+        if not args.no_flush:
+            flush_buf.fill_(1)
+
+    begin, end = shard_bounds(n_c, world, rank)
+    n_loc = end - begin
+    decider = ContextShardedDecider(model, ctx)
+    ctx_dev = decider.local_ctx
+    ws = model.workspace(max(n_loc, 1))
+    stream = _lib.stream_ptr(dev)
+    st = C.byref(model.state)
+
+    def device_step():
+        """prepare -> grid -> scan -> select, all inputs resident, no host round-trip."""
+        _lib.check(lib.crs_gp_prepare(st, 0, K, stream))
+        if n_loc:
+            _lib.check(lib.crs_posterior_grid(st, ctx_dev.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
+                                              ws["var"].data_ptr(), K, 0, stream))
+            _scan(lib, model, ws, n_loc, stream)
+            _lib.check(lib.crs_ocba_select(st, ctx_dev.data_ptr(), ws["mean"].data_ptr(), ws["var"].data_ptr(),
+                                           K, 0, 0, 2.0, ws["decision"].data_ptr(), stream))
+        if world > 1:
+            dist.all_gather_into_tensor(decider._gather, ws["decision"] if n_loc else decider._empty)
+
+    ctx_host = ctx.to(dtype).pin_memory()
+
+    def e2e_step():
+        if world == 1:
+            from contextual_rs_b200.contextual_rs_strategies import decide
+            dec = decide(model, ctx_host, True, 0, 2.0, prepare_arms=(0, K))
+            return dec.next_arm, dec.context
+        # sharded: every rank uploads its slice of the pinned host context set, then one all-gather
+        decider.local_ctx.copy_(ctx_host[begin:end], non_blocking=True)
+        rec = decider.decide(prepare_arms=(0, K))
+        return int(rec[REC_NEXT_ARM]), int(rec[REC_CONTEXT])
+
+    def timed_loop(fn, steps, per_kernel=False):
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for i in range(steps):
+            flush()
+            starts[i].record()
+            fn()
+            ends[i].record()
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in zip(starts, ends)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    for _ in range(W):
+        flush()
+        device_step()
+    for _ in range(W):
+        flush()
+        e2e_step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident value ---------------------------------------------------------------------
+    barrier()
+    dev_ms = timed_loop(device_step, K_steps)
+    barrier()
+    # ---- dominant-kernel duration (posterior grid), same region style -------------------------------
+    def grid_only():
+        if n_loc:
+            lib.crs_posterior_grid(st, ctx_dev.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
+                                   ws["var"].data_ptr(), K, 0, stream)
+    def scan_only():
+        if n_loc:
+            _scan(lib, model, ws, n_loc, stream)
+    def prep_only():
+        lib.crs_gp_prepare(st, 0, K, stream)
+    ksteps = min(K_steps, 500)
+    grid_ms = timed_loop(grid_only, ksteps)
+    scan_ms = timed_loop(scan_only, ksteps)
+    prep_ms = timed_loop(prep_only, ksteps)
+    barrier()
+    # ---- end to end through the public API -------------------------------------------------------
+    e2e_ms = timed_loop(e2e_step, K_steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    t_dev = sum(dev_ms) / 1e3
+    t_e2e = sum(e2e_ms) / 1e3
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e, sum(grid_ms) / len(grid_ms), sum(scan_ms) / len(scan_ms)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, grid_avg, scan_avg = t.tolist()
+    else:
+        grid_avg, scan_avg = sum(grid_ms) / len(grid_ms), sum(scan_ms) / len(scan_ms)
+    prep_avg = sum(prep_ms) / len(prep_ms)
+
+    if rank == 0:
+        value = K_steps / t_dev
+        flops = algorithmic_flops(K, n_loc, n_obs, d)
+        fp64_peak = 148 * 64 * 2 * 1.965e9 / 1e12 if dtype == torch.float64 else 148 * 128 * 2 * 1.965e9 / 1e12
+        achieved = flops / (grid_avg * 1e-3) / 1e12
+        scan_bytes = 2 * K * n_loc * w + n_loc * (w + 12)
+        out = {
+            "metric": "gp_c_ocba_decisions_per_sec", "value": value, "unit": "decisions/s",
+            "n_gpus": world, "steps": K_steps, "warmup": W, "ms_per_step": t_dev / K_steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": WORKLOADS[name], "arms": K, "contexts": n_c, "dim": d, "obs_per_arm": n_obs,
+                       "sharding": f"contexts/{world}" if world > 1 else "none",
+                       "l2": "flushed between timed steps (256 MiB write)" if not args.no_flush else "not flushed",
+                       "step": "prepare(all arms) + posterior grid + zeta scan + OCBA select"},
+            "e2e": {"value": K_steps / t_e2e, "unit": "decisions/s", "ms_per_step": t_e2e / K_steps * 1e3,
+                    "h2d_bytes_per_step": int(n_c * d * w), "d2h_bytes_per_step": 64 * world},
+            "gpu_launches": 4 * K_steps + 4 * K_steps + 3 * ksteps,
+            "roofline": {"kernel": "posterior_grid_kernel", "bound": "fp64_fma" if dtype == torch.float64 else "fp32_fma",
+                         "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                         "traffic": None, "avg_launch_ms": grid_avg,
+                         "peak_source": "nominal 148 SM x 64 (fp64) / 128 (fp32) FMA lanes x 2 x 1.965 GHz; "
+                                        "no fp64 figure in MEASURED_PEAKS.json",
+                         "algorithmic_flops_per_launch": flops},
+            "roofline_scan": {"kernel": "ocba_scan_kernel", "bound": "hbm", "achieved": scan_bytes / (scan_avg * 1e-3) / 1e9,
+                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": scan_bytes / (scan_avg * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                              "traffic": None, "avg_launch_ms": scan_avg, "peak_source": peak_src,
+                              "algorithmic_bytes_per_launch": scan_bytes},
+            "kernel_ms": {"gp_prepare": prep_avg, "posterior_grid": grid_avg, "ocba_scan": scan_avg},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            if name == "c2":
+                variant, steps, dt = time_cpu(desc, ctx, budget_s=15.0, max_steps=200)
+                scale = 1.0
+                sub = n_c
+            else:
+                sub = max(256, n_c // 64)
+                variant, steps, dt = time_cpu(desc, ctx[:sub], budget_s=15.0, max_steps=50)
+                scale = n_c / sub
+            out["cpu_baseline"] = {
+                "value": 1.0 / (dt * scale), "unit": "decisions/s", "cores": torch.get_num_threads(), "kind": "port",
+                "sample": f"{steps} decisions, oracle '{variant}' variant on {sub}/{n_c} contexts x {K} arms, "
+                          f"time scaled x{scale:.0f}; PyTorch CPU, {torch.get_num_threads()} threads"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,180 @@
+"""Multi-GPU decision + PCS: one process per GPU, ``torch.distributed`` for the (tiny) exchanges.
+
+Two partitions of the arm x context grid are supported:
+
+``contexts`` (default)
+    every rank holds the whole (small, ~MBs) GP state and owns a contiguous slice of the context
+    set.  Grid posterior, scan, step 2(b) and PCS counts are purely local; the only exchange of a
+    decision is ONE all-gather of the 64-byte ``crs_decision`` of each rank's local minimiser, and
+    the PCS estimate needs one all-gather of the per-context counts (or a scalar all-reduce).
+``arms`` (the partition BASELINE.json's north_star describes)
+    rank g owns arms [g*K/G, (g+1)*K/G) for ALL contexts.  After the local grid, ranks all-gather
+    their per-context local best (mean, variance, arm id), reduce it to the global best per
+    context, scan their own columns against it (``ext_best_*`` of ``crs_ocba_scan``), all-gather
+    the local minimisers, and all-reduce the two psi partial sums of step 2(b).
+
+The combination rules are pure functions of the gathered buffers so that they can be tested on
+the CPU with the gloo backend (tests/test_sharded_cpu.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import _lib
+
+# column layout of the float64 record every rank contributes to the decision all-gather
+REC_MIN_ZETA, REC_TIES, REC_CONTEXT, REC_ZETA_ARM, REC_BEST_ARM, REC_NEXT_ARM, REC_PSI_BEST, REC_PSI_REST = range(8)
+REC_WIDTH = 8
+
+
+def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced [begin, end) of ``total`` items for ``rank`` of ``world``."""
+    base, rem = divmod(total, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def decision_record(min_zeta: float, ties: int, context: int, zeta_arm: int, best_arm: int,
+                    next_arm: int, psi_best: float = 0.0, psi_rest: float = 0.0) -> Tensor:
+    """One rank's local minimiser as a float64 row (indices < 2^53 are exact in float64)."""
+    return torch.tensor([min_zeta, ties, context, zeta_arm, best_arm, next_arm, psi_best, psi_rest],
+                        dtype=torch.float64)
+
+
+def records_from_bytes(raw: Tensor, n_c: int, world: int) -> Tensor:
+    """``[world, 64]`` uint8 crs_decision structs (LOCAL context indices of a context-sharded
+    run) -> ``[world, REC_WIDTH]`` float64 records with GLOBAL context indices."""
+    out = torch.zeros(world, REC_WIDTH, dtype=torch.float64)
+    buf = raw.numpy()
+    for r in range(world):
+        d = _lib.Decision.from_buffer_copy(buf[r].tobytes())
+        begin, _ = shard_bounds(n_c, world, r)
+        out[r] = decision_record(d.min_zeta, d.tie_count, d.context + begin if d.context >= 0 else -1,
+                                 d.zeta_arm, d.best_arm, d.next_arm, d.psi_best, d.psi_rest)
+    return out
+
+
+def combine_context_sharded(records: Tensor) -> Tensor:
+    """``records``: ``[world, REC_WIDTH]`` (contexts already GLOBAL indices).  The global decision
+    is the record with the smallest zeta; equal zeta -> lowest global context (the reference's
+    first-minimum rule in flat context-major order); the tie count is summed over ranks that attain
+    the minimum.  Ranks with no contexts contribute min_zeta = +inf."""
+    z = records[:, REC_MIN_ZETA]
+    zmin = z.min()
+    at_min = z == zmin
+    ctx = torch.where(at_min, records[:, REC_CONTEXT], torch.full_like(z, float("inf")))
+    winner = int(torch.argmin(ctx))
+    out = records[winner].clone()
+    out[REC_TIES] = records[at_min, REC_TIES].sum()
+    return out
+
+
+def combine_local_best(means: Tensor, variances: Tensor, arms: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """Arm sharding, step 2: ``[world, n_c]`` gathered per-context local bests -> global best per
+    context (largest mean, lowest arm id on ties)."""
+    top = means.max(dim=0).values
+    cand = torch.where(means == top.unsqueeze(0), arms, torch.full_like(arms, torch.iinfo(arms.dtype).max))
+    arm = cand.min(dim=0).values
+    owner = (cand == arm.unsqueeze(0)).to(torch.int64).argmax(dim=0)
+    idx = owner.unsqueeze(0)
+    return means.gather(0, idx).squeeze(0), variances.gather(0, idx).squeeze(0), arm
+
+
+def combine_arm_sharded(records: Tensor, mean_at: Optional[Tensor] = None) -> Tensor:
+    """Arm sharding, step 3/4: every rank's record refers to the SAME context set; the global
+    minimiser is the smallest zeta, then the lowest context, then (same context) the larger mean of
+    the zeta arm / lower arm id is left to the per-rank rule.  psi partial sums are added."""
+    z = records[:, REC_MIN_ZETA]
+    zmin = z.min()
+    at_min = z == zmin
+    ctx = torch.where(at_min, records[:, REC_CONTEXT], torch.full_like(z, float("inf")))
+    cmin = ctx.min()
+    both = at_min & (records[:, REC_CONTEXT] == cmin)
+    arms = torch.where(both, records[:, REC_ZETA_ARM], torch.full_like(z, float("inf")))
+    winner = int(torch.argmin(arms))
+    out = records[winner].clone()
+    out[REC_TIES] = records[at_min, REC_TIES].sum()
+    return out
+
+
+def all_gather_rows(row: Tensor, group=None) -> Tensor:
+    """All-gather one equal-shaped tensor per rank into ``[world, ...]`` (NCCL on GPUs, gloo on CPU)."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(row.shape), dtype=row.dtype, device=row.device)
+    dist.all_gather_into_tensor(out, row.contiguous(), group=group) if row.is_cuda else \
+        dist.all_gather(list(out.unbind(0)), row.contiguous(), group=group)
+    return out
+
+
+class ContextShardedDecider:
+    """GP-C-OCBA decision (+ PCS) with the context set sharded over the ranks of ``group``.
+
+    Every rank must construct it with the same model description and the same full
+    ``context_set``; rank r keeps rows ``shard_bounds(n_c, world, r)``.
+    """
+
+    def __init__(self, model, context_set: Tensor, group=None):
+        self.model = model
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_c = context_set.shape[0]
+        self.begin, self.end = shard_bounds(self.n_c, self.world, self.rank)
+        self.local_ctx = context_set[self.begin:self.end].to(device=model.device, dtype=model.dtype).contiguous()
+        # raw 64-byte crs_decision structs are exchanged as bytes; an empty shard sends +inf
+        empty = _lib.Decision(min_zeta=float("inf"), context=-1, zeta_arm=-1, best_arm=-1, next_arm=-1)
+        self._empty = torch.frombuffer(bytearray(bytes(empty)), dtype=torch.uint8).to(model.device)
+        self._gather = torch.zeros(self.world, 64, dtype=torch.uint8, device=model.device)
+        self._gather_host = torch.zeros(self.world, 64, dtype=torch.uint8).pin_memory()
+
+    def decide(self, p_mode: int = _lib.CRS_P_COUNT, kernel_scale: float = 2.0,
+               prepare_arms: Optional[Tuple[int, int]] = None) -> Tensor:
+        """Returns the combined record (``REC_*`` columns, global context index) on the host."""
+        from .contextual_rs_strategies import _scan
+        m, lib = self.model, _lib.get()
+        n_loc = self.end - self.begin
+        if n_loc > 0:
+            ws = m.workspace(n_loc)
+            K = m.num_arms
+            with torch.cuda.device(m.device):
+                stream = _lib.stream_ptr(m.device)
+                if prepare_arms is not None and prepare_arms[1] > prepare_arms[0]:
+                    m.prepare(prepare_arms[0], prepare_arms[1], relearn=False)
+                st = C.byref(m.state)
+                _lib.check(lib.crs_posterior_grid(st, self.local_ctx.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
+                                                  ws["var"].data_ptr(), K, 0, stream), "crs_posterior_grid")
+                _scan(lib, m, ws, n_loc, stream)
+                _lib.check(lib.crs_ocba_select(st, self.local_ctx.data_ptr(), ws["mean"].data_ptr(),
+                                               ws["var"].data_ptr(), K, 0, p_mode, float(kernel_scale),
+                                               ws["decision"].data_ptr(), stream), "crs_ocba_select")
+            local = ws["decision"]
+        else:
+            local = self._empty
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._gather, local, group=self.group)
+            self._gather_host.copy_(self._gather, non_blocking=True)
+        else:
+            self._gather_host[0].copy_(local, non_blocking=True)
+        torch.cuda.current_stream(m.device).synchronize()
+        return combine_context_sharded(records_from_bytes(self._gather_host, self.n_c, self.world))
+
+    def pcs_counts(self, num_samples: int, seed: int, offset: int = 0) -> Tensor:
+        """Local success counts (global context indices key the stream, so the result does not
+        depend on the number of ranks); call ``all_gather_counts`` to assemble the full vector."""
+        from .generalized_pcs import pcs_counts
+        n_loc = self.end - self.begin
+        ws = self.model.workspace(max(n_loc, 1))
+        return pcs_counts(self.model, ws["mean"][:n_loc], ws["var"][:n_loc], num_samples, seed, offset,
+                          ctx_offset=self.begin, counts=ws["counts"][:n_loc], stats=ws["stats"])
+
+    def pcs_mean(self, num_samples: int, seed: int, offset: int = 0) -> Tensor:
+        """rho = mean over contexts: one scalar all-reduce of the summed counts."""
+        total = self.pcs_counts(num_samples, seed, offset).sum(dtype=torch.int64).to(torch.float64).reshape(1)
+        if self.world > 1:
+            dist.all_reduce(total, group=self.group)
+        return total / (float(num_samples) * self.n_c)

@@ -1,0 +1,406 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI of libcrs_b200.so) against the CPU
+oracle on the same seeded inputs and against the committed golden fixtures.
+
+Stated tolerances (BASELINE.json north_star): selected (arm, context) and best-arm indices
+bit-exact; posterior mean / variance within 1e-10 in fp64 and 1e-5 in fp32, *relative to the
+table's scale* (max |mean|, resp. max variance = the prior scale s^2 o) — a pure element-wise
+relative bound is meaningless where the mean crosses zero or in fp32 where var = o - ||v||^2
+cancels — plus an element-wise relative bound on the variance in fp64; PCS within
+5 MC standard errors of exact quadrature and count-identical to the CPU Philox restatement up to
+borderline draws (MUFU vs libm transcendental rounding).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle, ocba_oracle, pcs_oracle, philox_ref
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def crs():
+    import contextual_rs_b200 as crs
+    from contextual_rs_b200 import _lib
+    _lib.get()
+    return crs
+
+
+def _scaled_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+CASES = [
+    # K, n_c, d, n, kernel, train
+    (10, 10, 1, 20, "matern52", "full"),      # BASELINE config 1
+    (3, 4, 2, 10, "matern52", "rows"),        # shapes of the reference's test_gao_modellist
+    (100, 1024, 4, 20, "matern52", "rows"),   # BASELINE config 2
+    (100, 1024, 4, 20, "rbf", "rows"),
+    (17, 333, 3, 27, "matern52", "rows"),     # d not a power of two, ragged tiles
+    (9, 100, 5, 40, "rbf", "rows"),           # n in (32, 64] -> NB=64 variant
+    (2, 1, 1, 1, "matern52", "rand"),         # minimum sizes: K=2, one context, one observation
+    (5, 130, 8, 56, "matern52", "rand"),
+    (4, 64, 16, 12, "rbf", "rand"),           # maximum supported dimension
+]
+
+
+@pytest.mark.parametrize("K,n_c,d,n,kernel,train", CASES)
+def test_posterior_and_decision_fp64(crs, K, n_c, d, n, kernel, train):
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=K, n_c=n_c, d=d, n=n, kernel=kernel, train=train, seed=1)
+    model = crs.B200ModelListGP(desc, device=DEV, dtype=torch.float64)
+    model.check_status()
+    ref = gp_oracle.model_from_description(desc)
+    rp, p = ref.posterior(ctx), model.posterior(ctx)
+    assert p.mean.shape == (n_c, K) and p.variance.shape == (n_c, K)
+    assert _scaled_err(p.mean, rp.mean) < 1e-10
+    assert _scaled_err(p.variance, rp.variance) < 1e-10
+    torch.testing.assert_close(p.variance.cpu(), rp.variance, rtol=1e-9, atol=0)
+    # batch x 1 x d input (MinZeta's shape) gives batch x 1 x K
+    p3 = model.posterior(ctx.unsqueeze(1))
+    assert p3.mean.shape == (n_c, 1, K) and torch.equal(p3.mean.squeeze(1), p.mean)
+    # normalised train inputs are bit-identical to the oracle's (needed by the exact-match count)
+    for (a,), (b,) in zip(model.train_inputs, ref.train_inputs):
+        assert torch.equal(a.cpu(), b)
+    assert torch.equal(crs.empirical_best_arms(model, ctx).cpu(), ocba_oracle.best_arms_ref(ref, ctx))
+    for kw in ({}, {"use_kde": True, "kernel_scale": 1.0}, {"infer_p": True}, {"randomize_ties": False}):
+        arm, x = crs.gao_modellist(model, ctx, **kw)
+        rarm, rx = ocba_oracle.gao_modellist_ref(ref, ctx, **kw)
+        assert arm.dtype == torch.long and arm.dim() == 0
+        assert int(arm) == int(rarm), kw
+        assert torch.equal(x, rx) and x.data_ptr() == rx.data_ptr(), kw  # a view of context_set
+    # context_set already on the GPU: same decision, outputs on the GPU
+    arm_d, x_d = crs.gao_modellist(model, ctx.to(DEV))
+    rarm, rx = ocba_oracle.gao_modellist_ref(ref, ctx)
+    assert arm_d.device.type == "cuda" and int(arm_d) == int(rarm) and torch.equal(x_d.cpu(), rx)
+
+
+@pytest.mark.parametrize("K,n_c,d,n,kernel", [(100, 1024, 4, 20, "matern52"), (20, 257, 8, 50, "rbf")])
+def test_posterior_fp32(crs, K, n_c, d, n, kernel):
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=K, n_c=n_c, d=d, n=n, kernel=kernel, seed=2)
+    model = crs.B200ModelListGP(desc, device=DEV, dtype=torch.float32)
+    rp = gp_oracle.model_from_description(desc).posterior(ctx)  # fp64 truth
+    p = model.posterior(ctx.float())
+    assert p.mean.dtype == torch.float32
+    assert _scaled_err(p.mean, rp.mean) < 1e-5
+    assert _scaled_err(p.variance, rp.variance) < 1e-5
+    # decision logic on the GPU's own fp32 tables is index-exact against the oracle's logic
+    class Tab:
+        models = [None] * K
+        train_inputs = model.train_inputs
+        def posterior(self, X):
+            return type("P", (), {"mean": p.mean.cpu(), "variance": p.variance.cpu()})()
+    tab = Tab()
+    tab.train_inputs = [(t[0].cpu(),) for t in model.train_inputs]
+    for kw in ({}, {"use_kde": True, "kernel_scale": 1.0}):
+        arm, x = crs.gao_modellist(model, ctx.float(), **kw)
+        rarm, rx = ocba_oracle.gao_modellist_ref(tab, ctx.float(), **kw)
+        assert int(arm) == int(rarm) and torch.equal(x, rx)
+
+
+def test_wsc_fixture_replay(crs, golden):
+    """Real training data written by the reference (0000_ML_Gao.pt): ragged per-arm n as the
+    reference's own decision sequence is replayed, Branin-scale targets exercising Standardize."""
+    g = golden("wsc_branin_seed0.json")
+    X = torch.tensor(g["X"], dtype=torch.float64)
+    Y = torch.tensor(g["Y"], dtype=torch.float64).view(-1, 1)
+    ctx = torch.tensor(g["context_map"], dtype=torch.float64)
+    K = g["num_arms"]
+    gen = torch.Generator().manual_seed(3)
+    hyp = dict(lengthscale=0.3 + 0.5 * torch.rand(K, 1, generator=gen, dtype=torch.float64),
+               outputscale=0.5 + torch.rand(K, generator=gen, dtype=torch.float64),
+               noise=torch.full((K,), 1e-2, dtype=torch.float64),
+               mean_const=torch.zeros(K, dtype=torch.float64), kernel="matern52")
+    for upto in (200, 263, 400):
+        desc = dict(hyp)
+        desc["train_X"] = [X[:upto][X[:upto, 0] == k][:, 1:] for k in range(K)]
+        desc["train_Y"] = [Y[:upto][X[:upto, 0] == k] for k in range(K)]
+        assert len({t.shape[0] for t in desc["train_X"]}) > (1 if upto > 200 else 0)
+        model = crs.B200ModelListGP(desc, device=DEV)
+        ref = gp_oracle.model_from_description(desc)
+        rp, p = ref.posterior(ctx), model.posterior(ctx)
+        assert _scaled_err(p.mean, rp.mean) < 1e-10 and _scaled_err(p.variance, rp.variance) < 1e-10
+        for kw in ({}, {"use_kde": True, "kernel_scale": 1.0}):
+            arm, x = crs.gao_modellist(model, ctx, **kw)
+            rarm, rx = ocba_oracle.gao_modellist_ref(ref, ctx, **kw)
+            assert int(arm) == int(rarm) and torch.equal(x, rx)
+
+
+def _run_tables(crs, mean, var, model, ctx, p_mode=0, kernel_scale=2.0):
+    """scan + select on caller-supplied tables through the C ABI."""
+    from contextual_rs_b200 import _lib
+    lib = _lib.get()
+    n_c, K = mean.shape
+    dt = _lib.DTYPES[mean.dtype]
+    out = {k: torch.zeros(n_c, dtype=torch.int32, device=DEV) for k in ("best", "zarm", "ties")}
+    out["minz"] = torch.zeros(n_c, dtype=mean.dtype, device=DEV)
+    dec = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    ws = torch.zeros(int(lib.crs_scan_workspace_bytes()), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.crs_ocba_scan(mean.data_ptr(), var.data_ptr(), n_c, K, K, dt, 0, None, None, None,
+                                 out["best"].data_ptr(), out["minz"].data_ptr(), out["zarm"].data_ptr(),
+                                 out["ties"].data_ptr(), dec.data_ptr(), ws.data_ptr(), None))
+    if model is not None:
+        _lib.check(lib.crs_ocba_select(C.byref(model.state), ctx.data_ptr(), mean.data_ptr(), var.data_ptr(),
+                                       K, 0, p_mode, kernel_scale, dec.data_ptr(), None))
+    torch.cuda.synchronize()
+    host = dec.cpu().numpy().tobytes()
+    d = _lib.Decision.from_buffer_copy(host)
+    return d, out, dec
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_mock_tables_golden(crs, golden, dtype):
+    """The reference's MockModel tables (test/test_contextual_rs_strategies.py:169-176)."""
+    g = golden("mock_tables.json")
+    mean = torch.tensor(g["mean"], dtype=dtype, device=DEV)
+    var = torch.tensor(g["variance"], dtype=dtype, device=DEV)
+    ctx = torch.linspace(0, 1, 3, dtype=dtype).unsqueeze(-1)
+    zeta = torch.tensor(g["zeta"], dtype=dtype)
+    for case in g["decisions"]:
+        rows = [torch.cat([ctx[case["next_context"]].view(1, 1).repeat(c, 1), torch.full((3, 1), 0.123, dtype=dtype)])
+                for c in case["counts"]]
+        desc = {"train_X": rows, "train_Y": [torch.zeros(r.shape[0], 1, dtype=dtype) for r in rows],
+                "lengthscale": torch.ones(3, 1), "outputscale": torch.ones(3), "noise": torch.ones(3),
+                "mean_const": torch.zeros(3), "normalize": False, "standardize": False}
+        model = crs.B200ModelListGP(desc, device=DEV, dtype=dtype)
+        d, out, _ = _run_tables(crs, mean, var, model, ctx.to(DEV))
+        assert out["best"].cpu().tolist() == g["best_arms"]
+        torch.testing.assert_close(out["minz"].cpu(), zeta.min(dim=-1).values, rtol=0, atol=0)
+        assert (d.context, d.next_arm, d.tie_count) == (case["next_context"], case["next_arm"], 1)
+        assert d.min_zeta == float(zeta.min())
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_gao_iid_known_answer_tables(crs, golden, dtype):
+    """zeta scan on the tables behind the reference's pinned C-OCBA answer (arm 2, context 1)."""
+    g = golden("gao_iid_seed5.json")
+    c = g["cases"][dtype]
+    dt = getattr(torch, dtype)
+    means, vars_, nobs = (torch.tensor(c[k], dtype=dt) for k in ("means", "vars", "num_obs"))
+    p = nobs / nobs.sum()
+    mean_t = means.t().contiguous().to(DEV)
+    var_t = (vars_ / p).t().contiguous().to(DEV)
+    d, out, _ = _run_tables(crs, mean_t, var_t, None, None)
+    zeta, order = ocba_oracle.zeta_table(mean_t.cpu(), var_t.cpu())
+    flat = int(torch.argmin(zeta.view(-1)))
+    assert d.context == flat // 2 == g["expected"][1]
+    assert d.zeta_arm == int(order[d.context, flat % 2 + 1])
+    assert d.min_zeta == float(zeta.min())
+    assert 2 in (d.best_arm, d.zeta_arm)
+
+
+def test_tie_randomisation_contract(crs):
+    """strategies.py:147-154: ties are counted exactly, the r-th tied entry in flat order is
+    selectable, and the global RNG is consumed only when ties exist."""
+    from contextual_rs_b200 import _lib
+    lib = _lib.get()
+    mean = torch.tensor([[3.0, 1.0, 2.0], [0.5, 3.5, 2.5], [3.0, 2.0, 1.0], [9.0, 0.0, 1.0]], dtype=torch.float64, device=DEV)
+    var = torch.ones(4, 3, dtype=torch.float64, device=DEV)
+    d, out, dec = _run_tables(crs, mean, var, None, None)
+    zeta, order = ocba_oracle.zeta_table(mean.cpu(), var.cpu())
+    tied = (zeta.view(-1) == zeta.min()).nonzero().flatten().tolist()
+    assert d.tie_count == len(tied) == 3 and d.min_zeta == 0.5
+    assert (d.context, d.zeta_arm) == (0, 2)
+    seen = []
+    for r in range(3):
+        _lib.check(lib.crs_ocba_resolve_tie(mean.data_ptr(), var.data_ptr(), 4, 3, 3, 0, out["best"].data_ptr(),
+                                            out["minz"].data_ptr(), out["ties"].data_ptr(), r, dec.data_ptr(), None))
+        torch.cuda.synchronize()
+        dd = _lib.Decision.from_buffer_copy(dec.cpu().numpy().tobytes())
+        seen.append((dd.context, dd.zeta_arm))
+    expect = [(f // 2, int(order[f // 2, f % 2 + 1])) for f in tied]
+    assert seen == expect
+    # end to end: tied GP posteriors (two identical arms), RNG consumed iff randomize_ties
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=3, n_c=6, d=1, n=6, seed=9)
+    for key in ("train_X", "train_Y"):
+        desc[key] = [desc[key][0], desc[key][1], desc[key][1]]
+    for key in ("lengthscale", "outputscale", "noise", "mean_const"):
+        desc[key] = desc[key][[0, 1, 1]]
+    model = crs.B200ModelListGP(desc, device=DEV)
+    torch.manual_seed(5)
+    s0 = torch.get_rng_state()
+    crs.gao_modellist(model, ctx, randomize_ties=False)
+    assert torch.equal(s0, torch.get_rng_state())
+    ref = gp_oracle.model_from_description(desc)
+    zt, _ = ocba_oracle.zeta_table(ref.posterior(ctx).mean, ref.posterior(ctx).variance)
+    has_ties = int((zt.view(-1) == zt.min()).sum()) > 1
+    crs.gao_modellist(model, ctx, randomize_ties=True)
+    assert torch.equal(s0, torch.get_rng_state()) != has_ties
+
+
+def test_condition_on_observations_matches_oracle(crs):
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=6, n_c=40, d=2, n=9, seed=4)
+    model = crs.B200ModelListGP(desc, device=DEV)
+    ref = gp_oracle.model_from_description(desc)
+    gen = torch.Generator().manual_seed(0)
+    for it in range(12):  # crosses the n_cap = 24 boundary for arm 1 -> storage regrows
+        arm = 1 if it % 2 == 0 else int(torch.randint(6, (1,), generator=gen))
+        x = ctx[int(torch.randint(40, (1,), generator=gen))].view(1, -1)
+        y = torch.randn(1, 1, generator=gen, dtype=torch.float64)
+        model.condition_on_observations(arm, x, y)
+        ref.models[arm] = ref.models[arm].condition_on_observations(x, y)
+        rp, p = ref.posterior(ctx), model.posterior(ctx)
+        assert _scaled_err(p.mean, rp.mean) < 1e-10 and _scaled_err(p.variance, rp.variance) < 1e-10
+        arm_g, x_g = crs.gao_modellist(model, ctx)
+        arm_r, x_r = ocba_oracle.gao_modellist_ref(ref, ctx)
+        assert int(arm_g) == int(arm_r) and torch.equal(x_g, x_r)
+    assert model.num_observations()[1] >= 15
+
+
+def test_continuous_context_parity(crs):
+    from contextual_rs_b200.synthetic import make_problem
+    desc, _ = make_problem(K=8, n_c=16, d=3, n=8, train="rand", seed=6)
+    cand = torch.quasirandom.SobolEngine(3, scramble=True, seed=0).draw(512, dtype=torch.float64)
+    model = crs.B200ModelListGP(desc, device=DEV)
+    ref = gp_oracle.model_from_description(desc)
+    got = crs.MinZeta(model)(cand.unsqueeze(1))
+    want = ocba_oracle.min_zeta_ref(ref, cand.unsqueeze(1))
+    assert got.shape == (512,) and got.device == cand.device
+    torch.testing.assert_close(got, want, rtol=1e-9, atol=1e-12)
+    assert int(got.argmax()) == int(want.argmax())
+    for i in (int(want.argmax()), 0, 17):
+        a = crs.find_next_arm_given_context(cand[i].view(1, -1), model, kernel_scale=1.0)
+        b = ocba_oracle.find_next_arm_given_context_ref(cand[i].view(1, -1), ref, kernel_scale=1.0)
+        assert a.dim() == 0 and int(a) == int(b)
+    with pytest.raises(AssertionError):
+        crs.MinZeta(model)(cand)
+
+
+def test_philox_words(crs, golden):
+    from contextual_rs_b200 import _lib
+    lib = _lib.get()
+    for v in golden("philox_kat.json")["vectors"]:
+        ctr = torch.from_numpy(np.array([int(x, 16) for x in v["ctr"]], dtype=np.uint32).view(np.int32)).to(DEV)
+        out = torch.zeros(4, dtype=torch.int32, device=DEV)
+        _lib.check(lib.crs_philox_words(ctr.data_ptr(), 1, int(v["key"][0], 16), int(v["key"][1], 16), out.data_ptr(), None))
+        assert [f"{int(x) & 0xffffffff:08x}" for x in out.cpu()] == v["out"]
+    rng = np.random.default_rng(0)
+    ctr = rng.integers(0, 2 ** 32, size=(1000, 4), dtype=np.uint64).astype(np.uint32)
+    out = torch.zeros(4000, dtype=torch.int32, device=DEV)
+    _lib.check(lib.crs_philox_words(torch.from_numpy(ctr.view(np.int32)).to(DEV).data_ptr(), 1000, 123, 456, out.data_ptr(), None))
+    want = np.stack(philox_ref.philox4x32_10(ctr[:, 0], ctr[:, 1], ctr[:, 2], ctr[:, 3], 123, 456), axis=1)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32).reshape(1000, 4), want)
+
+
+@pytest.mark.parametrize("dtype,S", [(torch.float64, 8192), (torch.float32, 5003)])
+def test_pcs_counts_parity(crs, dtype, S):
+    from contextual_rs_b200.generalized_pcs import pcs_counts
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=12, n_c=48, d=2, n=10, seed=5)
+    model = crs.B200ModelListGP(desc, device=DEV, dtype=dtype)
+    p = model.posterior(ctx.to(dtype))
+    mean, var = p.mean.contiguous(), p.variance.contiguous()
+    stats = torch.zeros(2, dtype=torch.int64, device=DEV)
+    cnt = pcs_counts(model, mean, var, S, seed=77, offset=3, stats=stats).cpu().numpy()
+    want = philox_ref.pcs_counts_philox_ref(mean.cpu().numpy(), var.cpu().numpy(), S, seed=77, offset=3)
+    # shared Philox stream: identical up to borderline draws (MUFU vs libm rounding of the normals)
+    assert np.abs(cnt - want).max() <= 2 and (cnt != want).sum() <= 3
+    exact = pcs_oracle.pcs_exact_quadrature(mean.double().cpu().numpy(), var.double().cpu().numpy())
+    se = np.sqrt(np.maximum(exact * (1 - exact), 1e-4) / S)
+    assert np.all(np.abs(cnt / S - exact) < 5 * se)
+    drawn, skipped = stats.cpu().tolist()
+    assert drawn + skipped == 4 * ((S + 3) // 4) * 12 * 48
+    # sharding invariance: context / arm offsets only re-key the stream
+    half = pcs_counts(model, mean[24:], var[24:], S, seed=77, offset=3, ctx_offset=24).cpu().numpy()
+    assert np.array_equal(half, cnt[24:])
+    other = pcs_counts(model, mean, var, S, seed=78, offset=3).cpu().numpy()
+    assert not np.array_equal(other, cnt)
+
+
+def test_pcs_screening_is_exact(crs):
+    """Arms that cannot win (|z| <= 5.7683) are skipped without changing any count."""
+    from contextual_rs_b200.generalized_pcs import pcs_counts
+    gen = torch.Generator().manual_seed(1)
+    n_c, K, S = 32, 40, 4096
+    mean = torch.randn(n_c, K, generator=gen, dtype=torch.float64)
+    mean[:, 20:] -= 50.0  # hopeless arms
+    var = 0.05 + torch.rand(n_c, K, generator=gen, dtype=torch.float64)
+    stats = torch.zeros(2, dtype=torch.int64, device=DEV)
+    cnt = pcs_counts(None, mean.to(DEV), var.to(DEV), S, seed=5, stats=stats).cpu().numpy()
+    want = philox_ref.pcs_counts_philox_ref(mean.numpy(), var.numpy(), S, seed=5)
+    assert np.abs(cnt - want).max() <= 2
+    drawn, skipped = stats.cpu().tolist()
+    assert skipped >= S * n_c * 20 and drawn + skipped == S * n_c * K
+    # degenerate rows: a dominant best arm gives PCS = 1 exactly, equal arms give ~1/K
+    mean2 = torch.zeros(4, 5, dtype=torch.float64); mean2[:2, 3] = 100.0
+    var2 = torch.ones(4, 5, dtype=torch.float64)
+    c2 = pcs_counts(None, mean2.to(DEV), var2.to(DEV), S, seed=1).cpu().numpy()
+    assert c2[0] == S and c2[1] == S and abs(c2[2] / S - 0.2) < 0.04
+
+
+def test_estimate_current_generalized_pcs_dropin(crs):
+    from contextual_rs_b200.synthetic import make_problem
+    f = lambda X: (X > 0).to(torch.float64)
+    vals = []
+    for n in (4, 60):
+        desc, ctx = make_problem(K=3, n_c=10, d=2, n=n, seed=6)
+        model = crs.B200ModelListGP(desc, device=DEV)
+        ref = gp_oracle.model_from_description(desc)
+        arm_set = torch.arange(3.0, dtype=torch.float64).view(-1, 1)
+        per_ctx = []
+        rho = lambda x: (per_ctx.append(x), x.mean(dim=-2))[1]
+        v = crs.estimate_current_generalized_pcs(model, arm_set, ctx, 16384, None, f, rho, seed=4)
+        assert v.shape == torch.Size([]) and 0.0 <= float(v) <= 1.0  # test_generalized_pcs.py:290-301
+        assert per_ctx[0].shape == (10, 1)
+        rp = ref.posterior(ctx)
+        exact = pcs_oracle.pcs_exact_quadrature(rp.mean.numpy(), rp.variance.numpy())
+        se = np.sqrt(np.maximum(exact * (1 - exact), 1e-4) / 16384)
+        assert np.all(np.abs(per_ctx[0].squeeze(-1).cpu().numpy() - exact) < 5 * se)
+        worst = crs.estimate_current_generalized_pcs(model, arm_set, ctx, 16384, None, f,
+                                                     lambda x: x.min(dim=-2).values, seed=4)
+        assert abs(float(worst) - float(per_ctx[0].min())) < 1e-12
+        vals.append(float(v))
+        with pytest.raises(NotImplementedError):
+            crs.estimate_current_generalized_pcs(model, arm_set, ctx.repeat(3, 1, 1), 8, None, f, rho)
+        with pytest.raises(NotImplementedError):
+            crs.estimate_current_generalized_pcs(model, arm_set, ctx, 8, None, f, rho, use_approximation=True)
+        with pytest.raises(NotImplementedError):
+            crs.estimate_current_generalized_pcs(model, arm_set, ctx, 8, None, lambda X: X.clamp_min(0), rho)
+        with pytest.raises(AssertionError):
+            crs.estimate_current_generalized_pcs(model, arm_set.view(-1), ctx, 8, None, f, rho)
+    assert vals[1] > vals[0]  # more data -> higher PCS (test_generalized_pcs.py:303-329)
+    # default seeding consumes the global torch RNG like the reference's rsample does
+    torch.manual_seed(0)
+    a = crs.estimate_current_generalized_pcs(model, arm_set, ctx, 64, None, f, lambda x: x.mean(dim=-2))
+    torch.manual_seed(0)
+    b = crs.estimate_current_generalized_pcs(model, arm_set, ctx, 64, None, f, lambda x: x.mean(dim=-2))
+    assert float(a) == float(b)
+
+
+def test_full_size_properties(crs):
+    """Size-independent properties at BASELINE config-3 scale (256 arms x 8,192 contexts):
+    a random slice of the grid against the oracle, scan outputs against torch reductions of the
+    same device tables, and shard-invariance of the PCS counts."""
+    from contextual_rs_b200.generalized_pcs import pcs_counts
+    from contextual_rs_b200.synthetic import make_config
+    desc, ctx = make_config("c3")
+    model = crs.B200ModelListGP(desc, device=DEV)
+    p = model.posterior(ctx)
+    sel = torch.randperm(8192, generator=torch.Generator().manual_seed(0))[:64]
+    mu, var = gp_oracle.posterior_grid_batched(desc, ctx[sel])
+    assert _scaled_err(p.mean.cpu()[sel], mu) < 1e-10 and _scaled_err(p.variance.cpu()[sel], var) < 1e-10
+    arm, x = crs.gao_modellist(model, ctx)
+    ws = model.workspace(8192)
+    mean_d, var_d = ws["mean"], ws["var"]
+    best = mean_d.argmax(dim=-1)
+    assert torch.equal(ws["best_arm"].long(), best)
+    mb = mean_d.gather(1, best[:, None]); vb = var_d.gather(1, best[:, None])
+    zeta = (mb - mean_d).pow(2) / (vb + var_d)
+    zeta.scatter_(1, best[:, None], float("inf"))
+    assert torch.equal(ws["min_zeta"], zeta.min(dim=-1).values)
+    c_star = int(zeta.min(dim=-1).values.argmin())
+    assert torch.equal(x, ctx[c_star])
+    S = 1024
+    full = pcs_counts(model, mean_d, var_d, S, seed=3)
+    parts = torch.cat([pcs_counts(model, mean_d[i:i + 2048], var_d[i:i + 2048], S, seed=3, ctx_offset=i)
+                       for i in range(0, 8192, 2048)])
+    assert torch.equal(full, parts)
+    assert int(full.min()) >= 0 and int(full.max()) <= S

@@ -1,0 +1,97 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol of include/crs_b200.h, the
+ctypes mirrors match the header, host-side argument handling, and the product never falls back
+to the CPU.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    from contextual_rs_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "contextual_rs_b200", "csrc"), "-j8"], check=True)
+    return _lib.get()
+
+
+def test_header_symbols_all_exported(built_library):
+    from contextual_rs_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "crs_b200.h")).read()
+    declared = set(re.findall(r"CRS_API\s+[\w\s\*]+?\b(crs_\w+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(built_library, name), name
+    assert built_library.crs_abi_version() == 1
+    assert built_library.crs_scan_workspace_bytes() > 0
+    assert built_library.crs_status_string(2).startswith(b"unsupported")
+
+
+def test_struct_layouts_match_header():
+    from contextual_rs_b200 import _lib
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "crs_b200.h"
+    int main(void) {
+      printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(crs_gp_state), offsetof(crs_gp_state, train_x),
+             offsetof(crs_gp_state, status), sizeof(crs_decision), offsetof(crs_decision, context),
+             offsetof(crs_decision, reserved), sizeof(crs_decide_ws));
+      return 0;
+    }'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "t.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "t.c"), "-o", os.path.join(td, "t")], check=True)
+        out = subprocess.run([os.path.join(td, "t")], capture_output=True, text=True, check=True).stdout.split()
+    got = [C.sizeof(_lib.GPState), _lib.GPState.train_x.offset, _lib.GPState.status.offset,
+           C.sizeof(_lib.Decision), _lib.Decision.context.offset, _lib.Decision.reserved.offset,
+           C.sizeof(_lib.DecideWS)]
+    assert [int(x) for x in out] == got
+
+
+def test_argument_validation_without_gpu(built_library):
+    lib = built_library
+    assert lib.crs_gp_prepare(None, 0, 1, None) == 1  # CRS_ERR_INVALID_ARG
+    assert lib.crs_posterior_grid(None, None, 4, 0, 1, None, None, 1, 0, None) == 1
+    assert lib.crs_ocba_scan(None, None, 4, 3, 3, 0, 0, None, None, None, None, None, None, None, None, None, None) == 1
+    assert lib.crs_pcs_counts(None, None, 4, 3, 3, 0, 16, 0, 0, 0, 0, None, None, None) == 1
+    assert lib.crs_philox_words(None, 1, 0, 0, None, None) == 1
+
+
+def test_no_cpu_fallback():
+    import contextual_rs_b200 as crs
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=3, n_c=4, d=1, n=3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crs.B200ModelListGP(desc, device="cpu")
+    # the product package never imports the oracle
+    for root, _, files in os.walk(os.path.join(ROOT, "contextual_rs_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from contextual_rs_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="is missing"):
+        _lib.get()
+
+
+def test_strict_indicator_probe():
+    from contextual_rs_b200.generalized_pcs import _is_strict_indicator
+    assert _is_strict_indicator(lambda X: (X > 0).to(torch.float64))
+    assert _is_strict_indicator(lambda X: (X > 0).to(dtype=torch.float))
+    assert not _is_strict_indicator(lambda X: (X >= 0).to(torch.float64))
+    assert not _is_strict_indicator(lambda X: torch.sigmoid(X))
+    assert not _is_strict_indicator(lambda X: X.sum())
