@@ -32,7 +32,7 @@ class GPState(C.Structure):
     """``crs_gp_state``"""
     _fields_ = [
         ("num_arms", i32), ("n_cap", i32), ("dim", i32), ("dim_pad", i32),
-        ("kernel", i32), ("dtype", i32), ("flags", i32), ("reserved", i32),
+        ("kernel", i32), ("dtype", i32), ("flags", i32), ("n_max", i32),
         ("train_x", vp), ("train_y", vp), ("n_obs", vp), ("lengthscale", vp),
         ("outputscale", vp), ("noise", vp), ("mean_const", vp),
         ("norm_mins", vp), ("norm_ranges", vp), ("y_mean", vp), ("y_std", vp),

@@ -160,7 +160,7 @@ class B200ModelListGP:
         p = _lib.ptr
         return _lib.GPState(
             self.num_arms, self.n_cap, self.dim, self.dim_pad, _lib.KERNELS[self.kernel],
-            _lib.DTYPES[self.dtype], flags, 0,
+            _lib.DTYPES[self.dtype], flags, max(self._n_host) if self._n_host else 0,
             p(self.train_x), p(self.train_y), p(self.n_obs), p(self.lengthscale),
             p(self.outputscale), p(self.noise), p(self.mean_const),
             p(self.norm_mins), p(self.norm_ranges), p(self.y_mean), p(self.y_std),
@@ -206,6 +206,7 @@ class B200ModelListGP:
         self.train_y[arm, n:n + add] = Y
         self._n_host[arm] = n + add
         self.n_obs[arm] = n + add
+        self._state.n_max = self._state_frozen.n_max = max(self._n_host)
         self.prepare(arm, arm + 1, relearn=False)
         return self
 

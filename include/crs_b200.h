@@ -73,7 +73,7 @@ typedef struct crs_gp_state {
   int32_t kernel;     /* crs_kernel */
   int32_t dtype;      /* crs_dtype of the prepared arrays and of all tables */
   int32_t flags;      /* CRS_LEARN_* */
-  int32_t reserved;
+  int32_t n_max;      /* caller's bound on max n_obs (sizes the kernels' tiles); 0 = use n_cap */
   /* fitted description */
   const double* train_x;      /* [K, n_cap, d]  raw inputs */
   const double* train_y;      /* [K, n_cap]     raw targets */
