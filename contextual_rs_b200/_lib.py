@@ -22,6 +22,7 @@ CRS_MATERN52, CRS_RBF = 0, 1
 CRS_LEARN_NORMALIZE, CRS_LEARN_STANDARDIZE = 1, 2
 CRS_P_COUNT, CRS_P_KDE, CRS_P_INFER = 0, 1, 2
 CRS_MAX_DIM, CRS_MAX_OBS = 16, 160
+CRS_HEAD_ELEMS = 2 * CRS_MAX_DIM + 8
 KERNELS = {"matern52": CRS_MATERN52, "rbf": CRS_RBF}
 DTYPES = {torch.float64: CRS_F64, torch.float32: CRS_F32}
 
@@ -37,7 +38,7 @@ class GPState(C.Structure):
         ("outputscale", vp), ("noise", vp), ("mean_const", vp),
         ("norm_mins", vp), ("norm_ranges", vp), ("y_mean", vp), ("y_std", vp),
         ("xn", vp), ("xs", vp), ("alpha", vp), ("linv_t", vp),
-        ("ctx_sub", vp), ("ctx_mul", vp), ("arm_scal", vp), ("status", vp),
+        ("arm_head", vp), ("status", vp),
     ]
 
 
@@ -63,6 +64,7 @@ _SIGNATURES = {
     "crs_status_string": (C.c_char_p, [C.c_int]),
     "crs_last_cuda_error": (C.c_char_p, []),
     "crs_scan_workspace_bytes": (i64, []),
+    "crs_linv_stride": (i64, [i32]),
     "crs_gp_prepare": (C.c_int, [C.POINTER(GPState), i32, i32, vp]),
     "crs_posterior_grid": (C.c_int, [C.POINTER(GPState), vp, i64, i32, i32, vp, vp, i64, i32, vp]),
     "crs_ocba_scan": (C.c_int, [vp, vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -70,6 +72,8 @@ _SIGNATURES = {
     "crs_ocba_select": (C.c_int, [C.POINTER(GPState), vp, vp, vp, i64, i32, i32, f64, vp, vp]),
     "crs_pcs_counts": (C.c_int, [vp, vp, i64, i32, i64, i32, i64, u64, u32, i32, i64, vp, vp, vp]),
     "crs_philox_words": (C.c_int, [vp, i64, u32, u32, vp, vp]),
+    "crs_debug_corr": (C.c_int, [vp, i64, i32, i32, vp, vp]),
+    "crs_peak_probe": (C.c_int, [i32, i32, i32, vp, vp]),
     "crs_gao_decide_host": (C.c_int, [C.POINTER(GPState), vp, i64, i32, i32, i32, f64, i32,
                                       C.POINTER(DecideWS), C.POINTER(Decision), vp]),
 }

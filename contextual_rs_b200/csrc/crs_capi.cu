@@ -32,6 +32,8 @@ CRS_API const char* crs_last_cuda_error(void) { return g_cuda_err; }
 
 CRS_API int64_t crs_scan_workspace_bytes(void) { return scan_workspace_bytes(); }
 
+CRS_API int64_t crs_linv_stride(int32_t n_cap) { return n_cap > 0 ? (int64_t)linv_stride(n_cap) : 0; }
+
 CRS_API int crs_gp_prepare(const crs_gp_state* st, int32_t arm_begin, int32_t arm_end, void* stream) {
   return launch_gp_prepare(st, arm_begin, arm_end, (cudaStream_t)stream);
 }
@@ -74,6 +76,15 @@ CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32
 CRS_API int crs_philox_words(const uint32_t* ctr, int64_t n, uint32_t key0, uint32_t key1, uint32_t* out,
                      void* stream) {
   return launch_philox_words(ctr, n, key0, key1, out, (cudaStream_t)stream);
+}
+
+CRS_API int crs_debug_corr(const double* r2, int64_t n, int32_t kernel, int32_t variant, double* out,
+                           void* stream) {
+  return launch_debug_corr(r2, n, kernel, variant, out, (cudaStream_t)stream);
+}
+
+CRS_API int crs_peak_probe(int32_t kind, int32_t iters, int32_t blocks, void* out, void* stream) {
+  return launch_peak_probe(kind, iters, blocks, out, (cudaStream_t)stream);
 }
 
 CRS_API int crs_gao_decide_host(const crs_gp_state* st, const void* ctx_host, int64_t n_c,

@@ -41,6 +41,57 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
+// ---- layout of the prepared per-arm state (written by gp_prepare, bulk-copied by the grid kernel)
+// arm_head [K][kHeadElems] T : sub[16] | mul[16] | (o, m, ybar, ysd) | pad[4]
+constexpr int kHeadSub = 0, kHeadMul = CRS_MAX_DIM, kHeadScal = 2 * CRS_MAX_DIM;
+constexpr int kHeadElems = 2 * CRS_MAX_DIM + 8;
+// linv_t is stored panel-major: panel p = rows j in [0, min(n_cap, 32 (p+1))) x columns
+// [32 p, 32 p + 32), row-major with a fixed row stride of 32 — exactly the block the grid kernel
+// needs for its p-th chunk of v, so that one 1-D bulk copy stages it.
+constexpr int kPanel = 32;
+__host__ __device__ inline int panel_rows(int n_cap, int p) {
+  const int r = (p + 1) * kPanel;
+  return r < n_cap ? r : n_cap;
+}
+__host__ __device__ inline int num_panels(int n_cap) { return (n_cap + kPanel - 1) / kPanel; }
+__host__ __device__ inline long long panel_offset(int n_cap, int p) {
+  long long off = 0;
+  for (int q = 0; q < p; ++q) off += (long long)panel_rows(n_cap, q) * kPanel;
+  return off;
+}
+__host__ __device__ inline long long linv_stride(int n_cap) { return panel_offset(n_cap, num_panels(n_cap)); }
+
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 inline int dim_pad_of(int d) {
   int p = 1;
   while (p < d) p <<= 1;
@@ -78,6 +129,8 @@ int64_t scan_workspace_bytes();
 int launch_pcs_counts(const void* mean, const void* var, int64_t n_c, int K, int64_t ld, int dtype,
                       int64_t num_samples, uint64_t seed, uint32_t offset, int arm_offset,
                       int64_t ctx_offset, uint32_t* counts, uint64_t* stats, cudaStream_t s);
+int launch_debug_corr(const double* r2, int64_t n, int kernel, int variant, double* out, cudaStream_t s);
+int launch_peak_probe(int kind, int iters, int blocks, void* out, cudaStream_t s);
 int launch_philox_words(const uint32_t* ctr, int64_t n, uint32_t k0, uint32_t k1, uint32_t* out,
                         cudaStream_t s);
 

@@ -4,7 +4,8 @@
 //
 // One CTA per arm, everything in fp64 in shared memory, results cast to the compute dtype T.
 // The grid kernel wants a multiply-only inner loop, so instead of L we store
-//     linv_t[j][i] = o * (L^-1)[i][j]   (row j = column j of L^-1, zero above the diagonal)
+//     linv_t[j][i] = o * (L^-1)[i][j]   (row j = column j of L^-1, zero above the diagonal;
+//                                        stored in 32-column panels, see crs_common.cuh)
 //     alpha[i]     = o * (K^^-1 (y~ - m))[i]
 // which give  mu~ = m + c* . alpha  and  ||L^-1 k*||^2 = || sum_j linv_t[j][:] c*_j ||^2  for the
 // unscaled correlation vector c* = c(x~*, X~).
@@ -200,28 +201,33 @@ __global__ void __launch_bounds__(kPrepThreads) gp_prepare_kernel(crs_gp_state s
   // ---- write the prepared state --------------------------------------------------------------
   T* alpha = reinterpret_cast<T*>(st.alpha) + (size_t)k * ncap;
   for (int i = tid; i < ncap; i += nt) alpha[i] = i < n ? T(o * rhs[i]) : T(0);
-  T* lt = reinterpret_cast<T*>(st.linv_t) + (size_t)k * ncap * ncap;
-  for (int idx = tid; idx < ncap * ncap; idx += nt) {
-    const int j = idx / ncap, i = idx - j * ncap;
-    lt[idx] = (i >= j && i < n) ? T(o * A[i * lda + j]) : T(0);
+  // linv_t, panel-major (see crs_common.cuh): panel p holds rows j < min(ncap, 32 (p+1)) and
+  // columns [32 p, 32 p + 32); entry (j, i) = o * (L^-1)[i][j] for i >= j, zero otherwise.
+  T* lt = reinterpret_cast<T*>(st.linv_t) + (size_t)k * linv_stride(ncap);
+  const int ld = kPanel;
+  for (int p = 0; p < num_panels(ncap); ++p) {
+    T* pan = lt + panel_offset(ncap, p);
+    const int rows = panel_rows(ncap, p);
+    for (int idx = tid; idx < rows * ld; idx += nt) {
+      const int j = idx / ld, i = p * kPanel + (idx - j * ld);
+      pan[idx] = (i >= j && i < n) ? T(o * A[i * lda + j]) : T(0);
+    }
   }
-  if (tid < dp) {
-    T* sub = reinterpret_cast<T*>(st.ctx_sub) + (size_t)k * dp;
-    T* mul = reinterpret_cast<T*>(st.ctx_mul) + (size_t)k * dp;
+  T* head = reinterpret_cast<T*>(st.arm_head) + (size_t)k * kHeadElems;
+  if (tid < CRS_MAX_DIM) {
     if (tid < d) {
-      sub[tid] = T(tr[tid]);
-      mul[tid] = T(1.0 / (tr[CRS_MAX_DIM + tid] * st.lengthscale[(size_t)k * d + tid]));
+      head[kHeadSub + tid] = T(tr[tid]);
+      head[kHeadMul + tid] = T(1.0 / (tr[CRS_MAX_DIM + tid] * st.lengthscale[(size_t)k * d + tid]));
     } else {
-      sub[tid] = T(0);
-      mul[tid] = T(0);
+      head[kHeadSub + tid] = T(0);
+      head[kHeadMul + tid] = T(0);
     }
   }
   if (tid == 0) {
-    T* sc = reinterpret_cast<T*>(st.arm_scal) + (size_t)k * 4;
-    sc[0] = T(o);
-    sc[1] = T(m);
-    sc[2] = T(ybar);
-    sc[3] = T(ysd);
+    head[kHeadScal + 0] = T(o);
+    head[kHeadScal + 1] = T(m);
+    head[kHeadScal + 2] = T(ybar);
+    head[kHeadScal + 3] = T(ysd);
     st.status[k] = 0;
   }
 }

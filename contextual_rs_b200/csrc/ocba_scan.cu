@@ -349,7 +349,7 @@ ocba_select_kernel(crs_gp_state st, const T* __restrict__ ctx, const T* __restri
       }
       p = s;
     } else {
-      p = reinterpret_cast<const T*>(st.arm_scal)[(size_t)i * 4] / vr;  // prior var / posterior var
+      p = reinterpret_cast<const T*>(st.arm_head)[(size_t)i * kHeadElems + kHeadScal] / vr;  // prior var / posterior var
     }
     const T y = p / vr;
     if (i == best) s_best = y; else rest += y;

@@ -3,20 +3,22 @@
 // contextual_rs/contextual_rs_strategies.py:133-136 (and generalized_pcs.py:443-444,
 // continuous_context.py:68,96, experiments/wsc_experiments/main.py:460).
 //
-// Mapping: CTA = (tile of TB contexts) x (tile of AT arms); thread = one context.  The arm's
-// prepared state sits in shared memory and is read by warp-wide broadcast.  Per (context, arm):
+// Mapping: CTA = (tile of 128 contexts) x (tile of <= 8 arms); thread = one context.  An arm's
+// prepared state (head, alpha, scaled train inputs, first 32-column panel of o*L^-T) is staged in
+// shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier), double-buffered so that the
+// next arm of the tile streams in while the current one is computed.  Per (context, arm):
 //   phase A  c_j = corr(|| x~* - X~_j ||^2), j = 0..n-1   (direct differences; two observations
 //            per iteration for ILP), macc += c_j alpha_j, c_j parked in shared memory [j][thread]
 //   phase B  v = (o L^-1) c in register chunks of VB rows: v[i] += linv_t[j][i] c_j for i >= j,
-//            the matching column panel of linv_t staged in shared memory; q += sum v_i^2
+//            rows visited in 8-row segments so that the triangular structure is resolved at
+//            compile time (no per-row predicates); q += sum v_i^2
 //   mu = ybar + s (m + macc),  var = max(s^2 (o - q), floor)
 // The kernel is FP64/FP32-pipe bound (~55 flop per output byte); HBM traffic is the
 // context tile in and the two tables out.  Tables are [n_c, ld] arm-fastest, so each thread buffers
-// its AT results in shared memory and writes them as one contiguous run.
+// its results in shared memory and writes them as one contiguous run per arm tile.
 //
 // fp64 transcendental cost dominates at n ~ 20, so exp() is a 16-entry-table + degree-7 polynomial
-// (12 FP64 ops, coefficients in constant memory so that no uniform-register moves are issued) and
-// sqrt() is rsqrt.approx + two coupled Newton steps + one correction (branch-free).
+// (12 FP64 ops) and sqrt() is rsqrt.approx + coupled Newton steps + one correction (branch-free).
 #include "crs_common.cuh"
 
 namespace crs {
@@ -24,6 +26,10 @@ namespace {
 
 constexpr int kGridThreads = 128;
 constexpr int kMaxArmTile = 8;
+#ifndef CRS_GRID_MIN_BLOCKS
+#define CRS_GRID_MIN_BLOCKS 5
+#endif
+constexpr int kMinBlocks = CRS_GRID_MIN_BLOCKS;
 
 // ---- fp64 exp(x), x <= 0: x = (16 k + i) ln2/16 + r, exp(x) = 2^k * 2^(i/16) * e^r ------------
 __constant__ double kExpTable[16] = {
@@ -31,41 +37,39 @@ __constant__ double kExpTable[16] = {
     1.241857812073484, 1.2968395546510096, 1.3542555469368927, 1.4142135623730951,
     1.4768261459394993, 1.5422108254079407, 1.6104903319492543, 1.681792830507429,
     1.7562521603732995, 1.8340080864093424, 1.9152065613971474};
-__constant__ double kExpPoly[6] = {  // 1/7!, 1/6!, 1/5!, 1/4!, 1/3!, 1/2!
-    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
 
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ s_tab) {
   // t = x * 16/ln2 + 1.5*2^52: the integer n = 16 k + i lands in the low mantissa bits of t
   const double t = fma(x, 23.083120654223414, 6755399441055744.0);
   const double nd = t - 6755399441055744.0;
-  double r = fma(nd, -0.043321698784996581, x);        // ln2/16 (high part)
-  r = fma(nd, -1.4494042586539372e-18, r);             // ln2/16 (low part)
+  double r = fma(nd, -0.04332169878499658, x);   // ln2/16 (high part)
+  r = fma(nd, -1.4494042586539372e-18, r);       // ln2/16 (low part)
   int n = __double2loint(t);
-  n = max(n, -16000);                                   // exp(-693) ~ 1e-301: clamp instead of underflow
-  double p = kExpPoly[0];
-  p = fma(p, r, kExpPoly[1]);
-  p = fma(p, r, kExpPoly[2]);
-  p = fma(p, r, kExpPoly[3]);
-  p = fma(p, r, kExpPoly[4]);
-  p = fma(p, r, kExpPoly[5]);
+  n = max(n, -16000);                             // exp(-693) ~ 1e-301: clamp instead of underflow
+  double p = 1.0 / 5040.0;                        // e^r, |r| <= ln2/32: degree 7, error 1.2e-18
+  p = fma(p, r, 1.0 / 720.0);
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   const double y = s_tab[n & 15] * p;
   return __hiloint2double(__double2hiint(y) + ((n >> 4) << 20), __double2loint(y));
 }
 
-// sqrt(x) for x >= 0 (x = 0 returns ~1e-145, harmless: it only enters s and exp(-s)).
+// sqrt(x) for x > 0 (callers add 1e-290, harmless: the result only enters s and exp(-s)).
+template <int ITERS>
 __device__ __forceinline__ double sqrt_pos(double x) {
-  x = fmax(x, 1e-290);
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double g = x * y, h = 0.5 * y;
-  double r = fma(-h, g, 0.5);
-  g = fma(g, r, g);
-  h = fma(h, r, h);
-  r = fma(-h, g, 0.5);
-  g = fma(g, r, g);
-  h = fma(h, r, h);
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+  }
   const double e = fma(-g, g, x);
   return fma(e, h, g);
 }
@@ -74,7 +78,7 @@ template <typename T> struct Corr;
 template <> struct Corr<double> {
   static __device__ __forceinline__ double eval(double r2, int kernel, const double* s_tab) {
     if (kernel == CRS_MATERN52) {
-      const double s = sqrt_pos(5.0 * r2);                       // sqrt5 * r
+      const double s = sqrt_pos<2>(fma(r2, 5.0, 1e-290));        // sqrt5 * r
       const double poly = fma(s, fma(s, 1.0 / 3.0, 1.0), 1.0);  // 1 + s + s^2/3
       return poly * exp_neg(-s, s_tab);
     }
@@ -87,77 +91,146 @@ template <> struct Corr<float> {
   }
 };
 
+// 16-byte shared-memory vector loads (the compiler cannot prove the alignment of the runtime-sized
+// stage buffers, so it is spelled out).
+__device__ __forceinline__ void lds_vec(const double* p, double (&o)[2]) {
+  const double2 t = *reinterpret_cast<const double2*>(p);
+  o[0] = t.x; o[1] = t.y;
+}
+__device__ __forceinline__ void lds_vec(const float* p, float (&o)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+template <typename T> struct VecLen { static constexpr int value = 16 / sizeof(T); };
+
+// v[8 ib .. 8 ib + 7] += row[8 ib ..] * c for the column blocks ib >= FIRST of a VB-wide chunk
+template <typename T, int VB, int FIRST>
+__device__ __forceinline__ void axpy_blocks(T (&v)[VB], const T* __restrict__ row, T c) {
+  constexpr int W = VecLen<T>::value;
+#pragma unroll
+  for (int i = FIRST * 8; i < VB; i += W) {
+    T t[W];
+    lds_vec(row + i, t);
+#pragma unroll
+    for (int u = 0; u < W; ++u) v[i + u] = fma(t[u], c, v[i + u]);
+  }
+}
+
+// squared scaled distance to one staged training row (D % vector length handled by D >= W or scalar)
+template <typename T, int D>
+__device__ __forceinline__ T sq_dist(const T (&xq)[D], const T* __restrict__ xrow) {
+  constexpr int W = VecLen<T>::value;
+  T r = T(0);
+  if constexpr (D % W == 0) {
+#pragma unroll
+    for (int dd = 0; dd < D; dd += W) {
+      T t[W];
+      lds_vec(xrow + dd, t);
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+        const T df = xq[dd + u] - t[u];
+        r = fma(df, df, r);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) {
+      const T df = xq[dd] - xrow[dd];
+      r = fma(df, df, r);
+    }
+  }
+  return r;
+}
+
 template <typename T, int D, int VB>
-__global__ void __launch_bounds__(kGridThreads)
+__global__ void __launch_bounds__(kGridThreads, kMinBlocks)
 posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, int arm_begin,
                       int arm_end, int arm_tile, int n_rows, T* __restrict__ mean,
                       T* __restrict__ var, int64_t ld, int col_offset) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int ncap = st.n_cap, d = st.dim;
-  // shared layout (T): panel [n_rows][VB] | xs [n_rows][D] | alpha [n_rows] | sub [D] | mul [D] |
-  //                    tab [16] | c [n_rows][TB] | out [2][arm_tile][TB]
-  T* s_panel = reinterpret_cast<T*>(smem_raw);
-  T* s_xs = s_panel + n_rows * VB;
-  T* s_alpha = s_xs + n_rows * D;
-  T* s_sub = s_alpha + n_rows;
-  T* s_mul = s_sub + D;
-  T* s_tab = s_mul + D;
-  T* s_c = s_tab + 16;
+  // shared layout: bars[4] u64 | tab[16] T | stage[2] { head[40] | alpha[n_rows] | xs[n_rows][D] |
+  //                panel[n_rows][32] } | c[n_rows][128] | out[2][arm_tile][128]      (n_rows % 4 == 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  T* s_tab = reinterpret_cast<T*>(smem_raw + 32);
+  T* s_stage = s_tab + 16;
+  const int stage_elems = kHeadElems + n_rows + n_rows * D + n_rows * kPanel;
+  T* s_c = s_stage + 2 * stage_elems;
   T* s_out = s_c + n_rows * kGridThreads;
-
-  if (tid < 16) s_tab[tid] = (T)kExpTable[tid];
 
   const int64_t c = (int64_t)blockIdx.x * kGridThreads + tid;
   const bool live = c < n_c;
   const int a0 = arm_begin + blockIdx.y * arm_tile;
   const int a1 = min(a0 + arm_tile, arm_end);
+  const int na = a1 - a0;
+
+  const T* g_head = reinterpret_cast<const T*>(st.arm_head);
+  const T* g_alpha = reinterpret_cast<const T*>(st.alpha);
+  const T* g_xs = reinterpret_cast<const T*>(st.xs);
+  const T* g_lt = reinterpret_cast<const T*>(st.linv_t);
+  const long long lt_stride = linv_stride(ncap);
+
+  // TMA producer (thread 0): stage the state of the t-th arm of this tile into buffer t & 1
+  auto issue = [&](int t) {
+    const int k = a0 + t;
+    T* stg = s_stage + (t & 1) * stage_elems;
+    const int n = min(min(st.n_obs[k], ncap), n_rows);
+    const int n4 = (n + 3) & ~3;
+    const int rows0 = min(n, kPanel);
+    uint64_t* bar = &bars[t & 1];
+    mbar_expect_tx(bar, (uint32_t)sizeof(T) * (kHeadElems + n4 + n4 * D + rows0 * kPanel));
+    tma_bulk_g2s(stg, g_head + (size_t)k * kHeadElems, sizeof(T) * kHeadElems, bar);
+    if (n4) {
+      tma_bulk_g2s(stg + kHeadElems, g_alpha + (size_t)k * ncap, sizeof(T) * n4, bar);
+      tma_bulk_g2s(stg + kHeadElems + n_rows, g_xs + (size_t)k * ncap * D, sizeof(T) * n4 * D, bar);
+      tma_bulk_g2s(stg + kHeadElems + n_rows + n_rows * D, g_lt + (size_t)k * lt_stride,
+                   sizeof(T) * rows0 * kPanel, bar);
+    }
+  };
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+  }
+  if (tid < 16) s_tab[tid] = (T)kExpTable[tid];
+  __syncthreads();
+  if (tid == 0) {
+    issue(0);
+    if (na > 1) issue(1);
+  }
 
   T xraw[D];
 #pragma unroll
   for (int dd = 0; dd < D; ++dd) xraw[dd] = (live && dd < d) ? ctx[c * d + dd] : T(0);
+  uint32_t xphase = 0;
 
-  for (int k = a0; k < a1; ++k) {
+  for (int t = 0; t < na; ++t) {
+    const int k = a0 + t;
     const int n = min(min(st.n_obs[k], ncap), n_rows);
     const int n2 = (n + 1) & ~1;
-    const T* g_lt = reinterpret_cast<const T*>(st.linv_t) + (size_t)k * ncap * ncap;
-    __syncthreads();  // previous arm's readers are done with the shared state
-    {
-      const T* g_xs = reinterpret_cast<const T*>(st.xs) + (size_t)k * ncap * D;
-      for (int idx = tid; idx < n2 * D; idx += kGridThreads) s_xs[idx] = idx < n * D ? g_xs[idx] : T(0);
-      const T* g_al = reinterpret_cast<const T*>(st.alpha) + (size_t)k * ncap;
-      for (int idx = tid; idx < n2; idx += kGridThreads) s_alpha[idx] = idx < n ? g_al[idx] : T(0);
-      if (tid < D) {
-        s_sub[tid] = reinterpret_cast<const T*>(st.ctx_sub)[(size_t)k * D + tid];
-        s_mul[tid] = reinterpret_cast<const T*>(st.ctx_mul)[(size_t)k * D + tid];
-      }
-      // panel of chunk 0 (the only one when n <= VB)
-      const int rows0 = min(n, VB);
-      for (int idx = tid; idx < rows0 * VB; idx += kGridThreads) {
-        const int j = idx / VB, i = idx - j * VB;
-        s_panel[idx] = i < ncap ? g_lt[(size_t)j * ncap + i] : T(0);
-      }
-    }
-    __syncthreads();
+    T* stg = s_stage + (t & 1) * stage_elems;
+    const T* s_head = stg;
+    const T* s_alpha = stg + kHeadElems;
+    const T* s_xs = s_alpha + n_rows;
+    T* s_panel = stg + kHeadElems + n_rows + n_rows * D;
+    mbar_wait(&bars[t & 1], (uint32_t)(t >> 1) & 1u);
 
     // ---- phase A: correlations, two observations per iteration ------------------------------
     T xq[D];
 #pragma unroll
-    for (int dd = 0; dd < D; ++dd) xq[dd] = (xraw[dd] - s_sub[dd]) * s_mul[dd];
+    for (int dd = 0; dd < D; ++dd) xq[dd] = (xraw[dd] - s_head[kHeadSub + dd]) * s_head[kHeadMul + dd];
     T macc0 = T(0), macc1 = T(0);
+#pragma unroll 1
     for (int j = 0; j < n2; j += 2) {
-      T ra = T(0), rb = T(0);
-#pragma unroll
-      for (int dd = 0; dd < D; ++dd) {
-        const T da = xq[dd] - s_xs[j * D + dd];
-        const T db = xq[dd] - s_xs[(j + 1) * D + dd];
-        ra = fma(da, da, ra);
-        rb = fma(db, db, rb);
-      }
+      const T ra = sq_dist<T, D>(xq, s_xs + j * D);
+      const T rb = sq_dist<T, D>(xq, s_xs + (j + 1) * D);
       const T ca = Corr<T>::eval(ra, st.kernel, s_tab);
       const T cb = Corr<T>::eval(rb, st.kernel, s_tab);
       macc0 = fma(ca, s_alpha[j], macc0);
-      macc1 = fma(cb, s_alpha[j + 1], macc1);   // alpha is zero in the padded row
+      macc1 = fma(cb, s_alpha[j + 1], macc1);  // alpha (and xs) are zero in the padded row
       s_c[j * kGridThreads + tid] = ca;
       s_c[(j + 1) * kGridThreads + tid] = cb;
     }
@@ -165,27 +238,42 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
 
     // ---- phase B: v = (o L^-1) c, VB rows at a time -------------------------------------------
     T q = T(0);
-    for (int p0 = 0; p0 < n; p0 += VB) {
-      const int jend = min(n, p0 + VB);  // rows j <= last row of this chunk contribute
-      if (p0 > 0) {
+    for (int p0 = 0; p0 < n; p0 += kPanel) {
+      const int jend = min(n, p0 + VB);  // rows j < jend touch this chunk
+      if (p0 > 0) {                      // later panels of a long arm: staged on demand
         __syncthreads();
-        for (int idx = tid; idx < jend * VB; idx += kGridThreads) {
-          const int j = idx / VB, i = p0 + idx - j * VB;
-          s_panel[idx] = i < ncap ? g_lt[(size_t)j * ncap + i] : T(0);
+        if (tid == 0) {
+          fence_proxy_async();
+          const uint32_t bytes = (uint32_t)sizeof(T) * min(n, p0 + kPanel) * kPanel;
+          mbar_expect_tx(&bars[2], bytes);
+          tma_bulk_g2s(s_panel, g_lt + (size_t)k * lt_stride + panel_offset(ncap, p0 / kPanel), bytes, &bars[2]);
         }
-        __syncthreads();
+        mbar_wait(&bars[2], xphase);
+        xphase ^= 1u;
       }
       T v[VB];
 #pragma unroll
       for (int i = 0; i < VB; ++i) v[i] = T(0);
-      for (int j = 0; j < jend; ++j) {
-        const T cj = s_c[j * kGridThreads + tid];
-        const T* row = s_panel + j * VB;
+      // rows above this chunk: every column of the chunk is below the diagonal
+      for (int j = 0; j < p0; ++j)
+        axpy_blocks<T, VB, 0>(v, s_panel + j * kPanel, s_c[j * kGridThreads + tid]);
+      // rows inside the chunk, in 8-row segments: segment sg only reaches column blocks >= sg
+      const T* crow = s_c + (size_t)p0 * kGridThreads + tid;
+      const T* prow = s_panel + (size_t)p0 * kPanel;
+      const int rows_in = jend - p0;
 #pragma unroll
-        for (int ib = 0; ib < VB / 8; ++ib) {
-          if (p0 + ib * 8 + 7 >= j) {  // warp-uniform: entries above the diagonal are zero
+      for (int sg = 0; sg < VB / 8; ++sg) {
+        if (sg * 8 < rows_in) {
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii) v[ib * 8 + ii] = fma(row[ib * 8 + ii], cj, v[ib * 8 + ii]);
+          for (int jj = 0; jj < 8; ++jj) {
+            if (sg * 8 + jj < rows_in) {
+              const T cj = crow[(sg * 8 + jj) * kGridThreads];
+              const T* row = prow + (sg * 8 + jj) * kPanel;
+              if (sg == 0) axpy_blocks<T, VB, 0>(v, row, cj);
+              else if (sg == 1) axpy_blocks<T, VB, (VB > 8 ? 1 : 0)>(v, row, cj);
+              else if (sg == 2) axpy_blocks<T, VB, (VB > 16 ? 2 : 0)>(v, row, cj);
+              else axpy_blocks<T, VB, (VB > 24 ? 3 : 0)>(v, row, cj);
+            }
           }
         }
       }
@@ -193,17 +281,22 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
       for (int i = 0; i < VB; ++i) q = fma(v[i], v[i], q);
     }
 
-    const T* sc = reinterpret_cast<const T*>(st.arm_scal) + (size_t)k * 4;
-    const T o = sc[0], m = sc[1], ybar = sc[2], ysd = sc[3];
+    const T o = s_head[kHeadScal + 0], m = s_head[kHeadScal + 1];
+    const T ybar = s_head[kHeadScal + 2], ysd = s_head[kHeadScal + 3];
     const T mu = fma(ysd, m + (macc0 + macc1), ybar);
     T vr = (ysd * ysd) * (o - q);
     vr = vr > variance_floor<T>() ? vr : variance_floor<T>();  // also maps NaN to the floor
-    s_out[(k - a0) * kGridThreads + tid] = mu;
-    s_out[(arm_tile + (k - a0)) * kGridThreads + tid] = vr;
+    s_out[t * kGridThreads + tid] = mu;
+    s_out[(arm_tile + t) * kGridThreads + tid] = vr;
+
+    __syncthreads();  // every thread is done with this stage buffer
+    if (tid == 0 && t + 2 < na) {
+      fence_proxy_async();
+      issue(t + 2);
+    }
   }
 
   if (live) {
-    const int na = a1 - a0;
     T* mrow = mean + c * ld + col_offset + (a0 - arm_begin);
     T* vrow = var + c * ld + col_offset + (a0 - arm_begin);
     for (int a = 0; a < na; ++a) {
@@ -219,13 +312,13 @@ int launch_variant(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm
                    cudaStream_t s) {
   const int narms = arm_end - arm_begin;
   const int64_t ctx_tiles = (n_c + kGridThreads - 1) / kGridThreads;
-  // Arm tile: as large as possible (contiguous output runs, context tile reused) while keeping
-  // >= ~4 CTAs per SM in flight on 148 SMs for small problems.
+  // Arm tile: as large as possible (contiguous output runs, context tile reused, TMA prefetch of
+  // the next arm) while keeping >= ~4 CTAs per SM in flight on 148 SMs for small problems.
   int arm_tile = kMaxArmTile;
   while (arm_tile > 1 && ctx_tiles * ((narms + arm_tile - 1) / arm_tile) < 148 * 4) arm_tile >>= 1;
   auto smem_for = [&](int at) {
-    return sizeof(T) * ((size_t)n_rows * VB + (size_t)n_rows * D + n_rows + 2 * D + 16 +
-                        (size_t)n_rows * kGridThreads + 2 * (size_t)at * kGridThreads);
+    const size_t stage = kHeadElems + (size_t)n_rows + (size_t)n_rows * D + (size_t)n_rows * kPanel;
+    return 32 + sizeof(T) * (16 + 2 * stage + (size_t)n_rows * kGridThreads + 2 * (size_t)at * kGridThreads);
   };
   while (arm_tile > 1 && smem_for(arm_tile) > 227 * 1024) arm_tile >>= 1;
   const size_t smem = smem_for(arm_tile);
@@ -259,16 +352,39 @@ int dispatch_dim(const crs_gp_state* st, const void* ctx, int64_t n_c, int a0, i
 template <typename T>
 int dispatch_vb(const crs_gp_state* st, const void* ctx, int64_t n_c, int a0, int a1, void* mean,
                 void* var, int64_t ld, int col, cudaStream_t s) {
-  // n_max: the caller's bound on n_obs (0 = unknown -> the capacity).  Rows are padded to even.
-  int n_max = st->n_max > 0 && st->n_max <= st->n_cap ? st->n_max : st->n_cap;
-  const int n_rows = (n_max + 1) & ~1;
+  // n_max: the caller's bound on n_obs (0 = unknown -> the capacity).  Rows are padded to 4.
+  const int n_max = st->n_max > 0 && st->n_max <= st->n_cap ? st->n_max : st->n_cap;
+  const int n_rows = (n_max + 3) & ~3;
   if (n_max <= 8) return dispatch_dim<T, 8>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
   if (n_max <= 16) return dispatch_dim<T, 16>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
   if (n_max <= 24) return dispatch_dim<T, 24>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
   return dispatch_dim<T, 32>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
 }
 
+__global__ void debug_corr_kernel(const double* __restrict__ r2, int64_t n, int kernel, int variant,
+                                  double* __restrict__ out) {
+  __shared__ double s_tab[16];
+  if (threadIdx.x < 16) s_tab[threadIdx.x] = kExpTable[threadIdx.x];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = r2[i];
+  if (variant == 0) out[i] = Corr<double>::eval(x, kernel, s_tab);          // product path
+  else if (variant == 1) out[i] = correlation<double>(x, kernel);            // libdevice exp / sqrt
+  else if (variant == 2) out[i] = sqrt_pos<1>(x + 1e-290);
+  else if (variant == 3) out[i] = sqrt_pos<2>(x + 1e-290);
+  else out[i] = exp_neg(-x, s_tab);
+}
+
 }  // namespace
+
+int launch_debug_corr(const double* r2, int64_t n, int kernel, int variant, double* out, cudaStream_t s) {
+  if (!r2 || !out || n < 0) return CRS_ERR_INVALID_ARG;
+  if (n == 0) return CRS_OK;
+  debug_corr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(r2, n, kernel, variant, out);
+  CRS_CUDA_TRY(cudaGetLastError(), "debug_corr launch");
+  return CRS_OK;
+}
 
 int launch_posterior_grid(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm_begin,
                           int arm_end, void* mean, void* var, int64_t ld, int col_offset,
@@ -276,7 +392,7 @@ int launch_posterior_grid(const crs_gp_state* st, const void* ctx, int64_t n_c, 
   if (!st || !ctx || !mean || !var || n_c < 0 || arm_begin < 0 || arm_end > st->num_arms ||
       arm_begin > arm_end || ld < col_offset + (arm_end - arm_begin))
     return CRS_ERR_INVALID_ARG;
-  if (st->n_cap > CRS_MAX_OBS || st->dim_pad != dim_pad_of(st->dim)) return CRS_ERR_UNSUPPORTED;
+  if (st->n_cap > CRS_MAX_OBS || (st->n_cap & 7) || st->dim_pad != dim_pad_of(st->dim)) return CRS_ERR_UNSUPPORTED;
   if (n_c == 0 || arm_begin == arm_end) return CRS_OK;
   if (st->dtype == CRS_F64) return dispatch_vb<double>(st, ctx, n_c, arm_begin, arm_end, mean, var, ld, col_offset, s);
   if (st->dtype == CRS_F32) return dispatch_vb<float>(st, ctx, n_c, arm_begin, arm_end, mean, var, ld, col_offset, s);

@@ -148,10 +148,8 @@ class B200ModelListGP:
         self.xn = torch.zeros(K, ncap, d, dtype=T, device=dev)
         self.xs = torch.zeros(K, ncap, dp, dtype=T, device=dev)
         self.alpha = torch.zeros(K, ncap, dtype=T, device=dev)
-        self.linv_t = torch.zeros(K, ncap, ncap, dtype=T, device=dev)
-        self.ctx_sub = torch.zeros(K, dp, dtype=T, device=dev)
-        self.ctx_mul = torch.zeros(K, dp, dtype=T, device=dev)
-        self.arm_scal = torch.zeros(K, 4, dtype=T, device=dev)
+        self.linv_t = torch.zeros(K, int(_lib.get().crs_linv_stride(ncap)), dtype=T, device=dev)
+        self.arm_head = torch.zeros(K, _lib.CRS_HEAD_ELEMS, dtype=T, device=dev)
         self.status = torch.zeros(K, dtype=torch.int32, device=dev)
         self._state = self._make_state(flags)
         self._state_frozen = self._make_state(0)
@@ -165,7 +163,7 @@ class B200ModelListGP:
             p(self.outputscale), p(self.noise), p(self.mean_const),
             p(self.norm_mins), p(self.norm_ranges), p(self.y_mean), p(self.y_std),
             p(self.xn), p(self.xs), p(self.alpha), p(self.linv_t),
-            p(self.ctx_sub), p(self.ctx_mul), p(self.arm_scal), p(self.status))
+            p(self.arm_head), p(self.status))
 
     @property
     def state(self) -> _lib.GPState:

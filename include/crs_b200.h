@@ -90,10 +90,9 @@ typedef struct crs_gp_state {
   void* xn;        /* [K, n_cap, d]        T  normalised inputs == eval-mode model.train_inputs */
   void* xs;        /* [K, n_cap, dim_pad]  T  normalised / lengthscale */
   void* alpha;     /* [K, n_cap]           T  o * K^-1 (y~ - m) */
-  void* linv_t;    /* [K, n_cap, n_cap]    T  row j = o * (column j of L^-1), zero above diagonal */
-  void* ctx_sub;   /* [K, dim_pad]         T  Normalize mins */
-  void* ctx_mul;   /* [K, dim_pad]         T  1 / (range * lengthscale), 0 in padded dims */
-  void* arm_scal;  /* [K, 4]               T  (outputscale, mean_const, y_mean, y_std) */
+  void* linv_t;    /* [K, crs_linv_stride(n_cap)] T  o * L^-T in 32-column panels (see crs_linv_stride) */
+  void* arm_head;  /* [K, 40] T  Normalize mins[16] | 1/(range*lengthscale)[16] | (outputscale,
+                      mean_const, y_mean, y_std) | pad[4] */
   int32_t* status; /* [K]  0 = ok, j+1 = non-positive Cholesky pivot at column j */
 } crs_gp_state;
 
@@ -113,6 +112,11 @@ typedef struct crs_decision {
 CRS_API int crs_abi_version(void);
 CRS_API const char* crs_status_string(int status);
 CRS_API const char* crs_last_cuda_error(void);
+
+/* Elements per arm of crs_gp_state.linv_t for a given row capacity: o * L^-T is stored panel-major,
+ * panel p = rows j in [0, min(n_cap, 32 (p+1))) x columns [32 p, 32 p + 32), row-major,
+ * so that the grid kernel stages each panel with one TMA bulk copy. */
+CRS_API int64_t crs_linv_stride(int32_t n_cap);
 
 /* Bytes of workspace crs_ocba_scan needs; zero it once, the kernel leaves it zeroed. */
 CRS_API int64_t crs_scan_workspace_bytes(void);
@@ -196,6 +200,17 @@ CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32
 /* Raw Philox4x32-10 words for known-answer tests: out[4*i..4*i+3] = philox(ctr[4*i..], key). */
 CRS_API int crs_philox_words(const uint32_t* ctr, int64_t n, uint32_t key0, uint32_t key1, uint32_t* out,
                      void* stream);
+
+/* Test hook for the grid kernel's fp64 math: out[i] = f(r2[i]) with variant 0 = the kernel's
+ * correlation (table exp + Newton sqrt), 1 = the same formula on libdevice exp/sqrt, 2/3 = the
+ * kernel's sqrt with 1/2 Newton steps, 4 = the kernel's exp(-x). */
+CRS_API int crs_debug_corr(const double* r2, int64_t n, int32_t kernel, int32_t variant, double* out,
+                           void* stream);
+
+/* Pipe-peak probe for the roofline denominators that MEASURED_PEAKS.json lacks: `blocks` CTAs of
+ * 256 threads each run `iters` x 64 dependent-chain FMAs on 16 independent accumulators
+ * (kind 0 = FP64, 1 = FP32): flops = blocks * 256 * iters * 64 * 2.  out: >= 8 bytes, device. */
+CRS_API int crs_peak_probe(int32_t kind, int32_t iters, int32_t blocks, void* out, void* stream);
 
 /*
  * Whole decision through one call with HOST context buffers — the reference-facing entry that

@@ -404,3 +404,38 @@ def test_full_size_properties(crs):
                        for i in range(0, 8192, 2048)])
     assert torch.equal(full, parts)
     assert int(full.min()) >= 0 and int(full.max()) <= S
+
+
+def test_fp64_kernel_math(crs):
+    """The grid kernel's table-based exp and Newton sqrt against libm (fp64)."""
+    from contextual_rs_b200 import _lib
+    lib = _lib.get()
+    gen = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.zeros(1, dtype=torch.float64), 10.0 ** (torch.rand(20000, generator=gen, dtype=torch.float64) * 12 - 8),
+                   torch.tensor([1e-300, 1e-30, 1.0, 4.0, 700.0, 1e4, 1e6], dtype=torch.float64)]).to(DEV)
+    out = torch.empty_like(x)
+
+    def run(kernel, variant, inp=x):
+        _lib.check(lib.crs_debug_corr(inp.data_ptr(), inp.numel(), kernel, variant, out.data_ptr(), None))
+        torch.cuda.synchronize()
+        return out.cpu().clone()
+
+    xc = x.cpu()
+    for iters_variant in (2, 3):
+        s = run(0, iters_variant)
+        ref = (xc + 1e-290).sqrt()
+        assert float(((s - ref).abs() / ref).max()) < (3e-16 if iters_variant == 3 else 1e-12)
+    small = xc.clamp(max=690.0).to(DEV)  # the kernel's exp clamps below exp(-693) ~ 1e-301
+    e = run(0, 4, small)
+    ref = torch.exp(-small.cpu())
+    assert float(((e - ref).abs() / ref).max()) < 5e-16
+    for kernel in (0, 1):
+        got, lib_dev = run(kernel, 0), run(kernel, 1)
+        r = xc.sqrt()
+        want = ((1 + 5 ** 0.5 * r + 5.0 / 3.0 * xc) * torch.exp(-(5 ** 0.5) * r)) if kernel == 0 else torch.exp(-0.5 * xc)
+        assert float((got - want).abs().max()) < 1e-15  # absolute: correlations live in [0, 1]
+        assert float((lib_dev - want).abs().max()) < 1e-15
+        big = want > 1e-280
+        # exp(-s) amplifies the rounding of its argument by s: bound relative to (2 + s)
+        arg = (5 ** 0.5) * r if kernel == 0 else 0.5 * xc
+        assert float(((got - want).abs() / (want * (2 + arg)))[big].max()) < 4e-16
