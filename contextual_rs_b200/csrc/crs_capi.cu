@@ -32,7 +32,9 @@ CRS_API const char* crs_last_cuda_error(void) { return g_cuda_err; }
 
 CRS_API int64_t crs_scan_workspace_bytes(void) { return scan_workspace_bytes(); }
 
-CRS_API int64_t crs_linv_stride(int32_t n_cap) { return n_cap > 0 ? (int64_t)linv_stride(n_cap) : 0; }
+CRS_API int64_t crs_linv_stride(int32_t n_cap, int32_t dtype) {
+  return n_cap > 0 ? (int64_t)linv_stride(n_cap, dtype == CRS_F64 ? 8 : 4) : 0;
+}
 
 CRS_API int crs_gp_prepare(const crs_gp_state* st, int32_t arm_begin, int32_t arm_end, void* stream) {
   return launch_gp_prepare(st, arm_begin, arm_end, (cudaStream_t)stream);

@@ -46,20 +46,26 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 constexpr int kHeadSub = 0, kHeadMul = CRS_MAX_DIM, kHeadScal = 2 * CRS_MAX_DIM;
 constexpr int kHeadElems = 2 * CRS_MAX_DIM + 8;
 // linv_t is stored panel-major: panel p = rows j in [0, min(n_cap, 32 (p+1))) x columns
-// [32 p, 32 p + 32), row-major with a fixed row stride of 32 — exactly the block the grid kernel
-// needs for its p-th chunk of v, so that one 1-D bulk copy stages it.
+// [32 p, 32 p + 32), row-major with a fixed row stride — exactly the block the grid kernel needs for
+// its p-th chunk of v, so that one 1-D bulk copy stages it.  The row stride is 40 elements for fp64
+// (a 16-bank skew per row makes the DMMA fragment loads of 4 consecutive rows conflict-free) and 32
+// for fp32.
 constexpr int kPanel = 32;
+__host__ __device__ inline int panel_ld(int elem_size) { return elem_size == 8 ? 40 : 32; }
+template <typename T> struct PanelLd { static constexpr int value = sizeof(T) == 8 ? 40 : 32; };
 __host__ __device__ inline int panel_rows(int n_cap, int p) {
   const int r = (p + 1) * kPanel;
   return r < n_cap ? r : n_cap;
 }
 __host__ __device__ inline int num_panels(int n_cap) { return (n_cap + kPanel - 1) / kPanel; }
-__host__ __device__ inline long long panel_offset(int n_cap, int p) {
+__host__ __device__ inline long long panel_offset(int n_cap, int p, int elem_size) {
   long long off = 0;
-  for (int q = 0; q < p; ++q) off += (long long)panel_rows(n_cap, q) * kPanel;
+  for (int q = 0; q < p; ++q) off += (long long)panel_rows(n_cap, q) * panel_ld(elem_size);
   return off;
 }
-__host__ __device__ inline long long linv_stride(int n_cap) { return panel_offset(n_cap, num_panels(n_cap)); }
+__host__ __device__ inline long long linv_stride(int n_cap, int elem_size) {
+  return panel_offset(n_cap, num_panels(n_cap), elem_size);
+}
 
 // ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk) ------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -203,14 +203,14 @@ __global__ void __launch_bounds__(kPrepThreads) gp_prepare_kernel(crs_gp_state s
   for (int i = tid; i < ncap; i += nt) alpha[i] = i < n ? T(o * rhs[i]) : T(0);
   // linv_t, panel-major (see crs_common.cuh): panel p holds rows j < min(ncap, 32 (p+1)) and
   // columns [32 p, 32 p + 32); entry (j, i) = o * (L^-1)[i][j] for i >= j, zero otherwise.
-  T* lt = reinterpret_cast<T*>(st.linv_t) + (size_t)k * linv_stride(ncap);
-  const int ld = kPanel;
+  T* lt = reinterpret_cast<T*>(st.linv_t) + (size_t)k * linv_stride(ncap, sizeof(T));
+  const int ld = PanelLd<T>::value;
   for (int p = 0; p < num_panels(ncap); ++p) {
-    T* pan = lt + panel_offset(ncap, p);
+    T* pan = lt + panel_offset(ncap, p, sizeof(T));
     const int rows = panel_rows(ncap, p);
     for (int idx = tid; idx < rows * ld; idx += nt) {
       const int j = idx / ld, i = p * kPanel + (idx - j * ld);
-      pan[idx] = (i >= j && i < n) ? T(o * A[i * lda + j]) : T(0);
+      pan[idx] = (i >= j && i < n && i < (p + 1) * kPanel) ? T(o * A[i * lda + j]) : T(0);
     }
   }
   T* head = reinterpret_cast<T*>(st.arm_head) + (size_t)k * kHeadElems;

@@ -7,7 +7,8 @@
 namespace crs {
 namespace {
 
-template <typename T>
+// OP: 0 = fma, 1 = add, 2 = mul
+template <typename T, int OP>
 __global__ void __launch_bounds__(256) fma_probe_kernel(int iters, T seed, T* out) {
   T a[16];
 #pragma unroll
@@ -17,7 +18,7 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(int iters, T seed, T* ou
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, b);
+      for (int i = 0; i < 16; ++i) a[i] = OP == 0 ? fma(a[i], m, b) : (OP == 1 ? a[i] + b : a[i] * m);
     }
   }
   T s = T(0);
@@ -51,8 +52,10 @@ __global__ void __launch_bounds__(256) dmma_probe_kernel(int iters, double seed,
 
 int launch_peak_probe(int kind, int iters, int blocks, void* out, cudaStream_t s) {
   if (!out || iters < 1 || blocks < 1) return CRS_ERR_INVALID_ARG;
-  if (kind == 0) fma_probe_kernel<double><<<blocks, 256, 0, s>>>(iters, 1.0, (double*)out);
-  else if (kind == 1) fma_probe_kernel<float><<<blocks, 256, 0, s>>>(iters, 1.0f, (float*)out);
+  if (kind == 0) fma_probe_kernel<double, 0><<<blocks, 256, 0, s>>>(iters, 1.0, (double*)out);
+  else if (kind == 1) fma_probe_kernel<float, 0><<<blocks, 256, 0, s>>>(iters, 1.0f, (float*)out);
+  else if (kind == 3) fma_probe_kernel<double, 1><<<blocks, 256, 0, s>>>(iters, 1.0, (double*)out);
+  else if (kind == 4) fma_probe_kernel<double, 2><<<blocks, 256, 0, s>>>(iters, 1.0, (double*)out);
   else if (kind == 2) dmma_probe_kernel<<<blocks, 256, 0, s>>>(iters, 1.0, (double*)out);  // 16 DMMA / iter / warp
   else return CRS_ERR_INVALID_ARG;
   CRS_CUDA_TRY(cudaGetLastError(), "peak_probe launch");

@@ -19,6 +19,8 @@
 //
 // fp64 transcendental cost dominates at n ~ 20, so exp() is a 16-entry-table + degree-7 polynomial
 // (12 FP64 ops) and sqrt() is rsqrt.approx + coupled Newton steps + one correction (branch-free).
+#include <type_traits>
+#include <utility>
 #include "crs_common.cuh"
 
 namespace crs {
@@ -27,9 +29,13 @@ namespace {
 constexpr int kGridThreads = 128;
 constexpr int kMaxArmTile = 8;
 #ifndef CRS_GRID_MIN_BLOCKS
-#define CRS_GRID_MIN_BLOCKS 5
+#define CRS_GRID_MIN_BLOCKS 4
 #endif
 constexpr int kMinBlocks = CRS_GRID_MIN_BLOCKS;
+#ifndef CRS_PHASE_A_UNROLL
+#define CRS_PHASE_A_UNROLL 4
+#endif
+constexpr int kPhaseAUnroll = CRS_PHASE_A_UNROLL;  // divides 4 (rows are padded to a multiple of 4)
 
 // ---- fp64 exp(x), x <= 0: x = (16 k + i) ln2/16 + r, exp(x) = 2^k * 2^(i/16) * e^r ------------
 __constant__ double kExpTable[16] = {
@@ -142,22 +148,138 @@ __device__ __forceinline__ T sq_dist(const T (&xq)[D], const T* __restrict__ xro
   return r;
 }
 
+// ---- phase B ---------------------------------------------------------------------------------
+// q[context] = || (o L^-1) c ||^2 restricted to the VB rows [p0, p0 + VB) of v, for the 32 contexts
+// of one warp.  c lives in s_c[j][context] (row stride CS), the panel in s_panel[j][i - p0].
+
+// FP32: one context per thread, v in registers, rows in 8-row segments so that the triangular
+// structure is resolved at compile time.
+template <int VB, int CS>
+__device__ __forceinline__ float chunk_sqnorm(const float* __restrict__ s_panel, const float* __restrict__ s_c,
+                                              int p0, int jend, int tid, float*) {
+  constexpr int LD = PanelLd<float>::value;
+  float v[VB];
+#pragma unroll
+  for (int i = 0; i < VB; ++i) v[i] = 0.f;
+  for (int j = 0; j < p0; ++j)  // rows above this chunk: every column is below the diagonal
+    axpy_blocks<float, VB, 0>(v, s_panel + j * LD, s_c[j * CS + tid]);
+  const float* crow = s_c + (size_t)p0 * CS + tid;
+  const float* prow = s_panel + (size_t)p0 * LD;
+  const int rows_in = jend - p0;
+#pragma unroll
+  for (int sg = 0; sg < VB / 8; ++sg) {
+    if (sg * 8 < rows_in) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        if (sg * 8 + jj < rows_in) {
+          const float cj = crow[(sg * 8 + jj) * CS];
+          const float* row = prow + (sg * 8 + jj) * LD;
+          if (sg == 0) axpy_blocks<float, VB, 0>(v, row, cj);
+          else if (sg == 1) axpy_blocks<float, VB, (VB > 8 ? 1 : 0)>(v, row, cj);
+          else if (sg == 2) axpy_blocks<float, VB, (VB > 16 ? 2 : 0)>(v, row, cj);
+          else axpy_blocks<float, VB, (VB > 24 ? 3 : 0)>(v, row, cj);
+        }
+      }
+    }
+  }
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VB; ++i) q = fmaf(v[i], v[i], q);
+  return q;
+}
+
+// FP64: the contraction V[VB x 32] = Linv[VB x jend] C[jend x 32] runs on the FP64 tensor path
+// (mma.sync.m8n8k4.f64 -> SASS DMMA): same FLOP rate as DFMA on B200 (measured 37.1 vs 36.6
+// TFLOP/s) but one fragment load feeds 8 FMAs per lane instead of 2, which takes the kernel off
+// the shared-memory-wavefront limit the scalar version sat on (ncu, profiles/r01b).  A fragment:
+// Linv[p0 + 8 mt + lane/4][4 ks + lane%4]; B fragment: C[4 ks + lane%4][8 nt + lane/4]; tiles that
+// lie entirely above the diagonal are skipped.  Rows >= n of both operands are finite / zero.
+template <int VB, int CS>
+__device__ __forceinline__ double chunk_sqnorm(const double* __restrict__ s_panel, const double* __restrict__ s_c,
+                                               int p0, int jend, int tid, double* s_q) {
+  constexpr int LD = PanelLd<double>::value;
+  constexpr int MT = VB / 8;
+  const int lane = tid & 31, wbase = tid & ~31;
+  const int l4 = lane & 3, l8 = lane >> 2;
+  double acc[MT][4][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  const int ksteps = (jend + 3) >> 2;
+  const double* bptr = s_c + (size_t)l4 * CS + wbase + l8;
+  const double* aptr = s_panel + (size_t)l4 * LD + l8;
+  // one k-step (4 rows j) for the row tiles mt >= first (tiles above the diagonal are all zero)
+  auto kstep = [&](int ks, auto first_tag) {
+    constexpr int FIRST = decltype(first_tag)::value;
+    double b[4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) b[nt] = bptr[(size_t)ks * 4 * CS + nt * 8];
+#pragma unroll
+    for (int mt = FIRST; mt < MT; ++mt) {
+      const double a = aptr[(size_t)ks * 4 * LD + mt * 8];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1]) : "d"(a), "d"(b[nt]));
+    }
+  };
+  const int ks0 = p0 >> 2;  // k-steps above the chunk: every tile is below the diagonal
+  for (int ks = 0; ks < ks0; ++ks) kstep(ks, std::integral_constant<int, 0>{});
+  // k-steps inside the chunk: steps 2 sg, 2 sg + 1 only reach row tiles mt >= sg
+  [&]<int... SG>(std::integer_sequence<int, SG...>) {
+    (([&] {
+       if (ks0 + 2 * SG < ksteps) kstep(ks0 + 2 * SG, std::integral_constant<int, SG>{});
+       if (ks0 + 2 * SG + 1 < ksteps) kstep(ks0 + 2 * SG + 1, std::integral_constant<int, SG>{});
+     }()),
+     ...);
+  }(std::make_integer_sequence<int, MT>{});
+  // D fragment: V[p0 + 8 mt + l8][8 nt + 2 l4 + e]; sum of squares over rows = over mt and l8
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      q0 = fma(acc[mt][nt][0], acc[mt][nt][0], q0);
+      q1 = fma(acc[mt][nt][1], acc[mt][nt][1], q1);
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      q0 += __shfl_xor_sync(kFull, q0, o);
+      q1 += __shfl_xor_sync(kFull, q1, o);
+    }
+    if (l8 == 0) {
+      s_q[wbase + nt * 8 + 2 * l4] = q0;
+      s_q[wbase + nt * 8 + 2 * l4 + 1] = q1;
+    }
+  }
+  __syncwarp();
+  const double q = s_q[tid];
+  __syncwarp();
+  return q;
+}
+
+template <typename T> struct CStride { static constexpr int value = sizeof(T) == 8 ? kGridThreads + 8 : kGridThreads; };
+
 template <typename T, int D, int VB>
 __global__ void __launch_bounds__(kGridThreads, kMinBlocks)
 posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, int arm_begin,
                       int arm_end, int arm_tile, int n_rows, T* __restrict__ mean,
                       T* __restrict__ var, int64_t ld, int col_offset) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int LD = PanelLd<T>::value;   // panel row stride
+  constexpr int CS = CStride<T>::value;   // row stride of the parked correlations
   const int tid = threadIdx.x;
   const int ncap = st.n_cap, d = st.dim;
-  // shared layout: bars[4] u64 | tab[16] T | stage[2] { head[40] | alpha[n_rows] | xs[n_rows][D] |
-  //                panel[n_rows][32] } | c[n_rows][128] | out[2][arm_tile][128]      (n_rows % 4 == 0)
+  // shared layout: bars[4] u64 | tab[16] T | q[128] T | stage[2] { head[40] | alpha[n_rows] |
+  //                xs[n_rows][D] | panel[n_rows][LD] } | c[n_rows][CS] | out[2][arm_tile][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   T* s_tab = reinterpret_cast<T*>(smem_raw + 32);
-  T* s_stage = s_tab + 16;
-  const int stage_elems = kHeadElems + n_rows + n_rows * D + n_rows * kPanel;
+  T* s_q = s_tab + 16;
+  T* s_stage = s_q + kGridThreads;
+  const int stage_elems = kHeadElems + n_rows + n_rows * D + n_rows * LD;
   T* s_c = s_stage + 2 * stage_elems;
-  T* s_out = s_c + n_rows * kGridThreads;
+  T* s_out = s_c + n_rows * CS;
 
   const int64_t c = (int64_t)blockIdx.x * kGridThreads + tid;
   const bool live = c < n_c;
@@ -169,7 +291,7 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
   const T* g_alpha = reinterpret_cast<const T*>(st.alpha);
   const T* g_xs = reinterpret_cast<const T*>(st.xs);
   const T* g_lt = reinterpret_cast<const T*>(st.linv_t);
-  const long long lt_stride = linv_stride(ncap);
+  const long long lt_stride = linv_stride(ncap, sizeof(T));
 
   // TMA producer (thread 0): stage the state of the t-th arm of this tile into buffer t & 1
   auto issue = [&](int t) {
@@ -177,15 +299,15 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
     T* stg = s_stage + (t & 1) * stage_elems;
     const int n = min(min(st.n_obs[k], ncap), n_rows);
     const int n4 = (n + 3) & ~3;
-    const int rows0 = min(n, kPanel);
+    const int rows0 = min(n4, kPanel);
     uint64_t* bar = &bars[t & 1];
-    mbar_expect_tx(bar, (uint32_t)sizeof(T) * (kHeadElems + n4 + n4 * D + rows0 * kPanel));
+    mbar_expect_tx(bar, (uint32_t)sizeof(T) * (kHeadElems + n4 + n4 * D + rows0 * LD));
     tma_bulk_g2s(stg, g_head + (size_t)k * kHeadElems, sizeof(T) * kHeadElems, bar);
     if (n4) {
       tma_bulk_g2s(stg + kHeadElems, g_alpha + (size_t)k * ncap, sizeof(T) * n4, bar);
       tma_bulk_g2s(stg + kHeadElems + n_rows, g_xs + (size_t)k * ncap * D, sizeof(T) * n4 * D, bar);
       tma_bulk_g2s(stg + kHeadElems + n_rows + n_rows * D, g_lt + (size_t)k * lt_stride,
-                   sizeof(T) * rows0 * kPanel, bar);
+                   sizeof(T) * rows0 * LD, bar);
     }
   };
 
@@ -210,7 +332,7 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
   for (int t = 0; t < na; ++t) {
     const int k = a0 + t;
     const int n = min(min(st.n_obs[k], ncap), n_rows);
-    const int n2 = (n + 1) & ~1;
+    const int n4 = (n + 3) & ~3;
     T* stg = s_stage + (t & 1) * stage_elems;
     const T* s_head = stg;
     const T* s_alpha = stg + kHeadElems;
@@ -218,72 +340,54 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
     T* s_panel = stg + kHeadElems + n_rows + n_rows * D;
     mbar_wait(&bars[t & 1], (uint32_t)(t >> 1) & 1u);
 
-    // ---- phase A: correlations, two observations per iteration ------------------------------
+    // ---- phase A: correlations, kPhaseAUnroll observations per iteration (ILP) ----------------
+    // (runs to n4: the padded rows have zero xs / alpha, so they park a finite value and add 0)
     T xq[D];
 #pragma unroll
     for (int dd = 0; dd < D; ++dd) xq[dd] = (xraw[dd] - s_head[kHeadSub + dd]) * s_head[kHeadMul + dd];
-    T macc0 = T(0), macc1 = T(0);
+    T macc[kPhaseAUnroll];
+#pragma unroll
+    for (int u = 0; u < kPhaseAUnroll; ++u) macc[u] = T(0);
 #pragma unroll 1
-    for (int j = 0; j < n2; j += 2) {
-      const T ra = sq_dist<T, D>(xq, s_xs + j * D);
-      const T rb = sq_dist<T, D>(xq, s_xs + (j + 1) * D);
-      const T ca = Corr<T>::eval(ra, st.kernel, s_tab);
-      const T cb = Corr<T>::eval(rb, st.kernel, s_tab);
-      macc0 = fma(ca, s_alpha[j], macc0);
-      macc1 = fma(cb, s_alpha[j + 1], macc1);  // alpha (and xs) are zero in the padded row
-      s_c[j * kGridThreads + tid] = ca;
-      s_c[(j + 1) * kGridThreads + tid] = cb;
+    for (int j = 0; j < n4; j += kPhaseAUnroll) {
+      T r2[kPhaseAUnroll], cv[kPhaseAUnroll];
+#pragma unroll
+      for (int u = 0; u < kPhaseAUnroll; ++u) r2[u] = sq_dist<T, D>(xq, s_xs + (j + u) * D);
+#pragma unroll
+      for (int u = 0; u < kPhaseAUnroll; ++u) cv[u] = Corr<T>::eval(r2[u], st.kernel, s_tab);
+#pragma unroll
+      for (int u = 0; u < kPhaseAUnroll; ++u) {
+        macc[u] = fma(cv[u], s_alpha[j + u], macc[u]);
+        s_c[(j + u) * CS + tid] = cv[u];
+      }
     }
-    // (s_c is private per thread column: no barrier needed before phase B reads it back)
+    T macc_sum = T(0);
+#pragma unroll
+    for (int u = 0; u < kPhaseAUnroll; ++u) macc_sum += macc[u];
+    __syncwarp();  // phase B reads the correlations of the whole warp (fp64 MMA fragments)
 
-    // ---- phase B: v = (o L^-1) c, VB rows at a time -------------------------------------------
+    // ---- phase B: q = || (o L^-1) c ||^2, VB rows of v at a time -----------------------------
     T q = T(0);
     for (int p0 = 0; p0 < n; p0 += kPanel) {
-      const int jend = min(n, p0 + VB);  // rows j < jend touch this chunk
-      if (p0 > 0) {                      // later panels of a long arm: staged on demand
+      const int jend = min(n4, p0 + VB);  // rows j < jend touch this chunk
+      if (p0 > 0) {                       // later panels of a long arm: staged on demand
         __syncthreads();
         if (tid == 0) {
           fence_proxy_async();
-          const uint32_t bytes = (uint32_t)sizeof(T) * min(n, p0 + kPanel) * kPanel;
+          const uint32_t bytes = (uint32_t)sizeof(T) * min(n4, p0 + kPanel) * LD;
           mbar_expect_tx(&bars[2], bytes);
-          tma_bulk_g2s(s_panel, g_lt + (size_t)k * lt_stride + panel_offset(ncap, p0 / kPanel), bytes, &bars[2]);
+          tma_bulk_g2s(s_panel, g_lt + (size_t)k * lt_stride + panel_offset(ncap, p0 / kPanel, sizeof(T)),
+                       bytes, &bars[2]);
         }
         mbar_wait(&bars[2], xphase);
         xphase ^= 1u;
       }
-      T v[VB];
-#pragma unroll
-      for (int i = 0; i < VB; ++i) v[i] = T(0);
-      // rows above this chunk: every column of the chunk is below the diagonal
-      for (int j = 0; j < p0; ++j)
-        axpy_blocks<T, VB, 0>(v, s_panel + j * kPanel, s_c[j * kGridThreads + tid]);
-      // rows inside the chunk, in 8-row segments: segment sg only reaches column blocks >= sg
-      const T* crow = s_c + (size_t)p0 * kGridThreads + tid;
-      const T* prow = s_panel + (size_t)p0 * kPanel;
-      const int rows_in = jend - p0;
-#pragma unroll
-      for (int sg = 0; sg < VB / 8; ++sg) {
-        if (sg * 8 < rows_in) {
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            if (sg * 8 + jj < rows_in) {
-              const T cj = crow[(sg * 8 + jj) * kGridThreads];
-              const T* row = prow + (sg * 8 + jj) * kPanel;
-              if (sg == 0) axpy_blocks<T, VB, 0>(v, row, cj);
-              else if (sg == 1) axpy_blocks<T, VB, (VB > 8 ? 1 : 0)>(v, row, cj);
-              else if (sg == 2) axpy_blocks<T, VB, (VB > 16 ? 2 : 0)>(v, row, cj);
-              else axpy_blocks<T, VB, (VB > 24 ? 3 : 0)>(v, row, cj);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < VB; ++i) q = fma(v[i], v[i], q);
+      q += chunk_sqnorm<VB, CS>(s_panel, s_c, p0, jend, tid, s_q);
     }
 
     const T o = s_head[kHeadScal + 0], m = s_head[kHeadScal + 1];
     const T ybar = s_head[kHeadScal + 2], ysd = s_head[kHeadScal + 3];
-    const T mu = fma(ysd, m + (macc0 + macc1), ybar);
+    const T mu = fma(ysd, m + macc_sum, ybar);
     T vr = (ysd * ysd) * (o - q);
     vr = vr > variance_floor<T>() ? vr : variance_floor<T>();  // also maps NaN to the floor
     s_out[t * kGridThreads + tid] = mu;
@@ -317,8 +421,9 @@ int launch_variant(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm
   int arm_tile = kMaxArmTile;
   while (arm_tile > 1 && ctx_tiles * ((narms + arm_tile - 1) / arm_tile) < 148 * 4) arm_tile >>= 1;
   auto smem_for = [&](int at) {
-    const size_t stage = kHeadElems + (size_t)n_rows + (size_t)n_rows * D + (size_t)n_rows * kPanel;
-    return 32 + sizeof(T) * (16 + 2 * stage + (size_t)n_rows * kGridThreads + 2 * (size_t)at * kGridThreads);
+    const size_t stage = kHeadElems + (size_t)n_rows + (size_t)n_rows * D + (size_t)n_rows * PanelLd<T>::value;
+    return 32 + sizeof(T) * (16 + kGridThreads + 2 * stage + (size_t)n_rows * CStride<T>::value +
+                             2 * (size_t)at * kGridThreads);
   };
   while (arm_tile > 1 && smem_for(arm_tile) > 227 * 1024) arm_tile >>= 1;
   const size_t smem = smem_for(arm_tile);

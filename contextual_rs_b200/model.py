@@ -148,7 +148,7 @@ class B200ModelListGP:
         self.xn = torch.zeros(K, ncap, d, dtype=T, device=dev)
         self.xs = torch.zeros(K, ncap, dp, dtype=T, device=dev)
         self.alpha = torch.zeros(K, ncap, dtype=T, device=dev)
-        self.linv_t = torch.zeros(K, int(_lib.get().crs_linv_stride(ncap)), dtype=T, device=dev)
+        self.linv_t = torch.zeros(K, int(_lib.get().crs_linv_stride(ncap, _lib.DTYPES[T])), dtype=T, device=dev)
         self.arm_head = torch.zeros(K, _lib.CRS_HEAD_ELEMS, dtype=T, device=dev)
         self.status = torch.zeros(K, dtype=torch.int32, device=dev)
         self._state = self._make_state(flags)

@@ -90,7 +90,7 @@ typedef struct crs_gp_state {
   void* xn;        /* [K, n_cap, d]        T  normalised inputs == eval-mode model.train_inputs */
   void* xs;        /* [K, n_cap, dim_pad]  T  normalised / lengthscale */
   void* alpha;     /* [K, n_cap]           T  o * K^-1 (y~ - m) */
-  void* linv_t;    /* [K, crs_linv_stride(n_cap)] T  o * L^-T in 32-column panels (see crs_linv_stride) */
+  void* linv_t;    /* [K, crs_linv_stride(n_cap, dtype)] T  o * L^-T in 32-column panels */
   void* arm_head;  /* [K, 40] T  Normalize mins[16] | 1/(range*lengthscale)[16] | (outputscale,
                       mean_const, y_mean, y_std) | pad[4] */
   int32_t* status; /* [K]  0 = ok, j+1 = non-positive Cholesky pivot at column j */
@@ -114,9 +114,10 @@ CRS_API const char* crs_status_string(int status);
 CRS_API const char* crs_last_cuda_error(void);
 
 /* Elements per arm of crs_gp_state.linv_t for a given row capacity: o * L^-T is stored panel-major,
- * panel p = rows j in [0, min(n_cap, 32 (p+1))) x columns [32 p, 32 p + 32), row-major,
- * so that the grid kernel stages each panel with one TMA bulk copy. */
-CRS_API int64_t crs_linv_stride(int32_t n_cap);
+ * panel p = rows j in [0, min(n_cap, 32 (p+1))) x columns [32 p, 32 p + 32), row-major with a row
+ * stride of 40 (fp64) / 32 (fp32) elements, so that the grid kernel stages each panel with one TMA
+ * bulk copy and reads it bank-conflict-free. */
+CRS_API int64_t crs_linv_stride(int32_t n_cap, int32_t dtype);
 
 /* Bytes of workspace crs_ocba_scan needs; zero it once, the kernel leaves it zeroed. */
 CRS_API int64_t crs_scan_workspace_bytes(void);
