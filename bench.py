@@ -5,8 +5,8 @@
 
 A *step* is one whole GP-C-OCBA decision on a model whose caches are cold: per-arm Cholesky
 state (crs_gp_prepare, all arms), ModelListGP posterior over the arm x context grid
-(crs_posterior_grid), zeta scan + global argmin (crs_ocba_scan) and OCBA step 2(b)
-(crs_ocba_select) — what `gao_modellist(model, context_set)` does in the reference
+(crs_posterior_grid), zeta scan + global argmin + OCBA step 2(b) fused in one launch
+(crs_ocba_scan_select) — what `gao_modellist(model, context_set)` does in the reference
 (contextual_rs/contextual_rs_strategies.py:100-202) on a freshly fitted model.
 
   value : decisions/s with every input already resident in HBM (device timed, CUDA events).
@@ -206,7 +206,7 @@ def main():
     import torch.distributed as dist
     import contextual_rs_b200 as crs
     from contextual_rs_b200 import _lib
-    from contextual_rs_b200.contextual_rs_strategies import _scan
+    from contextual_rs_b200.contextual_rs_strategies import _scan, _scan_select
     from contextual_rs_b200.sharded import ContextShardedDecider, REC_CONTEXT, REC_NEXT_ARM, shard_bounds
     from contextual_rs_b200.synthetic import make_config
 
@@ -245,14 +245,12 @@ def main():
     st = C.byref(model.state)
 
     def device_step():
-        """prepare -> grid -> scan -> select, all inputs resident, no host round-trip."""
+        """prepare -> grid -> fused scan + select, all inputs resident, no host round-trip."""
         _lib.check(lib.crs_gp_prepare(st, 0, K, stream))
         if n_loc:
             _lib.check(lib.crs_posterior_grid(st, ctx_dev.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
                                               ws["var"].data_ptr(), K, 0, stream))
-            _scan(lib, model, ws, n_loc, stream)
-            _lib.check(lib.crs_ocba_select(st, ctx_dev.data_ptr(), ws["mean"].data_ptr(), ws["var"].data_ptr(),
-                                           K, 0, 0, 2.0, ws["decision"].data_ptr(), stream))
+            _scan_select(lib, model, ws, n_loc, 0, 2.0, stream, ctx_ptr=ctx_dev.data_ptr())
         if world > 1:
             dist.all_gather_into_tensor(decider._gather, ws["decision"] if n_loc else decider._empty)
 
@@ -344,10 +342,10 @@ def main():
             "config": {"workload": WORKLOADS[name], "arms": K, "contexts": n_c, "dim": d, "obs_per_arm": n_obs,
                        "sharding": f"contexts/{world}" if world > 1 else "none",
                        "l2": "flushed between timed steps (256 MiB write)" if not args.no_flush else "not flushed",
-                       "step": "prepare(all arms) + posterior grid + zeta scan + OCBA select"},
+                       "step": "3 kernels: prepare(all arms) + posterior grid + fused zeta scan / OCBA select"},
             "e2e": {"value": K_steps / t_e2e, "unit": "decisions/s", "ms_per_step": t_e2e / K_steps * 1e3,
                     "h2d_bytes_per_step": int(n_c * d * w), "d2h_bytes_per_step": 64 * world},
-            "gpu_launches": 4 * K_steps + 4 * K_steps + 3 * ksteps,
+            "gpu_launches": 3 * K_steps + 3 * K_steps + 3 * ksteps,
             "roofline": {"kernel": "posterior_grid_kernel", "bound": "fp64_fma" if dtype == torch.float64 else "fp32_fma",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                          "traffic": None, "avg_launch_ms": grid_avg,

@@ -65,10 +65,7 @@ def decide(model: B200ModelListGP, context_set: Tensor, randomize_ties: bool, p_
             K = model.num_arms
             _lib.check(lib.crs_posterior_grid(st, ws["ctx"].data_ptr(), n_c, 0, K, ws["mean"].data_ptr(),
                                               ws["var"].data_ptr(), K, 0, stream), "crs_posterior_grid")
-            _scan(lib, model, ws, n_c, stream)
-            _lib.check(lib.crs_ocba_select(st, ws["ctx"].data_ptr(), ws["mean"].data_ptr(), ws["var"].data_ptr(),
-                                           K, 0, p_mode, float(kernel_scale), ws["decision"].data_ptr(), stream),
-                       "crs_ocba_select")
+            _scan_select(lib, model, ws, n_c, p_mode, kernel_scale, stream)
             ws["decision_host"].copy_(ws["decision"], non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             if dec.reserved[0] != 0:
@@ -90,6 +87,18 @@ def decide(model: B200ModelListGP, context_set: Tensor, randomize_ties: bool, p_
             torch.cuda.current_stream(dev).synchronize()
     ws["valid_for"] = (ctx2.data_ptr(), n_c)
     return dec
+
+
+def _scan_select(lib, model: B200ModelListGP, ws: dict, n_c: int, p_mode: int, kernel_scale: float,
+                 stream: int, ctx_ptr: Optional[int] = None) -> None:
+    """zeta scan + global argmin + OCBA step 2(b) in one launch (``crs_ocba_scan_select``)."""
+    K = model.num_arms
+    _lib.check(lib.crs_ocba_scan_select(C.byref(model.state), ctx_ptr or ws["ctx"].data_ptr(),
+                                        ws["mean"].data_ptr(), ws["var"].data_ptr(), n_c, K, 0, p_mode,
+                                        float(kernel_scale), ws["best_arm"].data_ptr(),
+                                        ws["min_zeta"].data_ptr(), ws["min_arm"].data_ptr(),
+                                        ws["tie_cnt"].data_ptr(), ws["decision"].data_ptr(),
+                                        ws["scan_ws"].data_ptr(), stream), "crs_ocba_scan_select")
 
 
 def _scan(lib, model: B200ModelListGP, ws: dict, n_c: int, stream: int) -> None:

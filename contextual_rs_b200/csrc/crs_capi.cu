@@ -1,6 +1,7 @@
 // extern "C" surface of libcrs_b200.so (declared in include/crs_b200.h).
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include "crs_common.cuh"
 
 namespace crs {
@@ -65,7 +66,18 @@ CRS_API int crs_ocba_resolve_tie(const void* mean, const void* var, int64_t n_c,
 CRS_API int crs_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
                     int64_t ld, int32_t arm_offset, int32_t p_mode, double kernel_scale,
                     crs_decision* decision, void* stream) {
-  return launch_ocba_select(st, ctx, mean, var, ld, arm_offset, p_mode, kernel_scale, decision, (cudaStream_t)stream);
+  return launch_ocba_select(st, ctx, mean, var, ld, arm_offset, p_mode, kernel_scale, decision, nullptr, 0, (cudaStream_t)stream);
+}
+
+CRS_API int crs_ocba_scan_select(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
+                                 int64_t n_c, int64_t ld, int32_t arm_offset, int32_t p_mode,
+                                 double kernel_scale, int32_t* best_arm, void* min_zeta,
+                                 int32_t* min_arm, int32_t* tie_cnt, crs_decision* decision,
+                                 void* workspace, void* stream) {
+  if (!st) return CRS_ERR_INVALID_ARG;
+  return launch_ocba_scan_select(mean, var, n_c, st->num_arms, ld, st->dtype, arm_offset, nullptr, nullptr,
+                                 nullptr, best_arm, min_zeta, min_arm, tie_cnt, decision, workspace, st, ctx,
+                                 p_mode, kernel_scale, nullptr, 0, (cudaStream_t)stream);
 }
 
 CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
@@ -97,16 +109,55 @@ CRS_API int crs_gao_decide_host(const crs_gp_state* st, const void* ctx_host, in
   cudaStream_t s = (cudaStream_t)stream;
   const size_t w = st->dtype == CRS_F64 ? 8 : 4;
   const int K = st->num_arms;
+  // If decision_host is pinned (mapped under UVA) the last kernel writes the decision straight
+  // into it and the host spins on a sequence tag instead of paying a D2H copy + stream sync.
+  static thread_local const void* cached_host = nullptr;
+  static thread_local crs_decision* cached_dev = nullptr;
+  static thread_local int seq_counter = 0;
+  if (cached_host != decision_host) {
+    void* dptr = nullptr;
+    if (cudaHostGetDevicePointer(&dptr, decision_host, 0) == cudaSuccess) {
+      cached_dev = reinterpret_cast<crs_decision*>(dptr);
+    } else {
+      (void)cudaGetLastError();  // pageable memory: fall back to the copy path
+      cached_dev = nullptr;
+    }
+    cached_host = decision_host;
+  }
+  crs_decision* mirror = cached_dev;
+  const int seq = (++seq_counter == 0) ? ++seq_counter : seq_counter;
+  if (mirror) reinterpret_cast<volatile int32_t*>(decision_host->reserved)[1] = 0;
+
   CRS_CUDA_TRY(cudaMemcpyAsync(ws->ctx, ctx_host, (size_t)n_c * st->dim * w, cudaMemcpyHostToDevice, s), "ctx H2D");
   int rc;
   if (prep_end > prep_begin && (rc = launch_gp_prepare(st, prep_begin, prep_end, s)) != CRS_OK) return rc;
   if ((rc = launch_posterior_grid(st, ws->ctx, n_c, 0, K, ws->mean, ws->var, K, 0, s)) != CRS_OK) return rc;
-  if ((rc = launch_ocba_scan(ws->mean, ws->var, n_c, K, K, st->dtype, 0, nullptr, nullptr, nullptr,
-                             ws->best_arm, ws->min_zeta, ws->min_arm, ws->tie_cnt, ws->decision,
-                             ws->scan_ws, s)) != CRS_OK) return rc;
-  if ((rc = launch_ocba_select(st, ws->ctx, ws->mean, ws->var, K, 0, p_mode, kernel_scale, ws->decision, s)) != CRS_OK) return rc;
-  CRS_CUDA_TRY(cudaMemcpyAsync(decision_host, ws->decision, sizeof(crs_decision), cudaMemcpyDeviceToHost, s), "decision D2H");
-  CRS_CUDA_TRY(cudaStreamSynchronize(s), "decide sync");
+  if ((rc = launch_ocba_scan_select(ws->mean, ws->var, n_c, K, K, st->dtype, 0, nullptr, nullptr, nullptr,
+                                    ws->best_arm, ws->min_zeta, ws->min_arm, ws->tie_cnt, ws->decision,
+                                    ws->scan_ws, st, ws->ctx, p_mode, kernel_scale, mirror, seq, s)) != CRS_OK)
+    return rc;
+  if (mirror) {
+    volatile int32_t* tag = reinterpret_cast<volatile int32_t*>(decision_host->reserved) + 1;
+    struct timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    unsigned long long spins = 0;
+    while (*tag != seq) {
+      __builtin_ia32_pause();
+      if ((++spins & 0xfff) == 0) {
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) > 2.0) {
+          // never published (launch failure?): surface the error through a synchronise
+          CRS_CUDA_TRY(cudaStreamSynchronize(s), "decide sync");
+          if (*tag != seq) return CRS_ERR_CUDA;
+        }
+      }
+    }
+    __sync_synchronize();
+  } else {
+    CRS_CUDA_TRY(cudaMemcpyAsync(decision_host, ws->decision, sizeof(crs_decision), cudaMemcpyDeviceToHost, s), "decision D2H");
+    CRS_CUDA_TRY(cudaStreamSynchronize(s), "decide sync");
+  }
   if (decision_host->reserved[0] != 0) return CRS_ERR_NOT_PSD;
   if (randomize_ties && decision_host->tie_count > 1) return CRS_TIES_PENDING;
   return CRS_OK;

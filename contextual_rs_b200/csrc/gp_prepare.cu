@@ -18,7 +18,7 @@ constexpr int kPrepThreads = 256;
 constexpr double kMinRange = 1e-8;  // botorch Normalize(min_range)
 constexpr double kMinStdv = 1e-8;   // botorch Standardize(min_stdv)
 
-__device__ __forceinline__ double block_sum(double v, double* red, int tid, int nt) {
+__device__ __forceinline__ double group_sum(double v, double* red, int tid, int nt) {
   v = warp_sum(v);
   __syncthreads();
   if ((tid & 31) == 0) red[tid >> 5] = v;
@@ -28,11 +28,19 @@ __device__ __forceinline__ double block_sum(double v, double* red, int tid, int 
   return t;
 }
 
+__host__ __device__ inline size_t prep_group_doubles(int ncap, int dp) {
+  return (size_t)ncap * (ncap + 1) + (size_t)ncap * dp + ncap + 8 + 2 * CRS_MAX_DIM + 2;
+}
+
+// General variant: one 256-thread CTA per arm, any n <= CRS_MAX_OBS.
 template <typename T>
-__global__ void __launch_bounds__(kPrepThreads) gp_prepare_kernel(crs_gp_state st, int arm_begin) {
+__global__ void __launch_bounds__(kPrepThreads)
+gp_prepare_kernel(crs_gp_state st, int arm_begin, int arm_end) {
   extern __shared__ double smem[];
   const int k = arm_begin + blockIdx.x;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  if (k >= arm_end) return;
+  const int tid = threadIdx.x;
+  const int nt = blockDim.x;
   const int d = st.dim, dp = st.dim_pad, ncap = st.n_cap;
   int n = st.n_obs[k];
   if (n > ncap) n = ncap;
@@ -42,8 +50,8 @@ __global__ void __launch_bounds__(kPrepThreads) gp_prepare_kernel(crs_gp_state s
   double* rhs = xs + (size_t)ncap * dp; // [ncap]
   double* red = rhs + ncap;             // [8] reduction scratch
   double* tr = red + 8;                 // [2*CRS_MAX_DIM] mins, ranges
-  __shared__ int fail;
-  if (tid == 0) fail = 0;
+  volatile int* failp = reinterpret_cast<volatile int*>(tr + 2 * CRS_MAX_DIM);
+  if (tid == 0) *failp = 0;
 
   const double* X = st.train_x + (size_t)k * ncap * d;
   const double* Y = st.train_y + (size_t)k * ncap;
@@ -101,14 +109,14 @@ __global__ void __launch_bounds__(kPrepThreads) gp_prepare_kernel(crs_gp_state s
   if (st.flags & CRS_LEARN_STANDARDIZE) {
     double s = 0.0;
     for (int i = tid; i < n; i += nt) s += Y[i];
-    s = block_sum(s, red, tid, nt);
+    s = group_sum(s, red, tid, nt);
     ybar = n > 0 ? s / n : 0.0;
     double ss = 0.0;
     for (int i = tid; i < n; i += nt) {
       const double dv = Y[i] - ybar;
       ss += dv * dv;
     }
-    ss = block_sum(ss, red, tid, nt);
+    ss = group_sum(ss, red, tid, nt);
     ysd = n > 1 ? sqrt(ss / (n - 1)) : 1.0;
     if (!(ysd >= kMinStdv)) ysd = 1.0;
     if (tid == 0) {
@@ -143,7 +151,7 @@ __global__ void __launch_bounds__(kPrepThreads) gp_prepare_kernel(crs_gp_state s
     __syncthreads();
     const double ajj = A[j * lda + j];
     if (!(ajj > 0.0)) {
-      if (tid == 0) fail = j + 1;
+      if (tid == 0) *failp = j + 1;
       break;  // uniform: every thread read the same ajj
     }
     const double ljj = sqrt(ajj);
@@ -158,8 +166,8 @@ __global__ void __launch_bounds__(kPrepThreads) gp_prepare_kernel(crs_gp_state s
     }
   }
   __syncthreads();
-  if (fail) {
-    if (tid == 0) st.status[k] = fail;
+  if (*failp) {
+    if (tid == 0) st.status[k] = *failp;
     return;
   }
 
@@ -232,27 +240,243 @@ __global__ void __launch_bounds__(kPrepThreads) gp_prepare_kernel(crs_gp_state s
   }
 }
 
+// Small-arm variant (row capacity <= 32, i.e. every BASELINE config): one 128-thread CTA per arm.
+// The embarrassingly parallel phases (transforms, K^ fill, output) use all four warps; the
+// sequential ones run in warp 0 alone with lane = row / column and warp shuffles, so the ~10 n
+// CTA barriers of the general variant (ncu r01a: 52 % barrier stalls, 35 us) collapse to three:
+//   Cholesky     left-looking, lane i owns row i:  s_i = A[i][j] - sum_{k<j} L[i][k] L[j][k]
+//   alpha        column-oriented forward / backward substitution, r_i in a register per lane
+//   L^-1         lane c solves L x = e_c for column c (no synchronisation at all)
+constexpr int kSmallThreads = 128;
+constexpr int kSmallCap = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(kSmallThreads)
+gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
+  const int k = arm_begin + blockIdx.x;
+  if (k >= arm_end) return;
+  constexpr int lda = kSmallCap + 1;
+  __shared__ double A[kSmallCap * lda];   // K^ then L (lower)
+  __shared__ double B[kSmallCap * lda];   // L^-1 (lower)
+  __shared__ double xs[kSmallCap * CRS_MAX_DIM];
+  __shared__ double rhs[kSmallCap];
+  __shared__ double tr[2 * CRS_MAX_DIM];
+  __shared__ double s_stat[2];
+  __shared__ int fail;
+  const int tid = threadIdx.x, nt = kSmallThreads, lane = tid & 31, warp = tid >> 5;
+  const int d = st.dim, dp = st.dim_pad, ncap = st.n_cap;
+  const int n = min(st.n_obs[k], ncap);
+  const double* X = st.train_x + (size_t)k * ncap * d;
+  const double* Y = st.train_y + (size_t)k * ncap;
+  if (tid == 0) fail = 0;
+
+  // ---- Normalize bounds (warp 0: lane = dimension) and Standardize constants (warp 1) ---------
+  if (warp == 0 && lane < d) {
+    double mn, rg;
+    if (st.flags & CRS_LEARN_NORMALIZE) {
+      if (n > 0) {
+        mn = X[lane];
+        double mx = mn;
+        for (int i = 1; i < n; ++i) {
+          const double v = X[(size_t)i * d + lane];
+          mn = fmin(mn, v);
+          mx = fmax(mx, v);
+        }
+        rg = mx - mn;
+        if (rg < kMinRange) rg = 1.0;
+      } else {
+        mn = 0.0;
+        rg = 1.0;
+      }
+      st.norm_mins[(size_t)k * d + lane] = mn;
+      st.norm_ranges[(size_t)k * d + lane] = rg;
+    } else {
+      mn = st.norm_mins[(size_t)k * d + lane];
+      rg = st.norm_ranges[(size_t)k * d + lane];
+    }
+    tr[lane] = mn;
+    tr[CRS_MAX_DIM + lane] = rg;
+  }
+  if (warp == 1) {
+    double ybar, ysd;
+    if (st.flags & CRS_LEARN_STANDARDIZE) {
+      const double y = lane < n ? Y[lane] : 0.0;
+      ybar = n > 0 ? warp_sum(y) / n : 0.0;
+      const double dv = lane < n ? y - ybar : 0.0;
+      const double ss = warp_sum(dv * dv);
+      ysd = n > 1 ? sqrt(ss / (n - 1)) : 1.0;
+      if (!(ysd >= kMinStdv)) ysd = 1.0;
+      if (lane == 0) {
+        st.y_mean[k] = ybar;
+        st.y_std[k] = ysd;
+      }
+    } else {
+      ybar = st.y_mean[k];
+      ysd = st.y_std[k];
+    }
+    if (lane == 0) {
+      s_stat[0] = ybar;
+      s_stat[1] = ysd;
+    }
+  }
+  __syncthreads();
+  const double ybar = s_stat[0], ysd = s_stat[1];
+  const double o = st.outputscale[k], noise = st.noise[k], m = st.mean_const[k];
+
+  // ---- transformed inputs ----------------------------------------------------------------
+  T* xn_out = reinterpret_cast<T*>(st.xn) + (size_t)k * ncap * d;
+  T* xs_out = reinterpret_cast<T*>(st.xs) + (size_t)k * ncap * dp;
+  for (int idx = tid; idx < ncap * dp; idx += nt) {
+    const int i = idx / dp, dd = idx - i * dp;
+    double v = 0.0;
+    if (i < n && dd < d) {
+      const double x = X[(size_t)i * d + dd];
+      const double xn = (x - tr[dd]) / tr[CRS_MAX_DIM + dd];
+      v = xn / st.lengthscale[(size_t)k * d + dd];
+      xn_out[(size_t)i * d + dd] = (T(x) - T(tr[dd])) / T(tr[CRS_MAX_DIM + dd]);
+    } else if (dd < d) {
+      xn_out[(size_t)i * d + dd] = T(0);
+    }
+    xs[i * CRS_MAX_DIM + dd] = v;
+    xs_out[idx] = T(v);
+  }
+  if (tid < n) rhs[tid] = (Y[tid] - ybar) / ysd - m;
+  for (int idx = tid; idx < kSmallCap * lda; idx += nt) B[idx] = 0.0;
+  __syncthreads();
+
+  // ---- K^ (lower triangle), all warps --------------------------------------------------------
+  for (int idx = tid; idx < n * n; idx += nt) {
+    const int i = idx / n, j = idx - i * n;
+    if (j <= i) {
+      double r2 = 0.0;
+      for (int dd = 0; dd < d; ++dd) {
+        const double df = xs[i * CRS_MAX_DIM + dd] - xs[j * CRS_MAX_DIM + dd];
+        r2 += df * df;
+      }
+      double v = o * correlation<double>(r2, st.kernel);
+      if (i == j) v += noise;
+      A[i * lda + j] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- factorisation, alpha and L^-1: warp 0 alone ---------------------------------------------
+  if (warp == 0) {
+    const bool row = lane < n;
+    int bad = 0;
+    double dinv = 0.0;  // lane j keeps 1 / L[j][j]: the substitutions multiply instead of divide
+    for (int j = 0; j < n; ++j) {
+      double s0 = (row && lane >= j) ? A[lane * lda + j] : 0.0, s1 = 0.0;
+      if (row && lane >= j) {
+        int c = 0;
+        for (; c + 1 < j; c += 2) {  // two independent chains: the step is DFMA-latency bound
+          s0 = fma(-A[lane * lda + c], A[j * lda + c], s0);
+          s1 = fma(-A[lane * lda + c + 1], A[j * lda + c + 1], s1);
+        }
+        if (c < j) s0 = fma(-A[lane * lda + c], A[j * lda + c], s0);
+      }
+      const double s = s0 + s1;
+      const double sjj = __shfl_sync(kFull, s, j);
+      if (!(sjj > 0.0)) {
+        bad = j + 1;
+        break;  // uniform: every lane sees the same pivot
+      }
+      const double rs = rsqrt(sjj);
+      if (lane == j) dinv = rs;
+      if (row && lane >= j) A[lane * lda + j] = lane == j ? sjj * rs : s * rs;
+      __syncwarp();
+    }
+    if (bad) {
+      if (lane == 0) fail = bad;
+    } else {
+      // alpha = K^^-1 rhs
+      double r = row ? rhs[lane] : 0.0;
+      for (int j = 0; j < n; ++j) {
+        const double zj = __shfl_sync(kFull, r * dinv, j);
+        if (lane == j) r = zj;
+        else if (row && lane > j) r = fma(-A[lane * lda + j], zj, r);
+      }
+      for (int j = n - 1; j >= 0; --j) {
+        const double aj = __shfl_sync(kFull, r * dinv, j);
+        if (lane == j) r = aj;
+        else if (lane < j) r = fma(-A[j * lda + lane], aj, r);
+      }
+      if (row) rhs[lane] = r;
+      // column `lane` of X = L^-1 by forward substitution (entries above the diagonal stay 0)
+      for (int i = 0; i < n; ++i) {
+        const double di = __shfl_sync(kFull, dinv, i);
+        if (row && i >= lane) {
+          double a0 = i == lane ? 1.0 : 0.0, a1 = 0.0;
+          int c = lane;
+          for (; c + 1 < i; c += 2) {
+            a0 = fma(-A[i * lda + c], B[c * lda + lane], a0);
+            a1 = fma(-A[i * lda + c + 1], B[(c + 1) * lda + lane], a1);
+          }
+          if (c < i) a0 = fma(-A[i * lda + c], B[c * lda + lane], a0);
+          B[i * lda + lane] = (a0 + a1) * di;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (fail) {
+    if (tid == 0) st.status[k] = fail;
+    return;
+  }
+
+  // ---- write the prepared state, all warps -----------------------------------------------------
+  T* alpha = reinterpret_cast<T*>(st.alpha) + (size_t)k * ncap;
+  for (int i = tid; i < ncap; i += nt) alpha[i] = i < n ? T(o * rhs[i]) : T(0);
+  T* lt = reinterpret_cast<T*>(st.linv_t) + (size_t)k * linv_stride(ncap, sizeof(T));
+  constexpr int ld = PanelLd<T>::value;
+  for (int idx = tid; idx < ncap * ld; idx += nt) {  // n_cap <= 32: a single panel
+    const int j = idx / ld, i = idx - j * ld;
+    lt[idx] = (i >= j && i < n) ? T(o * B[i * lda + j]) : T(0);
+  }
+  T* head = reinterpret_cast<T*>(st.arm_head) + (size_t)k * kHeadElems;
+  if (tid < CRS_MAX_DIM) {
+    if (tid < d) {
+      head[kHeadSub + tid] = T(tr[tid]);
+      head[kHeadMul + tid] = T(1.0 / (tr[CRS_MAX_DIM + tid] * st.lengthscale[(size_t)k * d + tid]));
+    } else {
+      head[kHeadSub + tid] = T(0);
+      head[kHeadMul + tid] = T(0);
+    }
+  }
+  if (tid == 0) {
+    head[kHeadScal + 0] = T(o);
+    head[kHeadScal + 1] = T(m);
+    head[kHeadScal + 2] = T(ybar);
+    head[kHeadScal + 3] = T(ysd);
+    st.status[k] = 0;
+  }
+}
+
 }  // namespace
 
 int launch_gp_prepare(const crs_gp_state* st, int arm_begin, int arm_end, cudaStream_t s) {
   if (!st || arm_begin < 0 || arm_end > st->num_arms || arm_begin > arm_end) return CRS_ERR_INVALID_ARG;
   if (st->dim < 1 || st->dim > CRS_MAX_DIM || st->dim_pad != dim_pad_of(st->dim)) return CRS_ERR_UNSUPPORTED;
-  if (st->n_cap < 1 || st->n_cap > CRS_MAX_OBS) return CRS_ERR_UNSUPPORTED;
+  if (st->n_cap < 1 || st->n_cap > CRS_MAX_OBS || (st->n_cap & 7)) return CRS_ERR_UNSUPPORTED;
+  if (st->dtype != CRS_F64 && st->dtype != CRS_F32) return CRS_ERR_INVALID_ARG;
   if (arm_begin == arm_end) return CRS_OK;
-  const size_t ncap = st->n_cap;
-  const size_t smem = (ncap * (ncap + 1) + ncap * st->dim_pad + ncap + 8 + 2 * CRS_MAX_DIM) * sizeof(double);
-  const int grid = arm_end - arm_begin;
-  if (st->dtype == CRS_F64) {
-    CRS_CUDA_TRY(cudaFuncSetAttribute(gp_prepare_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "prepare attr");
-    gp_prepare_kernel<double><<<grid, kPrepThreads, smem, s>>>(*st, arm_begin);
-  } else if (st->dtype == CRS_F32) {
-    CRS_CUDA_TRY(cudaFuncSetAttribute(gp_prepare_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "prepare attr");
-    gp_prepare_kernel<float><<<grid, kPrepThreads, smem, s>>>(*st, arm_begin);
-  } else {
-    return CRS_ERR_INVALID_ARG;
+  const int narms = arm_end - arm_begin;
+  if (st->n_cap <= kSmallCap) {
+    if (st->dtype == CRS_F64) gp_prepare_small_kernel<double><<<narms, kSmallThreads, 0, s>>>(*st, arm_begin, arm_end);
+    else gp_prepare_small_kernel<float><<<narms, kSmallThreads, 0, s>>>(*st, arm_begin, arm_end);
+    CRS_CUDA_TRY(cudaGetLastError(), "gp_prepare launch");
+    return CRS_OK;
   }
-  CRS_CUDA_TRY(cudaGetLastError(), "gp_prepare launch");
-  return CRS_OK;
+  const size_t smem = prep_group_doubles(st->n_cap, st->dim_pad) * sizeof(double);
+  auto go = [&](auto kern) -> int {
+    if (smem > 48 * 1024)
+      CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "prepare attr");
+    kern<<<narms, kPrepThreads, smem, s>>>(*st, arm_begin, arm_end);
+    CRS_CUDA_TRY(cudaGetLastError(), "gp_prepare launch");
+    return CRS_OK;
+  };
+  if (st->dtype == CRS_F64) return go(gp_prepare_kernel<double>);
+  return go(gp_prepare_kernel<float>);
 }
 
 }  // namespace crs

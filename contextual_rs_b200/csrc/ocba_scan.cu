@@ -5,13 +5,16 @@
 // The reference sorts every row of the n_c x K table, gathers variances, builds five n_c x (K-1)
 // temporaries and arg-mins the flattened zeta.  Only the arg-max arm and the zeta minimum of each
 // row are needed, so one warp owns one context row: pass 1 finds the predicted best arm by warp
-// shuffle, pass 2 re-reads the row (L1-resident, the row was just streamed) for
+// shuffle, pass 2 evaluates
 //     zeta_j = (mu_b - mu_j)^2 / (var_b + var_j)          [same IEEE ops as the reference]
-// and a last-arriving CTA folds the per-CTA minima into the global decision.  HBM-bound: one read
-// of mean and var (2*K*n_c*w bytes) plus n_c*(w+12) bytes of per-context outputs.
+// on the row held in registers (K <= 256) or re-read from L1 (larger K), and the last-arriving CTA
+// folds the per-CTA minima into the global decision and — fused — runs OCBA step 2(b) for the
+// selected context, so that a whole decision needs no host round-trip between its kernels.
+// HBM-bound: one read of mean and var (2*K*n_c*w bytes) plus n_c*(w+12) bytes of outputs.
 #include <math_constants.h>
 #include <cfloat>
 #include <climits>
+#include <cstring>
 #include "crs_common.cuh"
 
 namespace crs {
@@ -28,6 +31,17 @@ struct __align__(16) ScanPartial {   // 32 bytes
   int zarm;            // zeta-minimising arm id there
   int best;            // predicted best arm id there
   int pad;
+};
+
+// step 2(b) arguments for the fused tail of the scan kernel (do_select = 0: scan only)
+struct SelectArgs {
+  crs_gp_state st;
+  const void* ctx;
+  double kernel_scale;
+  int p_mode;
+  int do_select;
+  crs_decision* host_mirror;  // mapped pinned host copy of the decision (may be null)
+  int seq;                    // written to reserved[1] of the mirror LAST: completion tag
 };
 
 __device__ __forceinline__ void combine(ScanPartial& a, const ScanPartial& b) {
@@ -54,6 +68,17 @@ __device__ __forceinline__ ScanPartial shfl_partial(const ScanPartial& p, int o)
   return r;
 }
 
+__device__ __forceinline__ ScanPartial empty_partial() {
+  ScanPartial p;
+  p.z = CUDART_INF;
+  p.cnt = 0;
+  p.ctx = INT_MAX;
+  p.zarm = -1;
+  p.best = -1;
+  p.pad = 0;
+  return p;
+}
+
 template <typename T> __device__ __forceinline__ T pos_inf();
 template <> __device__ __forceinline__ double pos_inf<double>() { return CUDART_INF; }
 template <> __device__ __forceinline__ float pos_inf<float>() { return CUDART_INF_F; }
@@ -66,125 +91,280 @@ template <typename T> __device__ __forceinline__ T zeta_of(T mu_b, T var_b, T mu
   return sq / den;
 }
 
+// Cheap lower bound on gap^2 / den: fp64 division is ~30 instructions, so candidates are screened
+// with an approximate reciprocal (rel. error < 1e-11 after one Newton step) and only those within
+// 1e-9 of the running minimum pay for the exact IEEE quotient the reference computes.  The
+// minimum, its position and its multiplicity are therefore bit-identical to the unscreened scan.
+__device__ __forceinline__ double approx_quot(double sq, double den) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  r = fma(fma(-den, r, 1.0), r, r);
+  return sq * r;
+}
+constexpr double kScreenSlack = 1.0 + 1e-9;  // fp32 divides exactly straight away (cheap)
+
+// running (min zeta, its mean, its column, multiplicity); ties: larger mean, then lower column
+template <typename T> struct ZMin {
+  T z, mu;
+  int col, cnt;
+  __device__ __forceinline__ void init() { z = pos_inf<T>(); mu = -pos_inf<T>(); col = INT_MAX; cnt = 0; }
+  __device__ __forceinline__ void add(T zz, T m, int a) {
+    if (zz < z) { z = zz; mu = m; col = a; cnt = 1; }
+    else if (zz == z) { ++cnt; if (m > mu) { mu = m; col = a; } }
+  }
+  // zeta of (mu_b, var_b) against (m, vr), exactly as the reference: squared_diffs / added_vars
+  __device__ __forceinline__ void add_pair(T mu_b, T var_b, T m, T vr, int a) {
+    const T gap = mu_b - m;
+    const T sq = gap * gap;
+    const T den = var_b + vr;
+    if constexpr (sizeof(T) == 8) {
+      if (!(approx_quot(sq, den) <= z * kScreenSlack)) return;  // cannot reach the minimum
+    }
+    add(sq / den, m, a);
+  }
+  __device__ __forceinline__ void warp_reduce() {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const T oz = __shfl_xor_sync(kFull, z, o);
+      const T omu = __shfl_xor_sync(kFull, mu, o);
+      const int oi = __shfl_xor_sync(kFull, col, o);
+      const int oc = __shfl_xor_sync(kFull, cnt, o);
+      if (oz < z) { z = oz; mu = omu; col = oi; cnt = oc; }
+      else if (oz == z) { cnt += oc; if (omu > mu || (omu == mu && oi < col)) { mu = omu; col = oi; } }
+    }
+  }
+};
+
+template <typename T> __device__ __forceinline__ void warp_argmax(T& bm, int& bi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const T om = __shfl_xor_sync(kFull, bm, o);
+    const int oi = __shfl_xor_sync(kFull, bi, o);
+    if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
+  }
+}
+
+// ---- OCBA step 2(b) for one CTA (strategies.py:158-202; continuous_context.py:110-132) ---------
+// p_i = exact-match count | KDE weight | prior/posterior variance ratio; y_i = p_i / var_i; psi of
+// the best arm vs the sum over the others.  The normalised training inputs of a chunk of arms are
+// staged in shared memory by TMA bulk copies issued back to back (ONE memory round trip per chunk
+// instead of one per arm — the step is pure latency), then one warp reduces one arm, lanes over
+// its training rows.
+// The stage buffer is the kernel's dynamic shared memory (stage_bytes of it).
+constexpr int kSelStageFused = 32 * 1024;    // fused tail of the scan kernel (small problems only)
+constexpr int kSelStageAlone = 160 * 1024;   // stand-alone select kernel
+
 template <typename T>
-__global__ void __launch_bounds__(kScanThreads)
+__device__ void select_block(const crs_gp_state& st, const T* __restrict__ ctx,
+                             const T* __restrict__ var, int64_t ld, int arm_offset, int p_mode,
+                             T kernel_scale, crs_decision* decision, unsigned char* s_stage_raw,
+                             int stage_bytes) {
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ T s_x[CRS_MAX_DIM];
+  __shared__ T s_v[256];
+  __shared__ int s_n[256];
+  __shared__ T s_red[32];
+  __shared__ T s_best;
+  __shared__ int s_bad;
+  T* s_stage = reinterpret_cast<T*>(s_stage_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int c = decision->context;
+  if (c < 0) return;  // uniform
+  const int best = decision->best_arm - arm_offset;
+  const int d = st.dim, ncap = st.n_cap, K = st.num_arms;
+  const int blk = ncap * d;  // elements of one arm's xn block
+  const bool rows = p_mode != CRS_P_INFER;
+  int chunk = min(min((int)(stage_bytes / (blk * sizeof(T))), 256), K);
+  if (chunk < 1) chunk = 1;  // (blk <= 160*16 elements always fits at least once)
+  if (tid < d) s_x[tid] = ctx[(int64_t)c * d + tid];
+  if (tid == 0) {
+    s_best = T(0);
+    s_bad = 0;
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const T* g_xn = reinterpret_cast<const T*>(st.xn);
+  T rest = T(0);
+  uint32_t phase = 0;
+  for (int c0 = 0; c0 < K; c0 += chunk) {
+    const int na = min(chunk, K - c0);
+    if (rows && tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&s_bar, (uint32_t)(na * blk * sizeof(T)));
+      for (int a = 0; a < na; ++a)
+        tma_bulk_g2s(s_stage + (size_t)a * blk, g_xn + (size_t)(c0 + a) * blk, (uint32_t)(blk * sizeof(T)), &s_bar);
+    }
+    for (int a = tid; a < na; a += blockDim.x) {
+      s_v[a] = var[(int64_t)c * ld + c0 + a];
+      s_n[a] = min(st.n_obs[c0 + a], ncap);
+      if (st.status[c0 + a] != 0) atomicMax(&s_bad, c0 + a + 1);
+    }
+    if (rows) {
+      mbar_wait(&s_bar, phase);
+      phase ^= 1u;
+    }
+    __syncthreads();
+    for (int a = warp; a < na; a += nw) {
+      const T vr = s_v[a];
+      T p;
+      if (!rows) {
+        p = reinterpret_cast<const T*>(st.arm_head)[(size_t)(c0 + a) * kHeadElems + kHeadScal] / vr;  // prior / posterior
+      } else {
+        const int n = s_n[a];
+        const T* xn = s_stage + (size_t)a * blk;
+        T acc = T(0);
+        for (int row = lane; row < n; row += 32) {
+          if (p_mode == CRS_P_COUNT) {
+            bool eq = true;
+            for (int dd = 0; dd < d; ++dd) eq = eq && (xn[row * d + dd] == s_x[dd]);
+            acc += eq ? T(1) : T(0);
+          } else {
+            T r2 = T(0);
+            for (int dd = 0; dd < d; ++dd) {
+              const T df = xn[row * d + dd] - s_x[dd];
+              r2 += df * df;
+            }
+            acc += exp(-kernel_scale * sqrt(r2));
+          }
+        }
+        p = warp_sum(acc);
+      }
+      if (lane == 0) {
+        const T y = p / vr;
+        if (c0 + a == best) s_best = y; else rest += y;
+      }
+    }
+    __syncthreads();  // the stage buffer is free for the next chunk
+  }
+  if (lane == 0) s_red[warp] = rest;
+  __syncthreads();
+  if (tid == 0) {
+    T tot = T(0);
+    for (int w = 0; w < nw; ++w) tot += s_red[w];
+    const T yb = s_best;
+    decision->psi_best = (double)yb;
+    decision->psi_rest = (double)tot;
+    decision->next_arm = (yb < tot) ? decision->best_arm : decision->zeta_arm;
+    decision->reserved[0] = s_bad;
+  }
+}
+
+__device__ __forceinline__ void publish(const crs_decision* dec, crs_decision* mirror, int seq) {
+  // thread 0 only: copy the finished decision to mapped host memory; the tag goes last
+  mirror->min_zeta = dec->min_zeta;
+  mirror->psi_best = dec->psi_best;
+  mirror->psi_rest = dec->psi_rest;
+  mirror->tie_count = dec->tie_count;
+  mirror->context = dec->context;
+  mirror->zeta_arm = dec->zeta_arm;
+  mirror->best_arm = dec->best_arm;
+  mirror->next_arm = dec->next_arm;
+  mirror->reserved[0] = dec->reserved[0];
+  __threadfence_system();
+  *reinterpret_cast<volatile int*>(&mirror->reserved[1]) = seq;
+  __threadfence_system();
+}
+
+// R > 0: the row (K <= 32 R) is held in registers; R == 0: pass 2 re-reads it (L1-resident).
+template <typename T, int R>
+__global__ void __launch_bounds__(kScanThreads, (R == 0 ? 4 : 1))
 ocba_scan_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n_c, int K,
                  int64_t ld, int arm_offset, const int32_t* __restrict__ ext_arm,
                  const T* __restrict__ ext_mean, const T* __restrict__ ext_var,
                  int32_t* __restrict__ best_arm, T* __restrict__ min_zeta,
                  int32_t* __restrict__ min_arm, int32_t* __restrict__ tie_cnt,
-                 ScanPartial* partials, unsigned int* ticket, crs_decision* decision) {
+                 ScanPartial* partials, unsigned int* ticket, crs_decision* decision,
+                 SelectArgs sel) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t warps_total = (int64_t)gridDim.x * kScanWarps;
-  ScanPartial acc;
-  acc.z = CUDART_INF;
-  acc.cnt = 0;
-  acc.ctx = INT_MAX;
-  acc.zarm = -1;
-  acc.best = -1;
-  acc.pad = 0;
+  const int nwarps = blockDim.x >> 5;
+  const int64_t warps_total = (int64_t)gridDim.x * nwarps;
+  ScanPartial acc = empty_partial();
 
-  for (int64_t c = (int64_t)blockIdx.x * kScanWarps + warp; c < n_c; c += warps_total) {
+  for (int64_t c = (int64_t)blockIdx.x * nwarps + warp; c < n_c; c += warps_total) {
     const T* mrow = mean + c * ld;
     const T* vrow = var + c * ld;
     T bm, vb;
     int bi;  // local column of the best arm (may fall outside [0, K) when it lives on a peer rank)
-    if (ext_arm == nullptr) {
-      bm = -pos_inf<T>();
-      bi = INT_MAX;
-      for (int a = lane; a < K; a += 32) {
-        const T m = mrow[a];
-        if (m > bm) {
-          bm = m;
-          bi = a;
-        }
+    ZMin<T> zm;
+    zm.init();
+    if constexpr (R > 0) {
+      T m[R], v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int a = lane + 32 * r;
+        m[r] = a < K ? mrow[a] : -pos_inf<T>();
+        v[r] = a < K ? vrow[a] : T(1);
+      }
+      if (ext_arm == nullptr) {
+        bm = -pos_inf<T>();
+        bi = INT_MAX;
+        T vcand = v[0];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (m[r] > bm) { bm = m[r]; bi = lane + 32 * r; vcand = v[r]; }
+        warp_argmax(bm, bi);
+        if (bi == INT_MAX) bi = 0;  // all-NaN row
+        vb = __shfl_sync(kFull, vcand, bi & 31);  // the winner's variance sits in its owner lane
+      } else {
+        bi = ext_arm[c] - arm_offset;
+        bm = ext_mean[c];
+        vb = ext_var[c];
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const T om = __shfl_xor_sync(kFull, bm, o);
-        const int oi = __shfl_xor_sync(kFull, bi, o);
-        if (om > bm || (om == bm && oi < bi)) {
-          bm = om;
-          bi = oi;
-        }
+      for (int r = 0; r < R; ++r) {
+        const int a = lane + 32 * r;
+        if (a < K && a != bi) zm.add_pair(bm, vb, m[r], v[r], a);
       }
-      if (bi == INT_MAX) bi = 0;  // all-NaN row
-      vb = vrow[bi];
     } else {
-      bi = ext_arm[c] - arm_offset;
-      bm = ext_mean[c];
-      vb = ext_var[c];
-    }
-
-    T zmin = pos_inf<T>(), zmu = -pos_inf<T>();
-    int zi = INT_MAX, cnt = 0;
-    for (int a = lane; a < K; a += 32) {
-      if (a == bi) continue;
-      const T m = mrow[a];
-      const T z = zeta_of<T>(bm, vb, m, vrow[a]);
-      if (z < zmin) {
-        zmin = z;
-        zmu = m;
-        zi = a;
-        cnt = 1;
-      } else if (z == zmin) {
-        ++cnt;
-        if (m > zmu) {
-          zmu = m;
-          zi = a;
+      if (ext_arm == nullptr) {
+        bm = -pos_inf<T>();
+        bi = INT_MAX;
+        for (int a = lane; a < K; a += 32) {
+          const T m = mrow[a];
+          if (m > bm) { bm = m; bi = a; }
         }
+        warp_argmax(bm, bi);
+        if (bi == INT_MAX) bi = 0;
+        vb = vrow[bi];
+      } else {
+        bi = ext_arm[c] - arm_offset;
+        bm = ext_mean[c];
+        vb = ext_var[c];
+      }
+      for (int a = lane; a < K; a += 32) {
+        if (a == bi) continue;
+        const T m = mrow[a];
+        zm.add_pair(bm, vb, m, vrow[a], a);
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const T oz = __shfl_xor_sync(kFull, zmin, o);
-      const T omu = __shfl_xor_sync(kFull, zmu, o);
-      const int oi = __shfl_xor_sync(kFull, zi, o);
-      const int oc = __shfl_xor_sync(kFull, cnt, o);
-      if (oz < zmin) {
-        zmin = oz;
-        zmu = omu;
-        zi = oi;
-        cnt = oc;
-      } else if (oz == zmin) {
-        cnt += oc;
-        if (omu > zmu || (omu == zmu && oi < zi)) {
-          zmu = omu;
-          zi = oi;
-        }
-      }
-    }
+    zm.warp_reduce();
     const int gbest = bi + arm_offset;
-    const int gz = zi == INT_MAX ? -1 : zi + arm_offset;
+    const int gz = zm.col == INT_MAX ? -1 : zm.col + arm_offset;
     if (lane == 0) {
       if (best_arm) best_arm[c] = gbest;
-      if (min_zeta) min_zeta[c] = zmin;
+      if (min_zeta) min_zeta[c] = zm.z;
       if (min_arm) min_arm[c] = gz;
-      if (tie_cnt) tie_cnt[c] = cnt;
+      if (tie_cnt) tie_cnt[c] = zm.cnt;
     }
     ScanPartial p;
-    p.z = (double)zmin;
-    p.cnt = cnt;
+    p.z = (double)zm.z;
+    p.cnt = zm.cnt;
     p.ctx = (int)c;
     p.zarm = gz;
     p.best = gbest;
     p.pad = 0;
-    if (cnt > 0) combine(acc, p);
+    if (zm.cnt > 0) combine(acc, p);
   }
 
   if (decision == nullptr) return;
 
-  __shared__ ScanPartial s_part[kScanWarps];
+  __shared__ ScanPartial s_part[kScanWarps];  // blockDim <= kScanThreads
   __shared__ bool s_last;
   if (lane == 0) s_part[warp] = acc;
   __syncthreads();
   if (warp == 0) {
-    ScanPartial p = lane < kScanWarps ? s_part[lane] : acc;
-    if (lane >= kScanWarps) {
-      p.z = CUDART_INF;
-      p.cnt = 0;
-      p.ctx = INT_MAX;
-    }
+    ScanPartial p = lane < nwarps ? s_part[lane] : empty_partial();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const ScanPartial q = shfl_partial(p, o);
@@ -201,14 +381,8 @@ ocba_scan_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t 
   if (!s_last) return;
   __threadfence();
   // last CTA: fold all per-CTA partials
-  ScanPartial p;
-  p.z = CUDART_INF;
-  p.cnt = 0;
-  p.ctx = INT_MAX;
-  p.zarm = -1;
-  p.best = -1;
-  p.pad = 0;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += kScanThreads) {
+  ScanPartial p = empty_partial();
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
     // written by other CTAs: read through L2 (ld.global.cg), never a stale L1 line
     const int4 w0 = __ldcg(reinterpret_cast<const int4*>(partials + b));
     const int4 w1 = __ldcg(reinterpret_cast<const int4*>(partials + b) + 1);
@@ -230,15 +404,23 @@ ocba_scan_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t 
   if (lane == 0) s_part[warp] = p;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < kScanWarps; ++w) combine(p, s_part[w]);
+    for (int w = 1; w < nwarps; ++w) combine(p, s_part[w]);
     decision->min_zeta = p.z;
     decision->tie_count = p.cnt;
     decision->context = p.ctx == INT_MAX ? -1 : p.ctx;
     decision->zeta_arm = p.zarm;
     decision->best_arm = p.best;
     decision->next_arm = -1;
+    decision->reserved[0] = 0;
     *ticket = 0;  // leave the workspace ready for the next launch
   }
+  if (sel.do_select) {
+    __syncthreads();  // decision fields are visible to the whole CTA
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    select_block<T>(sel.st, reinterpret_cast<const T*>(sel.ctx), var, ld, arm_offset, sel.p_mode,
+                    (T)sel.kernel_scale, decision, dyn_smem, kSelStageFused);
+  }
+  if (sel.host_mirror && threadIdx.x == 0) publish(decision, sel.host_mirror, sel.seq);
 }
 
 // ---- tie randomisation (rare path; strategies.py:147-154) -----------------------------------
@@ -302,104 +484,103 @@ resolve_tie_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_
   }
 }
 
-// ---- OCBA step 2(b) (strategies.py:158-202; continuous_context.py:110-132) --------------------
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 ocba_select_kernel(crs_gp_state st, const T* __restrict__ ctx, const T* __restrict__ var,
-                   int64_t ld, int arm_offset, int p_mode, T kernel_scale,
-                   crs_decision* decision) {
-  __shared__ T s_x[CRS_MAX_DIM];
-  __shared__ T s_red[8];
-  __shared__ T s_best;
-  __shared__ int s_bad;
-  const int tid = threadIdx.x;
-  const int c = decision->context;
-  const int best = decision->best_arm - arm_offset;
-  const int d = st.dim, ncap = st.n_cap, K = st.num_arms;
-  if (c < 0) return;
-  if (tid < d) s_x[tid] = ctx[(int64_t)c * d + tid];
-  if (tid == 0) {
-    s_best = T(0);
-    s_bad = 0;
-  }
-  __syncthreads();
-  T rest = T(0);
-  for (int i = tid; i < K; i += blockDim.x) {
-    const T vr = var[(int64_t)c * ld + i];
-    const int n = min(st.n_obs[i], ncap);
-    const T* xn = reinterpret_cast<const T*>(st.xn) + (size_t)i * ncap * d;
-    T p;
-    if (p_mode == CRS_P_COUNT) {
-      int cnt = 0;
-      for (int row = 0; row < n; ++row) {
-        bool eq = true;
-        for (int dd = 0; dd < d; ++dd) eq = eq && (xn[row * d + dd] == s_x[dd]);
-        cnt += eq ? 1 : 0;
-      }
-      p = T(cnt);
-    } else if (p_mode == CRS_P_KDE) {
-      T s = T(0);
-      for (int row = 0; row < n; ++row) {
-        T r2 = T(0);
-        for (int dd = 0; dd < d; ++dd) {
-          const T df = xn[row * d + dd] - s_x[dd];
-          r2 += df * df;
-        }
-        s += exp(-kernel_scale * sqrt(r2));
-      }
-      p = s;
-    } else {
-      p = reinterpret_cast<const T*>(st.arm_head)[(size_t)i * kHeadElems + kHeadScal] / vr;  // prior var / posterior var
-    }
-    const T y = p / vr;
-    if (i == best) s_best = y; else rest += y;
-    if (st.status[i] != 0) atomicMax(&s_bad, i + 1);
-  }
-  rest = warp_sum(rest);
-  if ((tid & 31) == 0) s_red[tid >> 5] = rest;
-  __syncthreads();
-  if (tid == 0) {
-    T tot = T(0);
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w];
-    const T yb = s_best;
-    decision->psi_best = (double)yb;
-    decision->psi_rest = (double)tot;
-    decision->next_arm = (yb < tot) ? decision->best_arm : decision->zeta_arm;
-    decision->reserved[0] = s_bad;
-  }
+                   int64_t ld, int arm_offset, int p_mode, T kernel_scale, crs_decision* decision,
+                   crs_decision* host_mirror, int seq, int stage_bytes) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  select_block<T>(st, ctx, var, ld, arm_offset, p_mode, kernel_scale, decision, dyn_smem, stage_bytes);
+  if (host_mirror && threadIdx.x == 0) publish(decision, host_mirror, seq);
+}
+
+template <typename T>
+int scan_dispatch(const void* mean, const void* var, int64_t n_c, int K, int64_t ld, int arm_offset,
+                  const int32_t* ext_best_arm, const void* ext_best_mean, const void* ext_best_var,
+                  int32_t* best_arm, void* min_zeta, int32_t* min_arm, int32_t* tie_cnt,
+                  crs_decision* decision, void* workspace, const SelectArgs& sel, cudaStream_t s) {
+  // K <= 1024: the whole row sits in registers (all loads of a row in flight at once — the kernel
+  // is HBM-latency bound otherwise, ncu r01a: 66 % long-scoreboard stalls, 8 % L1 hit on the
+  // re-read); the wide variants run 128-thread CTAs to keep >= 12 warps per SM.
+  const int threads = (K > 256 && K <= 1024) ? 128 : kScanThreads;
+  const int wpb = threads / 32;
+  int blocks = (int)((n_c + wpb - 1) / wpb);
+  const int max_blocks = kScanMaxBlocks;
+  if (blocks > max_blocks) blocks = max_blocks;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace);
+  ScanPartial* partials = workspace ? reinterpret_cast<ScanPartial*>(reinterpret_cast<char*>(workspace) + 64) : nullptr;
+  const size_t dyn = sel.do_select ? kSelStageFused : 0;
+  auto go = [&](auto kern) {
+    kern<<<blocks, threads, dyn, s>>>((const T*)mean, (const T*)var, n_c, K, ld, arm_offset,
+                                      ext_best_arm, (const T*)ext_best_mean, (const T*)ext_best_var,
+                                      best_arm, (T*)min_zeta, min_arm, tie_cnt, partials, ticket,
+                                      decision, sel);
+  };
+  if (K <= 32) go(ocba_scan_kernel<T, 1>);
+  else if (K <= 64) go(ocba_scan_kernel<T, 2>);
+  else if (K <= 128) go(ocba_scan_kernel<T, 4>);
+  else if (K <= 256) go(ocba_scan_kernel<T, 8>);
+  else if (K <= 512) go(ocba_scan_kernel<T, 16>);
+  else if (K <= 1024) go(ocba_scan_kernel<T, 32>);
+  else go(ocba_scan_kernel<T, 0>);
+  CRS_CUDA_TRY(cudaGetLastError(), "ocba_scan launch");
+  return CRS_OK;
 }
 
 }  // namespace
 
 int64_t scan_workspace_bytes() { return (int64_t)kScanMaxBlocks * sizeof(ScanPartial) + 64; }
 
+int launch_ocba_scan_select(const void* mean, const void* var, int64_t n_c, int K, int64_t ld,
+                            int dtype, int arm_offset, const int32_t* ext_best_arm,
+                            const void* ext_best_mean, const void* ext_best_var, int32_t* best_arm,
+                            void* min_zeta, int32_t* min_arm, int32_t* tie_cnt,
+                            crs_decision* decision, void* workspace, const crs_gp_state* st,
+                            const void* ctx, int p_mode, double kernel_scale,
+                            crs_decision* host_mirror, int seq, cudaStream_t s) {
+  if (!mean || !var || n_c < 0 || n_c > INT_MAX || K < 1 || ld < K) return CRS_ERR_INVALID_ARG;
+  if (decision && !workspace) return CRS_ERR_INVALID_ARG;
+  if (ext_best_arm && (!ext_best_mean || !ext_best_var)) return CRS_ERR_INVALID_ARG;
+  if (st && (!ctx || !decision || p_mode < 0 || p_mode > 2 || st->num_arms != K)) return CRS_ERR_INVALID_ARG;
+  if (host_mirror && !decision) return CRS_ERR_INVALID_ARG;
+  if (n_c == 0) return CRS_OK;
+  SelectArgs sel;
+  memset(&sel, 0, sizeof(sel));
+  // Fusing step 2(b) into the scan's last CTA saves a launch, but its 32 KB stage buffer shrinks the
+  // L1 the K > 256 row re-read relies on: fuse only where the decision is latency-bound anyway.
+  const bool fuse = st && (n_c * (int64_t)K <= (1 << 20));
+  if (fuse) {
+    sel.st = *st;
+    sel.ctx = ctx;
+    sel.kernel_scale = kernel_scale;
+    sel.p_mode = p_mode;
+    sel.do_select = 1;
+    sel.host_mirror = host_mirror;
+    sel.seq = seq;
+  } else if (!st) {
+    sel.host_mirror = host_mirror;
+    sel.seq = seq;
+  }
+  int rc;
+  if (dtype == CRS_F64)
+    rc = scan_dispatch<double>(mean, var, n_c, K, ld, arm_offset, ext_best_arm, ext_best_mean, ext_best_var,
+                               best_arm, min_zeta, min_arm, tie_cnt, decision, workspace, sel, s);
+  else if (dtype == CRS_F32)
+    rc = scan_dispatch<float>(mean, var, n_c, K, ld, arm_offset, ext_best_arm, ext_best_mean, ext_best_var,
+                              best_arm, min_zeta, min_arm, tie_cnt, decision, workspace, sel, s);
+  else
+    return CRS_ERR_INVALID_ARG;
+  if (rc != CRS_OK || !st || fuse) return rc;
+  return launch_ocba_select(st, ctx, mean, var, ld, arm_offset, p_mode, kernel_scale, decision, host_mirror, seq, s);
+}
+
 int launch_ocba_scan(const void* mean, const void* var, int64_t n_c, int K, int64_t ld, int dtype,
                      int arm_offset, const int32_t* ext_best_arm, const void* ext_best_mean,
                      const void* ext_best_var, int32_t* best_arm, void* min_zeta, int32_t* min_arm,
                      int32_t* tie_cnt, crs_decision* decision, void* workspace, cudaStream_t s) {
-  if (!mean || !var || n_c < 0 || n_c > INT_MAX || K < 1 || ld < K) return CRS_ERR_INVALID_ARG;
-  if (decision && !workspace) return CRS_ERR_INVALID_ARG;
-  if (ext_best_arm && (!ext_best_mean || !ext_best_var)) return CRS_ERR_INVALID_ARG;
-  if (n_c == 0) return CRS_OK;
-  int blocks = (int)((n_c + kScanWarps - 1) / kScanWarps);
-  if (blocks > kScanMaxBlocks) blocks = kScanMaxBlocks;
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace);
-  ScanPartial* partials = workspace ? reinterpret_cast<ScanPartial*>(reinterpret_cast<char*>(workspace) + 64) : nullptr;
-  if (dtype == CRS_F64) {
-    ocba_scan_kernel<double><<<blocks, kScanThreads, 0, s>>>(
-        (const double*)mean, (const double*)var, n_c, K, ld, arm_offset, ext_best_arm,
-        (const double*)ext_best_mean, (const double*)ext_best_var, best_arm, (double*)min_zeta,
-        min_arm, tie_cnt, partials, ticket, decision);
-  } else if (dtype == CRS_F32) {
-    ocba_scan_kernel<float><<<blocks, kScanThreads, 0, s>>>(
-        (const float*)mean, (const float*)var, n_c, K, ld, arm_offset, ext_best_arm,
-        (const float*)ext_best_mean, (const float*)ext_best_var, best_arm, (float*)min_zeta,
-        min_arm, tie_cnt, partials, ticket, decision);
-  } else {
-    return CRS_ERR_INVALID_ARG;
-  }
-  CRS_CUDA_TRY(cudaGetLastError(), "ocba_scan launch");
-  return CRS_OK;
+  return launch_ocba_scan_select(mean, var, n_c, K, ld, dtype, arm_offset, ext_best_arm, ext_best_mean,
+                                 ext_best_var, best_arm, min_zeta, min_arm, tie_cnt, decision, workspace,
+                                 nullptr, nullptr, 0, 0.0, nullptr, 0, s);
 }
 
 int launch_ocba_resolve_tie(const void* mean, const void* var, int64_t n_c, int K, int64_t ld,
@@ -419,15 +600,25 @@ int launch_ocba_resolve_tie(const void* mean, const void* var, int64_t n_c, int 
 
 int launch_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
                        int64_t ld, int arm_offset, int p_mode, double kernel_scale,
-                       crs_decision* decision, cudaStream_t s) {
+                       crs_decision* decision, crs_decision* host_mirror, int seq, cudaStream_t s) {
   (void)mean;
   if (!st || !ctx || !var || !decision || p_mode < 0 || p_mode > 2) return CRS_ERR_INVALID_ARG;
-  if (st->dtype == CRS_F64)
-    ocba_select_kernel<double><<<1, 256, 0, s>>>(*st, (const double*)ctx, (const double*)var, ld, arm_offset, p_mode, kernel_scale, decision);
-  else if (st->dtype == CRS_F32)
-    ocba_select_kernel<float><<<1, 256, 0, s>>>(*st, (const float*)ctx, (const float*)var, ld, arm_offset, p_mode, (float)kernel_scale, decision);
-  else
+  const int threads = st->num_arms >= 32 ? 1024 : (st->num_arms >= 8 ? 256 : 64);
+  const size_t blk = (size_t)st->n_cap * st->dim * (st->dtype == CRS_F64 ? 8 : 4);
+  size_t stage = blk * (size_t)(st->num_arms < 256 ? st->num_arms : 256);
+  if (stage > (size_t)kSelStageAlone) stage = kSelStageAlone;
+  if (stage < blk) stage = blk;
+  if (st->dtype == CRS_F64) {
+    auto kern = ocba_select_kernel<double>;
+    if (stage > 48 * 1024) CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage), "select attr");
+    kern<<<1, threads, stage, s>>>(*st, (const double*)ctx, (const double*)var, ld, arm_offset, p_mode, kernel_scale, decision, host_mirror, seq, (int)stage);
+  } else if (st->dtype == CRS_F32) {
+    auto kern = ocba_select_kernel<float>;
+    if (stage > 48 * 1024) CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage), "select attr");
+    kern<<<1, threads, stage, s>>>(*st, (const float*)ctx, (const float*)var, ld, arm_offset, p_mode, (float)kernel_scale, decision, host_mirror, seq, (int)stage);
+  } else {
     return CRS_ERR_INVALID_ARG;
+  }
   CRS_CUDA_TRY(cudaGetLastError(), "ocba_select launch");
   return CRS_OK;
 }

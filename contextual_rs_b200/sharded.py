@@ -135,7 +135,7 @@ class ContextShardedDecider:
     def decide(self, p_mode: int = _lib.CRS_P_COUNT, kernel_scale: float = 2.0,
                prepare_arms: Optional[Tuple[int, int]] = None) -> Tensor:
         """Returns the combined record (``REC_*`` columns, global context index) on the host."""
-        from .contextual_rs_strategies import _scan
+        from .contextual_rs_strategies import _scan_select
         m, lib = self.model, _lib.get()
         n_loc = self.end - self.begin
         if n_loc > 0:
@@ -148,10 +148,7 @@ class ContextShardedDecider:
                 st = C.byref(m.state)
                 _lib.check(lib.crs_posterior_grid(st, self.local_ctx.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
                                                   ws["var"].data_ptr(), K, 0, stream), "crs_posterior_grid")
-                _scan(lib, m, ws, n_loc, stream)
-                _lib.check(lib.crs_ocba_select(st, self.local_ctx.data_ptr(), ws["mean"].data_ptr(),
-                                               ws["var"].data_ptr(), K, 0, p_mode, float(kernel_scale),
-                                               ws["decision"].data_ptr(), stream), "crs_ocba_select")
+                _scan_select(lib, m, ws, n_loc, p_mode, kernel_scale, stream, ctx_ptr=self.local_ctx.data_ptr())
             local = ws["decision"]
         else:
             local = self._empty

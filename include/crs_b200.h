@@ -106,7 +106,7 @@ typedef struct crs_decision {
   int32_t zeta_arm;    /* arm id attaining min_zeta at that context (strategies.py:157,201) */
   int32_t best_arm;    /* predicted best arm at that context */
   int32_t next_arm;    /* the decision                              (strategies.py:199-201) */
-  int32_t reserved[4];
+  int32_t reserved[4]; /* [0] = (first arm whose Cholesky failed)+1 or 0; [1] = completion tag */
 } crs_decision;
 
 CRS_API int crs_abi_version(void);
@@ -185,6 +185,17 @@ CRS_API int crs_ocba_select(const crs_gp_state* st, const void* ctx, const void*
                     crs_decision* decision, void* stream);
 
 /*
+ * crs_ocba_scan + crs_ocba_select in ONE launch (the last-arriving CTA of the scan runs step 2(b)):
+ * the decision path of gao_modellist without a kernel boundary between argmin and arm choice.
+ * Same outputs as the two calls; K = st->num_arms, dtype = st->dtype.
+ */
+CRS_API int crs_ocba_scan_select(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
+                                 int64_t n_c, int64_t ld, int32_t arm_offset, int32_t p_mode,
+                                 double kernel_scale, int32_t* best_arm, void* min_zeta,
+                                 int32_t* min_arm, int32_t* tie_cnt, crs_decision* decision,
+                                 void* workspace, void* stream);
+
+/*
  * Replaces the sampling half of estimate_current_generalized_pcs for a ModelListGP
  * (contextual_rs/generalized_pcs.py:441-475): for every context, the number of the S posterior
  * draws in which the predicted-best arm beats every other arm (func_I = strict indicator).  Draws
@@ -217,9 +228,11 @@ CRS_API int crs_peak_probe(int32_t kind, int32_t iters, int32_t blocks, void* ou
  * Whole decision through one call with HOST context buffers — the reference-facing entry that
  * stands in for `gao_modellist(model, context_set, ...)` when context_set lives on the CPU, as it
  * does in the reference's driver (experiments/wsc_experiments/main.py:226-228).
- * Copies ctx_host (pinned or pageable, [n_c, d] T) to ws_ctx, optionally re-prepares arms
- * [prep_begin, prep_end), runs grid -> scan -> select on `stream`, copies the decision back to
- * decision_host and synchronises the stream.  Returns CRS_TIES_PENDING if randomize_ties and
+ * Copies ctx_host (pinned or pageable, [n_c, d] T) to ws->ctx, optionally re-prepares arms
+ * [prep_begin, prep_end) and runs grid -> fused scan + select on `stream`.  If decision_host is
+ * pinned memory the last kernel writes the decision straight into it (mapped, zero-copy) and the
+ * call spins on a completion tag (decision_host->reserved[1]); otherwise it copies the decision
+ * back and synchronises the stream.  Either way the decision is complete on return.  Returns CRS_TIES_PENDING if randomize_ties and
  * tie_count > 1 (the caller then draws r, calls crs_ocba_resolve_tie + crs_ocba_select).
  * ws_* are caller-owned device buffers: ctx [n_c,d] T, mean/var [n_c,K] T, best_arm/min_arm/
  * tie_cnt [n_c] int32, min_zeta [n_c] T, decision (device), scan workspace.

@@ -151,6 +151,17 @@ def _run_tables(crs, mean, var, model, ctx, p_mode=0, kernel_scale=2.0):
     torch.cuda.synchronize()
     host = dec.cpu().numpy().tobytes()
     d = _lib.Decision.from_buffer_copy(host)
+    if model is not None:  # the fused scan + select launch must give the identical decision
+        dec2 = torch.zeros(64, dtype=torch.uint8, device=DEV)
+        out2 = {k: torch.zeros_like(v) for k, v in out.items()}
+        _lib.check(lib.crs_ocba_scan_select(C.byref(model.state), ctx.data_ptr(), mean.data_ptr(), var.data_ptr(),
+                                            n_c, K, 0, p_mode, kernel_scale, out2["best"].data_ptr(),
+                                            out2["minz"].data_ptr(), out2["zarm"].data_ptr(), out2["ties"].data_ptr(),
+                                            dec2.data_ptr(), ws.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert dec2.cpu().numpy().tobytes() == host
+        for k in out:
+            assert torch.equal(out[k], out2[k]), k
     return d, out, dec
 
 
