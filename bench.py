@@ -187,6 +187,91 @@ def run_reference(args, name):
     }))
 
 
+
+# ------------------------------------------------------------------------------------------- PCS
+PCS_CONFIG = "c3: generalized-PCS MC estimate, 2^16 samples, 256 arms x 8,192 contexts, fp32"
+
+
+def pcs_issue_peak(sm_mhz: float) -> float:
+    """Issue-slot roofline of the PCS kernel in draws/s: 148 SMs x 4 schedulers x 32 lanes x clock
+    / 21.4 SASS instructions per N(0,1) draw (Philox4x32-10 + Box-Muller + FMA + max; ncu r01)."""
+    return 148 * 4 * 32 * sm_mhz * 1e6 / 21.4
+
+
+def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
+    """PCS MC samples/s on config 3 (fp32).  Contexts are sharded over ranks; counts are combined
+    with one all-reduce.  'value' counts S*n_c*K nominal draws ("equivalent samples"), the executed
+    draws after the exact screen are reported beside it."""
+    import torch.distributed as dist
+    import contextual_rs_b200 as crs
+    from contextual_rs_b200.generalized_pcs import pcs_counts
+    from contextual_rs_b200.sharded import shard_bounds
+    from contextual_rs_b200.synthetic import make_config
+    desc, ctx = make_config("c3")
+    K, n_c = len(desc["train_X"]), ctx.shape[0]
+    model = crs.B200ModelListGP(desc, device=dev, dtype=torch.float32)
+    b, e = shard_bounds(n_c, world, rank)
+    post = model.posterior(ctx[b:e].float())
+    mean, var = post.mean.contiguous(), post.variance.contiguous()
+    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    total = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def step(i):
+        c = pcs_counts(model, mean, var, num_samples, seed=0, offset=i, ctx_offset=b, stats=stats)
+        total[0] = c.sum(dtype=torch.int64).to(torch.float64)
+        if world > 1:
+            dist.all_reduce(total)
+
+    step(0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = []
+    for i in range(reps):
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step(1 + i)
+        t.record()
+        t.synchronize()
+        ms.append(s.elapsed_time(t))
+    t_step = sum(ms) / len(ms) * 1e-3
+    tt = torch.tensor([t_step], dtype=torch.float64, device=dev)
+    st = stats.to(torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(st)
+    t_step = float(tt)
+    drawn, skipped = st.tolist()
+    nominal = float(num_samples) * n_c * K
+    out = {"metric": "pcs_mc_samples_per_sec", "value": nominal / t_step, "unit": "equivalent N(0,1) draws/s",
+           "config": {"workload": PCS_CONFIG, "samples": num_samples, "arms": K, "contexts": n_c,
+                      "sharding": f"contexts/{world}" if world > 1 else "none"},
+           "ms_per_estimate": t_step * 1e3, "executed_draws_per_sec": drawn / t_step,
+           "executed_fraction": drawn / (drawn + skipped), "pcs_mean": float(total) / (num_samples * n_c),
+           "gpu_launches": reps + 1}
+    peak = pcs_issue_peak(1965.0)
+    out["roofline"] = {"kernel": "pcs_counts_kernel", "bound": "issue", "achieved": drawn / t_step / world / 1e9,
+                       "peak": peak / 1e9, "unit": "G draws/s", "frac": drawn / t_step / world / peak, "traffic": None,
+                       "peak_source": "148 SM x 4 schedulers x 32 lanes x 1.965 GHz / 21.4 instr per draw (SASS, ncu)"}
+    if cpu and world == 1 and rank == 0:
+        from oracle import pcs_oracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        sub_c, sub_s = 64, 2048
+        g = torch.Generator().manual_seed(0)
+        mu, vr = mean[:sub_c].double().cpu(), var[:sub_c].double().cpu()
+        pcs_oracle.pcs_marginal_ref(mu, vr, 256, generator=g)
+        t0 = time.perf_counter()
+        n_rep = 0
+        while time.perf_counter() - t0 < 10.0:
+            pcs_oracle.pcs_marginal_ref(mu, vr, sub_s, generator=g)
+            n_rep += 1
+        dt = (time.perf_counter() - t0) / n_rep
+        out["cpu_baseline"] = {"value": sub_s * sub_c * K / dt, "unit": "N(0,1) draws/s", "cores": torch.get_num_threads(),
+                               "kind": "port", "sample": f"{n_rep} x marginal sampler (oracle.pcs_marginal_ref) on {sub_c} contexts x {K} arms x "
+                               f"{sub_s} samples, fp64, PyTorch CPU; the reference's joint sampler is O(n_c^3) and cannot run at this size"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------- GPU
 def main():
     ap = argparse.ArgumentParser()
@@ -198,6 +283,7 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (profiling only)")
+    ap.add_argument("--no-pcs", action="store_true", help="skip the PCS (config 3) sub-benchmark")
     args = ap.parse_args()
     name = args.workload
     if args.impl == "reference":
@@ -331,7 +417,8 @@ def main():
     if rank == 0:
         value = K_steps / t_dev
         flops = algorithmic_flops(K, n_loc, n_obs, d)
-        fp64_peak = 148 * 64 * 2 * 1.965e9 / 1e12 if dtype == torch.float64 else 148 * 128 * 2 * 1.965e9 / 1e12
+        from contextual_rs_b200.peaks import measure_fma_peak
+        fp64_peak = measure_fma_peak(0 if dtype == torch.float64 else 1, dev)  # live FMA micro-kernel
         achieved = flops / (grid_avg * 1e-3) / 1e12
         scan_bytes = 2 * K * n_loc * w + n_loc * (w + 12)
         out = {
@@ -349,8 +436,8 @@ def main():
             "roofline": {"kernel": "posterior_grid_kernel", "bound": "fp64_fma" if dtype == torch.float64 else "fp32_fma",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                          "traffic": None, "avg_launch_ms": grid_avg,
-                         "peak_source": "nominal 148 SM x 64 (fp64) / 128 (fp32) FMA lanes x 2 x 1.965 GHz; "
-                                        "no fp64 figure in MEASURED_PEAKS.json",
+                         "peak_source": "measured in this run by crs_peak_probe (pure FMA micro-kernel, 16 chains/thread, "
+                                        "CUDA events); MEASURED_PEAKS.json has no fp64/fp32-FMA figure (nominal 37.2 / 74.5)",
                          "algorithmic_flops_per_launch": flops},
             "roofline_scan": {"kernel": "ocba_scan_kernel", "bound": "hbm", "achieved": scan_bytes / (scan_avg * 1e-3) / 1e9,
                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": scan_bytes / (scan_avg * 1e-3) / 1e9 / peaks["hbm_gbs"],
@@ -372,6 +459,13 @@ def main():
                 "value": 1.0 / (dt * scale), "unit": "decisions/s", "cores": torch.get_num_threads(), "kind": "port",
                 "sample": f"{steps} decisions, oracle '{variant}' variant on {sub}/{n_c} contexts x {K} arms, "
                           f"time scaled x{scale:.0f}; PyTorch CPU, {torch.get_num_threads()} threads"}
+    pcs = None
+    if not args.no_pcs and name == "c2":
+        pcs = run_pcs(dev, world, rank, cpu=not args.no_cpu_baseline)
+    if rank == 0:
+        if pcs is not None:
+            out["pcs"] = pcs
+            out["gpu_launches"] += pcs["gpu_launches"]
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -49,7 +49,8 @@ __device__ __forceinline__ float approx_sqrt(float x) {
 
 // (wa, wb) -> two N(0,1) draws; see oracle/philox_ref.py for the stream definition.
 __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1) {
-  const float a = (__uint_as_float(0x3f800000u | (wa >> 9)) - 1.0f) + 5.9604644775390625e-8f;
+  // (1 + m 2^-23) - (1 - 2^-24) = m 2^-23 + 2^-24 exactly: one FADD builds the open-interval uniform
+  const float a = __uint_as_float(0x3f800000u | (wa >> 9)) - 0.99999994039535522f;
   const float b = __uint_as_float(0x3f800000u | (wb >> 9)) - 1.0f;
   const float rad = approx_sqrt(-1.3862943611198906f * __log2f(a));  // sqrt(-2 ln a)
   float sn, cs;
@@ -173,24 +174,44 @@ pcs_counts_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t
           mr[s] = -CUDART_INF_F;
         }
       }
+      // two competitor arms per iteration: two independent Philox / Box-Muller chains in flight
       int e = 0;
-      for (; e < M; ++e) {
+      for (; e + 1 < M; e += 2) {
         bool alive = false;
 #pragma unroll
         for (int s = 0; s < 4; ++s) alive = alive || (yb[s] > mr[s]);
         if (!__any_sync(kFull, alive)) break;  // every sample of every lane already failed
-        const Cand cd = cand[e];
-        const Words w = philox4x32_10((uint32_t)q, cw, (uint32_t)cd.arm, offset, k0, k1);
-        float z[4];
-        box_muller(w.x, w.y, z[0], z[1]);
-        box_muller(w.z, w.w, z[2], z[3]);
+        const Cand c0 = cand[e], c1 = cand[e + 1];
+        const Words w0 = philox4x32_10((uint32_t)q, cw, (uint32_t)c0.arm, offset, k0, k1);
+        const Words w1 = philox4x32_10((uint32_t)q, cw, (uint32_t)c1.arm, offset, k0, k1);
+        float z0[4], z1[4];
+        box_muller(w0.x, w0.y, z0[0], z0[1]);
+        box_muller(w1.x, w1.y, z1[0], z1[1]);
+        box_muller(w0.z, w0.w, z0[2], z0[3]);
+        box_muller(w1.z, w1.w, z1[2], z1[3]);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) mr[s] = fmaxf(mr[s], fmaf(cd.sd, z[s], cd.mu));
+        for (int s = 0; s < 4; ++s)
+          mr[s] = fmaxf(mr[s], fmaxf(fmaf(c0.sd, z0[s], c0.mu), fmaf(c1.sd, z1[s], c1.mu)));
+      }
+      if (e < M) {
+        bool alive = false;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) alive = alive || (yb[s] > mr[s]);
+        if (__any_sync(kFull, alive)) {
+          const Cand cd = cand[e];
+          const Words w = philox4x32_10((uint32_t)q, cw, (uint32_t)cd.arm, offset, k0, k1);
+          float z[4];
+          box_muller(w.x, w.y, z[0], z[1]);
+          box_muller(w.z, w.w, z[2], z[3]);
+#pragma unroll
+          for (int s = 0; s < 4; ++s) mr[s] = fmaxf(mr[s], fmaf(cd.sd, z[s], cd.mu));
+          ++e;
+        }
       }
 #pragma unroll
       for (int s = 0; s < 4; ++s) hits += (s < ns && yb[s] > mr[s]) ? 1u : 0u;
       if (active) {
-        drawn += 4ull * (unsigned long long)(e + 1);
+        drawn += 4ull * (unsigned long long)(e + 1);  // e competitor arms + the best arm
         skipped += 4ull * (unsigned long long)(K - 1 - e);
       }
     }

@@ -450,3 +450,37 @@ def test_fp64_kernel_math(crs):
         # exp(-s) amplifies the rounding of its argument by s: bound relative to (2 + s)
         arg = (5 ** 0.5) * r if kernel == 0 else 0.5 * xc
         assert float(((got - want).abs() / (want * (2 + arg)))[big].max()) < 4e-16
+
+
+def test_sequential_loop_matches_oracle_loop(crs):
+    """The cached-grid / dirty-column loop (SequentialRS) against the reference's loop structure
+    (experiments/wsc_experiments/main.py:345-470) restated with the oracle: identical decision
+    sequence, identical best-arm readout, PCS within MC error of exact quadrature."""
+    from contextual_rs_b200.rs_loop import SequentialRS
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=8, n_c=50, d=2, n=6, seed=11)
+    model = crs.B200ModelListGP(desc, device=DEV)
+    ref = gp_oracle.model_from_description(desc)
+    gen = torch.Generator().manual_seed(3)
+    noise = torch.randn(40, generator=gen, dtype=torch.float64)
+
+    def truth(arm, x, it):
+        return torch.sin(10.0 * torch.cat([torch.tensor([arm / 7.0], dtype=torch.float64), x])).sum() + 0.1 * noise[it]
+
+    S = 8192
+    loop = SequentialRS(model, ctx, kernel_scale=1.0, num_pcs_samples=S, pcs_seed=5)
+    for it in range(20):
+        rarm, rx = ocba_oracle.gao_modellist_ref(ref, ctx, kernel_scale=1.0)
+        rp = ref.posterior(ctx)
+        out = loop.step(lambda arm, x: truth(arm, x, it))
+        assert out["next_arm"] == int(rarm) and torch.equal(out["next_context"], rx), it
+        assert torch.equal(out["best_arms"].cpu(), rp.mean.argmax(dim=-1))
+        exact = pcs_oracle.pcs_exact_quadrature(rp.mean.numpy(), rp.variance.numpy()).mean()
+        assert abs(float(out["pcs"]) - exact) < 5 * np.sqrt(0.25 / (S * 50)) + 2e-3
+        y = truth(int(rarm), rx, it)
+        ref.models[int(rarm)] = ref.models[int(rarm)].condition_on_observations(rx.view(1, -1), y.view(1, 1))
+    # the cached grid equals a from-scratch posterior of the updated model
+    p = model.posterior(ctx)
+    assert torch.equal(p.mean, loop.ws["mean"]) and torch.equal(p.variance, loop.ws["var"])
+    rp = ref.posterior(ctx)
+    assert _scaled_err(p.mean, rp.mean) < 1e-10 and _scaled_err(p.variance, rp.variance) < 1e-10
