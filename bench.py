@@ -193,15 +193,18 @@ PCS_CONFIG = "c3: generalized-PCS MC estimate, 2^16 samples, 256 arms x 8,192 co
 
 
 def pcs_issue_peak(sm_mhz: float) -> float:
-    """Issue-slot roofline of the PCS kernel in draws/s: 148 SMs x 4 schedulers x 32 lanes x clock
-    / 21.4 SASS instructions per N(0,1) draw (Philox4x32-10 + Box-Muller + FMA + max; ncu r01)."""
+    """Issue-slot roofline of the PCS kernel in EXECUTED draws/s: 148 SMs x 4 schedulers x 32 lanes
+    x clock / 21.4 SASS instructions per N(0,1) draw — the instruction cost of Philox4x32-10 +
+    Box-Muller + FMA + max measured on the brute-force version of the kernel (ncu, profiles/r01b)."""
     return 148 * 4 * 32 * sm_mhz * 1e6 / 21.4
 
 
 def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
     """PCS MC samples/s on config 3 (fp32).  Contexts are sharded over ranks; counts are combined
-    with one all-reduce.  'value' counts S*n_c*K nominal draws ("equivalent samples"), the executed
-    draws after the exact screen are reported beside it."""
+    with one all-reduce.  'value' counts the S*n_c*K nominal draws of the estimator ("equivalent
+    samples"); the draws actually executed — samples stop at their first failure / when no
+    remaining arm can win, which leaves every count identical — are reported beside it and are
+    what the roofline fraction is computed from."""
     import torch.distributed as dist
     import contextual_rs_b200 as crs
     from contextual_rs_b200.generalized_pcs import pcs_counts

@@ -3,14 +3,21 @@
 // (contextual_rs/generalized_pcs.py:441-475): draw posterior samples at every (arm, context),
 // order arms by posterior mean, delta = y_(1) - max_{j>=2} y_(j), func_I = (delta > 0), mean over
 // samples.  The reference materialises an S x K x n_c sample tensor (550 GB at config 3); here
-// nothing S-sized ever leaves the SM: each thread owns a quad of 4 samples, draws its normals from
-// Philox4x32-10 keyed by (seed; sample/4, context, arm, offset) and keeps only a running max.
+// nothing S-sized ever leaves the SM.
 //
-// Exact screening: the Box-Muller variates are built from 23-bit uniforms, so |z| <= 5.7683.  An
-// arm j with  mu_j + ZB*sd_j < mu_b - ZB*sd_b  (ZB = 5.77) can never beat the best arm b in ANY
-// draw of this stream, so it is dropped before sampling without changing a single count.  A quad
-// also stops early once all of its 4 samples have already failed.  Both shortcuts leave the counts
-// identical to the unscreened estimator; executed / skipped draws are reported in `stats`.
+// Stream: Philox4x32-10 keyed (seed; sample, context, arm >> 2, offset) -> the draws of one sample
+// at 4 consecutive arms (Box-Muller on 23-bit uniforms, |z| <= 5.7683).  Because a (sample,
+// context) outcome does not depend on the order in which arms are visited, the kernel may stop a
+// sample as soon as its outcome is decided — all of the following leave every count IDENTICAL to
+// the brute-force estimator (tests: count-for-count against the CPU restatement):
+//   screen   arm j with mu_j + ZB sd_j < mu_b - ZB sd_b (ZB = 5.77) can never win: dropped up front;
+//   order    arm blocks are visited by decreasing threat  (mu_j - mu_b) / sqrt(sd_j^2 + sd_b^2);
+//   fail     the first block in which some y_j >= y_b ends the sample (failure);
+//   bound    if no remaining arm can reach y_b (suffix max of mu_j + ZB sd_j < y_b) the sample ends
+//            (success);
+//   compact  every 4 blocks the surviving samples of the CTA are re-packed into a dense list, so
+//            that warps stay full while most samples have already finished.
+// Executed and skipped draws are reported in `stats`.
 #include <math_constants.h>
 #include "crs_common.cuh"
 
@@ -18,7 +25,14 @@ namespace crs {
 namespace {
 
 constexpr int kPcsThreads = 256;
-constexpr int kQuadsPerThread = 16;              // quads of 4 samples per thread per work item
+#ifndef CRS_PCS_CHUNK
+#define CRS_PCS_CHUNK 4096
+#endif
+constexpr int kPcsChunk = CRS_PCS_CHUNK;                  // samples processed per compaction cycle
+#ifndef CRS_PCS_ROUND
+#define CRS_PCS_ROUND 4
+#endif
+constexpr int kPcsRound = CRS_PCS_ROUND;         // arm blocks per round (between compactions)
 constexpr float kZBound = 5.77f;                 // > sqrt(-2 ln 2^-24) = 5.7683 + MUFU slack
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
@@ -59,30 +73,62 @@ __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, 
   z1 = rad * sn;
 }
 
-struct Cand { float mu, sd; int arm; };  // centred mean, std-dev, global arm id
+struct Alive { uint32_t sample; float yb; };
 
+// shared-memory plan of one context: the candidate arm blocks in visiting order
+struct Plan {
+  float4* mu;      // [nb] centred means of the 4 arms of a block (-inf: not a competitor)
+  float4* sd;      // [nb] std-devs (0 for non-competitors)
+  float* ub;       // [nb] max over the block of mu + ZB sd
+  uint32_t* id;    // [nb] global arm-block id (Philox counter word)
+  float* key;      // [np2] sort key (threat), descending
+  int* ord;        // [np2] visiting order -> entry of the arrays above
+  // the same plan permuted into visiting order (what the sampling loop reads)
+  float4* vmu;     // [nb]
+  float4* vsd;     // [nb]
+  float* suf;      // [nb] suffix max of ub in visiting order
+  uint32_t* vid;   // [nb]
+};
+
+#ifndef CRS_PCS_MIN_BLOCKS
+#define CRS_PCS_MIN_BLOCKS 3
+#endif
 template <typename T>
-__global__ void __launch_bounds__(kPcsThreads)
+__global__ void __launch_bounds__(kPcsThreads, CRS_PCS_MIN_BLOCKS)
 pcs_counts_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n_c, int K,
                   int64_t ld, int64_t num_samples, uint32_t k0, uint32_t k1, uint32_t offset,
-                  int arm_offset, int64_t ctx_offset, int chunks_per_ctx, uint32_t* counts,
-                  unsigned long long* stats) {
+                  int blk_offset, int64_t ctx_offset, int splits, int nbmax, int np2,
+                  uint32_t* counts, unsigned long long* stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Cand* cand = reinterpret_cast<Cand*>(smem_raw);  // [K]
+  Plan pl;
+  pl.mu = reinterpret_cast<float4*>(smem_raw);
+  pl.sd = pl.mu + nbmax;
+  pl.vmu = pl.sd + nbmax;
+  pl.vsd = pl.vmu + nbmax;
+  pl.ub = reinterpret_cast<float*>(pl.vsd + nbmax);
+  pl.suf = pl.ub + nbmax;
+  pl.id = reinterpret_cast<uint32_t*>(pl.suf + nbmax);
+  pl.vid = pl.id + nbmax;
+  pl.key = reinterpret_cast<float*>(pl.vid + nbmax);
+  pl.ord = reinterpret_cast<int*>(pl.key + np2);
+  Alive* list0 = reinterpret_cast<Alive*>(pl.ord + np2);
+  Alive* list1 = list0 + kPcsChunk;
   __shared__ T s_bm[kPcsThreads / 32];
   __shared__ int s_bi[kPcsThreads / 32];
-  __shared__ int s_m;       // number of competitive arms
-  __shared__ int s_best;
+  __shared__ int s_nb, s_best;
   __shared__ float s_sdb;
-  __shared__ unsigned int s_cnt;
+  __shared__ int s_cnt[2];
+  __shared__ unsigned int s_hits;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t nq = (num_samples + 3) >> 2;
-  const int64_t items = n_c * chunks_per_ctx;
-  unsigned long long drawn = 0, skipped = 0;
+  const int64_t items = n_c * splits;
+  const int nblk_all = (K + 3) >> 2;
+  unsigned long long drawn = 0;
+  long long skipped = 0;
 
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-    const int64_t c = item / chunks_per_ctx;
-    const int chunk = (int)(item - c * chunks_per_ctx);
+    const int64_t c = item / splits;
+    const int sp = (int)(item - c * splits);
+    const int64_t s_lo = num_samples * sp / splits, s_hi = num_samples * (sp + 1) / splits;
     const T* mrow = mean + c * ld;
     const T* vrow = var + c * ld;
     __syncthreads();
@@ -91,35 +137,20 @@ pcs_counts_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t
     int bi = 0x7fffffff;
     for (int a = tid; a < K; a += kPcsThreads) {
       const T m = mrow[a];
-      if (m > bm) {
-        bm = m;
-        bi = a;
-      }
+      if (m > bm) { bm = m; bi = a; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const T om = __shfl_xor_sync(kFull, bm, o);
       const int oi = __shfl_xor_sync(kFull, bi, o);
-      if (om > bm || (om == bm && oi < bi)) {
-        bm = om;
-        bi = oi;
-      }
+      if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
     }
-    if (lane == 0) {
-      s_bm[warp] = bm;
-      s_bi[warp] = bi;
-    }
-    if (tid == 0) {
-      s_m = 0;
-      s_cnt = 0;
-    }
+    if (lane == 0) { s_bm[warp] = bm; s_bi[warp] = bi; }
+    if (tid == 0) { s_nb = 0; s_hits = 0; }
     __syncthreads();
     if (tid == 0) {
       for (int w = 1; w < kPcsThreads / 32; ++w)
-        if (s_bm[w] > bm || (s_bm[w] == bm && s_bi[w] < bi)) {
-          bm = s_bm[w];
-          bi = s_bi[w];
-        }
+        if (s_bm[w] > bm || (s_bm[w] == bm && s_bi[w] < bi)) { bm = s_bm[w]; bi = s_bi[w]; }
       if (bi == 0x7fffffff) bi = 0;
       s_best = bi;
       s_bm[0] = mrow[bi];
@@ -130,102 +161,174 @@ pcs_counts_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t
     const T mu_b = s_bm[0];
     const float sd_b = s_sdb;
     const float low_b = -kZBound * sd_b;  // lowest value the best arm's draw can take
-    // ---- exact screen + compaction -----------------------------------------------------------
-    for (int a0 = 0; a0 < K; a0 += kPcsThreads) {
-      const int a = a0 + tid;
+    // ---- plan: screen, threat key, compaction of the candidate arm blocks -------------------
+    for (int b0 = 0; b0 < nblk_all; b0 += kPcsThreads) {
+      const int blk = b0 + tid;
+      float mu4[4], sd4[4], key = -CUDART_INF_F, ub = -CUDART_INF_F;
       bool keep = false;
-      float mu = 0.f, sd = 0.f;
-      if (a < K && a != best) {
-        mu = (float)(mrow[a] - mu_b);  // centred in the grid dtype, then fp32
-        sd = (float)sqrt((double)vrow[a]);
-        keep = !(fmaf(sd, kZBound, mu) < low_b);
+      if (blk < nblk_all) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int a = 4 * blk + u;
+          mu4[u] = -CUDART_INF_F;
+          sd4[u] = 0.f;
+          if (a < K && a != best) {
+            const float mu = (float)(mrow[a] - mu_b);  // centred in the grid dtype, then fp32
+            const float sd = (float)sqrt((double)vrow[a]);
+            const float top = fmaf(sd, kZBound, mu);
+            if (!(top < low_b)) {  // exact screen: can it ever reach the best arm's lowest draw?
+              mu4[u] = mu;
+              sd4[u] = sd;
+              ub = fmaxf(ub, top);
+              key = fmaxf(key, mu * rsqrtf(fmaf(sd, sd, sd_b * sd_b) + 1e-30f));
+              keep = true;
+            }
+          }
+        }
+        if (blk == (best >> 2)) { keep = true; key = CUDART_INF_F; }  // the best arm's block goes first
       }
       const unsigned ball = __ballot_sync(kFull, keep);
       int base = 0;
-      if (lane == 0 && ball) base = atomicAdd(&s_m, __popc(ball));
+      if (lane == 0 && ball) base = atomicAdd(&s_nb, __popc(ball));
       base = __shfl_sync(kFull, base, 0);
       if (keep) {
         const int pos = base + __popc(ball & ((1u << lane) - 1u));
-        cand[pos].mu = mu;
-        cand[pos].sd = sd;
-        cand[pos].arm = a + arm_offset;
+        pl.mu[pos] = make_float4(mu4[0], mu4[1], mu4[2], mu4[3]);
+        pl.sd[pos] = make_float4(sd4[0], sd4[1], sd4[2], sd4[3]);
+        pl.ub[pos] = ub;
+        pl.id[pos] = (uint32_t)(blk + blk_offset);
+        pl.key[pos] = key;
+        pl.ord[pos] = pos;
       }
     }
     __syncthreads();
-    const int M = s_m;
+    const int nb = s_nb;
+    int n2 = 1;
+    while (n2 < nb) n2 <<= 1;
+    for (int i = nb + tid; i < n2; i += kPcsThreads) { pl.key[i] = -CUDART_INF_F; pl.ord[i] = -1; }
+    __syncthreads();
+    // bitonic sort of (key, ord), descending key (ties: lower entry first keeps it deterministic)
+    for (int k = 2; k <= n2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < n2; i += kPcsThreads) {
+          const int p = i ^ j;
+          if (p > i) {
+            const float ka = pl.key[i], kb = pl.key[p];
+            const int oa = pl.ord[i], ob = pl.ord[p];
+            const bool a_first = ka > kb || (ka == kb && (unsigned)oa < (unsigned)ob);
+            const bool desc = (i & k) == 0;
+            if (desc != a_first) {
+              pl.key[i] = kb; pl.key[p] = ka;
+              pl.ord[i] = ob; pl.ord[p] = oa;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // suffix max of the upper bounds in visiting order
+    for (int e = tid; e < nb; e += kPcsThreads) {
+      const int idx = pl.ord[e];
+      pl.suf[e] = pl.ub[idx];
+      pl.vmu[e] = pl.mu[idx];
+      pl.vsd[e] = pl.sd[idx];
+      pl.vid[e] = pl.id[idx];
+    }
+    __syncthreads();
+    for (int off = 1; off < nb; off <<= 1) {
+      float vals[(8192 / 4 + kPcsThreads - 1) / kPcsThreads];
+      int cnt = 0;
+      for (int e = tid; e < nb; e += kPcsThreads, ++cnt)
+        vals[cnt] = e + off < nb ? fmaxf(pl.suf[e], pl.suf[e + off]) : pl.suf[e];
+      __syncthreads();
+      cnt = 0;
+      for (int e = tid; e < nb; e += kPcsThreads, ++cnt) pl.suf[e] = vals[cnt];
+      __syncthreads();
+    }
     const uint32_t cw = (uint32_t)(c + ctx_offset);
-    // ---- sampling ------------------------------------------------------------------------------
-    unsigned int hits = 0;
-    const int64_t q0 = (int64_t)chunk * kPcsThreads * kQuadsPerThread;
-    for (int qq = 0; qq < kQuadsPerThread; ++qq) {
-      const int64_t q = q0 + (int64_t)qq * kPcsThreads + tid;
-      const bool active = q < nq;
-      if (!__any_sync(kFull, active)) break;
-      const int ns = active ? (int)min((int64_t)4, num_samples - 4 * q) : 0;
-      float yb[4], mr[4];
-      {
-        const Words w = philox4x32_10((uint32_t)q, cw, (uint32_t)(best + arm_offset), offset, k0, k1);
+    const int bslot = best & 3;
+
+    // blocks [e0, e1) of the plan for one sample; returns 0 = undecided, 1 = success, 2 = failure
+    auto run = [&](uint32_t smp, float& yb, int e0, int e1) -> int {
+      for (int e = e0; e < e1; ++e) {
+        if (e > 0 && pl.suf[e] < yb) return 1;  // nothing left can reach y_b
+        const Words w = philox4x32_10(smp, cw, pl.vid[e], offset, k0, k1);
         float z[4];
         box_muller(w.x, w.y, z[0], z[1]);
         box_muller(w.z, w.w, z[2], z[3]);
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          yb[s] = s < ns ? sd_b * z[s] : -CUDART_INF_F;  // padded samples count as failures
-          mr[s] = -CUDART_INF_F;
+        drawn += 4;
+        if (e == 0) yb = sd_b * z[bslot];
+        const float4 mu = pl.vmu[e], sd = pl.vsd[e];
+        const float top = fmaxf(fmaxf(fmaf(sd.x, z[0], mu.x), fmaf(sd.y, z[1], mu.y)),
+                                fmaxf(fmaf(sd.z, z[2], mu.z), fmaf(sd.w, z[3], mu.w)));
+        if (top >= yb) return 2;  // delta = y_b - max_j y_j <= 0: func_I = 0
+      }
+      return e1 >= nb ? 1 : 0;
+    };
+
+    // ---- sampling with compaction ------------------------------------------------------------
+    unsigned int hits = 0;
+    const unsigned long long drawn_before = drawn;
+    for (int64_t base = s_lo; base < s_hi; base += kPcsChunk) {
+      const int chn = (int)min((int64_t)kPcsChunk, s_hi - base);
+      if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+      __syncthreads();
+      // round 0: every sample of the chunk, blocks [0, R)
+      for (int off = 0; off < chn; off += kPcsThreads) {
+        const int i = off + tid;
+        int st = 3;  // inactive lane
+        float yb = 0.f;
+        const uint32_t smp = (uint32_t)(base + i);
+        if (i < chn) st = run(smp, yb, 0, min(kPcsRound, nb));
+        hits += st == 1 ? 1u : 0u;
+        const unsigned ball = __ballot_sync(kFull, st == 0);
+        int pos = 0;
+        if (lane == 0 && ball) pos = atomicAdd(&s_cnt[0], __popc(ball));
+        pos = __shfl_sync(kFull, pos, 0) + __popc(ball & ((1u << lane) - 1u));
+        if (st == 0) list0[pos] = Alive{smp, yb};
+      }
+      __syncthreads();
+      // later rounds: only the survivors, densely packed
+      int cur = 0;
+      for (int e0 = kPcsRound; e0 < nb; e0 += kPcsRound) {
+        const int n_al = s_cnt[cur];
+        if (n_al == 0) break;  // uniform
+        const Alive* src = cur ? list1 : list0;
+        Alive* dst = cur ? list0 : list1;
+        for (int off = 0; off < n_al; off += kPcsThreads) {
+          const int i = off + tid;
+          int st = 3;
+          Alive al = Alive{0u, 0.f};
+          if (i < n_al) {
+            al = src[i];
+            st = run(al.sample, al.yb, e0, min(e0 + kPcsRound, nb));
+          }
+          hits += st == 1 ? 1u : 0u;
+          const unsigned ball = __ballot_sync(kFull, st == 0);
+          int pos = 0;
+          if (lane == 0 && ball) pos = atomicAdd(&s_cnt[cur ^ 1], __popc(ball));
+          pos = __shfl_sync(kFull, pos, 0) + __popc(ball & ((1u << lane) - 1u));
+          if (st == 0) dst[pos] = al;
         }
-      }
-      // two competitor arms per iteration: two independent Philox / Box-Muller chains in flight
-      int e = 0;
-      for (; e + 1 < M; e += 2) {
-        bool alive = false;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) alive = alive || (yb[s] > mr[s]);
-        if (!__any_sync(kFull, alive)) break;  // every sample of every lane already failed
-        const Cand c0 = cand[e], c1 = cand[e + 1];
-        const Words w0 = philox4x32_10((uint32_t)q, cw, (uint32_t)c0.arm, offset, k0, k1);
-        const Words w1 = philox4x32_10((uint32_t)q, cw, (uint32_t)c1.arm, offset, k0, k1);
-        float z0[4], z1[4];
-        box_muller(w0.x, w0.y, z0[0], z0[1]);
-        box_muller(w1.x, w1.y, z1[0], z1[1]);
-        box_muller(w0.z, w0.w, z0[2], z0[3]);
-        box_muller(w1.z, w1.w, z1[2], z1[3]);
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-          mr[s] = fmaxf(mr[s], fmaxf(fmaf(c0.sd, z0[s], c0.mu), fmaf(c1.sd, z1[s], c1.mu)));
-      }
-      if (e < M) {
-        bool alive = false;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) alive = alive || (yb[s] > mr[s]);
-        if (__any_sync(kFull, alive)) {
-          const Cand cd = cand[e];
-          const Words w = philox4x32_10((uint32_t)q, cw, (uint32_t)cd.arm, offset, k0, k1);
-          float z[4];
-          box_muller(w.x, w.y, z[0], z[1]);
-          box_muller(w.z, w.w, z[2], z[3]);
-#pragma unroll
-          for (int s = 0; s < 4; ++s) mr[s] = fmaxf(mr[s], fmaf(cd.sd, z[s], cd.mu));
-          ++e;
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < 4; ++s) hits += (s < ns && yb[s] > mr[s]) ? 1u : 0u;
-      if (active) {
-        drawn += 4ull * (unsigned long long)(e + 1);  // e competitor arms + the best arm
-        skipped += 4ull * (unsigned long long)(K - 1 - e);
+        __syncthreads();
+        if (tid == 0) s_cnt[cur] = 0;
+        cur ^= 1;
+        __syncthreads();
       }
     }
     hits = warp_sum(hits);
-    if (lane == 0 && hits) atomicAdd(&s_cnt, hits);
+    if (lane == 0 && hits) atomicAdd(&s_hits, hits);
     __syncthreads();
-    if (tid == 0 && s_cnt) atomicAdd(counts + c, s_cnt);
+    if (tid == 0 && s_hits) atomicAdd(counts + c, s_hits);
+    if (tid == 0) skipped += (long long)(s_hi - s_lo) * K;  // nominal draws of this item
+    (void)drawn_before;
   }
   if (stats) {
     drawn = warp_sum(drawn);
     skipped = warp_sum(skipped);
     if (lane == 0) {
       atomicAdd(stats, drawn);
-      atomicAdd(stats + 1, skipped);
+      atomicAdd(stats + 1, (unsigned long long)(skipped - (long long)drawn));  // nominal - executed
     }
   }
 }
@@ -247,32 +350,36 @@ int launch_pcs_counts(const void* mean, const void* var, int64_t n_c, int K, int
                       int64_t num_samples, uint64_t seed, uint32_t offset, int arm_offset,
                       int64_t ctx_offset, uint32_t* counts, uint64_t* stats, cudaStream_t s) {
   if (!mean || !var || !counts || n_c < 0 || K < 1 || ld < K || num_samples < 0) return CRS_ERR_INVALID_ARG;
-  if (num_samples > 0xffffffffLL) return CRS_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)K * sizeof(Cand);
-  if (smem > 200 * 1024) return CRS_ERR_UNSUPPORTED;
+  if (arm_offset & 3) return CRS_ERR_INVALID_ARG;  // the stream is keyed by blocks of 4 arms
+  if (num_samples > 0xffffffffLL || K > 8192) return CRS_ERR_UNSUPPORTED;
   if (n_c == 0) return CRS_OK;
   CRS_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)n_c, s), "pcs memset");
   if (stats) CRS_CUDA_TRY(cudaMemsetAsync(stats, 0, 2 * sizeof(uint64_t), s), "pcs memset stats");
   if (num_samples == 0) return CRS_OK;
-  const int64_t nq = (num_samples + 3) / 4;
-  const int64_t per_item = (int64_t)kPcsThreads * kQuadsPerThread;
-  const int chunks = (int)((nq + per_item - 1) / per_item);
-  const int64_t items = n_c * chunks;
-  int blocks = (int)(items < 148 * 8 ? items : 148 * 8);
+  const int nbmax = (K + 3) / 4;
+  int np2 = 1;
+  while (np2 < nbmax) np2 <<= 1;
+  const size_t smem = (size_t)nbmax * (4 * 16 + 4 * 4) + (size_t)np2 * 8 + 2 * (size_t)kPcsChunk * sizeof(Alive);
+  // enough work items to fill the machine: split the samples of a context when contexts are few
+  const int64_t max_splits = (num_samples + kPcsChunk - 1) / kPcsChunk;
+  int64_t splits = (148 * 4 + n_c - 1) / n_c;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int64_t items = n_c * splits;
+  const int blocks = (int)(items < 148 * 8 ? items : 148 * 8);
   const uint32_t k0 = (uint32_t)(seed & 0xffffffffu), k1 = (uint32_t)(seed >> 32);
-  if (dtype == CRS_F64) {
-    auto kern = pcs_counts_kernel<double>;
-    if (smem > 48 * 1024) CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pcs attr");
-    kern<<<blocks, kPcsThreads, smem, s>>>((const double*)mean, (const double*)var, n_c, K, ld, num_samples, k0, k1, offset, arm_offset, ctx_offset, chunks, counts, (unsigned long long*)stats);
-  } else if (dtype == CRS_F32) {
-    auto kern = pcs_counts_kernel<float>;
-    if (smem > 48 * 1024) CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pcs attr");
-    kern<<<blocks, kPcsThreads, smem, s>>>((const float*)mean, (const float*)var, n_c, K, ld, num_samples, k0, k1, offset, arm_offset, ctx_offset, chunks, counts, (unsigned long long*)stats);
-  } else {
-    return CRS_ERR_INVALID_ARG;
-  }
-  CRS_CUDA_TRY(cudaGetLastError(), "pcs_counts launch");
-  return CRS_OK;
+  auto go = [&](auto kern, auto* m, auto* v) -> int {
+    if (smem > 48 * 1024)
+      CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pcs attr");
+    kern<<<blocks, kPcsThreads, smem, s>>>(m, v, n_c, K, ld, num_samples, k0, k1, offset, arm_offset >> 2,
+                                           ctx_offset, (int)splits, nbmax, np2, counts,
+                                           (unsigned long long*)stats);
+    CRS_CUDA_TRY(cudaGetLastError(), "pcs_counts launch");
+    return CRS_OK;
+  };
+  if (dtype == CRS_F64) return go(pcs_counts_kernel<double>, (const double*)mean, (const double*)var);
+  if (dtype == CRS_F32) return go(pcs_counts_kernel<float>, (const float*)mean, (const float*)var);
+  return CRS_ERR_INVALID_ARG;
 }
 
 int launch_philox_words(const uint32_t* ctr, int64_t n, uint32_t k0, uint32_t k1, uint32_t* out,

@@ -175,3 +175,129 @@ class ContextShardedDecider:
         if self.world > 1:
             dist.all_reduce(total, group=self.group)
         return total / (float(num_samples) * self.n_c)
+
+
+def sub_description(desc: dict, a0: int, a1: int) -> dict:
+    """The fitted model description restricted to arms [a0, a1)."""
+    out = dict(desc)
+    for key in ("train_X", "train_Y"):
+        out[key] = list(desc[key][a0:a1])
+    for key in ("lengthscale", "outputscale", "noise", "mean_const", "norm_mins", "norm_ranges", "y_mean", "y_std"):
+        if desc.get(key) is not None:
+            out[key] = desc[key][a0:a1]
+    return out
+
+
+class ArmShardedDecider:
+    """GP-C-OCBA decision (+ PCS) with the ARMS sharded over the ranks — the partition
+    BASELINE.json's north_star describes (each arm is an independent GP).
+
+    Rank g owns arms ``shard_bounds(K, world, g)`` for ALL contexts.  Exchanges per decision:
+      1. all-gather of the per-context local best (mean, variance, arm id): ``3 x n_c`` doubles/rank;
+      2. all-gather of each rank's 64-byte ``crs_decision`` (local zeta minimiser against the
+         global best, ``ext_best_*`` of ``crs_ocba_scan``);
+      3. all-reduce of the two psi partial sums of step 2(b).
+    PCS needs every arm of a context, so the grid is re-sharded by context with one all-to-all and
+    the counts are summed with one all-reduce.
+    """
+
+    def __init__(self, desc: dict, context_set: Tensor, device, dtype=torch.float64, group=None):
+        from .model import B200ModelListGP
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.K = len(desc["train_X"])
+        self.a0, self.a1 = shard_bounds(self.K, self.world, self.rank)
+        self.model = B200ModelListGP(sub_description(desc, self.a0, self.a1), device=device, dtype=dtype)
+        m = self.model
+        self.n_c = context_set.shape[0]
+        self.ctx = context_set.to(device=m.device, dtype=m.dtype).contiguous()
+        self.ws = m.workspace(self.n_c)
+        self.ws["ctx"].copy_(self.ctx)
+        self._ext_arm = torch.zeros(self.n_c, dtype=torch.int32, device=m.device)
+        self._pack = torch.zeros(3, self.n_c, dtype=torch.float64, device=m.device)
+        self._pack_all = torch.zeros(self.world, 3, self.n_c, dtype=torch.float64, device=m.device)
+        self._dec_all = torch.zeros(self.world, 64, dtype=torch.uint8, device=m.device)
+
+    def decide(self, p_mode: int = _lib.CRS_P_COUNT, kernel_scale: float = 2.0) -> Tensor:
+        """Returns the combined record (``REC_*`` columns) on the host, identical on every rank."""
+        m, ws, lib = self.model, self.ws, _lib.get()
+        n_c, Kl, dt = self.n_c, m.num_arms, _lib.DTYPES[m.dtype]
+        with torch.cuda.device(m.device):
+            stream = _lib.stream_ptr(m.device)
+            st = C.byref(m.state)
+            # local grid and local per-context best
+            m.posterior_tables(ws["ctx"], ws["mean"], ws["var"], arms=(0, Kl))
+            _lib.check(lib.crs_ocba_scan(ws["mean"].data_ptr(), ws["var"].data_ptr(), n_c, Kl, Kl, dt, self.a0,
+                                         None, None, None, ws["best_arm"].data_ptr(), None, None, None, None,
+                                         None, stream), "crs_ocba_scan")
+            loc = (ws["best_arm"].long() - self.a0).unsqueeze(1)
+            self._pack[0] = ws["mean"].gather(1, loc).squeeze(1).double()
+            self._pack[1] = ws["var"].gather(1, loc).squeeze(1).double()
+            self._pack[2] = ws["best_arm"].double()
+            # 1. global best per context
+            if self.world > 1:
+                dist.all_gather_into_tensor(self._pack_all, self._pack, group=self.group)
+            else:
+                self._pack_all[0] = self._pack
+            bm, bv, barm = combine_local_best(self._pack_all[:, 0], self._pack_all[:, 1],
+                                              self._pack_all[:, 2].to(torch.int64))
+            bm_t, bv_t = bm.to(m.dtype).contiguous(), bv.to(m.dtype).contiguous()
+            self._ext_arm.copy_(barm.to(torch.int32))
+            # 2. local zeta minimiser against the global best
+            _lib.check(lib.crs_ocba_scan(ws["mean"].data_ptr(), ws["var"].data_ptr(), n_c, Kl, Kl, dt, self.a0,
+                                         self._ext_arm.data_ptr(), bm_t.data_ptr(), bv_t.data_ptr(),
+                                         None, ws["min_zeta"].data_ptr(), ws["min_arm"].data_ptr(),
+                                         ws["tie_cnt"].data_ptr(), ws["decision"].data_ptr(),
+                                         ws["scan_ws"].data_ptr(), stream), "crs_ocba_scan")
+            if self.world > 1:
+                dist.all_gather_into_tensor(self._dec_all, ws["decision"], group=self.group)
+            else:
+                self._dec_all[0] = ws["decision"]
+            raw = self._dec_all.cpu()
+            recs = torch.zeros(self.world, REC_WIDTH, dtype=torch.float64)
+            for r in range(self.world):
+                d = _lib.Decision.from_buffer_copy(raw[r].numpy().tobytes())
+                recs[r] = decision_record(d.min_zeta if d.context >= 0 else float("inf"), d.tie_count,
+                                          d.context, d.zeta_arm, d.best_arm, -1)
+            out = combine_arm_sharded(recs)
+            c_star, zeta_arm = int(out[REC_CONTEXT]), int(out[REC_ZETA_ARM])
+            best = int(barm[c_star])
+            # 3. psi partial sums at the selected context
+            glob = _lib.Decision(min_zeta=float(out[REC_MIN_ZETA]), tie_count=int(out[REC_TIES]), context=c_star,
+                                 zeta_arm=zeta_arm, best_arm=best, next_arm=-1)
+            ws["decision"].copy_(torch.frombuffer(bytearray(bytes(glob)), dtype=torch.uint8))
+            _lib.check(lib.crs_ocba_select(st, ws["ctx"].data_ptr(), ws["mean"].data_ptr(), ws["var"].data_ptr(),
+                                           Kl, self.a0, p_mode, float(kernel_scale), ws["decision"].data_ptr(),
+                                           stream), "crs_ocba_select")
+            psi = ws["decision"].view(torch.float64)[1:3].clone()  # psi_best, psi_rest partials
+            if self.world > 1:
+                dist.all_reduce(psi, group=self.group)
+            psi_h = psi.cpu()
+        out[REC_BEST_ARM] = best
+        out[REC_PSI_BEST], out[REC_PSI_REST] = psi_h[0], psi_h[1]
+        out[REC_NEXT_ARM] = best if float(psi_h[0]) < float(psi_h[1]) else zeta_arm
+        return out
+
+    def pcs_mean(self, num_samples: int, seed: int, offset: int = 0) -> Tensor:
+        """Context re-shard (one all-to-all of the local grid) + local counts + one all-reduce."""
+        from .generalized_pcs import pcs_counts
+        m, ws = self.model, self.ws
+        b, e = shard_bounds(self.n_c, self.world, self.rank)
+        if self.world > 1:
+            splits = [shard_bounds(self.n_c, self.world, r) for r in range(self.world)]
+            arms = [shard_bounds(self.K, self.world, r) for r in range(self.world)]
+            full = []
+            for tab in (ws["mean"], ws["var"]):
+                send = [tab[s0:s1].contiguous() for s0, s1 in splits]
+                recv = [torch.empty(e - b, a1 - a0, dtype=m.dtype, device=m.device) for a0, a1 in arms]
+                dist.all_to_all(recv, send, group=self.group)
+                full.append(torch.cat(recv, dim=1).contiguous())
+            mean, var = full
+        else:
+            mean, var = ws["mean"], ws["var"]
+        counts = pcs_counts(m, mean, var, num_samples, seed, offset, ctx_offset=b)
+        total = counts.sum(dtype=torch.int64).to(torch.float64).reshape(1)
+        if self.world > 1:
+            dist.all_reduce(total, group=self.group)
+        return total / (float(num_samples) * self.n_c)

@@ -200,9 +200,10 @@ CRS_API int crs_ocba_scan_select(const crs_gp_state* st, const void* ctx, const 
  * (contextual_rs/generalized_pcs.py:441-475): for every context, the number of the S posterior
  * draws in which the predicted-best arm beats every other arm (func_I = strict indicator).  Draws
  * are per-(context, arm) marginals from a Philox4x32-10 stream keyed by
- * (seed; sample/4, context + ctx_offset, arm + arm_offset, offset); nothing S-sized touches HBM.
- * counts: [n_c] uint32.  stats (may be NULL): [2] uint64 = {draws executed, draws skipped by the
- * exact |z| <= 5.7683 screen}.
+ * (seed; sample, context + ctx_offset, (arm + arm_offset) >> 2, offset) — one call yields the draws
+ * of a sample at 4 consecutive arms, so arm_offset must be a multiple of 4; nothing S-sized touches
+ * HBM.  counts: [n_c] uint32.  stats (may be NULL): [2] uint64 = {draws executed, nominal S*K*n_c
+ * minus executed}: samples stop at their first failure / when no remaining arm can win (exact).
  */
 CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
                    int32_t dtype, int64_t num_samples, uint64_t seed, uint32_t offset,

@@ -10,12 +10,14 @@ own definition, the reference draws with ``torch.randn`` inside ``posterior.rsam
 (``contextual_rs/generalized_pcs.py:449-451``):
 
     key     = (seed & 0xffffffff, seed >> 32)
-    counter = (q, context, arm, offset)        q = sample index // 4
-    words (w0, w1, w2, w3) -> samples 4q..4q+3 of N(0,1) for that (context, arm):
+    counter = (sample, context, arm >> 2, offset)
+    words (w0, w1, w2, w3) -> the N(0,1) draws of that sample at arms 4*(arm>>2) + 0..3:
         u(w)  = (w >> 9) * 2^-23                          in [0, 1), exact in fp32
         (z0, z1) = BoxMuller(u(w0) + 2^-24, u(w1)),  (z2, z3) = BoxMuller(u(w2) + 2^-24, u(w3))
         BoxMuller(a, b) = sqrt(-2 ln a) * (cos 2 pi b, sin 2 pi b)
     |z| <= sqrt(-2 ln 2^-24) = 5.7683 — the bound the kernel's exact screening relies on.
+Keying by (sample, arm block) makes every (sample, context) pair independent of the order in
+which the kernel visits arms, which is what lets it stop a sample at its first failure.
 """
 from __future__ import annotations
 
@@ -60,15 +62,16 @@ def box_muller(wa: np.ndarray, wb: np.ndarray):
 
 def pcs_normals(num_samples: int, context: int, arms: np.ndarray, seed: int, offset: int) -> np.ndarray:
     """N(0,1) draws ``z[arm, sample]`` (float32) for one context under the layout above."""
-    arms = np.asarray(arms, dtype=np.uint32).reshape(-1, 1)
-    nq = (num_samples + 3) // 4
-    q = np.arange(nq, dtype=np.uint32).reshape(1, -1)
-    w0, w1, w2, w3 = philox4x32_10(q, np.uint32(context), arms, np.uint32(offset),
+    arms = np.asarray(arms, dtype=np.uint32).reshape(-1)
+    blocks = np.unique(arms >> np.uint32(2))
+    smp = np.arange(num_samples, dtype=np.uint32).reshape(1, -1)
+    w0, w1, w2, w3 = philox4x32_10(smp, np.uint32(context), blocks.reshape(-1, 1), np.uint32(offset),
                                    seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     z0, z1 = box_muller(w0, w1)
     z2, z3 = box_muller(w2, w3)
-    z = np.stack([z0, z1, z2, z3], axis=-1).reshape(arms.shape[0], nq * 4)
-    return z[:, :num_samples]
+    zblk = np.stack([z0, z1, z2, z3], axis=1)  # [block, arm & 3, sample]
+    pos = np.searchsorted(blocks, arms >> np.uint32(2))
+    return zblk[pos, arms & np.uint32(3), :]
 
 
 def pcs_counts_philox_ref(mean: np.ndarray, variance: np.ndarray, num_samples: int, seed: int,
