@@ -91,17 +91,33 @@ template <typename T> __device__ __forceinline__ T zeta_of(T mu_b, T var_b, T mu
   return sq / den;
 }
 
-// Cheap lower bound on gap^2 / den: fp64 division is ~30 instructions, so candidates are screened
-// with an approximate reciprocal (rel. error < 1e-11 after one Newton step) and only those within
-// 1e-9 of the running minimum pay for the exact IEEE quotient the reference computes.  The
-// minimum, its position and its multiplicity are therefore bit-identical to the unscreened scan.
+// fp64 division is ~30 instructions, so the row minimum is located with an approximate quotient
+// (rcp.approx + one Newton step: relative error < 1e-11) and only the entries within 2e-9 of the
+// approximate minimum — a superset of the true minimisers — pay for the exact IEEE quotient the
+// reference computes.  The minimum, its position and its multiplicity are therefore bit-identical
+// to the unscreened scan.
 __device__ __forceinline__ double approx_quot(double sq, double den) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
   r = fma(fma(-den, r, 1.0), r, r);
   return sq * r;
 }
-constexpr double kScreenSlack = 1.0 + 1e-9;  // fp32 divides exactly straight away (cheap)
+constexpr double kScreenSlack = 1.0 + 2e-9;
+__device__ __forceinline__ float approx_quot(float sq, float den) { return sq / den; }  // fp32: exact already
+
+// cheap stand-in for zeta used to find the candidates of the row minimum
+template <typename T> __device__ __forceinline__ T zeta_approx(T mu_b, T var_b, T m, T vr) {
+  const T gap = mu_b - m;
+  return approx_quot(gap * gap, var_b + vr);
+}
+template <typename T> __device__ __forceinline__ T screen_threshold(T zt_min) {
+  return sizeof(T) == 8 ? (T)(zt_min * (T)kScreenSlack) : zt_min;
+}
+template <typename T> __device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
 
 // running (min zeta, its mean, its column, multiplicity); ties: larger mean, then lower column
 template <typename T> struct ZMin {
@@ -113,14 +129,9 @@ template <typename T> struct ZMin {
     else if (zz == z) { ++cnt; if (m > mu) { mu = m; col = a; } }
   }
   // zeta of (mu_b, var_b) against (m, vr), exactly as the reference: squared_diffs / added_vars
-  __device__ __forceinline__ void add_pair(T mu_b, T var_b, T m, T vr, int a) {
+  __device__ __forceinline__ void add_exact(T mu_b, T var_b, T m, T vr, int a) {
     const T gap = mu_b - m;
-    const T sq = gap * gap;
-    const T den = var_b + vr;
-    if constexpr (sizeof(T) == 8) {
-      if (!(approx_quot(sq, den) <= z * kScreenSlack)) return;  // cannot reach the minimum
-    }
-    add(sq / den, m, a);
+    add((gap * gap) / (var_b + vr), m, a);
   }
   __device__ __forceinline__ void warp_reduce() {
 #pragma unroll
@@ -266,97 +277,15 @@ __device__ __forceinline__ void publish(const crs_decision* dec, crs_decision* m
   __threadfence_system();
 }
 
-// R > 0: the row (K <= 32 R) is held in registers; R == 0: pass 2 re-reads it (L1-resident).
-template <typename T, int R>
-__global__ void __launch_bounds__(kScanThreads, (R == 0 ? 4 : 1))
-ocba_scan_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n_c, int K,
-                 int64_t ld, int arm_offset, const int32_t* __restrict__ ext_arm,
-                 const T* __restrict__ ext_mean, const T* __restrict__ ext_var,
-                 int32_t* __restrict__ best_arm, T* __restrict__ min_zeta,
-                 int32_t* __restrict__ min_arm, int32_t* __restrict__ tie_cnt,
-                 ScanPartial* partials, unsigned int* ticket, crs_decision* decision,
-                 SelectArgs sel) {
+// Fold the per-CTA minima into the global decision (ticket atomic: the last-arriving CTA reduces
+// all partials) and optionally run the fused step 2(b).  `sel_smem`: stage buffer for the fused
+// select (nullptr = the kernel's dynamic shared memory).
+template <typename T>
+__device__ void scan_tail(ScanPartial acc, ScanPartial* partials, unsigned int* ticket,
+                          crs_decision* decision, const SelectArgs& sel, const T* __restrict__ var,
+                          int64_t ld, int arm_offset, unsigned char* sel_smem) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
-  const int64_t warps_total = (int64_t)gridDim.x * nwarps;
-  ScanPartial acc = empty_partial();
-
-  for (int64_t c = (int64_t)blockIdx.x * nwarps + warp; c < n_c; c += warps_total) {
-    const T* mrow = mean + c * ld;
-    const T* vrow = var + c * ld;
-    T bm, vb;
-    int bi;  // local column of the best arm (may fall outside [0, K) when it lives on a peer rank)
-    ZMin<T> zm;
-    zm.init();
-    if constexpr (R > 0) {
-      T m[R], v[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int a = lane + 32 * r;
-        m[r] = a < K ? mrow[a] : -pos_inf<T>();
-        v[r] = a < K ? vrow[a] : T(1);
-      }
-      if (ext_arm == nullptr) {
-        bm = -pos_inf<T>();
-        bi = INT_MAX;
-        T vcand = v[0];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (m[r] > bm) { bm = m[r]; bi = lane + 32 * r; vcand = v[r]; }
-        warp_argmax(bm, bi);
-        if (bi == INT_MAX) bi = 0;  // all-NaN row
-        vb = __shfl_sync(kFull, vcand, bi & 31);  // the winner's variance sits in its owner lane
-      } else {
-        bi = ext_arm[c] - arm_offset;
-        bm = ext_mean[c];
-        vb = ext_var[c];
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int a = lane + 32 * r;
-        if (a < K && a != bi) zm.add_pair(bm, vb, m[r], v[r], a);
-      }
-    } else {
-      if (ext_arm == nullptr) {
-        bm = -pos_inf<T>();
-        bi = INT_MAX;
-        for (int a = lane; a < K; a += 32) {
-          const T m = mrow[a];
-          if (m > bm) { bm = m; bi = a; }
-        }
-        warp_argmax(bm, bi);
-        if (bi == INT_MAX) bi = 0;
-        vb = vrow[bi];
-      } else {
-        bi = ext_arm[c] - arm_offset;
-        bm = ext_mean[c];
-        vb = ext_var[c];
-      }
-      for (int a = lane; a < K; a += 32) {
-        if (a == bi) continue;
-        const T m = mrow[a];
-        zm.add_pair(bm, vb, m, vrow[a], a);
-      }
-    }
-    zm.warp_reduce();
-    const int gbest = bi + arm_offset;
-    const int gz = zm.col == INT_MAX ? -1 : zm.col + arm_offset;
-    if (lane == 0) {
-      if (best_arm) best_arm[c] = gbest;
-      if (min_zeta) min_zeta[c] = zm.z;
-      if (min_arm) min_arm[c] = gz;
-      if (tie_cnt) tie_cnt[c] = zm.cnt;
-    }
-    ScanPartial p;
-    p.z = (double)zm.z;
-    p.cnt = zm.cnt;
-    p.ctx = (int)c;
-    p.zarm = gz;
-    p.best = gbest;
-    p.pad = 0;
-    if (zm.cnt > 0) combine(acc, p);
-  }
-
   if (decision == nullptr) return;
 
   __shared__ ScanPartial s_part[kScanWarps];  // blockDim <= kScanThreads
@@ -418,9 +347,323 @@ ocba_scan_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t 
     __syncthreads();  // decision fields are visible to the whole CTA
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     select_block<T>(sel.st, reinterpret_cast<const T*>(sel.ctx), var, ld, arm_offset, sel.p_mode,
-                    (T)sel.kernel_scale, decision, dyn_smem, kSelStageFused);
+                    (T)sel.kernel_scale, decision, sel_smem ? sel_smem : dyn_smem, kSelStageFused);
   }
   if (sel.host_mirror && threadIdx.x == 0) publish(decision, sel.host_mirror, sel.seq);
+}
+
+// One row of the scan.  WPR warps share a row (WPR = 1: a warp per row; WPR = 4: the 4 warps of a
+// 128-thread CTA split a row of up to 1024 columns, 8 per lane, so that the whole row is in flight
+// at once with ~100 registers per thread instead of 250).  R = columns per lane held in registers
+// (K <= 32 R WPR); R == 0: generic path, pass 2 re-reads the row (L1 / L2).
+// Column owned by (warp w of the row, lane, slot r): a = (r WPR + w) 32 + lane.
+template <typename T, int R, int WPR>
+__global__ void __launch_bounds__(WPR == 4 ? 128 : kScanThreads, (R == 0 ? 4 : (WPR == 4 ? 4 : 1)))
+ocba_scan_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n_c, int K,
+                 int64_t ld, int arm_offset, const int32_t* __restrict__ ext_arm,
+                 const T* __restrict__ ext_mean, const T* __restrict__ ext_var,
+                 int32_t* __restrict__ best_arm, T* __restrict__ min_zeta,
+                 int32_t* __restrict__ min_arm, int32_t* __restrict__ tie_cnt,
+                 ScanPartial* partials, unsigned int* ticket, crs_decision* decision,
+                 SelectArgs sel) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  ScanPartial acc = empty_partial();
+  // cross-warp exchange for WPR = 4 (double-buffered by row parity: one barrier per stage)
+  __shared__ T s_xm[2][4], s_xv[2][4], s_xz[2][4], s_zz[2][4], s_zmu[2][4];
+  __shared__ int s_xi[2][4], s_zc[2][4], s_zn[2][4];
+
+  const int64_t row0 = WPR == 4 ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * nwarps + warp;
+  const int64_t row_step = WPR == 4 ? (int64_t)gridDim.x : (int64_t)gridDim.x * nwarps;
+  const int w = WPR == 4 ? warp : 0;
+  int par = 0;
+  for (int64_t c = row0; c < n_c; c += row_step, par ^= 1) {
+    const T* mrow = mean + c * ld;
+    const T* vrow = var + c * ld;
+    T bm, vb;
+    int bi;  // local column of the best arm (may fall outside [0, K) when it lives on a peer rank)
+    ZMin<T> zm;
+    zm.init();
+    if constexpr (R > 0) {
+      T m[R], v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int a = (r * WPR + w) * 32 + lane;
+        if ((r * WPR + w + 1) * 32 <= K) {  // warp-uniform: a full 32-column segment
+          m[r] = mrow[a];
+          v[r] = vrow[a];
+        } else {
+          m[r] = a < K ? mrow[a] : -pos_inf<T>();  // sentinels: never the best, zeta = +inf
+          v[r] = a < K ? vrow[a] : T(1);
+        }
+      }
+      if (ext_arm == nullptr) {
+        bm = m[0];
+        int br = 0;
+#pragma unroll
+        for (int r = 1; r < R; ++r)
+          if (m[r] > bm) { bm = m[r]; br = r; }
+        T vcand = v[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) vcand = br == r ? v[r] : vcand;
+        bi = (br * WPR + w) * 32 + lane;
+        if (!(bm > -pos_inf<T>())) bi = INT_MAX;  // sentinel / NaN: not a candidate
+        const int mine = bi;
+        warp_argmax(bm, bi);
+        const unsigned own = __ballot_sync(kFull, mine == bi && bi != INT_MAX);
+        vb = __shfl_sync(kFull, vcand, own ? __ffs(own) - 1 : 0);  // the winner's variance sits in its owner lane
+        if constexpr (WPR == 4) {
+          if (lane == 0) { s_xm[par][w] = bm; s_xv[par][w] = vb; s_xi[par][w] = bi; }
+          __syncthreads();
+          bm = s_xm[par][0]; vb = s_xv[par][0]; bi = s_xi[par][0];
+#pragma unroll
+          for (int q = 1; q < 4; ++q) {
+            const T om = s_xm[par][q];
+            const int oi = s_xi[par][q];
+            if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; vb = s_xv[par][q]; }
+          }
+        }
+        if (bi == INT_MAX) { bi = 0; vb = vrow[0]; bm = mrow[0]; }  // all-NaN row
+      } else {
+        bi = ext_arm[c] - arm_offset;
+        bm = ext_mean[c];
+        vb = ext_var[c];
+      }
+      // slot of the best arm in this lane (or -1): excluded from the zeta minimum
+      const int rb = ((bi & 31) == lane && ((bi >> 5) % WPR) == w && bi >= 0) ? (bi >> 5) / WPR : -1;
+      // pass 2a: approximate zeta (no IEEE division), row minimum of the approximation
+      T zt_min = pos_inf<T>();
+#ifdef CRS_SCAN_EXPERIMENT
+      T vsum = T(0);
+#pragma unroll
+      for (int r = 0; r < R; ++r) vsum += v[r];
+      zt_min = vsum;
+#else
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const T zt = zeta_approx<T>(bm, vb, m[r], v[r]);
+        if (r != rb) zt_min = fmin(zt_min, zt);
+      }
+#endif
+      zt_min = warp_min<T>(zt_min);
+      if constexpr (WPR == 4) {
+        if (lane == 0) s_xz[par][w] = zt_min;
+        __syncthreads();
+        zt_min = fmin(fmin(s_xz[par][0], s_xz[par][1]), fmin(s_xz[par][2], s_xz[par][3]));
+      }
+      const T thr = screen_threshold<T>(zt_min);
+      // pass 2b: mark the (typically one per row) candidates within the screening slack; only
+      // they divide exactly.  Branch-free marking keeps the unrolled loop free of phi-moves.
+      unsigned cand = 0;
+#ifndef CRS_SCAN_EXPERIMENT
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        cand |= (r != rb && zeta_approx<T>(bm, vb, m[r], v[r]) <= thr) ? (1u << r) : 0u;
+#endif
+      while (__any_sync(kFull, cand != 0)) {
+        if (cand) {
+          const int r = __ffs(cand) - 1;
+          cand &= cand - 1;
+          T mm = m[0], vv = v[0];
+#pragma unroll
+          for (int q = 1; q < R; ++q) {
+            mm = q == r ? m[q] : mm;
+            vv = q == r ? v[q] : vv;
+          }
+          zm.add_exact(bm, vb, mm, vv, (r * WPR + w) * 32 + lane);
+        }
+      }
+    } else {
+      if (ext_arm == nullptr) {
+        bm = -pos_inf<T>();
+        bi = INT_MAX;
+        for (int a = lane; a < K; a += 32) {
+          const T m = mrow[a];
+          if (m > bm) { bm = m; bi = a; }
+        }
+        warp_argmax(bm, bi);
+        if (bi == INT_MAX) bi = 0;
+        vb = vrow[bi];
+      } else {
+        bi = ext_arm[c] - arm_offset;
+        bm = ext_mean[c];
+        vb = ext_var[c];
+      }
+      T zt_min = pos_inf<T>();
+      for (int a = lane; a < K; a += 32)
+        if (a != bi) zt_min = fmin(zt_min, zeta_approx<T>(bm, vb, mrow[a], vrow[a]));
+      const T thr = screen_threshold<T>(warp_min<T>(zt_min));
+      for (int a = lane; a < K; a += 32) {
+        if (a == bi) continue;
+        const T m = mrow[a], vr = vrow[a];
+        if (zeta_approx<T>(bm, vb, m, vr) <= thr) zm.add_exact(bm, vb, m, vr, a);
+      }
+    }
+    zm.warp_reduce();
+    if constexpr (WPR == 4) {
+      if (lane == 0) { s_zz[par][w] = zm.z; s_zmu[par][w] = zm.mu; s_zc[par][w] = zm.col; s_zn[par][w] = zm.cnt; }
+      __syncthreads();
+      if (warp != 0) continue;  // warp 0 finishes the row
+      zm.z = s_zz[par][0]; zm.mu = s_zmu[par][0]; zm.col = s_zc[par][0]; zm.cnt = s_zn[par][0];
+#pragma unroll
+      for (int q = 1; q < 4; ++q) {
+        const T oz = s_zz[par][q], omu = s_zmu[par][q];
+        const int oi = s_zc[par][q], oc = s_zn[par][q];
+        if (oz < zm.z) { zm.z = oz; zm.mu = omu; zm.col = oi; zm.cnt = oc; }
+        else if (oz == zm.z) { zm.cnt += oc; if (omu > zm.mu || (omu == zm.mu && oi < zm.col)) { zm.mu = omu; zm.col = oi; } }
+      }
+    }
+    const int gbest = bi + arm_offset;
+    const int gz = zm.col == INT_MAX ? -1 : zm.col + arm_offset;
+    if (lane == 0) {
+      if (best_arm) best_arm[c] = gbest;
+      if (min_zeta) min_zeta[c] = zm.z;
+      if (min_arm) min_arm[c] = gz;
+      if (tie_cnt) tie_cnt[c] = zm.cnt;
+    }
+    ScanPartial p;
+    p.z = (double)zm.z;
+    p.cnt = zm.cnt;
+    p.ctx = (int)c;
+    p.zarm = gz;
+    p.best = gbest;
+    p.pad = 0;
+    if (zm.cnt > 0) combine(acc, p);
+  }
+
+  scan_tail<T>(acc, partials, ticket, decision, sel, var, ld, arm_offset, nullptr);
+}
+
+// Wide rows (256 < K, row pair <= 32 KB): one 128-thread CTA per row, rows double-buffered in
+// shared memory by TMA bulk copies (cp.async.bulk + mbarrier) so that the next row streams in from
+// HBM while the current one is scanned — with the register-resident variant load and compute of a
+// row were serialised (measured: 223 us loads-only + 165 us math = 386 us at config 4).
+template <typename T>
+__global__ void __launch_bounds__(128, 6)
+ocba_scan_tma_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n_c, int K,
+                     int64_t ld, int arm_offset, const int32_t* __restrict__ ext_arm,
+                     const T* __restrict__ ext_mean, const T* __restrict__ ext_var,
+                     int32_t* __restrict__ best_arm, T* __restrict__ min_zeta,
+                     int32_t* __restrict__ min_arm, int32_t* __restrict__ tie_cnt,
+                     ScanPartial* partials, unsigned int* ticket, crs_decision* decision,
+                     SelectArgs sel, int kpad) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  // dynamic smem: [select stage (kSelStageFused bytes, only if fused)] | stage0 {m[kpad], v[kpad]} | stage1
+  unsigned char* base = dyn_smem + (sel.do_select ? kSelStageFused : 0);
+  T* s_m[2] = {reinterpret_cast<T*>(base), reinterpret_cast<T*>(base) + 2 * kpad};
+  T* s_v[2] = {s_m[0] + kpad, s_m[1] + kpad};
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ T s_xm[2][4], s_xz[2][4], s_zz[2][4], s_zmu[2][4];
+  __shared__ int s_xi[2][4], s_zc[2][4], s_zn[2][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t row_bytes = (uint32_t)(K * sizeof(T));
+  ScanPartial acc = empty_partial();
+
+  for (int s = 0; s < 2; ++s)
+    for (int i = K + tid; i < kpad; i += 128) {  // sentinels behind the row: never best, zeta = +inf
+      s_m[s][i] = -pos_inf<T>();
+      s_v[s][i] = T(1);
+    }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t c, int st) {
+    mbar_expect_tx(&bars[st], 2 * row_bytes);
+    tma_bulk_g2s(s_m[st], mean + c * ld, row_bytes, &bars[st]);
+    tma_bulk_g2s(s_v[st], var + c * ld, row_bytes, &bars[st]);
+  };
+  const int64_t step = gridDim.x;
+  if (tid == 0) {
+    if ((int64_t)blockIdx.x < n_c) issue(blockIdx.x, 0);
+    if ((int64_t)blockIdx.x + step < n_c) issue(blockIdx.x + step, 1);
+  }
+  int it = 0;
+  for (int64_t c = blockIdx.x; c < n_c; c += step, ++it) {
+    const int st = it & 1, par = it & 1;
+    mbar_wait(&bars[st], (uint32_t)(it >> 1) & 1u);
+    const T* rm = s_m[st];
+    const T* rv = s_v[st];
+    T bm, vb;
+    int bi;
+    if (ext_arm == nullptr) {
+      bm = -pos_inf<T>();
+      bi = INT_MAX;
+      for (int a = tid; a < kpad; a += 128) {
+        const T m = rm[a];
+        if (m > bm) { bm = m; bi = a; }
+      }
+      warp_argmax(bm, bi);
+      if (lane == 0) { s_xm[par][warp] = bm; s_xi[par][warp] = bi; }
+      __syncthreads();
+      bm = s_xm[par][0]; bi = s_xi[par][0];
+#pragma unroll
+      for (int q = 1; q < 4; ++q) {
+        const T om = s_xm[par][q];
+        const int oi = s_xi[par][q];
+        if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
+      }
+      if (bi == INT_MAX) { bi = 0; bm = rm[0]; }  // all-NaN row
+      vb = rv[bi];
+    } else {
+      bi = ext_arm[c] - arm_offset;
+      bm = ext_mean[c];
+      vb = ext_var[c];
+    }
+    // pass 2a: minimum of the approximate zeta
+    T zt_min = pos_inf<T>();
+    for (int a = tid; a < kpad; a += 128) {
+      const T zt = zeta_approx<T>(bm, vb, rm[a], rv[a]);
+      if (a != bi) zt_min = fmin(zt_min, zt);
+    }
+    zt_min = warp_min<T>(zt_min);
+    if (lane == 0) s_xz[par][warp] = zt_min;
+    __syncthreads();
+    const T thr = screen_threshold<T>(fmin(fmin(s_xz[par][0], s_xz[par][1]), fmin(s_xz[par][2], s_xz[par][3])));
+    // pass 2b: exact quotient for the candidates only
+    ZMin<T> zm;
+    zm.init();
+    for (int a = tid; a < kpad; a += 128) {
+      const T m = rm[a], vr = rv[a];
+      if (a != bi && zeta_approx<T>(bm, vb, m, vr) <= thr) zm.add_exact(bm, vb, m, vr, a);
+    }
+    zm.warp_reduce();
+    if (lane == 0) { s_zz[par][warp] = zm.z; s_zmu[par][warp] = zm.mu; s_zc[par][warp] = zm.col; s_zn[par][warp] = zm.cnt; }
+    __syncthreads();  // also: every thread is done reading this stage
+    if (tid == 0 && c + 2 * step < n_c) {
+      fence_proxy_async();
+      issue(c + 2 * step, st);
+    }
+    if (warp == 0) {
+      zm.z = s_zz[par][0]; zm.mu = s_zmu[par][0]; zm.col = s_zc[par][0]; zm.cnt = s_zn[par][0];
+#pragma unroll
+      for (int q = 1; q < 4; ++q) {
+        const T oz = s_zz[par][q], omu = s_zmu[par][q];
+        const int oi = s_zc[par][q], oc = s_zn[par][q];
+        if (oz < zm.z) { zm.z = oz; zm.mu = omu; zm.col = oi; zm.cnt = oc; }
+        else if (oz == zm.z) { zm.cnt += oc; if (omu > zm.mu || (omu == zm.mu && oi < zm.col)) { zm.mu = omu; zm.col = oi; } }
+      }
+      const int gbest = bi + arm_offset;
+      const int gz = zm.col == INT_MAX ? -1 : zm.col + arm_offset;
+      if (lane == 0) {
+        if (best_arm) best_arm[c] = gbest;
+        if (min_zeta) min_zeta[c] = zm.z;
+        if (min_arm) min_arm[c] = gz;
+        if (tie_cnt) tie_cnt[c] = zm.cnt;
+      }
+      ScanPartial p;
+      p.z = (double)zm.z;
+      p.cnt = zm.cnt;
+      p.ctx = (int)c;
+      p.zarm = gz;
+      p.best = gbest;
+      p.pad = 0;
+      if (zm.cnt > 0) combine(acc, p);
+    }
+  }
+  scan_tail<T>(acc, partials, ticket, decision, sel, var, ld, arm_offset, dyn_smem);
 }
 
 // ---- tie randomisation (rare path; strategies.py:147-154) -----------------------------------
@@ -501,12 +744,13 @@ int scan_dispatch(const void* mean, const void* var, int64_t n_c, int K, int64_t
                   crs_decision* decision, void* workspace, const SelectArgs& sel, cudaStream_t s) {
   // K <= 1024: the whole row sits in registers (all loads of a row in flight at once — the kernel
   // is HBM-latency bound otherwise, ncu r01a: 66 % long-scoreboard stalls, 8 % L1 hit on the
-  // re-read); the wide variants run 128-thread CTAs to keep >= 12 warps per SM.
-  const int threads = (K > 256 && K <= 1024) ? 128 : kScanThreads;
+  // re-read).  K <= 256: one warp per row; wider rows: the 4 warps of a 128-thread CTA share a row.
+  const bool wide = K > 256 && K <= 1024;
+  const int threads = wide ? 128 : kScanThreads;
   const int wpb = threads / 32;
-  int blocks = (int)((n_c + wpb - 1) / wpb);
-  const int max_blocks = kScanMaxBlocks;
-  if (blocks > max_blocks) blocks = max_blocks;
+  int64_t want = wide ? n_c : (n_c + wpb - 1) / wpb;
+  const int max_blocks = wide ? 148 * 16 : kScanMaxBlocks;  // partials[] holds kScanMaxBlocks * 2
+  int blocks = (int)(want < max_blocks ? want : max_blocks);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace);
   ScanPartial* partials = workspace ? reinterpret_cast<ScanPartial*>(reinterpret_cast<char*>(workspace) + 64) : nullptr;
   const size_t dyn = sel.do_select ? kSelStageFused : 0;
@@ -516,20 +760,33 @@ int scan_dispatch(const void* mean, const void* var, int64_t n_c, int K, int64_t
                                       best_arm, (T*)min_zeta, min_arm, tie_cnt, partials, ticket,
                                       decision, sel);
   };
-  if (K <= 32) go(ocba_scan_kernel<T, 1>);
-  else if (K <= 64) go(ocba_scan_kernel<T, 2>);
-  else if (K <= 128) go(ocba_scan_kernel<T, 4>);
-  else if (K <= 256) go(ocba_scan_kernel<T, 8>);
-  else if (K <= 512) go(ocba_scan_kernel<T, 16>);
-  else if (K <= 1024) go(ocba_scan_kernel<T, 32>);
-  else go(ocba_scan_kernel<T, 0>);
+  const size_t esz = sizeof(T);
+  const int kpad = (K + 127) & ~127;
+  const size_t tma_smem = dyn + 4 * (size_t)kpad * esz;
+  const bool tma_ok = K > 256 && tma_smem <= 96 * 1024 && (K * esz) % 16 == 0 && (ld * esz) % 16 == 0 &&
+                      ((uintptr_t)mean % 16 == 0) && ((uintptr_t)var % 16 == 0);
+  if (tma_ok) {
+    auto kern = ocba_scan_tma_kernel<T>;
+    if (tma_smem > 48 * 1024)
+      CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem), "scan attr");
+    const int tblocks = (int)(n_c < 148 * 6 ? n_c : 148 * 6);
+    kern<<<tblocks, 128, tma_smem, s>>>((const T*)mean, (const T*)var, n_c, K, ld, arm_offset, ext_best_arm,
+                                        (const T*)ext_best_mean, (const T*)ext_best_var, best_arm, (T*)min_zeta,
+                                        min_arm, tie_cnt, partials, ticket, decision, sel, kpad);
+  } else if (K <= 32) go(ocba_scan_kernel<T, 1, 1>);
+  else if (K <= 64) go(ocba_scan_kernel<T, 2, 1>);
+  else if (K <= 128) go(ocba_scan_kernel<T, 4, 1>);
+  else if (K <= 256) go(ocba_scan_kernel<T, 8, 1>);
+  else if (K <= 512) go(ocba_scan_kernel<T, 4, 4>);
+  else if (K <= 1024) go(ocba_scan_kernel<T, 8, 4>);
+  else go(ocba_scan_kernel<T, 0, 1>);
   CRS_CUDA_TRY(cudaGetLastError(), "ocba_scan launch");
   return CRS_OK;
 }
 
 }  // namespace
 
-int64_t scan_workspace_bytes() { return (int64_t)kScanMaxBlocks * sizeof(ScanPartial) + 64; }
+int64_t scan_workspace_bytes() { return (int64_t)kScanMaxBlocks * 2 * sizeof(ScanPartial) + 64; }
 
 int launch_ocba_scan_select(const void* mean, const void* var, int64_t n_c, int K, int64_t ld,
                             int dtype, int arm_offset, const int32_t* ext_best_arm,
