@@ -15,8 +15,10 @@
 //   fail     the first block in which some y_j >= y_b ends the sample (failure);
 //   bound    if no remaining arm can reach y_b (suffix max of mu_j + ZB sd_j < y_b) the sample ends
 //            (success);
-//   compact  every 4 blocks the surviving samples of the CTA are re-packed into a dense list, so
-//            that warps stay full while most samples have already finished.
+//   pool     every lane owns one live sample and its own position in the visiting order; a lane
+//            whose sample is decided takes the next unassigned sample in the same iteration, so
+//            warps stay full although samples live for very different numbers of blocks (the
+//            per-lane plan reads are shared-memory gathers of 40 bytes per block).
 // Executed and skipped draws are reported in `stats`.
 #include <math_constants.h>
 #include "crs_common.cuh"
@@ -25,32 +27,36 @@ namespace crs {
 namespace {
 
 constexpr int kPcsThreads = 256;
-#ifndef CRS_PCS_CHUNK
-#define CRS_PCS_CHUNK 4096
-#endif
-constexpr int kPcsChunk = CRS_PCS_CHUNK;                  // samples processed per compaction cycle
-#ifndef CRS_PCS_ROUND
-#define CRS_PCS_ROUND 4
-#endif
-constexpr int kPcsRound = CRS_PCS_ROUND;         // arm blocks per round (between compactions)
+constexpr int kPcsSplitSamples = 4096;           // smallest sample range worth a work item of its own
 constexpr float kZBound = 5.77f;                 // > sqrt(-2 ln 2^-24) = 5.7683 + MUFU slack
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
 
 struct Words { uint32_t x, y, z, w; };
 
+// round keys k + r * W, computed on the host and read from the kernel-parameter constant bank:
+// the key schedule costs no instruction
+struct RoundKeys { uint32_t k0[10], k1[10]; };
+
+__host__ __device__ inline RoundKeys round_keys(uint32_t k0, uint32_t k1) {
+  RoundKeys rk;
+  for (int r = 0; r < 10; ++r) {
+    rk.k0[r] = k0 + (uint32_t)r * kPhiloxW0;
+    rk.k1[r] = k1 + (uint32_t)r * kPhiloxW1;
+  }
+  return rk;
+}
+
 __device__ __forceinline__ Words philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
+                                               const RoundKeys& rk) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
     const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
-    c0 = hi1 ^ c1 ^ k0;
+    c0 = hi1 ^ c1 ^ rk.k0[r];
     c1 = lo1;
-    c2 = hi0 ^ c3 ^ k1;
+    c2 = hi0 ^ c3 ^ rk.k1[r];
     c3 = lo0;
-    k0 += kPhiloxW0;
-    k1 += kPhiloxW1;
   }
   return Words{c0, c1, c2, c3};
 }
@@ -61,19 +67,31 @@ __device__ __forceinline__ float approx_sqrt(float x) {
   return r;
 }
 
+__device__ __forceinline__ float approx_log2(float x) {  // x >= 2^-24: never subnormal
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // (wa, wb) -> two N(0,1) draws; see oracle/philox_ref.py for the stream definition.
 __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1) {
   // (1 + m 2^-23) - (1 - 2^-24) = m 2^-23 + 2^-24 exactly: one FADD builds the open-interval uniform
   const float a = __uint_as_float(0x3f800000u | (wa >> 9)) - 0.99999994039535522f;
   const float b = __uint_as_float(0x3f800000u | (wb >> 9)) - 1.0f;
-  const float rad = approx_sqrt(-1.3862943611198906f * __log2f(a));  // sqrt(-2 ln a)
+  const float rad = approx_sqrt(-1.3862943611198906f * approx_log2(a));  // sqrt(-2 ln a)
   float sn, cs;
   __sincosf(6.2831853071795865f * b, &sn, &cs);
   z0 = rad * cs;
   z1 = rad * sn;
 }
 
-struct Alive { uint32_t sample; float yb; };
+// one candidate arm block in visiting order (48 bytes: two LDS.128 + one LDS.64 per step)
+struct __align__(16) Entry {
+  float4 mu, sd;     // centred means / std-devs of the 4 arms (-inf / 0: not a competitor)
+  float suf_next;    // max of mu + ZB sd over all LATER entries (-inf behind the last one)
+  uint32_t id;       // global arm-block id (Philox counter word)
+  float pad[2];
+};
 
 // shared-memory plan of one context: the candidate arm blocks in visiting order
 struct Plan {
@@ -83,41 +101,34 @@ struct Plan {
   uint32_t* id;    // [nb] global arm-block id (Philox counter word)
   float* key;      // [np2] sort key (threat), descending
   int* ord;        // [np2] visiting order -> entry of the arrays above
-  // the same plan permuted into visiting order (what the sampling loop reads)
-  float4* vmu;     // [nb]
-  float4* vsd;     // [nb]
   float* suf;      // [nb] suffix max of ub in visiting order
-  uint32_t* vid;   // [nb]
+  Entry* ent;      // [nb] the plan in visiting order: what the sampling loop gathers
 };
 
 #ifndef CRS_PCS_MIN_BLOCKS
-#define CRS_PCS_MIN_BLOCKS 3
+#define CRS_PCS_MIN_BLOCKS 4
 #endif
 template <typename T>
 __global__ void __launch_bounds__(kPcsThreads, CRS_PCS_MIN_BLOCKS)
 pcs_counts_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n_c, int K,
-                  int64_t ld, int64_t num_samples, uint32_t k0, uint32_t k1, uint32_t offset,
+                  int64_t ld, int64_t num_samples, const __grid_constant__ RoundKeys rk, uint32_t offset,
                   int blk_offset, int64_t ctx_offset, int splits, int nbmax, int np2,
                   uint32_t* counts, unsigned long long* stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // [ plan in visiting order | scratch of the plan build ]
   Plan pl;
-  pl.mu = reinterpret_cast<float4*>(smem_raw);
+  pl.ent = reinterpret_cast<Entry*>(smem_raw);
+  pl.mu = reinterpret_cast<float4*>(pl.ent + nbmax);
   pl.sd = pl.mu + nbmax;
-  pl.vmu = pl.sd + nbmax;
-  pl.vsd = pl.vmu + nbmax;
-  pl.ub = reinterpret_cast<float*>(pl.vsd + nbmax);
+  pl.ub = reinterpret_cast<float*>(pl.sd + nbmax);
   pl.suf = pl.ub + nbmax;
   pl.id = reinterpret_cast<uint32_t*>(pl.suf + nbmax);
-  pl.vid = pl.id + nbmax;
-  pl.key = reinterpret_cast<float*>(pl.vid + nbmax);
+  pl.key = reinterpret_cast<float*>(pl.id + nbmax);
   pl.ord = reinterpret_cast<int*>(pl.key + np2);
-  Alive* list0 = reinterpret_cast<Alive*>(pl.ord + np2);
-  Alive* list1 = list0 + kPcsChunk;
   __shared__ T s_bm[kPcsThreads / 32];
   __shared__ int s_bi[kPcsThreads / 32];
   __shared__ int s_nb, s_best;
   __shared__ float s_sdb;
-  __shared__ int s_cnt[2];
   __shared__ unsigned int s_hits;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t items = n_c * splits;
@@ -230,9 +241,9 @@ pcs_counts_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t
     for (int e = tid; e < nb; e += kPcsThreads) {
       const int idx = pl.ord[e];
       pl.suf[e] = pl.ub[idx];
-      pl.vmu[e] = pl.mu[idx];
-      pl.vsd[e] = pl.sd[idx];
-      pl.vid[e] = pl.id[idx];
+      pl.ent[e].mu = pl.mu[idx];
+      pl.ent[e].sd = pl.sd[idx];
+      pl.ent[e].id = pl.id[idx];
     }
     __syncthreads();
     for (int off = 1; off < nb; off <<= 1) {
@@ -245,83 +256,60 @@ pcs_counts_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t
       for (int e = tid; e < nb; e += kPcsThreads, ++cnt) pl.suf[e] = vals[cnt];
       __syncthreads();
     }
+    for (int e = tid; e < nb; e += kPcsThreads) pl.ent[e].suf_next = e + 1 < nb ? pl.suf[e + 1] : -CUDART_INF_F;
+    __syncthreads();
     const uint32_t cw = (uint32_t)(c + ctx_offset);
     const int bslot = best & 3;
 
-    // blocks [e0, e1) of the plan for one sample; returns 0 = undecided, 1 = success, 2 = failure
-    auto run = [&](uint32_t smp, float& yb, int e0, int e1) -> int {
-      for (int e = e0; e < e1; ++e) {
-        if (e > 0 && pl.suf[e] < yb) return 1;  // nothing left can reach y_b
-        const Words w = philox4x32_10(smp, cw, pl.vid[e], offset, k0, k1);
-        float z[4];
-        box_muller(w.x, w.y, z[0], z[1]);
-        box_muller(w.z, w.w, z[2], z[3]);
-        drawn += 4;
-        if (e == 0) yb = sd_b * z[bslot];
-        const float4 mu = pl.vmu[e], sd = pl.vsd[e];
-        const float top = fmaxf(fmaxf(fmaf(sd.x, z[0], mu.x), fmaf(sd.y, z[1], mu.y)),
-                                fmaxf(fmaf(sd.z, z[2], mu.z), fmaf(sd.w, z[3], mu.w)));
-        if (top >= yb) return 2;  // delta = y_b - max_j y_j <= 0: func_I = 0
-      }
-      return e1 >= nb ? 1 : 0;
-    };
-
-    // ---- sampling with compaction ------------------------------------------------------------
-    unsigned int hits = 0;
-    const unsigned long long drawn_before = drawn;
-    for (int64_t base = s_lo; base < s_hi; base += kPcsChunk) {
-      const int chn = (int)min((int64_t)kPcsChunk, s_hi - base);
-      if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
-      __syncthreads();
-      // round 0: every sample of the chunk, blocks [0, R)
-      for (int off = 0; off < chn; off += kPcsThreads) {
-        const int i = off + tid;
-        int st = 3;  // inactive lane
-        float yb = 0.f;
-        const uint32_t smp = (uint32_t)(base + i);
-        if (i < chn) st = run(smp, yb, 0, min(kPcsRound, nb));
-        hits += st == 1 ? 1u : 0u;
-        const unsigned ball = __ballot_sync(kFull, st == 0);
-        int pos = 0;
-        if (lane == 0 && ball) pos = atomicAdd(&s_cnt[0], __popc(ball));
-        pos = __shfl_sync(kFull, pos, 0) + __popc(ball & ((1u << lane) - 1u));
-        if (st == 0) list0[pos] = Alive{smp, yb};
-      }
-      __syncthreads();
-      // later rounds: only the survivors, densely packed
-      int cur = 0;
-      for (int e0 = kPcsRound; e0 < nb; e0 += kPcsRound) {
-        const int n_al = s_cnt[cur];
-        if (n_al == 0) break;  // uniform
-        const Alive* src = cur ? list1 : list0;
-        Alive* dst = cur ? list0 : list1;
-        for (int off = 0; off < n_al; off += kPcsThreads) {
-          const int i = off + tid;
-          int st = 3;
-          Alive al = Alive{0u, 0.f};
-          if (i < n_al) {
-            al = src[i];
-            st = run(al.sample, al.yb, e0, min(e0 + kPcsRound, nb));
-          }
-          hits += st == 1 ? 1u : 0u;
-          const unsigned ball = __ballot_sync(kFull, st == 0);
-          int pos = 0;
-          if (lane == 0 && ball) pos = atomicAdd(&s_cnt[cur ^ 1], __popc(ball));
-          pos = __shfl_sync(kFull, pos, 0) + __popc(ball & ((1u << lane) - 1u));
-          if (st == 0) dst[pos] = al;
+    // ---- sampling: a pool of 32 live samples per warp ---------------------------------------
+    // The warp owns a contiguous range of the item's samples; `wnext` is warp-uniform.  The step
+    // is branch-free: lanes without a sample (only at the very end) compute on entry 0 and are
+    // masked out of the tallies.
+    const unsigned int n_item = (unsigned int)(s_hi - s_lo);
+    const unsigned int w_hi = (unsigned int)((uint64_t)n_item * (warp + 1) / (kPcsThreads / 32));
+    unsigned int wnext = (unsigned int)((uint64_t)n_item * warp / (kPcsThreads / 32));
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    unsigned int hits = 0, steps = 0;
+    uint32_t smp = 0;
+    float yb = 0.f;
+    int e = 0;
+    bool active = false;
+    for (;;) {
+      const unsigned act = __ballot_sync(kFull, active);
+      if (act != kFull && wnext < w_hi) {  // hand the next unassigned samples to the idle lanes
+        const unsigned int my = wnext + __popc(~act & lt_mask);
+        if (!active && my < w_hi) {
+          smp = (uint32_t)(s_lo + my);
+          active = true;
         }
-        __syncthreads();
-        if (tid == 0) s_cnt[cur] = 0;
-        cur ^= 1;
-        __syncthreads();
+        wnext += __popc(~act);
+      } else if (!act) {
+        break;
       }
+      const Entry* en = pl.ent + e;
+      const float4 mu = en->mu, sd = en->sd;
+      const float2 sv = *reinterpret_cast<const float2*>(&en->suf_next);
+      const Words w = philox4x32_10(smp, cw, __float_as_uint(sv.y), offset, rk);
+      float z0, z1, z2, z3;
+      box_muller(w.x, w.y, z0, z1);
+      box_muller(w.z, w.w, z2, z3);
+      const float zb = (bslot & 2) ? ((bslot & 1) ? z3 : z2) : ((bslot & 1) ? z1 : z0);
+      yb = e == 0 ? sd_b * zb : yb;
+      const float top = fmaxf(fmaxf(fmaf(sd.x, z0, mu.x), fmaf(sd.y, z1, mu.y)),
+                              fmaxf(fmaf(sd.z, z2, mu.z), fmaf(sd.w, z3, mu.w)));
+      const bool fail = top >= yb;   // delta = y_b - max_j y_j <= 0: func_I = 0
+      const bool done = sv.x < yb;   // nothing left can reach y_b (or nothing left at all)
+      steps += active ? 1u : 0u;
+      hits += (active && !fail && done) ? 1u : 0u;
+      active = active && !(fail || done);
+      e = active ? e + 1 : 0;
     }
+    drawn += 4ull * steps;
     hits = warp_sum(hits);
     if (lane == 0 && hits) atomicAdd(&s_hits, hits);
     __syncthreads();
     if (tid == 0 && s_hits) atomicAdd(counts + c, s_hits);
     if (tid == 0) skipped += (long long)(s_hi - s_lo) * K;  // nominal draws of this item
-    (void)drawn_before;
   }
   if (stats) {
     drawn = warp_sum(drawn);
@@ -337,7 +325,7 @@ __global__ void philox_words_kernel(const uint32_t* __restrict__ ctr, int64_t n,
                                     uint32_t k1, uint32_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const Words w = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], k0, k1);
+  const Words w = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], round_keys(k0, k1));
   out[4 * i] = w.x;
   out[4 * i + 1] = w.y;
   out[4 * i + 2] = w.z;
@@ -356,22 +344,22 @@ int launch_pcs_counts(const void* mean, const void* var, int64_t n_c, int K, int
   CRS_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)n_c, s), "pcs memset");
   if (stats) CRS_CUDA_TRY(cudaMemsetAsync(stats, 0, 2 * sizeof(uint64_t), s), "pcs memset stats");
   if (num_samples == 0) return CRS_OK;
-  const int nbmax = (K + 3) / 4;
+  const int nbmax = ((K + 3) / 4 + 3) & ~3;  // array stride: keeps every float4 array 16-byte aligned
   int np2 = 1;
   while (np2 < nbmax) np2 <<= 1;
-  const size_t smem = (size_t)nbmax * (4 * 16 + 4 * 4) + (size_t)np2 * 8 + 2 * (size_t)kPcsChunk * sizeof(Alive);
+  const size_t smem = (size_t)nbmax * (sizeof(Entry) + 2 * 16 + 3 * 4) + (size_t)np2 * 8;
   // enough work items to fill the machine: split the samples of a context when contexts are few
-  const int64_t max_splits = (num_samples + kPcsChunk - 1) / kPcsChunk;
+  const int64_t max_splits = (num_samples + kPcsSplitSamples - 1) / kPcsSplitSamples;
   int64_t splits = (148 * 4 + n_c - 1) / n_c;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   const int64_t items = n_c * splits;
   const int blocks = (int)(items < 148 * 8 ? items : 148 * 8);
-  const uint32_t k0 = (uint32_t)(seed & 0xffffffffu), k1 = (uint32_t)(seed >> 32);
+  const RoundKeys rk = round_keys((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
   auto go = [&](auto kern, auto* m, auto* v) -> int {
     if (smem > 48 * 1024)
       CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pcs attr");
-    kern<<<blocks, kPcsThreads, smem, s>>>(m, v, n_c, K, ld, num_samples, k0, k1, offset, arm_offset >> 2,
+    kern<<<blocks, kPcsThreads, smem, s>>>(m, v, n_c, K, ld, num_samples, rk, offset, arm_offset >> 2,
                                            ctx_offset, (int)splits, nbmax, np2, counts,
                                            (unsigned long long*)stats);
     CRS_CUDA_TRY(cudaGetLastError(), "pcs_counts launch");

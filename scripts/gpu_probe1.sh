@@ -1,6 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python scripts/sqrt_test.py 2>&1 | tail -3
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+python -m pytest tests -m gpu -x -q -k "pcs or PCS" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
 for cfg in c3 c5 c4; do python scripts/pcs_run.py 65536 $cfg 2>&1 | tail -1; done
-python scripts/pcs_run.py 65536 c4 f64 2>&1 | tail -1
