@@ -27,6 +27,7 @@ namespace crs {
 namespace {
 
 constexpr int kPcsThreads = 256;
+constexpr int kPcsTail = 8;                       // survivors per warp handed to the flattened tail
 constexpr int kPcsSplitSamples = 4096;           // smallest sample range worth a work item of its own
 constexpr float kZBound = 5.77f;                 // > sqrt(-2 ln 2^-24) = 5.7683 + MUFU slack
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
@@ -67,6 +68,12 @@ __device__ __forceinline__ float approx_sqrt(float x) {
   return r;
 }
 
+__device__ __forceinline__ uint32_t mantissa_bits(uint32_t w) {
+  uint32_t r;
+  asm("mad.hi.u32 %0, %1, 0x800000, 0x3f800000;" : "=r"(r) : "r"(w));
+  return r;
+}
+
 __device__ __forceinline__ float approx_log2(float x) {  // x >= 2^-24: never subnormal
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -76,8 +83,10 @@ __device__ __forceinline__ float approx_log2(float x) {  // x >= 2^-24: never su
 // (wa, wb) -> two N(0,1) draws; see oracle/philox_ref.py for the stream definition.
 __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1) {
   // (1 + m 2^-23) - (1 - 2^-24) = m 2^-23 + 2^-24 exactly: one FADD builds the open-interval uniform
-  const float a = __uint_as_float(0x3f800000u | (wa >> 9)) - 0.99999994039535522f;
-  const float b = __uint_as_float(0x3f800000u | (wb >> 9)) - 1.0f;
+  // 0x3f800000 | (w >> 9) as one multiply-add (hi32(w * 2^23) + 0x3f800000): runs on the FMA pipe and
+  // keeps the ALU pipe — the busiest one of this kernel — for the Philox XORs
+  const float a = __uint_as_float(mantissa_bits(wa)) - 0.99999994039535522f;
+  const float b = __uint_as_float(mantissa_bits(wb)) - 1.0f;
   const float rad = approx_sqrt(-1.3862943611198906f * approx_log2(a));  // sqrt(-2 ln a)
   float sn, cs;
   __sincosf(6.2831853071795865f * b, &sn, &cs);
@@ -269,42 +278,71 @@ pcs_counts_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t
     const unsigned int w_hi = (unsigned int)((uint64_t)n_item * (warp + 1) / (kPcsThreads / 32));
     unsigned int wnext = (unsigned int)((uint64_t)n_item * warp / (kPcsThreads / 32));
     const unsigned int lt_mask = (1u << lane) - 1u;
-    unsigned int hits = 0, steps = 0;
+    unsigned int hits = 0, steps = 0, wsteps = 0;  // wsteps: warp-uniform count of pooled lane-steps
     uint32_t smp = 0;
     float yb = 0.f;
     int e = 0;
     bool active = false;
+    // one visit of plan entry `en` by sample `sm`: the 4 draws, max over the competitors of the block
+    auto visit = [&](uint32_t sm, const Entry* en, float& suf_next, float& zb) -> float {
+      const float4 mu = en->mu, sd = en->sd;
+      const float2 sv = *reinterpret_cast<const float2*>(&en->suf_next);
+      const Words w = philox4x32_10(sm, cw, __float_as_uint(sv.y), offset, rk);
+      float z0, z1, z2, z3;
+      box_muller(w.x, w.y, z0, z1);
+      box_muller(w.z, w.w, z2, z3);
+      zb = (bslot & 2) ? ((bslot & 1) ? z3 : z2) : ((bslot & 1) ? z1 : z0);
+      suf_next = sv.x;
+      return fmaxf(fmaxf(fmaf(sd.x, z0, mu.x), fmaf(sd.y, z1, mu.y)),
+                   fmaxf(fmaf(sd.z, z2, mu.z), fmaf(sd.w, z3, mu.w)));
+    };
+    unsigned act;
     for (;;) {
-      const unsigned act = __ballot_sync(kFull, active);
+      act = __ballot_sync(kFull, active);
       if (act != kFull && wnext < w_hi) {  // hand the next unassigned samples to the idle lanes
         const unsigned int my = wnext + __popc(~act & lt_mask);
         if (!active && my < w_hi) {
           smp = (uint32_t)(s_lo + my);
           active = true;
         }
+        wsteps += min((unsigned int)__popc(~act), w_hi - wnext);
         wnext += __popc(~act);
-      } else if (!act) {
-        break;
+      } else if (__popc(act) <= kPcsTail) {
+        // out of fresh samples and few survivors left: finish them in the flattened tail below —
+        // unless one of them has not drawn its y_b yet (entry 0): then one more pooled step
+        if (!__any_sync(kFull, active && e == 0)) break;
       }
-      const Entry* en = pl.ent + e;
-      const float4 mu = en->mu, sd = en->sd;
-      const float2 sv = *reinterpret_cast<const float2*>(&en->suf_next);
-      const Words w = philox4x32_10(smp, cw, __float_as_uint(sv.y), offset, rk);
-      float z0, z1, z2, z3;
-      box_muller(w.x, w.y, z0, z1);
-      box_muller(w.z, w.w, z2, z3);
-      const float zb = (bslot & 2) ? ((bslot & 1) ? z3 : z2) : ((bslot & 1) ? z1 : z0);
+      wsteps += __popc(act);  // lanes stepping in this iteration (+ the refilled ones counted above)
+      float suf_next, zb;
+      const float top = visit(smp, pl.ent + e, suf_next, zb);
       yb = e == 0 ? sd_b * zb : yb;
-      const float top = fmaxf(fmaxf(fmaf(sd.x, z0, mu.x), fmaf(sd.y, z1, mu.y)),
-                              fmaxf(fmaf(sd.z, z2, mu.z), fmaf(sd.w, z3, mu.w)));
-      const bool fail = top >= yb;   // delta = y_b - max_j y_j <= 0: func_I = 0
-      const bool done = sv.x < yb;   // nothing left can reach y_b (or nothing left at all)
-      steps += active ? 1u : 0u;
+      const bool fail = top >= yb;       // delta = y_b - max_j y_j <= 0: func_I = 0
+      const bool done = suf_next < yb;   // nothing left can reach y_b (or nothing left at all)
       hits += (active && !fail && done) ? 1u : 0u;
       active = active && !(fail || done);
       e = active ? e + 1 : 0;
     }
-    drawn += 4ull * steps;
+    // flattened tail: the few long-lived samples left each spread their remaining entries over the
+    // 32 lanes.  Entries behind the point where the sequential visit would have stopped cannot
+    // fail (their mu + ZB sd is below y_b), so the outcome — and every count — is unchanged.
+    while (act) {
+      const int src = __ffs(act) - 1;
+      act &= act - 1;
+      const uint32_t t_smp = __shfl_sync(kFull, smp, src);
+      const float t_yb = __shfl_sync(kFull, yb, src);
+      for (int base = __shfl_sync(kFull, e, src); base < nb; base += 32) {
+        const int ee = base + lane;
+        const bool valid = ee < nb;
+        float suf_next, zb;
+        const float top = visit(t_smp, pl.ent + (valid ? ee : nb - 1), suf_next, zb);
+        steps += valid ? 1u : 0u;
+        const unsigned fm = __ballot_sync(kFull, valid && top >= t_yb);
+        const unsigned dm = __ballot_sync(kFull, valid && suf_next < t_yb);
+        if (fm) break;
+        if (dm) { hits += lane == 0 ? 1u : 0u; break; }
+      }
+    }
+    drawn += 4ull * steps + (lane == 0 ? 4ull * wsteps : 0ull);
     hits = warp_sum(hits);
     if (lane == 0 && hits) atomicAdd(&s_hits, hits);
     __syncthreads();
@@ -350,11 +388,11 @@ int launch_pcs_counts(const void* mean, const void* var, int64_t n_c, int K, int
   const size_t smem = (size_t)nbmax * (sizeof(Entry) + 2 * 16 + 3 * 4) + (size_t)np2 * 8;
   // enough work items to fill the machine: split the samples of a context when contexts are few
   const int64_t max_splits = (num_samples + kPcsSplitSamples - 1) / kPcsSplitSamples;
-  int64_t splits = (148 * 4 + n_c - 1) / n_c;
+  int64_t splits = (148 * CRS_PCS_MIN_BLOCKS + n_c - 1) / n_c;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   const int64_t items = n_c * splits;
-  const int blocks = (int)(items < 148 * 8 ? items : 148 * 8);
+  const int blocks = (int)(items < 148 * CRS_PCS_MIN_BLOCKS * 2 ? items : 148 * CRS_PCS_MIN_BLOCKS * 2);
   const RoundKeys rk = round_keys((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
   auto go = [&](auto kern, auto* m, auto* v) -> int {
     if (smem > 48 * 1024)
