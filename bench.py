@@ -13,8 +13,14 @@ state (crs_gp_prepare, all arms), ModelListGP posterior over the arm x context g
   e2e   : decisions/s through the public drop-in `contextual_rs_b200.gao_modellist(model,
           context_set)` with the context set in pinned HOST memory: host->device copy of the
           contexts and device->host read of the decision inside every timed step.
-  N > 1 : the context set is sharded over the ranks (one process per GPU, NCCL); every decision
-          ends in one 64-byte-per-rank all-gather.  Fixed total work -> "strong" scaling.
+  N > 1 : default workload (c2, a 65-us decision): every rank runs its own independent replication
+          of the decision stream (own seeded problem of the same shape, no collective on the data
+          path — the way the reference's experiments use many workers) -> "weak" scaling, value =
+          decisions of all ranks / max-over-ranks time.  With --workload c3|c4|c5 (or --shard) ONE
+          decision is sharded over the ranks by contexts (NCCL: one 64-byte-per-rank all-gather per
+          decision) -> "strong" scaling.  The `pcs` (config 3) and `headline` (config 4: decision +
+          2^16-sample PCS over 1,000 arms x 65,536 contexts, target < 10 ms on 8 GPUs) sub-objects
+          are always context-sharded over all ranks.
 
 The L2 is flushed (256 MiB write) between timed steps; each step is bracketed by its own pair of
 CUDA events on the launching stream and the per-step durations are summed.
@@ -180,8 +186,8 @@ def run_reference(args, name):
     print(json.dumps({
         "impl": "reference", "metric": "gp_c_ocba_decisions_per_sec", "value": val, "unit": "decisions/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt_full * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[name]},
+        "higher_is_better": True, "scaling": "weak" if name == "c2" else "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOADS[name]},
         "cpu_baseline": {"value": val, "unit": "decisions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -190,13 +196,6 @@ def run_reference(args, name):
 
 # ------------------------------------------------------------------------------------------- PCS
 PCS_CONFIG = "c3: generalized-PCS MC estimate, 2^16 samples, 256 arms x 8,192 contexts, fp32"
-
-
-def pcs_issue_peak(sm_mhz: float) -> float:
-    """Issue-slot roofline of the PCS kernel in EXECUTED draws/s: 148 SMs x 4 schedulers x 32 lanes
-    x clock / 21.4 SASS instructions per N(0,1) draw — the instruction cost of Philox4x32-10 +
-    Box-Muller + FMA + max measured on the brute-force version of the kernel (ncu, profiles/r01b)."""
-    return 148 * 4 * 32 * sm_mhz * 1e6 / 21.4
 
 
 def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
@@ -252,10 +251,12 @@ def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
            "ms_per_estimate": t_step * 1e3, "executed_draws_per_sec": drawn / t_step,
            "executed_fraction": drawn / (drawn + skipped), "pcs_mean": float(total) / (num_samples * n_c),
            "gpu_launches": reps + 1}
-    peak = pcs_issue_peak(1965.0)
+    from contextual_rs_b200.peaks import measure_pcs_draw_peak
+    peak = measure_pcs_draw_peak(dev)  # live micro-kernel: the bare draw sequence on registers
     out["roofline"] = {"kernel": "pcs_counts_kernel", "bound": "issue", "achieved": drawn / t_step / world / 1e9,
                        "peak": peak / 1e9, "unit": "G draws/s", "frac": drawn / t_step / world / peak, "traffic": None,
-                       "peak_source": "148 SM x 4 schedulers x 32 lanes x 1.965 GHz / 21.4 instr per draw (SASS, ncu)"}
+                       "peak_source": "measured in this run by crs_peak_probe kind 5 (Philox4x32-10 + 2 Box-Muller + 4 FMA + max "
+                                      "per 4 draws on registers, no memory, no control flow); achieved = EXECUTED draws/s"}
     if cpu and world == 1 and rank == 0:
         from oracle import pcs_oracle
         torch.set_num_threads(os.cpu_count() or 1)
@@ -275,6 +276,54 @@ def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
     return out
 
 
+# -------------------------------------------------------------------------------------- headline
+HEADLINE_CONFIG = ("c4: one GP-C-OCBA decision (fp64, cold caches) + one 2^16-sample generalized-PCS estimate over "
+                   "1,000 arms x 65,536 Sobol contexts, 8-D, 18 obs/arm")
+
+
+def run_headline(dev, world, rank, reps=3, num_samples=1 << 16):
+    """BASELINE.json's target: decision + 2^16-sample PCS over 1,000 arms x 65,536 contexts in
+    under 10 ms on 8 GPUs.  Contexts are sharded over the ranks; a step is prepare(all arms) +
+    grid + scan/select + 64-byte all-gather, then PCS counts + one scalar all-reduce."""
+    import torch.distributed as dist
+    import contextual_rs_b200 as crs
+    from contextual_rs_b200.sharded import ContextShardedDecider, REC_CONTEXT, REC_NEXT_ARM
+    from contextual_rs_b200.synthetic import make_config
+    desc, ctx = make_config("c4")
+    K, n_c = len(desc["train_X"]), ctx.shape[0]
+    model = crs.B200ModelListGP(desc, device=dev, dtype=torch.float64)
+    decider = ContextShardedDecider(model, ctx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rec = decider.decide(prepare_arms=(0, K))
+    pcs = decider.pcs_mean(num_samples, seed=0, offset=0)
+    barrier()
+    t_dec, t_pcs = [], []
+    for i in range(reps):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        rec = decider.decide(prepare_arms=(0, K))
+        e1.record()
+        pcs = decider.pcs_mean(num_samples, seed=0, offset=1 + i)
+        e2.record()
+        e2.synchronize()
+        t_dec.append(e0.elapsed_time(e1))
+        t_pcs.append(e1.elapsed_time(e2))
+        barrier()
+    t = torch.tensor([sum(t_dec) / reps, sum(t_pcs) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    d_ms, p_ms = t.tolist()
+    return {"workload": HEADLINE_CONFIG, "n_gpus": world, "sharding": f"contexts/{world}" if world > 1 else "none",
+            "ms_per_step": d_ms + p_ms, "decision_ms": d_ms, "pcs_ms": p_ms, "target_ms": 10.0, "target_gpus": 8,
+            "steps": reps, "next_arm": int(rec[REC_NEXT_ARM]), "next_context": int(rec[REC_CONTEXT]),
+            "pcs_mean": float(pcs), "pcs_equivalent_draws_per_sec": float(num_samples) * n_c * K / (p_ms * 1e-3)}
+
+
 # ------------------------------------------------------------------------------------------- GPU
 def main():
     ap = argparse.ArgumentParser()
@@ -286,7 +335,8 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (profiling only)")
-    ap.add_argument("--no-pcs", action="store_true", help="skip the PCS (config 3) sub-benchmark")
+    ap.add_argument("--no-pcs", action="store_true", help="skip the PCS (config 3) and headline (config 4) sub-benchmarks")
+    ap.add_argument("--shard", action="store_true", help="N > 1: shard ONE decision over the ranks even for c2")
     args = ap.parse_args()
     name = args.workload
     if args.impl == "reference":
@@ -312,7 +362,10 @@ def main():
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     w = 8 if dtype == torch.float64 else 4
 
-    desc, ctx = make_config(name)
+    # N > 1: c2 runs one independent replication per rank (weak scaling); the larger workloads
+    # shard one decision over the ranks by contexts (strong scaling)
+    sharded = world > 1 and (name != "c2" or args.shard)
+    desc, ctx = make_config(name) if (sharded or world == 1) else make_config(name, seed=rank)
     K, n_c, d = len(desc["train_X"]), ctx.shape[0], ctx.shape[1]
     n_obs = desc["train_X"][0].shape[0]
     model = crs.B200ModelListGP(desc, device=dev, dtype=dtype)
@@ -325,10 +378,15 @@ def main():
         if not args.no_flush:
             flush_buf.fill_(1)
 
-    begin, end = shard_bounds(n_c, world, rank)
+    if sharded:
+        begin, end = shard_bounds(n_c, world, rank)
+        decider = ContextShardedDecider(model, ctx)
+        ctx_dev = decider.local_ctx
+    else:
+        begin, end = 0, n_c
+        decider = None
+        ctx_dev = ctx.to(device=dev, dtype=dtype).contiguous()
     n_loc = end - begin
-    decider = ContextShardedDecider(model, ctx)
-    ctx_dev = decider.local_ctx
     ws = model.workspace(max(n_loc, 1))
     stream = _lib.stream_ptr(dev)
     st = C.byref(model.state)
@@ -340,13 +398,13 @@ def main():
             _lib.check(lib.crs_posterior_grid(st, ctx_dev.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
                                               ws["var"].data_ptr(), K, 0, stream))
             _scan_select(lib, model, ws, n_loc, 0, 2.0, stream, ctx_ptr=ctx_dev.data_ptr())
-        if world > 1:
+        if sharded:
             dist.all_gather_into_tensor(decider._gather, ws["decision"] if n_loc else decider._empty)
 
     ctx_host = ctx.to(dtype).pin_memory()
 
     def e2e_step():
-        if world == 1:
+        if not sharded:
             from contextual_rs_b200.contextual_rs_strategies import decide
             dec = decide(model, ctx_host, True, 0, 2.0, prepare_arms=(0, K))
             return dec.next_arm, dec.context
@@ -418,7 +476,8 @@ def main():
     prep_avg = sum(prep_ms) / len(prep_ms)
 
     if rank == 0:
-        value = K_steps / t_dev
+        mult = 1 if (sharded or world == 1) else world  # replicas: every rank made K_steps decisions
+        value = mult * K_steps / t_dev
         flops = algorithmic_flops(K, n_loc, n_obs, d)
         from contextual_rs_b200.peaks import measure_fma_peak
         fp64_peak = measure_fma_peak(0 if dtype == torch.float64 else 1, dev)  # live FMA micro-kernel
@@ -427,15 +486,17 @@ def main():
         out = {
             "metric": "gp_c_ocba_decisions_per_sec", "value": value, "unit": "decisions/s",
             "n_gpus": world, "steps": K_steps, "warmup": W, "ms_per_step": t_dev / K_steps * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": WORKLOADS[name], "arms": K, "contexts": n_c, "dim": d, "obs_per_arm": n_obs,
-                       "sharding": f"contexts/{world}" if world > 1 else "none",
+                       "sharding": (f"contexts/{world}: one decision sharded over the ranks, 64-byte all-gather per decision"
+                                    if sharded else (f"replicas x{world}: one independent decision stream per GPU, no "
+                                                     "collective on the data path" if world > 1 else "none")),
                        "l2": "flushed between timed steps (256 MiB write)" if not args.no_flush else "not flushed",
                        "step": "3 kernels: prepare(all arms) + posterior grid + fused zeta scan / OCBA select"},
-            "e2e": {"value": K_steps / t_e2e, "unit": "decisions/s", "ms_per_step": t_e2e / K_steps * 1e3,
-                    "h2d_bytes_per_step": int(n_c * d * w), "d2h_bytes_per_step": 64 * world},
-            "gpu_launches": 3 * K_steps + 3 * K_steps + 3 * ksteps,
+            "e2e": {"value": mult * K_steps / t_e2e, "unit": "decisions/s", "ms_per_step": t_e2e / K_steps * 1e3,
+                    "h2d_bytes_per_step": int(n_c * d * w) * mult, "d2h_bytes_per_step": 64 * world},
+            "gpu_launches": (3 * K_steps + 3 * K_steps + 3 * ksteps) * mult,
             "roofline": {"kernel": "posterior_grid_kernel", "bound": "fp64_fma" if dtype == torch.float64 else "fp32_fma",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                          "traffic": None, "avg_launch_ms": grid_avg,
@@ -462,13 +523,16 @@ def main():
                 "value": 1.0 / (dt * scale), "unit": "decisions/s", "cores": torch.get_num_threads(), "kind": "port",
                 "sample": f"{steps} decisions, oracle '{variant}' variant on {sub}/{n_c} contexts x {K} arms, "
                           f"time scaled x{scale:.0f}; PyTorch CPU, {torch.get_num_threads()} threads"}
-    pcs = None
+    pcs = headline = None
     if not args.no_pcs and name == "c2":
+        del flush_buf
         pcs = run_pcs(dev, world, rank, cpu=not args.no_cpu_baseline)
+        headline = run_headline(dev, world, rank)
     if rank == 0:
         if pcs is not None:
             out["pcs"] = pcs
-            out["gpu_launches"] += pcs["gpu_launches"]
+            out["headline"] = headline
+            out["gpu_launches"] += pcs["gpu_launches"] + 4 * 4 * world  # headline: 4 kernels x (1 + 3) steps per rank
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -144,6 +144,7 @@ int launch_pcs_counts(const void* mean, const void* var, int64_t n_c, int K, int
                       int64_t ctx_offset, uint32_t* counts, uint64_t* stats, cudaStream_t s);
 int launch_debug_corr(const double* r2, int64_t n, int kernel, int variant, double* out, cudaStream_t s);
 int launch_peak_probe(int kind, int iters, int blocks, void* out, cudaStream_t s);
+int launch_pcs_probe(int iters, int blocks, void* out, cudaStream_t s);
 int launch_philox_words(const uint32_t* ctr, int64_t n, uint32_t k0, uint32_t k1, uint32_t* out,
                         cudaStream_t s);
 

@@ -359,6 +359,26 @@ pcs_counts_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t
   }
 }
 
+// Peak probe for the PCS roofline (crs_peak_probe kind 5): the bare draw sequence of one plan
+// step — Philox4x32-10, two Box-Muller pairs, 4 FMA, max, compare — on register operands, no
+// memory, no control flow besides the loop.  draws = blocks * 256 * iters * 4.
+__global__ void __launch_bounds__(kPcsThreads)
+pcs_probe_kernel(int iters, const __grid_constant__ RoundKeys rk, float* out) {
+  const uint32_t smp = blockIdx.x * kPcsThreads + threadIdx.x;
+  const float4 mu = make_float4(-0.1f, -0.2f, -0.3f, -0.4f), sd = make_float4(1.f, 1.1f, 1.2f, 1.3f);
+  unsigned int hits = 0;
+  for (int it = 0; it < iters; ++it) {
+    const Words w = philox4x32_10(smp, 7u, (uint32_t)it, 0u, rk);
+    float z0, z1, z2, z3;
+    box_muller(w.x, w.y, z0, z1);
+    box_muller(w.z, w.w, z2, z3);
+    const float top = fmaxf(fmaxf(fmaf(sd.x, z0, mu.x), fmaf(sd.y, z1, mu.y)),
+                            fmaxf(fmaf(sd.z, z2, mu.z), fmaf(sd.w, z3, mu.w)));
+    hits += top >= 3.0f ? 1u : 0u;
+  }
+  if (hits == 0xffffffffu) out[0] = 1.f;  // keep the loop alive
+}
+
 __global__ void philox_words_kernel(const uint32_t* __restrict__ ctr, int64_t n, uint32_t k0,
                                     uint32_t k1, uint32_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -406,6 +426,12 @@ int launch_pcs_counts(const void* mean, const void* var, int64_t n_c, int K, int
   if (dtype == CRS_F64) return go(pcs_counts_kernel<double>, (const double*)mean, (const double*)var);
   if (dtype == CRS_F32) return go(pcs_counts_kernel<float>, (const float*)mean, (const float*)var);
   return CRS_ERR_INVALID_ARG;
+}
+
+int launch_pcs_probe(int iters, int blocks, void* out, cudaStream_t s) {
+  pcs_probe_kernel<<<blocks, kPcsThreads, 0, s>>>(iters, round_keys(1u, 2u), (float*)out);
+  CRS_CUDA_TRY(cudaGetLastError(), "pcs_probe launch");
+  return CRS_OK;
 }
 
 int launch_philox_words(const uint32_t* ctr, int64_t n, uint32_t k0, uint32_t k1, uint32_t* out,

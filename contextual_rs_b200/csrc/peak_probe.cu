@@ -1,6 +1,7 @@
 // crs_peak_probe: micro-kernels that measure the pipe peaks the roofline fractions are quoted
 // against (MEASURED_PEAKS.json has no fp64 / fp32-FMA / Philox figure): kind 0 = FP64 FMA,
-// 1 = FP32 FMA, 2 = Philox4x32-10 + Box-Muller + FMA + max (the PCS inner loop, no screening).
+// 1 = FP32 FMA, 2 = FP64 mma.sync m8n8k4, 5 = Philox4x32-10 + Box-Muller + FMA + max (the bare PCS
+// draw sequence, pcs_philox.cu).
 // Each thread runs `iters` rounds of 16 independent accumulator chains (kinds 0/1).
 #include "crs_common.cuh"
 
@@ -57,6 +58,7 @@ int launch_peak_probe(int kind, int iters, int blocks, void* out, cudaStream_t s
   else if (kind == 3) fma_probe_kernel<double, 1><<<blocks, 256, 0, s>>>(iters, 1.0, (double*)out);
   else if (kind == 4) fma_probe_kernel<double, 2><<<blocks, 256, 0, s>>>(iters, 1.0, (double*)out);
   else if (kind == 2) dmma_probe_kernel<<<blocks, 256, 0, s>>>(iters, 1.0, (double*)out);  // 16 DMMA / iter / warp
+  else if (kind == 5) return launch_pcs_probe(iters, blocks, out, s);  // Philox + Box-Muller + FMA + max
   else return CRS_ERR_INVALID_ARG;
   CRS_CUDA_TRY(cudaGetLastError(), "peak_probe launch");
   return CRS_OK;

@@ -222,7 +222,9 @@ CRS_API int crs_debug_corr(const double* r2, int64_t n, int32_t kernel, int32_t 
 
 /* Pipe-peak probe for the roofline denominators that MEASURED_PEAKS.json lacks: `blocks` CTAs of
  * 256 threads each run `iters` x 64 dependent-chain FMAs on 16 independent accumulators
- * (kind 0 = FP64, 1 = FP32): flops = blocks * 256 * iters * 64 * 2.  out: >= 8 bytes, device. */
+ * (kind 0 = FP64, 1 = FP32): flops = blocks * 256 * iters * 64 * 2; kind 2 = FP64 mma.sync m8n8k4;
+ * kind 5 = the bare PCS draw sequence (Philox4x32-10 + 2 Box-Muller + 4 FMA + max per iteration,
+ * registers only): draws = blocks * 256 * iters * 4.  out: >= 8 bytes, device. */
 CRS_API int crs_peak_probe(int32_t kind, int32_t iters, int32_t blocks, void* out, void* stream);
 
 /*
