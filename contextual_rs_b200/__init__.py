@@ -1,5 +1,6 @@
 """contextual_rs_b200 — B200 (sm_100a) implementation of contextual_rs's per-iteration decision
-hot path: ModelListGP grid posterior, GP-C-OCBA allocation and Monte-Carlo generalized PCS,
+hot path: ModelListGP grid posterior, GP-C-OCBA allocation, Monte-Carlo generalized PCS and the
+LEVI grid acquisition,
 behind the reference's own function signatures.  All compute is in ``libcrs_b200.so``
 (hand-written CUDA, C ABI in ``include/crs_b200.h``); there is no CPU fallback.
 """
@@ -7,8 +8,10 @@ from .model import B200ModelListGP, B200Posterior, from_botorch
 from .contextual_rs_strategies import gao_modellist
 from .continuous_context import MinZeta, find_next_arm_given_context
 from .generalized_pcs import estimate_current_generalized_pcs, empirical_best_arms
+from .levi import PredictiveEI, discrete_levi
 
 __all__ = [
     "B200ModelListGP", "B200Posterior", "from_botorch", "gao_modellist", "MinZeta",
     "find_next_arm_given_context", "estimate_current_generalized_pcs", "empirical_best_arms",
+    "PredictiveEI", "discrete_levi",
 ]

@@ -57,7 +57,12 @@ class DecideWS(C.Structure):
                 ("min_arm", vp), ("tie_cnt", vp), ("decision", vp), ("scan_ws", vp)]
 
 
-assert C.sizeof(Decision) == 64
+class LeviDecision(C.Structure):
+    """``crs_levi_decision``"""
+    _fields_ = [("value", f64), ("context", i32), ("arm", i32), ("reserved", i64)]
+
+
+assert C.sizeof(Decision) == 64 and C.sizeof(LeviDecision) == 24
 
 _SIGNATURES = {
     "crs_abi_version": (C.c_int, []),
@@ -72,6 +77,7 @@ _SIGNATURES = {
     "crs_ocba_select": (C.c_int, [C.POINTER(GPState), vp, vp, vp, i64, i32, i32, f64, vp, vp]),
     "crs_ocba_scan_select": (C.c_int, [C.POINTER(GPState), vp, vp, vp, i64, i64, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp]),
     "crs_pcs_counts": (C.c_int, [vp, vp, i64, i32, i64, i32, i64, u64, u32, i32, i64, vp, vp, vp]),
+    "crs_levi_scan": (C.c_int, [C.POINTER(GPState), vp, vp, i64, i64, vp, vp, i64, vp, vp, vp, vp]),
     "crs_philox_words": (C.c_int, [vp, i64, u32, u32, vp, vp]),
     "crs_debug_corr": (C.c_int, [vp, i64, i32, i32, vp, vp]),
     "crs_peak_probe": (C.c_int, [i32, i32, i32, vp, vp]),

@@ -87,6 +87,12 @@ CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32
   return launch_pcs_counts(mean, var, n_c, K, ld, dtype, num_samples, seed, offset, arm_offset, ctx_offset, counts, stats, (cudaStream_t)stream);
 }
 
+CRS_API int crs_levi_scan(const crs_gp_state* st, const void* mean, const void* var, int64_t n_c,
+                          int64_t ld, const void* weights, void* ei_out, int64_t ld_ei, void* max_ei,
+                          int32_t* max_arm, crs_levi_decision* decision, void* stream) {
+  return launch_levi_scan(st, mean, var, n_c, ld, weights, ei_out, ld_ei, max_ei, max_arm, decision, (cudaStream_t)stream);
+}
+
 CRS_API int crs_philox_words(const uint32_t* ctr, int64_t n, uint32_t key0, uint32_t key1, uint32_t* out,
                      void* stream) {
   return launch_philox_words(ctr, n, key0, key1, out, (cudaStream_t)stream);

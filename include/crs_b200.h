@@ -109,6 +109,14 @@ typedef struct crs_decision {
   int32_t reserved[4]; /* [0] = (first arm whose Cholesky failed)+1 or 0; [1] = completion tag */
 } crs_decision;
 
+/* Result of crs_levi_scan; device memory, 24 bytes. */
+typedef struct crs_levi_decision {
+  double value;      /* max over contexts of (weight *) max over arms of EI  (levi.py:220-224) */
+  int32_t context;   /* context_idx                                          (levi.py:224) */
+  int32_t arm;       /* next_alternative = max_idcs[context_idx]             (levi.py:225) */
+  int64_t reserved;
+} crs_levi_decision;
+
 CRS_API int crs_abi_version(void);
 CRS_API const char* crs_status_string(int status);
 CRS_API const char* crs_last_cuda_error(void);
@@ -213,6 +221,21 @@ CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32
 /* Raw Philox4x32-10 words for known-answer tests: out[4*i..4*i+3] = philox(ctr[4*i..], key). */
 CRS_API int crs_philox_words(const uint32_t* ctr, int64_t n, uint32_t key0, uint32_t key1, uint32_t* out,
                      void* stream);
+
+/*
+ * LEVI grid acquisition on a posterior grid — replaces `_compute_all_EI_reviewer`
+ * (contextual_rs/levi.py:132-172), `PredictiveEI.forward` (:183-196) and `discrete_levi`
+ * (:199-227):  Delta_a = -|mu_a - max_{j != a} mu_j|,  sigma~_a = var_a / sqrt(var_a + noise_a
+ * stdv_a^2) with var clamped at 1e-9,  EI_a = sigma~_a (pdf(u) + u cdf(u)),  u = Delta_a / sigma~_a.
+ * mean/var: [n_c, ld] T tables of the st->num_arms arms (T = st->dtype); noise and y_std are read
+ * from `st` (levi.py:158-161: likelihood noise x outcome_transform._stdvs_sq).  Outputs:
+ * max_ei[n_c] T = row maximum of EI (times weights[c] if weights != NULL, levi.py:221-223),
+ * max_arm[n_c] = its arm (first index on ties), optional ei_out [n_c, ld_ei] T = the full EI table,
+ * optional decision = first arg-max over contexts.  K >= 2.
+ */
+CRS_API int crs_levi_scan(const crs_gp_state* st, const void* mean, const void* var, int64_t n_c,
+                          int64_t ld, const void* weights, void* ei_out, int64_t ld_ei, void* max_ei,
+                          int32_t* max_arm, crs_levi_decision* decision, void* stream);
 
 /* Test hook for the grid kernel's fp64 math: out[i] = f(r2[i]) with variant 0 = the kernel's
  * correlation (table exp + Newton sqrt), 1 = the same formula on libdevice exp/sqrt, 2/3 = the

@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import gp_oracle, ocba_oracle, pcs_oracle, philox_ref
+from oracle import gp_oracle, levi_oracle, ocba_oracle, pcs_oracle, philox_ref
 
 pytestmark = pytest.mark.gpu
 
@@ -484,3 +484,69 @@ def test_sequential_loop_matches_oracle_loop(crs):
     assert torch.equal(p.mean, loop.ws["mean"]) and torch.equal(p.variance, loop.ws["var"])
     rp = ref.posterior(ctx)
     assert _scaled_err(p.mean, rp.mean) < 1e-10 and _scaled_err(p.variance, rp.variance) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------ LEVI
+@pytest.mark.parametrize("K,n_c,d,n,kernel", [(10, 10, 1, 20, "matern52"), (100, 1024, 4, 20, "matern52"),
+                                              (37, 333, 3, 11, "rbf"), (2, 5, 2, 6, "matern52")])
+def test_levi_matches_oracle_fp64(crs, K, n_c, d, n, kernel):
+    """discrete_levi / PredictiveEI / the EI table (contextual_rs/levi.py:132-227): indices
+    bit-exact, EI within 1e-9 of the table's scale (the posterior itself is within 1e-10)."""
+    from contextual_rs_b200.levi import PredictiveEI, _compute_all_EI_reviewer, discrete_levi
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=K, n_c=n_c, d=d, n=n, kernel=kernel, seed=3)
+    model = crs.B200ModelListGP(desc, device=DEV, dtype=torch.float64)
+    ref = gp_oracle.model_from_description(desc)
+    X = ctx.unsqueeze(-2)
+    want = levi_oracle.compute_all_ei_reviewer(X, ref)
+    got = _compute_all_EI_reviewer(X, model)
+    assert got.shape == (n_c, K) and got.device == ctx.device
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 1e-9 * scale
+    torch.testing.assert_close(PredictiveEI(model)(X), want.max(dim=-1).values, rtol=0, atol=1e-9 * scale)
+    arm, x = discrete_levi(model, ctx)
+    rarm, rx = levi_oracle.discrete_levi_ref(ref, ctx)
+    assert arm.dtype == torch.long and arm.dim() == 0
+    assert int(arm) == int(rarm) and torch.equal(x, rx)
+    g = torch.Generator().manual_seed(4)
+    w = torch.rand(n_c, dtype=torch.float64, generator=g)
+    arm, x = discrete_levi(model, ctx, w)
+    rarm, rx = levi_oracle.discrete_levi_ref(ref, ctx, w)
+    assert int(arm) == int(rarm) and torch.equal(x, rx)
+
+
+def test_levi_tables_and_fp32(crs):
+    """Kernel-level check on raw tables (ties at the top of a row, clamped variances) + fp32."""
+    import ctypes as C
+    from contextual_rs_b200 import _lib
+    from contextual_rs_b200.levi import discrete_levi
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=6, n_c=40, d=2, n=9, seed=8)
+    for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 2e-5)):
+        model = crs.B200ModelListGP(desc, device=DEV, dtype=dtype)
+        g = torch.Generator().manual_seed(2)
+        mean = torch.randn(40, 6, generator=g, dtype=torch.float64).to(dtype)
+        mean[3, 4] = mean[3].max()          # exact tie with the row maximum
+        mean[5, :] = 1.5                    # all arms tied
+        var = (0.05 + torch.rand(40, 6, generator=g, dtype=torch.float64)).to(dtype)
+        var[7, 2] = 1e-12                   # below the 1e-9 clamp
+        st = model.state
+        noise_orig = (model.description()["noise"].double() * model.description()["y_std"].double() ** 2)
+        want = levi_oracle.ei_from_tables(mean.unsqueeze(-2), var.unsqueeze(-2), noise_orig.to(torch.float64))
+        ei = torch.empty(40, 6, dtype=dtype, device=DEV)
+        mx = torch.empty(40, dtype=dtype, device=DEV)
+        am = torch.empty(40, dtype=torch.int32, device=DEV)
+        dec = torch.zeros(24, dtype=torch.uint8, device=DEV)
+        md, vd = mean.to(DEV), var.to(DEV)
+        _lib.check(_lib.get().crs_levi_scan(C.byref(st), md.data_ptr(), vd.data_ptr(), 40, 6, None, ei.data_ptr(), 6,
+                                            mx.data_ptr(), am.data_ptr(), dec.data_ptr(), None))
+        torch.cuda.synchronize()
+        scale = float(want.abs().max())
+        assert float((ei.cpu().double() - want.double()).abs().max()) <= tol * scale
+        if dtype == torch.float64:
+            wmax = want.max(dim=-1)
+            assert torch.equal(am.cpu().long(), wmax.indices)
+            d = _lib.LeviDecision.from_buffer_copy(dec.cpu().numpy().tobytes())
+            assert d.context == int(wmax.values.argmax()) and d.arm == int(wmax.indices[d.context])
+    arm, x = discrete_levi(crs.B200ModelListGP(desc, device=DEV, dtype=torch.float32), ctx.float())
+    assert 0 <= int(arm) < 6 and x.shape == (2,)

@@ -225,3 +225,60 @@ def test_randomize_ties_consumes_rng_only_on_ties():
     s1 = torch.get_rng_state()
     assert int(ocba_oracle.pick_minimiser(zeta.view(-1), True)) == 0
     assert torch.equal(s1, torch.get_rng_state())
+
+
+# ------------------------------------------------------------------------------------------ LEVI
+def _levi_scalar(mean_row, var_row, noise_orig):
+    """levi.py:147-168 for one context in scalar ``math`` arithmetic (independent of torch)."""
+    import math
+    out = []
+    for a, (mu, v) in enumerate(zip(mean_row, var_row)):
+        other = max(m for j, m in enumerate(mean_row) if j != a)
+        delta = -abs(mu - other)
+        v = max(v, 1e-9)
+        sigma = v / math.sqrt(v + noise_orig[a])
+        u = delta / sigma
+        cdf = 0.5 * (1.0 + math.erf(u / math.sqrt(2.0)))
+        pdf = math.exp(-0.5 * u * u) / math.sqrt(2.0 * math.pi)
+        out.append(sigma * (pdf + u * cdf))
+    return out
+
+
+def test_levi_oracle_known_answer(golden):
+    """The reference holds no LEVI test; the known answer is hand-derived on the mock posterior
+    tables of test/test_contextual_rs_strategies.py:169-176 with scalar arithmetic."""
+    from oracle import levi_oracle
+    g = golden("mock_tables.json")
+    mean = torch.tensor(g["mean"], dtype=torch.float64)
+    var = torch.tensor(g["variance"], dtype=torch.float64)
+    noise = torch.tensor([0.5, 0.25, 1.0], dtype=torch.float64)
+    ei = levi_oracle.ei_from_tables(mean.unsqueeze(-2), var.unsqueeze(-2), noise)
+    want = torch.tensor([_levi_scalar(m, v, noise.tolist()) for m, v in zip(g["mean"], g["variance"])],
+                        dtype=torch.float64)
+    torch.testing.assert_close(ei, want, rtol=1e-12, atol=1e-15)
+    # best arm of a row: Delta = -(gap to the runner-up); ties at the top give Delta = 0
+    tie = levi_oracle.ei_from_tables(torch.tensor([[[1.0, 3.0, 3.0]]], dtype=torch.float64),
+                                     torch.tensor([[[1.0, 1.0, 4.0]]], dtype=torch.float64),
+                                     torch.zeros(3, dtype=torch.float64))
+    # u = 0 for both tied arms: EI = sigma * pdf(0) with sigma = sqrt(var) when the noise is zero
+    torch.testing.assert_close(tie[0, 1:], torch.tensor([1.0, 2.0], dtype=torch.float64) * 0.3989422804014327)
+
+    class _M:
+        def __init__(self, n, s):
+            self.noise, self.y_std = torch.tensor(n, dtype=torch.float64), torch.tensor(s, dtype=torch.float64)
+
+    class _Model:
+        models = [_M(0.5, 1.0), _M(1.0, 0.5), _M(0.25, 2.0)]  # noise * stdv^2 = 0.5, 0.25, 1.0
+
+        def posterior(self, X):
+            return _TablePosterior(mean.unsqueeze(-2), var.unsqueeze(-2))
+
+    ctx = torch.arange(6.0, dtype=torch.float64).view(3, 2)
+    arm, x = levi_oracle.discrete_levi_ref(_Model(), ctx)
+    row_max = want.max(dim=-1)
+    c_star = int(row_max.values.argmax())
+    assert (int(arm), x.tolist()) == (int(row_max.indices[c_star]), ctx[c_star].tolist())
+    w = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64)  # weights move the decision to context 2
+    arm_w, x_w = levi_oracle.discrete_levi_ref(_Model(), ctx, w)
+    assert (int(arm_w), x_w.tolist()) == (int(row_max.indices[2]), ctx[2].tolist())
+    torch.testing.assert_close(levi_oracle.predictive_ei(ctx.unsqueeze(-2), _Model()), row_max.values)
