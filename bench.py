@@ -111,6 +111,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(workload, kernel, dtype):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+    capture of the same workload (profiles/r01c_traffic.json; fp64 captures only), else None."""
+    path = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    if dtype != "f64" or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get(workload, {}).get(kernel)
+
+
 def algorithmic_flops(K, n_c, n, d):
     """distance + kernel eval + mean dot + triangular solve + squared norm."""
     return K * n_c * (n * (3 * d + 10) + 2 * n + n * n)
@@ -499,13 +509,15 @@ def main():
             "gpu_launches": (3 * K_steps + 3 * K_steps + 3 * ksteps) * mult,
             "roofline": {"kernel": "posterior_grid_kernel", "bound": "fp64_fma" if dtype == torch.float64 else "fp32_fma",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": None, "avg_launch_ms": grid_avg,
+                         "traffic": ncu_traffic(name, "posterior_grid_kernel", args.dtype) if world == 1 else None,
+                         "avg_launch_ms": grid_avg,
                          "peak_source": "measured in this run by crs_peak_probe (pure FMA micro-kernel, 16 chains/thread, "
                                         "CUDA events); MEASURED_PEAKS.json has no fp64/fp32-FMA figure (nominal 37.2 / 74.5)",
                          "algorithmic_flops_per_launch": flops},
             "roofline_scan": {"kernel": "ocba_scan_kernel", "bound": "hbm", "achieved": scan_bytes / (scan_avg * 1e-3) / 1e9,
                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": scan_bytes / (scan_avg * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                              "traffic": None, "avg_launch_ms": scan_avg, "peak_source": peak_src,
+                              "traffic": ncu_traffic(name, "ocba_scan_kernel", args.dtype) if world == 1 else None,
+                              "avg_launch_ms": scan_avg, "peak_source": peak_src,
                               "algorithmic_bytes_per_launch": scan_bytes},
             "kernel_ms": {"gp_prepare": prep_avg, "posterior_grid": grid_avg, "ocba_scan": scan_avg},
             "clocks": clocks,
