@@ -49,6 +49,8 @@ WORKLOADS = {
     "c3": "c3: GP-C-OCBA decision, 256 arms x 8,192 contexts, 4-D, 20 obs/arm, Matern-5/2",
     "c4": "c4: GP-C-OCBA decision, 1,000 arms x 65,536 Sobol contexts, 8-D, 18 obs/arm, Matern-5/2",
     "c5": "c5: GP-C-OCBA decision, 1,000 arms x 16,384 contexts, 4-D, 20 obs/arm, Matern-5/2",
+    "loop": "c5 loop: sequential R&S, 1,000 arms x 16,384 contexts, 4-D, 20 obs/arm growing by one per iteration; "
+            "every iteration = GP-C-OCBA decision on the cached grid + 2^16-sample PCS + dirty-arm update",
 }
 
 
@@ -334,6 +336,95 @@ def run_headline(dev, world, rank, reps=3, num_samples=1 << 16):
             "pcs_mean": float(pcs), "pcs_equivalent_draws_per_sec": float(num_samples) * n_c * K / (p_ms * 1e-3)}
 
 
+# ------------------------------------------------------------------------------------------ loop
+def run_loop(args, dev, world, rank):
+    """BASELINE config 5: the end-to-end sequential loop (experiments/wsc_experiments/main.py:345-470)
+    with the context set sharded over the ranks.  One step = decide (scan + step 2(b) on the cached
+    grid, 64-byte all-gather, decision read back by the host) -> simulate -> PCS (2^16 samples, one
+    all-reduce) -> condition the sampled arm on the new observation and refresh its grid column."""
+    import torch.distributed as dist
+    import contextual_rs_b200 as crs
+    from contextual_rs_b200.peaks import measure_pcs_draw_peak
+    from contextual_rs_b200.sharded import ShardedSequentialRS
+    from contextual_rs_b200.synthetic import make_config
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    desc, ctx = make_config("c5")
+    K, n_c, d = len(desc["train_X"]), ctx.shape[0], ctx.shape[1]
+    S = 1 << 16
+    model = crs.B200ModelListGP(desc, device=dev, dtype=dtype)
+    loop = ShardedSequentialRS(model, ctx.to(dtype), kernel_scale=1.0, num_pcs_samples=S, pcs_seed=0)
+    gen = torch.Generator().manual_seed(7)
+    W, steps = max(args.warmup, 3), args.steps
+    noise = 0.1 * torch.randn(W + steps, generator=gen, dtype=torch.float64)
+    it_box = [0]
+
+    def truth(arm, x):  # the synthetic sine surface of SURVEY.md §8d; identical on every rank
+        full = torch.cat([torch.tensor([arm / (K - 1.0)], dtype=torch.float64), x.double()])
+        return torch.sin(10.0 * full).sum() + noise[it_box[0]]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stats = model.workspace(max(loop.n_loc, 1))["stats"]
+    for _ in range(W):
+        loop.step(truth)
+        it_box[0] += 1
+    barrier()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    drawn = 0.0
+    barrier()
+    for i in range(steps):
+        ev[i][0].record()
+        out = loop.decide()
+        ev[i][1].record()
+        y = truth(out["next_arm"], out["next_context"])
+        pcs = loop.pcs()
+        ev[i][2].record()
+        drawn += float(stats[0])
+        loop.observe(out["next_arm"], out["next_context"].view(1, -1), y.reshape(1, 1))
+        loop.iteration += 1
+        it_box[0] += 1
+        ev[i][3].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    parts = torch.tensor([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in ev], dtype=torch.float64).sum(dim=0)
+    t = torch.cat([parts, parts.sum().reshape(1), torch.tensor([drawn], dtype=torch.float64)]).to(dev)
+    if world > 1:
+        tmax = t[:4].clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dsum = t[4:].clone()
+        dist.all_reduce(dsum)
+        t = torch.cat([tmax, dsum])
+    dec_ms, pcs_ms, obs_ms, tot_ms, drawn_all = t.tolist()
+    if rank == 0:
+        peak = measure_pcs_draw_peak(dev)
+        w = 8 if dtype == torch.float64 else 4
+        val = steps / (tot_ms * 1e-3)
+        print(json.dumps({
+            "metric": "rs_loop_iterations_per_sec", "value": val, "unit": "iterations/s (decision + 2^16-sample PCS + update)",
+            "n_gpus": world, "steps": steps, "warmup": W, "ms_per_step": tot_ms / steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": WORKLOADS["loop"], "arms": K, "contexts": n_c, "dim": d, "pcs_samples": S,
+                       "sharding": f"contexts/{world}" if world > 1 else "none",
+                       "l2": "no flush needed: the grid tables a step re-reads (2 x %d MB per rank) exceed the 126 MB L2" % (K * n_c * w // world // 1000000)},
+            "breakdown_ms": {"decide": dec_ms / steps, "pcs": pcs_ms / steps, "observe": obs_ms / steps},
+            "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": (d + 1) * 8 * world, "d2h_bytes_per_step": 64 * world,
+                    "note": "the loop is host-driven: every iteration reads the decision back and uploads the new observation"},
+            "gpu_launches": 5 * steps * world,
+            "roofline": {"kernel": "pcs_counts_kernel", "bound": "issue", "achieved": drawn_all / (pcs_ms * 1e-3) / world / 1e9,
+                         "peak": peak / 1e9, "unit": "G draws/s", "frac": drawn_all / (pcs_ms * 1e-3) / world / peak, "traffic": None,
+                         "peak_source": "crs_peak_probe kind 5 measured in this run; achieved = EXECUTED draws/s per GPU"},
+            "pcs_last": float(pcs), "clocks": clocks}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------- GPU
 def main():
     ap = argparse.ArgumentParser()
@@ -368,6 +459,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if name == "loop":
+        if args.steps == 3000:
+            args.steps = 20
+        return run_loop(args, dev, world, rank)
     W, K_steps = max(args.warmup, 3), args.steps
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     w = 8 if dtype == torch.float64 else 4

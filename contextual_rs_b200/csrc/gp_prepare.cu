@@ -269,16 +269,28 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
   const double* X = st.train_x + (size_t)k * ncap * d;
   const double* Y = st.train_y + (size_t)k * ncap;
   if (tid == 0) fail = 0;
+  // one coalesced round trip brings the arm's raw data on chip; every later phase reads shared
+  // memory (the per-dimension min/max loop used to pay one global-memory latency per observation)
+  __shared__ double s_x[kSmallCap * CRS_MAX_DIM];
+  __shared__ double s_y[kSmallCap];
+  __shared__ double s_dinv[kSmallCap];
+  for (int idx = tid; idx < n * d; idx += nt) s_x[idx] = X[idx];
+  if (tid < n) s_y[tid] = Y[tid];
+  const double o = st.outputscale[k], noise = st.noise[k], m = st.mean_const[k];
+  const double ls = tid < d ? st.lengthscale[(size_t)k * d + tid] : 1.0;
+  __shared__ double s_ls[CRS_MAX_DIM];
+  if (tid < d) s_ls[tid] = ls;
+  __syncthreads();
 
   // ---- Normalize bounds (warp 0: lane = dimension) and Standardize constants (warp 1) ---------
   if (warp == 0 && lane < d) {
     double mn, rg;
     if (st.flags & CRS_LEARN_NORMALIZE) {
       if (n > 0) {
-        mn = X[lane];
+        mn = s_x[lane];
         double mx = mn;
         for (int i = 1; i < n; ++i) {
-          const double v = X[(size_t)i * d + lane];
+          const double v = s_x[i * d + lane];
           mn = fmin(mn, v);
           mx = fmax(mx, v);
         }
@@ -300,7 +312,7 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
   if (warp == 1) {
     double ybar, ysd;
     if (st.flags & CRS_LEARN_STANDARDIZE) {
-      const double y = lane < n ? Y[lane] : 0.0;
+      const double y = lane < n ? s_y[lane] : 0.0;
       ybar = n > 0 ? warp_sum(y) / n : 0.0;
       const double dv = lane < n ? y - ybar : 0.0;
       const double ss = warp_sum(dv * dv);
@@ -321,7 +333,6 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
   }
   __syncthreads();
   const double ybar = s_stat[0], ysd = s_stat[1];
-  const double o = st.outputscale[k], noise = st.noise[k], m = st.mean_const[k];
 
   // ---- transformed inputs ----------------------------------------------------------------
   T* xn_out = reinterpret_cast<T*>(st.xn) + (size_t)k * ncap * d;
@@ -330,9 +341,9 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
     const int i = idx / dp, dd = idx - i * dp;
     double v = 0.0;
     if (i < n && dd < d) {
-      const double x = X[(size_t)i * d + dd];
+      const double x = s_x[i * d + dd];
       const double xn = (x - tr[dd]) / tr[CRS_MAX_DIM + dd];
-      v = xn / st.lengthscale[(size_t)k * d + dd];
+      v = xn / s_ls[dd];
       xn_out[(size_t)i * d + dd] = (T(x) - T(tr[dd])) / T(tr[CRS_MAX_DIM + dd]);
     } else if (dd < d) {
       xn_out[(size_t)i * d + dd] = T(0);
@@ -340,7 +351,7 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
     xs[i * CRS_MAX_DIM + dd] = v;
     xs_out[idx] = T(v);
   }
-  if (tid < n) rhs[tid] = (Y[tid] - ybar) / ysd - m;
+  if (tid < n) rhs[tid] = (s_y[tid] - ybar) / ysd - m;
   for (int idx = tid; idx < kSmallCap * lda; idx += nt) B[idx] = 0.0;
   __syncthreads();
 
@@ -360,7 +371,7 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
   }
   __syncthreads();
 
-  // ---- factorisation, alpha and L^-1: warp 0 alone ---------------------------------------------
+  // ---- factorisation: warp 0 alone -----------------------------------------------------------
   if (warp == 0) {
     const bool row = lane < n;
     int bad = 0;
@@ -386,35 +397,44 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
       if (row && lane >= j) A[lane * lda + j] = lane == j ? sjj * rs : s * rs;
       __syncwarp();
     }
-    if (bad) {
-      if (lane == 0) fail = bad;
-    } else {
-      // alpha = K^^-1 rhs
-      double r = row ? rhs[lane] : 0.0;
-      for (int j = 0; j < n; ++j) {
-        const double zj = __shfl_sync(kFull, r * dinv, j);
-        if (lane == j) r = zj;
-        else if (row && lane > j) r = fma(-A[lane * lda + j], zj, r);
-      }
-      for (int j = n - 1; j >= 0; --j) {
-        const double aj = __shfl_sync(kFull, r * dinv, j);
-        if (lane == j) r = aj;
-        else if (lane < j) r = fma(-A[j * lda + lane], aj, r);
-      }
-      if (row) rhs[lane] = r;
-      // column `lane` of X = L^-1 by forward substitution (entries above the diagonal stay 0)
-      for (int i = 0; i < n; ++i) {
-        const double di = __shfl_sync(kFull, dinv, i);
-        if (row && i >= lane) {
-          double a0 = i == lane ? 1.0 : 0.0, a1 = 0.0;
-          int c = lane;
-          for (; c + 1 < i; c += 2) {
-            a0 = fma(-A[i * lda + c], B[c * lda + lane], a0);
-            a1 = fma(-A[i * lda + c + 1], B[(c + 1) * lda + lane], a1);
-          }
-          if (c < i) a0 = fma(-A[i * lda + c], B[c * lda + lane], a0);
-          B[i * lda + lane] = (a0 + a1) * di;
+    if (bad && lane == 0) fail = bad;
+    s_dinv[lane] = dinv;
+  }
+  __syncthreads();
+  if (fail) {
+    if (tid == 0) st.status[k] = fail;
+    return;
+  }
+  // ---- alpha (warp 1) and L^-1 (warp 0) side by side: both only read L ---------------------------
+  if (warp == 1) {
+    const bool row = lane < n;
+    const double dinv = s_dinv[lane];
+    double r = row ? rhs[lane] : 0.0;
+    for (int j = 0; j < n; ++j) {  // L z = rhs
+      const double zj = __shfl_sync(kFull, r * dinv, j);
+      if (lane == j) r = zj;
+      else if (row && lane > j) r = fma(-A[lane * lda + j], zj, r);
+    }
+    for (int j = n - 1; j >= 0; --j) {  // L^T a = z
+      const double aj = __shfl_sync(kFull, r * dinv, j);
+      if (lane == j) r = aj;
+      else if (lane < j) r = fma(-A[j * lda + lane], aj, r);
+    }
+    if (row) rhs[lane] = r;
+  } else if (warp == 0) {
+    const bool row = lane < n;
+    // column `lane` of X = L^-1 by forward substitution (entries above the diagonal stay 0)
+    for (int i = 0; i < n; ++i) {
+      const double di = s_dinv[i];
+      if (row && i >= lane) {
+        double a0 = i == lane ? 1.0 : 0.0, a1 = 0.0;
+        int c = lane;
+        for (; c + 1 < i; c += 2) {
+          a0 = fma(-A[i * lda + c], B[c * lda + lane], a0);
+          a1 = fma(-A[i * lda + c + 1], B[(c + 1) * lda + lane], a1);
         }
+        if (c < i) a0 = fma(-A[i * lda + c], B[c * lda + lane], a0);
+        B[i * lda + lane] = (a0 + a1) * di;
       }
     }
   }
@@ -437,7 +457,7 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
   if (tid < CRS_MAX_DIM) {
     if (tid < d) {
       head[kHeadSub + tid] = T(tr[tid]);
-      head[kHeadMul + tid] = T(1.0 / (tr[CRS_MAX_DIM + tid] * st.lengthscale[(size_t)k * d + tid]));
+      head[kHeadMul + tid] = T(1.0 / (tr[CRS_MAX_DIM + tid] * s_ls[tid]));
     } else {
       head[kHeadSub + tid] = T(0);
       head[kHeadMul + tid] = T(0);

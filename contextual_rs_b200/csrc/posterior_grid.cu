@@ -21,6 +21,7 @@
 // (12 FP64 ops) and sqrt() is rsqrt.approx + coupled Newton steps + one correction (branch-free).
 #include <type_traits>
 #include <utility>
+#include <cstdlib>
 #include "crs_common.cuh"
 
 namespace crs {
@@ -419,7 +420,11 @@ int launch_variant(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm
   // Arm tile: as large as possible (contiguous output runs, context tile reused, TMA prefetch of
   // the next arm) while keeping >= ~4 CTAs per SM in flight on 148 SMs for small problems.
   int arm_tile = kMaxArmTile;
-  while (arm_tile > 1 && ctx_tiles * ((narms + arm_tile - 1) / arm_tile) < 148 * 4) arm_tile >>= 1;
+  static const int min_ctas = [] {
+    const char* e = getenv("CRS_GRID_MIN_CTAS");  // tuning hook (scripts/gpu_tune_k1.sh)
+    return e ? atoi(e) : 148 * 4;
+  }();
+  while (arm_tile > 1 && ctx_tiles * ((narms + arm_tile - 1) / arm_tile) < min_ctas) arm_tile >>= 1;
   auto smem_for = [&](int at) {
     const size_t stage = kHeadElems + (size_t)n_rows + (size_t)n_rows * D + (size_t)n_rows * PanelLd<T>::value;
     return 32 + sizeof(T) * (16 + kGridThreads + 2 * stage + (size_t)n_rows * CStride<T>::value +

@@ -301,3 +301,96 @@ class ArmShardedDecider:
         if self.world > 1:
             dist.all_reduce(total, group=self.group)
         return total / (float(num_samples) * self.n_c)
+
+
+class ShardedSequentialRS:
+    """The sequential R&S loop of ``contextual_rs_b200.rs_loop.SequentialRS`` with the context set
+    sharded over the ranks (BASELINE config 5: decision + PCS per iteration at 1/2/4/8 GPUs).
+
+    Every rank keeps the whole GP state (replicated: each observation is applied by every rank —
+    one arm's ``crs_gp_prepare`` + one column of the LOCAL grid) and the posterior grid of its own
+    context slice.  Exchanges per iteration: one 64-byte-per-rank all-gather (decision) and one
+    scalar all-reduce (PCS, ``rho`` = mean) or one all-gather of the int32 counts (general ``rho``).
+    Tie randomisation is not supported across ranks (lowest context wins, like
+    ``ContextShardedDecider``).
+    """
+
+    def __init__(self, model, context_set: Tensor, infer_p: bool = False, use_kde: bool = False,
+                 kernel_scale: float = 1.0, num_pcs_samples: int = 64, pcs_seed: int = 0, rho=None,
+                 group=None):
+        from .contextual_rs_strategies import _p_mode
+        self.model = model
+        self.group = group
+        self.context_host = context_set.detach().cpu()
+        self.dec = ContextShardedDecider(model, context_set, group=group)
+        self.world, self.rank, self.n_c = self.dec.world, self.dec.rank, self.dec.n_c
+        self.n_loc = self.dec.end - self.dec.begin
+        self.p_mode = _p_mode(infer_p, use_kde)
+        self.kernel_scale = kernel_scale
+        self.num_pcs_samples, self.pcs_seed, self.rho = num_pcs_samples, pcs_seed, rho
+        self.iteration = 0
+        self._refresh(0, model.num_arms)
+
+    def _refresh(self, a0: int, a1: int) -> None:
+        if self.n_loc:
+            ws = self.model.workspace(self.n_loc)
+            self.model.posterior_tables(self.dec.local_ctx, ws["mean"], ws["var"], arms=(a0, a1))
+
+    def decide(self) -> dict:
+        """Scan + step 2(b) on the cached local grid, then the 64-byte all-gather."""
+        from .contextual_rs_strategies import _scan_select
+        m, d = self.model, self.dec
+        if self.n_loc:
+            ws = m.workspace(self.n_loc)
+            with torch.cuda.device(m.device):
+                _scan_select(_lib.get(), m, ws, self.n_loc, self.p_mode, self.kernel_scale,
+                             _lib.stream_ptr(m.device), ctx_ptr=d.local_ctx.data_ptr())
+            local = ws["decision"]
+        else:
+            local = d._empty
+        if self.world > 1:
+            dist.all_gather_into_tensor(d._gather, local, group=self.group)
+            d._gather_host.copy_(d._gather, non_blocking=True)
+        else:
+            d._gather_host[0].copy_(local, non_blocking=True)
+        torch.cuda.current_stream(m.device).synchronize()
+        rec = combine_context_sharded(records_from_bytes(d._gather_host, self.n_c, self.world))
+        c = int(rec[REC_CONTEXT])
+        return {"next_arm": int(rec[REC_NEXT_ARM]), "context_index": c, "next_context": self.context_host[c],
+                "min_zeta": float(rec[REC_MIN_ZETA])}
+
+    def pcs(self) -> Tensor:
+        counts = self.dec.pcs_counts(self.num_pcs_samples, self.pcs_seed, offset=self.iteration)
+        if self.rho is None:  # mean over contexts: one scalar all-reduce
+            total = counts.sum(dtype=torch.int64).to(torch.float64).reshape(1)
+            if self.world > 1:
+                dist.all_reduce(total, group=self.group)
+            return (total / (float(self.num_pcs_samples) * self.n_c)).squeeze(0)
+        if self.world > 1:  # general rho: gather the per-context counts (padded to equal shards)
+            width = (self.n_c + self.world - 1) // self.world
+            pad = torch.full((width,), -1, dtype=torch.int32, device=counts.device)
+            pad[: self.n_loc] = counts[: self.n_loc]
+            allc = torch.empty(self.world, width, dtype=torch.int32, device=counts.device)
+            dist.all_gather_into_tensor(allc, pad, group=self.group)
+            counts = allc[allc >= 0]
+        pcs_c = (counts.to(self.model.dtype) / float(self.num_pcs_samples)).unsqueeze(-1)
+        return self.rho(pcs_c).squeeze(-1)
+
+    def observe(self, arm: int, x: Tensor, y: Tensor) -> None:
+        m = self.model
+        cap_before = m.n_cap
+        m.condition_on_observations(int(arm), x, y)
+        if m.n_cap != cap_before:
+            self._refresh(0, m.num_arms)
+        else:
+            self._refresh(int(arm), int(arm) + 1)
+
+    def step(self, evaluate) -> dict:
+        """decide -> simulate -> PCS -> update (``experiments/wsc_experiments/main.py:392-468``);
+        ``evaluate`` must return the same value on every rank."""
+        out = self.decide()
+        y = evaluate(out["next_arm"], out["next_context"])
+        out["pcs"] = self.pcs()
+        self.observe(out["next_arm"], out["next_context"].view(1, -1), torch.as_tensor(y).reshape(1, 1))
+        self.iteration += 1
+        return out

@@ -10,3 +10,4 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127
 tail -1 gpurun_out/bench_c5_n$N.json | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('c5 n=$N', d['scaling'], 'value %.1f e2e %.1f' % (d['value'], d['e2e']['value']), d['kernel_ms'])" || tail -5 gpurun_out/bench_c5_n$N.err
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 bench.py --impl reference --gpus $N --steps 3 --warmup 1 | cut -c1-200
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus $N --workload loop --steps 10 --warmup 3 > gpurun_out/bench_loop_n$N.json 2> gpurun_out/bench_loop_n$N.err; echo "bench loop n=$N rc=$?"; tail -1 gpurun_out/bench_loop_n$N.json | cut -c1-1500; tail -3 gpurun_out/bench_loop_n$N.err

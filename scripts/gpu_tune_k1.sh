@@ -1,14 +1,7 @@
 #!/bin/bash
-# K1 tuning sweep: rebuild with different settings on the GPU box and time the grid kernel.
-mkdir -p gpurun_out
-for cfg in "4 2" "4 4" "5 4" "3 4"; do
-  set -- $cfg
-  touch contextual_rs_b200/csrc/posterior_grid.cu
-  make -C contextual_rs_b200/csrc -j8 EXTRA="-DCRS_GRID_MIN_BLOCKS=$1 -DCRS_PHASE_A_UNROLL=$2" > /dev/null 2>&1 || echo "build failed $cfg"
-  for wl in c2 c5 c4; do
-    python bench.py --workload $wl --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/t_$wl.json 2> gpurun_out/t_$wl.err || tail -3 gpurun_out/t_$wl.err
-    python -c "
-import json; d=json.load(open('gpurun_out/t_$wl.json')); print('minblocks $1 unroll $2 $wl grid_ms %.4f frac %.3f value %.1f' % (d['kernel_ms']['posterior_grid'], d['roofline']['frac'], d['value']))"
-  done
+for v in 592 370 296 148 74; do
+  echo "CRS_GRID_MIN_CTAS=$v: $(CRS_GRID_MIN_CTAS=$v python bench.py --steps 300 --warmup 5 --no-cpu-baseline --no-pcs | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('step %.1f us' % (d['ms_per_step']*1e3), {k: round(v*1e3,1) for k,v in d['kernel_ms'].items()})")"
 done
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+for v in 592 296; do
+  echo "c3 CRS_GRID_MIN_CTAS=$v: $(CRS_GRID_MIN_CTAS=$v python bench.py --workload c3 --steps 50 --warmup 5 --no-cpu-baseline --no-pcs | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('step %.1f us' % (d['ms_per_step']*1e3), {k: round(v*1e3,1) for k,v in d['kernel_ms'].items()})")"
+done
