@@ -93,6 +93,12 @@ CRS_API int crs_levi_scan(const crs_gp_state* st, const void* mean, const void* 
   return launch_levi_scan(st, mean, var, n_c, ld, weights, ei_out, ld_ei, max_ei, max_arm, decision, (cudaStream_t)stream);
 }
 
+CRS_API int crs_min_zeta_grad(const crs_gp_state* st, const void* ctx, int64_t n_c, const void* mean,
+                              const void* var, int64_t ld, const int32_t* best_arm,
+                              const int32_t* min_arm, void* grad, void* stream) {
+  return launch_min_zeta_grad(st, ctx, n_c, mean, var, ld, best_arm, min_arm, grad, (cudaStream_t)stream);
+}
+
 CRS_API int crs_philox_words(const uint32_t* ctr, int64_t n, uint32_t key0, uint32_t key1, uint32_t* out,
                      void* stream) {
   return launch_philox_words(ctr, n, key0, key1, out, (cudaStream_t)stream);

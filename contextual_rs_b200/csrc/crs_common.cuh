@@ -139,6 +139,9 @@ int launch_ocba_scan_select(const void* mean, const void* var, int64_t n_c, int 
                             const void* ctx, int p_mode, double kernel_scale,
                             crs_decision* host_mirror, int seq, cudaStream_t s);
 int64_t scan_workspace_bytes();
+int launch_min_zeta_grad(const crs_gp_state* st, const void* ctx, int64_t n_c, const void* mean,
+                         const void* var, int64_t ld, const int32_t* best_arm, const int32_t* min_arm,
+                         void* grad, cudaStream_t s);
 int launch_levi_scan(const crs_gp_state* st, const void* mean, const void* var, int64_t n_c, int64_t ld,
                      const void* weights, void* ei_out, int64_t ld_ei, void* max_ei, int32_t* max_arm,
                      crs_levi_decision* decision, cudaStream_t s);

@@ -237,6 +237,17 @@ CRS_API int crs_levi_scan(const crs_gp_state* st, const void* mean, const void* 
                           int64_t ld, const void* weights, void* ei_out, int64_t ld_ei, void* max_ei,
                           int32_t* max_arm, crs_levi_decision* decision, void* stream);
 
+/*
+ * Backward of `MinZeta.forward` (contextual_rs/continuous_context.py:57-74): grad[c, :] =
+ * d(-min_j zeta_{c,j}) / d(ctx[c, :]), what `optimize_acqf` obtains by autograd in
+ * experiments/continuous_experiments/main.py:252-263.  mean/var: the [n_c, ld] tables of
+ * crs_posterior_grid for `ctx`; best_arm/min_arm: the per-context outputs of crs_ocba_scan (global
+ * arm ids of `st`, -1 = none).  grad: [n_c, d] T.  Only the two arms zeta* involves are touched.
+ */
+CRS_API int crs_min_zeta_grad(const crs_gp_state* st, const void* ctx, int64_t n_c, const void* mean,
+                              const void* var, int64_t ld, const int32_t* best_arm,
+                              const int32_t* min_arm, void* grad, void* stream);
+
 /* Test hook for the grid kernel's fp64 math: out[i] = f(r2[i]) with variant 0 = the kernel's
  * correlation (table exp + Newton sqrt), 1 = the same formula on libdevice exp/sqrt, 2/3 = the
  * kernel's sqrt with 1/2 Newton steps, 4 = the kernel's exp(-x). */

@@ -550,3 +550,46 @@ def test_levi_tables_and_fp32(crs):
             assert d.context == int(wmax.values.argmax()) and d.arm == int(wmax.indices[d.context])
     arm, x = discrete_levi(crs.B200ModelListGP(desc, device=DEV, dtype=torch.float32), ctx.float())
     assert 0 <= int(arm) < 6 and x.shape == (2,)
+
+
+# ------------------------------------------------------------------------- MinZeta gradient
+@pytest.mark.parametrize("K,d,n,kernel,dtype", [(6, 2, 9, "matern52", torch.float64), (11, 8, 18, "matern52", torch.float64),
+                                                (5, 3, 40, "rbf", torch.float64), (6, 2, 9, "matern52", torch.float32)])
+def test_min_zeta_gradient_matches_autograd_of_the_oracle(crs, K, d, n, kernel, dtype):
+    """d(-min zeta)/d(context): the analytic backward kernel against torch autograd through the
+    oracle's MinZeta (continuous_context.py:57-74), plus a finite-difference spot check and a few
+    optimiser steps over the contexts (what optimize_acqf does, main.py:252-263)."""
+    from contextual_rs_b200.synthetic import make_problem
+    desc, _ = make_problem(K=K, n_c=16, d=d, n=n, kernel=kernel, train="rand", seed=9)
+    model = crs.B200ModelListGP(desc, device=DEV, dtype=dtype)
+    ref = gp_oracle.model_from_description(desc)
+    g = torch.Generator().manual_seed(1)
+    X0 = torch.rand(200, 1, d, generator=g, dtype=torch.float64)
+    Xr = X0.clone().requires_grad_(True)
+    want = ocba_oracle.min_zeta_ref(ref, Xr)
+    want.sum().backward()
+    Xg = X0.to(dtype).clone().requires_grad_(True)
+    acq = crs.MinZeta(model)
+    got = acq(Xg)
+    assert got.requires_grad and got.shape == (200,)
+    (got * torch.arange(1, 201, dtype=dtype)).sum().backward()  # non-trivial upstream gradient
+    mine = Xg.grad.double() / torch.arange(1, 201, dtype=torch.float64).view(-1, 1, 1)
+    scale = float(Xr.grad.abs().max())
+    tol = 1e-8 if dtype == torch.float64 else 2e-3
+    assert float((mine - Xr.grad).abs().max()) <= tol * scale
+    if dtype == torch.float64:
+        # central finite differences of the CUDA forward itself
+        eps = 1e-6
+        for k in range(min(d, 3)):
+            dx = torch.zeros(1, 1, d, dtype=dtype); dx[..., k] = eps
+            fd = (acq(X0 + dx) - acq(X0 - dx)) / (2 * eps)
+            assert float((fd - mine[:, 0, k]).abs().max()) <= 1e-5 * scale
+        # gradient ascent on the acquisition value moves every context uphill
+        X = X0[:32].clone().requires_grad_(True)
+        opt = torch.optim.SGD([X], lr=1e-3 / max(scale, 1.0))
+        v0 = acq(X).detach().clone()
+        for _ in range(5):
+            opt.zero_grad()
+            (-acq(X).sum()).backward()
+            opt.step()
+        assert bool((acq(X).detach() >= v0 - 1e-12).all())
