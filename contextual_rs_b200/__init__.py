@@ -7,11 +7,12 @@ behind the reference's own function signatures.  All compute is in ``libcrs_b200
 from .model import B200ModelListGP, B200Posterior, from_botorch
 from .contextual_rs_strategies import gao_modellist
 from .continuous_context import MinZeta, find_next_arm_given_context
-from .generalized_pcs import estimate_current_generalized_pcs, empirical_best_arms
+from .generalized_pcs import (estimate_current_generalized_pcs, estimate_lookahead_generalized_pcs_modellist,
+                              empirical_best_arms)
 from .levi import PredictiveEI, discrete_levi
 
 __all__ = [
     "B200ModelListGP", "B200Posterior", "from_botorch", "gao_modellist", "MinZeta",
     "find_next_arm_given_context", "estimate_current_generalized_pcs", "empirical_best_arms",
-    "PredictiveEI", "discrete_levi",
+    "PredictiveEI", "discrete_levi", "estimate_lookahead_generalized_pcs_modellist",
 ]

@@ -101,6 +101,98 @@ def estimate_current_generalized_pcs(
     return rho_vals.squeeze(-1).to(context_set.device)  # :479
 
 
+def estimate_lookahead_generalized_pcs_modellist(
+    candidate: Tensor,
+    model,
+    model_sampler,
+    context_set: Tensor,
+    num_samples: int,
+    base_samples: Optional[Tensor],
+    func_I: Callable[[Tensor], Tensor],
+    rho: Callable[[Tensor], Tensor],
+    use_approximation: bool = False,
+    *,
+    seed: Optional[int] = None,
+    fantasy_base: Optional[Tensor] = None,
+) -> Tensor:
+    r"""One-step look-ahead generalized PCS for a ModelListGP
+    (``contextual_rs/generalized_pcs.py:203-315``): for every candidate ``(arm, context)`` the
+    arm's GP is conditioned on a fantasy observation at that context — the posterior mean when
+    ``model_sampler is None`` (certainty equivalent, ``:262-265``), else ``num_fantasies`` draws of
+    the noisy posterior (``arm_model.fantasize``, ``:259-260``) — and the PCS of the fantasy model
+    is estimated like :func:`estimate_current_generalized_pcs`, averaged over fantasies (``:311``).
+
+    Only the fantasised arm's grid column changes, so a candidate costs one ``crs_gp_prepare`` of
+    one arm, one column of ``crs_posterior_grid`` and one ``crs_pcs_counts`` launch.
+
+    Args:
+        candidate: ``n x 1 x (d_c + 1)``; column 0 is the arm index (as a float).
+        model_sampler: ``None``, an ``int`` number of fantasies, or any object with a
+            ``sample_shape`` (BoTorch ``MCSampler``); its base samples are NOT replicated — the
+            standard-normal fantasy draws come from ``fantasy_base`` (``n x num_fantasies``) or
+            the global torch RNG.
+        seed: Philox seed of the PCS estimates (default: drawn from the global torch RNG).
+    Returns:
+        ``n``-dim tensor on ``candidate.device``.
+    """
+    assert context_set.dim() == 2  # :224
+    assert context_set.shape[-1] + 1 == candidate.shape[-1]  # :225
+    assert candidate.dim() == 3 and candidate.shape[-2] == 1  # :226
+    m = _as_b200(model)
+    if use_approximation:  # :228-229
+        raise NotImplementedError
+    if base_samples is not None:
+        raise NotImplementedError(
+            "base_samples cannot be honoured: samples are generated inside the kernel from a "
+            "Philox stream and never materialised (pass seed= to pin the stream)")
+    if not _is_strict_indicator(func_I):
+        raise NotImplementedError("only the strict indicator func_I = (X > 0) is fused into the PCS kernel")
+    if model_sampler is None:
+        num_fantasies = 1
+    elif isinstance(model_sampler, int):
+        num_fantasies = model_sampler
+    else:
+        num_fantasies = int(tuple(model_sampler.sample_shape)[0])
+    n, n_c, K = candidate.shape[0], context_set.shape[0], m.num_arms
+    m.reserve(1)  # a fantasy append must not re-create the workspace
+    ws = m.workspace(n_c)
+    ws["ctx"].copy_(context_set.to(dtype=m.dtype), non_blocking=True)
+    m.posterior_tables(ws["ctx"], ws["mean"], ws["var"], arms=(0, K))
+    ws["valid_for"] = None
+    if seed is None:
+        seed = int(torch.randint(2 ** 62, (1,)))
+    if model_sampler is not None and fantasy_base is None:
+        fantasy_base = torch.randn(n, num_fantasies, dtype=torch.float64)
+    noise_orig = (m.noise * m.y_std * m.y_std).cpu()
+    out = torch.zeros(n, dtype=torch.float64)
+    for i in range(n):
+        arm = int(candidate[i, 0, 0])
+        if not 0 <= arm < K:
+            raise ValueError(f"candidate {i}: arm index {arm} out of range")
+        x = candidate[i, :, 1:].to(torch.float64)
+        at_x = m.posterior(x.to(m.dtype), arms=(arm, arm + 1))
+        mu_x, var_x = float(at_x.mean), float(at_x.variance)
+        if model_sampler is None:
+            ys = [mu_x]
+        else:  # fantasize(): noisy posterior draw, in the outcome's original units
+            sd = (var_x + float(noise_orig[arm])) ** 0.5
+            ys = [mu_x + sd * float(z) for z in fantasy_base[i]]
+        keep_m, keep_v = ws["mean"][:, arm].clone(), ws["var"][:, arm].clone()
+        vals = []
+        for f, y in enumerate(ys):
+            m.condition_on_observations(arm, x, torch.tensor([[y]], dtype=torch.float64))
+            m.posterior_tables(ws["ctx"], ws["mean"], ws["var"], arms=(arm, arm + 1))
+            counts = pcs_counts(m, ws["mean"], ws["var"], num_samples, seed, offset=i * num_fantasies + f,
+                                counts=ws["counts"], stats=ws["stats"])
+            pcs_c_est = (counts.to(m.dtype) / float(num_samples)).unsqueeze(-1)
+            vals.append(rho(pcs_c_est).squeeze(-1).double().cpu())  # :309
+            m.pop_observations(arm, 1)
+        ws["mean"][:, arm] = keep_m
+        ws["var"][:, arm] = keep_v
+        out[i] = torch.stack(vals).mean()  # :311
+    return out.to(device=candidate.device, dtype=candidate.dtype)
+
+
 def empirical_best_arms(model, context_set: Tensor, reuse_grid: bool = False) -> Tensor:
     """``model.posterior(context_map).mean.t().argmax(dim=0)`` of
     ``experiments/wsc_experiments/main.py:459-468`` — a by-product of the scan kernel."""

@@ -208,6 +208,24 @@ class B200ModelListGP:
         self.prepare(arm, arm + 1, relearn=False)
         return self
 
+    def reserve(self, extra: int = 1) -> None:
+        """Make room for ``extra`` more observations on any arm WITHOUT touching the data (grows
+        the row capacity now, so that later appends do not re-create the workspaces)."""
+        need = max(self._n_host) + int(extra)
+        if need > self.n_cap:
+            self._grow(_round_up(need + 8, 8))
+
+    def pop_observations(self, arm: int, count: int = 1) -> "B200ModelListGP":
+        """Undo the last ``count`` appends to one arm (fantasy roll-back) and rebuild its state."""
+        n = self._n_host[arm]
+        if count < 0 or count > n:
+            raise ValueError("cannot remove more observations than the arm holds")
+        self._n_host[arm] = n - count
+        self.n_obs[arm] = n - count
+        self._state.n_max = self._state_frozen.n_max = max(self._n_host)
+        self.prepare(arm, arm + 1, relearn=False)
+        return self
+
     def _grow(self, new_cap: int) -> None:
         if new_cap > _lib.CRS_MAX_OBS:
             raise RuntimeError(f"more than {_lib.CRS_MAX_OBS} observations on one arm is not supported yet")

@@ -96,3 +96,29 @@ def pcs_exact_quadrature(mean: np.ndarray, variance: np.ndarray, num_nodes: int 
         f = w * np.exp(logp)
         out[c] = h * (f.sum() - 0.5 * (f[0] + f[-1]))
     return out
+
+
+def lookahead_pcs_tables_ref(model, candidate: Tensor, context_set: Tensor, fantasy_base: Optional[Tensor] = None):
+    """Fantasy posterior tables of ``estimate_lookahead_generalized_pcs_modellist``
+    (contextual_rs/generalized_pcs.py:246-276): for every candidate ``(arm, x)`` the arm's oracle GP
+    is conditioned on Y = posterior mean at x (``fantasy_base is None``: certainty equivalent,
+    :262-265) or on ``mean + sqrt(var + noise * stdv^2) * z`` for each z in ``fantasy_base[i]``
+    (``fantasize``, :259-260).  Yields ``(i, f, mean [n_c, K], variance [n_c, K])``."""
+    base = model.posterior(context_set)
+    for i in range(candidate.shape[0]):
+        arm = int(candidate[i, 0, 0])
+        x = candidate[i, :, 1:]
+        sub = model.models[arm]
+        px = sub.posterior(x)
+        mu_x, var_x = px.mean.reshape(()), px.variance.reshape(())
+        if fantasy_base is None:
+            ys = [mu_x]
+        else:
+            sd = (var_x + sub.noise * sub.y_std * sub.y_std).sqrt()
+            ys = [mu_x + sd * z for z in fantasy_base[i]]
+        for f, y in enumerate(ys):
+            fm = sub.condition_on_observations(x, y.reshape(1, 1))
+            pf = fm.posterior(context_set)
+            mean, var = base.mean.clone(), base.variance.clone()
+            mean[:, arm], var[:, arm] = pf.mean.squeeze(-1), pf.variance.squeeze(-1)
+            yield i, f, mean, var

@@ -593,3 +593,47 @@ def test_min_zeta_gradient_matches_autograd_of_the_oracle(crs, K, d, n, kernel, 
             (-acq(X).sum()).backward()
             opt.step()
         assert bool((acq(X).detach() >= v0 - 1e-12).all())
+
+
+# --------------------------------------------------------------------------------- lookahead PCS
+def test_lookahead_pcs_modellist(crs):
+    """estimate_lookahead_generalized_pcs_modellist (generalized_pcs.py:203-315): shape and [0, 1]
+    like the reference's test (test/test_generalized_pcs.py:162-240), plus every value within MC
+    error of exact quadrature on the oracle's fantasy tables, and the model left untouched."""
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=3, n_c=4, d=2, n=10, train="rand", seed=13)
+    model = crs.B200ModelListGP(desc, device=DEV)
+    ref = gp_oracle.model_from_description(desc)
+    before = model.posterior(ctx)
+    g = torch.Generator().manual_seed(0)
+    cand = torch.cat([torch.randint(0, 3, (5, 1, 1), generator=g).double(), torch.rand(5, 1, 2, generator=g, dtype=torch.float64)], dim=-1)
+    func_I = lambda X: (X > 0).to(torch.float64)
+    rho = lambda X: X.mean(dim=-2)
+    S = 1 << 14
+    tol = 5 * np.sqrt(0.25 / (S * 4)) + 2e-3
+    # certainty equivalent
+    pcs = crs.estimate_lookahead_generalized_pcs_modellist(cand, model, None, ctx, S, None, func_I, rho, seed=3)
+    assert pcs.shape == (5,) and torch.equal(pcs, pcs.clamp(min=0, max=1))
+    want = torch.zeros(5, dtype=torch.float64)
+    for i, f, mean, var in pcs_oracle.lookahead_pcs_tables_ref(ref, cand, ctx):
+        want[i] += pcs_oracle.pcs_exact_quadrature(mean.numpy(), var.numpy()).mean()
+    assert float((pcs - want).abs().max()) < tol
+    # two fantasies per candidate with shared standard-normal draws
+    zb = torch.randn(5, 2, generator=g, dtype=torch.float64)
+    pcs2 = crs.estimate_lookahead_generalized_pcs_modellist(cand, model, 2, ctx, S, None, func_I, rho, seed=4, fantasy_base=zb)
+    assert pcs2.shape == (5,) and torch.equal(pcs2, pcs2.clamp(min=0, max=1))
+    want2 = torch.zeros(5, dtype=torch.float64)
+    for i, f, mean, var in pcs_oracle.lookahead_pcs_tables_ref(ref, cand, ctx, zb):
+        want2[i] += pcs_oracle.pcs_exact_quadrature(mean.numpy(), var.numpy()).mean() / 2
+    assert float((pcs2 - want2).abs().max()) < tol
+    # sampler object with a sample_shape, global RNG for the fantasies
+    class _Sampler:
+        sample_shape = torch.Size([2])
+    pcs3 = crs.estimate_lookahead_generalized_pcs_modellist(cand, model, _Sampler(), ctx, 1024, None, func_I, rho)
+    assert pcs3.shape == (5,) and torch.equal(pcs3, pcs3.clamp(min=0, max=1))
+    with pytest.raises(NotImplementedError):
+        crs.estimate_lookahead_generalized_pcs_modellist(cand, model, None, ctx, 16, None, func_I, rho, use_approximation=True)
+    # the fantasies were rolled back
+    after = model.posterior(ctx)
+    assert torch.equal(before.mean, after.mean) and torch.equal(before.variance, after.variance)
+    assert model.num_observations() == [10, 10, 10]
