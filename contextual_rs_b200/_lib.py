@@ -71,6 +71,7 @@ _SIGNATURES = {
     "crs_scan_workspace_bytes": (i64, []),
     "crs_linv_stride": (i64, [i32, i32]),
     "crs_gp_prepare": (C.c_int, [C.POINTER(GPState), i32, i32, vp]),
+    "crs_gp_mll": (C.c_int, [C.POINTER(GPState), i32, i32, vp, vp, vp]),
     "crs_posterior_grid": (C.c_int, [C.POINTER(GPState), vp, i64, i32, i32, vp, vp, i64, i32, vp]),
     "crs_ocba_scan": (C.c_int, [vp, vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "crs_ocba_resolve_tie": (C.c_int, [vp, vp, i64, i32, i64, i32, vp, vp, vp, i64, vp, vp]),

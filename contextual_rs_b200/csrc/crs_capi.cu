@@ -99,6 +99,11 @@ CRS_API int crs_min_zeta_grad(const crs_gp_state* st, const void* ctx, int64_t n
   return launch_min_zeta_grad(st, ctx, n_c, mean, var, ld, best_arm, min_arm, grad, (cudaStream_t)stream);
 }
 
+CRS_API int crs_gp_mll(const crs_gp_state* st, int32_t arm_begin, int32_t arm_end, double* value,
+                       double* grad, void* stream) {
+  return launch_gp_mll(st, arm_begin, arm_end, value, grad, (cudaStream_t)stream);
+}
+
 CRS_API int crs_philox_words(const uint32_t* ctr, int64_t n, uint32_t key0, uint32_t key1, uint32_t* out,
                      void* stream) {
   return launch_philox_words(ctr, n, key0, key1, out, (cudaStream_t)stream);

@@ -139,6 +139,8 @@ int launch_ocba_scan_select(const void* mean, const void* var, int64_t n_c, int 
                             const void* ctx, int p_mode, double kernel_scale,
                             crs_decision* host_mirror, int seq, cudaStream_t s);
 int64_t scan_workspace_bytes();
+int launch_gp_mll(const crs_gp_state* st, int arm_begin, int arm_end, double* value, double* grad,
+                  cudaStream_t s);
 int launch_min_zeta_grad(const crs_gp_state* st, const void* ctx, int64_t n_c, const void* mean,
                          const void* var, int64_t ld, const int32_t* best_arm, const int32_t* min_arm,
                          void* grad, cudaStream_t s);

@@ -248,6 +248,21 @@ CRS_API int crs_min_zeta_grad(const crs_gp_state* st, const void* ctx, int64_t n
                               const void* var, int64_t ld, const int32_t* best_arm,
                               const int32_t* min_arm, void* grad, void* stream);
 
+/*
+ * Exact marginal log-likelihood of arms [arm_begin, arm_end) at the hyper-parameters currently in
+ * `st` (lengthscale, outputscale, noise, mean_const) and its gradient — the objective of
+ * `fit_gpytorch_mll(ExactMarginalLogLikelihood(m.likelihood, m))` in
+ * contextual_rs/experiment_utils.py:41-47, 108-115.  Uses the frozen transforms of `st`
+ * (norm_mins/norm_ranges, y_mean/y_std, as learnt by crs_gp_prepare) and only the fitted-description
+ * arrays; the prepared arrays are not touched.
+ *   value[k]          = log N(y~_k | m 1, o C(l) + noise I)        (-inf if not positive definite)
+ *   grad[k, 0..d-1]   = d value / d lengthscale_j;  grad[k, d] = d/d outputscale;
+ *   grad[k, d+1]      = d/d noise;  grad[k, d+2] = d/d mean_const
+ * value: [K] f64, grad: [K, d+3] f64 (rows outside the arm range are not written).  n_obs <= 128.
+ */
+CRS_API int crs_gp_mll(const crs_gp_state* st, int32_t arm_begin, int32_t arm_end, double* value,
+                       double* grad, void* stream);
+
 /* Test hook for the grid kernel's fp64 math: out[i] = f(r2[i]) with variant 0 = the kernel's
  * correlation (table exp + Newton sqrt), 1 = the same formula on libdevice exp/sqrt, 2/3 = the
  * kernel's sqrt with 1/2 Newton steps, 4 = the kernel's exp(-x). */

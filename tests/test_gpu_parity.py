@@ -637,3 +637,89 @@ def test_lookahead_pcs_modellist(crs):
     after = model.posterior(ctx)
     assert torch.equal(before.mean, after.mean) and torch.equal(before.variance, after.variance)
     assert model.num_observations() == [10, 10, 10]
+
+
+# ------------------------------------------------------------------------------ hyper-parameter fit
+def _fit_problem(K=5, n=14, d=3, seed=2):
+    g = torch.Generator().manual_seed(seed)
+    rows, ys = [], []
+    for k in range(K):
+        nk = n + k  # ragged arms
+        Xk = torch.rand(nk, d, generator=g, dtype=torch.float64)
+        yk = torch.sin(6.0 * Xk + k).sum(-1) * (0.5 + k) + 0.05 * torch.randn(nk, generator=g, dtype=torch.float64) + 3.0 * k
+        rows.append(torch.cat([torch.full((nk, 1), float(k), dtype=torch.float64), Xk], dim=-1))
+        ys.append(yk)
+    return torch.cat(rows), torch.cat(ys).reshape(-1, 1), K
+
+
+@pytest.mark.parametrize("kernel", ["matern52", "rbf"])
+def test_gp_mll_value_and_gradient_match_oracle_autograd(crs, kernel):
+    """crs_gp_mll against the oracle's torch MLL + autograd at random hyper-parameters: value and
+    gradient to 1e-9 relative (the objective IS pinned to rounding; the optimiser is not)."""
+    import ctypes as C
+    from contextual_rs_b200 import _lib
+    from oracle import fit_oracle
+    X, Y, K = _fit_problem()
+    d = X.shape[1] - 1
+    g = torch.Generator().manual_seed(5)
+    tx = [X[X[:, 0] == k][:, 1:] for k in range(K)]
+    ty = [Y[X[:, 0] == k] for k in range(K)]
+    desc = {"train_X": tx, "train_Y": ty, "kernel": kernel, "normalize": True, "standardize": True,
+            "lengthscale": 0.2 + torch.rand(K, d, generator=g, dtype=torch.float64),
+            "outputscale": 0.5 + torch.rand(K, generator=g, dtype=torch.float64),
+            "noise": 0.01 + 0.1 * torch.rand(K, generator=g, dtype=torch.float64),
+            "mean_const": 0.3 * torch.randn(K, generator=g, dtype=torch.float64)}
+    model = crs.B200ModelListGP(desc, device=DEV)
+    val = torch.empty(K, dtype=torch.float64, device=DEV)
+    grad = torch.empty(K, d + 3, dtype=torch.float64, device=DEV)
+    _lib.check(_lib.get().crs_gp_mll(C.byref(model.state), 0, K, val.data_ptr(), grad.data_ptr(), None))
+    torch.cuda.synchronize()
+    for k in range(K):
+        mins, ranges, ym, ys = fit_oracle.transforms(tx[k], ty[k].reshape(-1))
+        Xn, yt = (tx[k] - mins) / ranges, (ty[k].reshape(-1) - ym) / ys
+        p = [desc[n][k].clone().requires_grad_(True) for n in ("lengthscale", "outputscale", "noise", "mean_const")]
+        v = fit_oracle.exact_mll(Xn, yt, *p, kernel)
+        gs = torch.autograd.grad(v, p)
+        want = torch.cat([gs[0], gs[1].reshape(1), gs[2].reshape(1), gs[3].reshape(1)])
+        assert abs(float(val[k]) - float(v.detach())) <= 1e-10 * abs(float(v.detach()))
+        assert float((grad[k].cpu() - want).abs().max()) <= 1e-9 * float(want.abs().max())
+    # not positive definite -> -inf, zero gradient, no crash
+    model.noise.fill_(-10.0)
+    _lib.check(_lib.get().crs_gp_mll(C.byref(model.state), 0, K, val.data_ptr(), grad.data_ptr(), None))
+    assert bool(torch.isinf(val).all()) and float(grad.abs().max()) == 0.0
+
+
+def test_fit_modellist_reaches_the_scipy_optimum(crs):
+    """fit_modellist / fit_modellist_with_reuse (experiment_utils.py:15-48, 68-121): the batched
+    device L-BFGS and the oracle's scipy L-BFGS-B start from gpytorch's initial values and must end
+    at the same optimum: objective within 1e-6, hyper-parameters within 2 %, posterior within 1e-3
+    of scale.  (Optimiser tolerance, not arithmetic parity: see contextual_rs_b200/fit.py.)"""
+    from contextual_rs_b200.fit import fit_modellist, fit_modellist_with_reuse
+    from oracle import fit_oracle
+    X, Y, K = _fit_problem()
+    model = fit_modellist(X, Y, K, device=DEV)
+    rdesc, robj = fit_oracle.fit_modellist_ref(X, Y, K)
+    got = model.description()
+    obj = model.fit_info["objective"]
+    assert float((obj - robj).max()) <= 1e-6, (obj, robj)   # never worse than scipy
+    assert float((obj - robj).abs().max()) <= 1e-5
+    for name in ("lengthscale", "outputscale", "mean_const"):
+        torch.testing.assert_close(got[name], rdesc[name], rtol=2e-2, atol=2e-3)
+    torch.testing.assert_close(got["noise"], rdesc["noise"], rtol=5e-2, atol=2e-4)
+    for name in ("norm_mins", "norm_ranges", "y_mean", "y_std"):
+        torch.testing.assert_close(got[name], rdesc[name], rtol=1e-13, atol=1e-13)
+    ctx = torch.rand(64, 3, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    p, rp = model.posterior(ctx), gp_oracle.model_from_description(rdesc).posterior(ctx)
+    assert _scaled_err(p.mean, rp.mean) < 1e-3 and _scaled_err(p.variance, rp.variance) < 1e-2
+    # reuse: add one observation to arm 2 only -> only arm 2 is re-fitted, the others are kept bit for bit
+    X2 = torch.cat([X, torch.tensor([[2.0, 0.3, 0.6, 0.9]], dtype=torch.float64)])
+    Y2 = torch.cat([Y, torch.tensor([[6.5]], dtype=torch.float64)])
+    model2 = fit_modellist_with_reuse(X2, Y2, K, old_model=model, device=DEV)
+    d2 = model2.description()
+    keep = [0, 1, 3, 4]
+    for name in ("lengthscale", "outputscale", "noise", "mean_const", "y_mean", "y_std"):
+        assert torch.equal(d2[name][keep], got[name][keep])
+    assert model2.num_observations()[2] == model.num_observations()[2] + 1
+    assert int(model2.fit_info["iterations"][2]) > 0 and int(model2.fit_info["iterations"][[0, 1, 3, 4]].sum()) == 0
+    arm, x = crs.gao_modellist(model2, ctx)
+    assert 0 <= int(arm) < K

@@ -282,3 +282,33 @@ def test_levi_oracle_known_answer(golden):
     arm_w, x_w = levi_oracle.discrete_levi_ref(_Model(), ctx, w)
     assert (int(arm_w), x_w.tolist()) == (int(row_max.indices[2]), ctx[2].tolist())
     torch.testing.assert_close(levi_oracle.predictive_ei(ctx.unsqueeze(-2), _Model()), row_max.values)
+
+
+# ------------------------------------------------------------------------------- fit oracle
+def test_fit_oracle_objective_and_optimum():
+    """The restated MLL: equals the closed form on a 1-point GP, its autograd gradient matches
+    finite differences, and the scipy L-BFGS-B fit ends at a stationary point that beats the
+    initial values (the reference pins no fitted value: experiment_utils.py has no test)."""
+    import math
+    from oracle import fit_oracle
+    # one observation: log N(y | m, o + s2)
+    v = fit_oracle.exact_mll(torch.zeros(1, 2, dtype=torch.float64), torch.tensor([0.7], dtype=torch.float64),
+                             torch.ones(2, dtype=torch.float64), torch.tensor(1.5, dtype=torch.float64),
+                             torch.tensor(0.5, dtype=torch.float64), torch.tensor(0.2, dtype=torch.float64), "matern52")
+    assert abs(float(v) - (-0.5 * 0.25 / 2.0 - 0.5 * math.log(2.0) - 0.5 * math.log(2 * math.pi))) < 1e-14
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(14, 3, generator=g, dtype=torch.float64)
+    Y = torch.sin(6 * X).sum(-1) + 0.05 * torch.randn(14, generator=g, dtype=torch.float64)
+    mins, ranges, ym, ys = fit_oracle.transforms(X, Y)
+    Xn, yt = (X - mins) / ranges, (Y - ym) / ys
+    raw = torch.tensor([0.3, -0.2, 0.1, 0.4, 0.05, 0.1], dtype=torch.float64, requires_grad=True)
+    f = fit_oracle.objective(raw, Xn, yt, "matern52")
+    (gr,) = torch.autograd.grad(f, raw)
+    for k in range(6):
+        e = torch.zeros(6, dtype=torch.float64); e[k] = 1e-6
+        fd = (fit_oracle.objective(raw.detach() + e, Xn, yt, "matern52") - fit_oracle.objective(raw.detach() - e, Xn, yt, "matern52")) / 2e-6
+        assert abs(float(fd) - float(gr[k])) < 1e-7
+    hp, fbest = fit_oracle.fit_arm(X, Y)
+    raw0 = torch.zeros(6, dtype=torch.float64); raw0[4] = 2.0
+    assert fbest < float(fit_oracle.objective(raw0, Xn, yt, "matern52")) - 0.1
+    assert float(hp["noise"]) >= 1e-4 and bool((hp["lengthscale"] > 0).all())
