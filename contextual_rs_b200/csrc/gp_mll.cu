@@ -193,7 +193,7 @@ int launch_gp_mll(const crs_gp_state* st, int arm_begin, int arm_end, double* va
   if (n > kMllMaxObs) return CRS_ERR_UNSUPPORTED;
   if (arm_begin == arm_end) return CRS_OK;
   const size_t smem = sizeof(double) * ((size_t)n * (n + 1) + (size_t)n * st->dim + n + 8 * (CRS_MAX_DIM + 4) + CRS_MAX_DIM);
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)
     CRS_CUDA_TRY(cudaFuncSetAttribute(gp_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "mll attr");
   gp_mll_kernel<<<arm_end - arm_begin, kMllThreads, smem, s>>>(*st, arm_begin, arm_end, value, grad);
   CRS_CUDA_TRY(cudaGetLastError(), "gp_mll launch");

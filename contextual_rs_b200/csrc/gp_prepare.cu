@@ -489,7 +489,7 @@ int launch_gp_prepare(const crs_gp_state* st, int arm_begin, int arm_end, cudaSt
   }
   const size_t smem = prep_group_doubles(st->n_cap, st->dim_pad) * sizeof(double);
   auto go = [&](auto kern) -> int {
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
       CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "prepare attr");
     kern<<<narms, kPrepThreads, smem, s>>>(*st, arm_begin, arm_end);
     CRS_CUDA_TRY(cudaGetLastError(), "gp_prepare launch");

@@ -842,7 +842,7 @@ int scan_dispatch(const void* mean, const void* var, int64_t n_c, int K, int64_t
                       ((uintptr_t)mean % 16 == 0) && ((uintptr_t)var % 16 == 0);
   if (tma_ok) {
     auto launch = [&](auto kern) -> int {
-      if (tma_smem > 48 * 1024)
+      if (tma_smem + 8 * 1024 > 48 * 1024)  // static shared memory (~4 KB) counts against the 48 KB default
         CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem), "scan attr");
       int per_sm = (int)((220 * 1024) / (tma_smem + 1024 + 4096));
       if (per_sm > 16) per_sm = 16;
@@ -952,11 +952,11 @@ int launch_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean
   if (stage < blk) stage = blk;
   if (st->dtype == CRS_F64) {
     auto kern = ocba_select_kernel<double>;
-    if (stage > 48 * 1024) CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage), "select attr");
+    if (stage > 40 * 1024) CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage), "select attr");
     kern<<<1, threads, stage, s>>>(*st, (const double*)ctx, (const double*)var, ld, arm_offset, p_mode, kernel_scale, decision, host_mirror, seq, (int)stage);
   } else if (st->dtype == CRS_F32) {
     auto kern = ocba_select_kernel<float>;
-    if (stage > 48 * 1024) CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage), "select attr");
+    if (stage > 40 * 1024) CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage), "select attr");
     kern<<<1, threads, stage, s>>>(*st, (const float*)ctx, (const float*)var, ld, arm_offset, p_mode, (float)kernel_scale, decision, host_mirror, seq, (int)stage);
   } else {
     return CRS_ERR_INVALID_ARG;

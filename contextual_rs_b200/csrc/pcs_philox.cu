@@ -415,7 +415,7 @@ int launch_pcs_counts(const void* mean, const void* var, int64_t n_c, int K, int
   const int blocks = (int)(items < 148 * CRS_PCS_MIN_BLOCKS * 2 ? items : 148 * CRS_PCS_MIN_BLOCKS * 2);
   const RoundKeys rk = round_keys((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
   auto go = [&](auto kern, auto* m, auto* v) -> int {
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
       CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pcs attr");
     kern<<<blocks, kPcsThreads, smem, s>>>(m, v, n_c, K, ld, num_samples, rk, offset, arm_offset >> 2,
                                            ctx_offset, (int)splits, nbmax, np2, counts,

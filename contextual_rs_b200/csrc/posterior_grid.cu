@@ -436,7 +436,7 @@ int launch_variant(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm
   const int arm_tiles = (narms + arm_tile - 1) / arm_tile;
   if (arm_tiles > 65535) return CRS_ERR_UNSUPPORTED;
   auto kern = posterior_grid_kernel<T, D, VB>;
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)
     CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "grid attr");
   dim3 grid((unsigned)ctx_tiles, (unsigned)arm_tiles);
   kern<<<grid, kGridThreads, smem, s>>>(*st, reinterpret_cast<const T*>(ctx), n_c, arm_begin,

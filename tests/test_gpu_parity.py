@@ -723,3 +723,69 @@ def test_fit_modellist_reaches_the_scipy_optimum(crs):
     assert int(model2.fit_info["iterations"][2]) > 0 and int(model2.fit_info["iterations"][[0, 1, 3, 4]].sum()) == 0
     arm, x = crs.gao_modellist(model2, ctx)
     assert 0 <= int(arm) < K
+
+
+# ----------------------------------------------------------- every dispatch branch of the scan / PCS
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("K", [2, 33, 129, 256, 300, 600, 1000, 1024, 1500, 3000])
+def test_scan_all_row_widths(crs, K, dtype):
+    """crs_ocba_scan on raw tables for every kernel variant (register rows K <= 256, TMA-staged
+    rows with 1 or 4 warps per row up to 1024, generic beyond): best arm, min zeta, zeta arm and
+    tie count bit-identical to torch reductions of `squared_diffs / added_vars`
+    (contextual_rs_strategies.py:139-149), including exact ties and a tied row maximum."""
+    from contextual_rs_b200 import _lib
+    lib = _lib.get()
+    n_c = 257
+    g = torch.Generator().manual_seed(K)
+    mean = torch.randn(n_c, K, generator=g, dtype=torch.float64).to(dtype)
+    var = (0.1 + torch.rand(n_c, K, generator=g, dtype=torch.float64)).to(dtype)
+    if K >= 4:
+        mean[3, K - 1] = mean[3, 1]; var[3, K - 1] = var[3, 1]       # two arms with identical zeta
+        mean[5, K // 2] = mean[5].max()                               # tied row maximum (lowest id wins)
+        mean[7] = mean[7, 0]                                          # all arms equal: zeta = 0 everywhere
+    md, vd = mean.to(DEV), var.to(DEV)
+    out = {k: torch.zeros(n_c, dtype=torch.int32, device=DEV) for k in ("best", "zarm", "ties")}
+    minz = torch.zeros(n_c, dtype=dtype, device=DEV)
+    dec = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    wsb = torch.zeros(int(lib.crs_scan_workspace_bytes()), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.crs_ocba_scan(md.data_ptr(), vd.data_ptr(), n_c, K, K, _lib.DTYPES[dtype], 0, None, None, None,
+                                 out["best"].data_ptr(), minz.data_ptr(), out["zarm"].data_ptr(), out["ties"].data_ptr(),
+                                 dec.data_ptr(), wsb.data_ptr(), None))
+    torch.cuda.synchronize()
+    best = mean.argmax(dim=-1)
+    assert torch.equal(out["best"].cpu().long(), best)
+    mb, vb = mean.gather(1, best[:, None]), var.gather(1, best[:, None])
+    zeta = (mb - mean).pow(2) / (vb + var)
+    zeta.scatter_(1, best[:, None], float("inf"))
+    zmin = zeta.min(dim=-1).values
+    assert torch.equal(minz.cpu(), zmin)
+    assert torch.equal(out["ties"].cpu().long(), (zeta == zmin[:, None]).sum(dim=-1))
+    za = out["zarm"].cpu().long()
+    assert bool((zeta.gather(1, za[:, None]).squeeze(1) == zmin).all())
+    d = _lib.Decision.from_buffer_copy(dec.cpu().numpy().tobytes())
+    gmin = zmin.min()
+    assert d.min_zeta == float(gmin) and d.context == int((zmin == gmin).nonzero()[0])
+    assert d.tie_count == int((zeta == gmin).sum())
+
+
+def test_wide_model_decision_and_pcs(crs):
+    """K = 300 arms: the fused scan + select of the TMA-staged variant (4 warps per row) and a PCS
+    plan of 75 arm blocks with K not a multiple of the block size beyond 1024 arms."""
+    from contextual_rs_b200.generalized_pcs import pcs_counts
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=300, n_c=96, d=3, n=7, seed=17)
+    model = crs.B200ModelListGP(desc, device=DEV)
+    ref = gp_oracle.model_from_description(desc)
+    arm, x = crs.gao_modellist(model, ctx)
+    rarm, rx = ocba_oracle.gao_modellist_ref(ref, ctx)
+    assert int(arm) == int(rarm) and torch.equal(x, rx)
+    arm, x = crs.gao_modellist(model, ctx, use_kde=True, kernel_scale=1.0)
+    rarm, rx = ocba_oracle.gao_modellist_ref(ref, ctx, use_kde=True, kernel_scale=1.0)
+    assert int(arm) == int(rarm) and torch.equal(x, rx)
+    g = torch.Generator().manual_seed(3)
+    mean = torch.randn(5, 1301, generator=g, dtype=torch.float64)
+    var = 0.05 + torch.rand(5, 1301, generator=g, dtype=torch.float64)
+    S = 512
+    cnt = pcs_counts(None, mean.to(DEV), var.to(DEV), S, seed=9).cpu().numpy()
+    want = philox_ref.pcs_counts_philox_ref(mean.numpy(), var.numpy(), S, seed=9)
+    assert np.abs(cnt - want).max() <= 2 and (cnt != want).sum() <= 2
