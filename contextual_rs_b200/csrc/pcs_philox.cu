@@ -117,11 +117,14 @@ struct Plan {
 #ifndef CRS_PCS_MIN_BLOCKS
 #define CRS_PCS_MIN_BLOCKS 4
 #endif
+constexpr int kPcsTicketRing = 64;
+__device__ unsigned long long g_pcs_tickets[kPcsTicketRing];
 template <typename T>
 __global__ void __launch_bounds__(kPcsThreads, CRS_PCS_MIN_BLOCKS)
 pcs_counts_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n_c, int K,
                   int64_t ld, int64_t num_samples, const __grid_constant__ RoundKeys rk, uint32_t offset,
                   int blk_offset, int64_t ctx_offset, int splits, int nbmax, int np2,
+                  unsigned long long* __restrict__ ticket,
                   uint32_t* counts, unsigned long long* stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // [ plan in visiting order | scratch of the plan build ]
@@ -145,7 +148,14 @@ pcs_counts_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t
   unsigned long long drawn = 0;
   long long skipped = 0;
 
-  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+  // Work items (context x sample range) cost anything between 4 and 60 plan entries per sample, so
+  // they are handed out dynamically: a CTA takes the next item from a global ticket when it is done.
+  __shared__ long long s_item;
+  for (;;) {
+    if (tid == 0) s_item = (long long)atomicAdd(ticket, 1ull);
+    __syncthreads();
+    const int64_t item = s_item;
+    if (item >= items) break;
     const int64_t c = item / splits;
     const int sp = (int)(item - c * splits);
     const int64_t s_lo = num_samples * sp / splits, s_hi = num_samples * (sp + 1) / splits;
@@ -408,17 +418,28 @@ int launch_pcs_counts(const void* mean, const void* var, int64_t n_c, int K, int
   const size_t smem = (size_t)nbmax * (sizeof(Entry) + 2 * 16 + 3 * 4) + (size_t)np2 * 8;
   // enough work items to fill the machine: split the samples of a context when contexts are few
   const int64_t max_splits = (num_samples + kPcsSplitSamples - 1) / kPcsSplitSamples;
-  int64_t splits = (148 * CRS_PCS_MIN_BLOCKS + n_c - 1) / n_c;
+  // ~16 items per resident CTA, so that the dynamic hand-out can even out their very different costs
+  int64_t splits = (16 * 148 * CRS_PCS_MIN_BLOCKS + n_c - 1) / n_c;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   const int64_t items = n_c * splits;
   const int blocks = (int)(items < 148 * CRS_PCS_MIN_BLOCKS * 2 ? items : 148 * CRS_PCS_MIN_BLOCKS * 2);
+  // ticket of this launch: a small ring of device counters, so that launches in flight on different
+  // streams do not share one
+  static unsigned long long* rings[64] = {nullptr};  // per device: the symbol lives in each context
+  static unsigned int next_slot = 0;
+  int dev = 0;
+  CRS_CUDA_TRY(cudaGetDevice(&dev), "pcs get device");
+  if (dev < 0 || dev >= 64) return CRS_ERR_UNSUPPORTED;
+  if (!rings[dev]) CRS_CUDA_TRY(cudaGetSymbolAddress((void**)&rings[dev], g_pcs_tickets), "pcs ticket symbol");
+  unsigned long long* ticket = rings[dev] + (next_slot++ % kPcsTicketRing);
+  CRS_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s), "pcs memset ticket");
   const RoundKeys rk = round_keys((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
   auto go = [&](auto kern, auto* m, auto* v) -> int {
     if (smem > 40 * 1024)
       CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pcs attr");
     kern<<<blocks, kPcsThreads, smem, s>>>(m, v, n_c, K, ld, num_samples, rk, offset, arm_offset >> 2,
-                                           ctx_offset, (int)splits, nbmax, np2, counts,
+                                           ctx_offset, (int)splits, nbmax, np2, ticket, counts,
                                            (unsigned long long*)stats);
     CRS_CUDA_TRY(cudaGetLastError(), "pcs_counts launch");
     return CRS_OK;
