@@ -558,66 +558,130 @@ __device__ __forceinline__ unsigned int zeta_key(float mu_b, float var_b, float 
   return __float_as_uint((gap * gap) * r);
 }
 
-// Wide rows (256 < K <= 1024): one CTA of NW warps per row, rows double-buffered in shared memory
-// by TMA bulk copies (cp.async.bulk + mbarrier).  A thread takes its R = kpad / (32 NW) entries of
-// the row into registers, the stage is handed back to the TMA engine after the single CTA barrier
-// of the row (arg-max exchange) — two rows are in flight while one is scanned — and the per-warp
-// zeta minima of a row are folded by warp 0 one row later (exchange buffers double-buffered by
-// parity).  NW = 1 (a warp per row, 32 entries per lane, 6-13 single-warp CTAs per SM) has the
-// fewest instructions per row and is the throughput configuration; NW = 4 is kept for the fused
-// scan + select of small, latency-bound problems.
-template <typename T, int R, int NW>
-__global__ void __launch_bounds__(32 * NW, NW == 4 ? ((sizeof(T) == 8 && R == 8) ? 5 : 6) : 1)
-ocba_scan_tma_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n_c, int K,
+// Wide rows (256 < K <= 1024): a warp per row, rows staged in shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier), NS stages per warp.  The row stays in shared memory while it is
+// scanned and nothing row-sized lives in registers (~50 registers per thread, so 12-28 warps per SM
+// cover the TMA latency and the long per-row dependency chains):
+//   pass 1  arg-max of the means (lane-strided reads, shuffle reduction); the best arm's entry is
+//           then overwritten with -inf in the stage, which turns its zeta key into +inf — no
+//           per-entry "is this the best arm" test in the hot loop;
+//   pass 2  32-bit screening keys, written over the means in the stage, running minimum,
+//           REDUX.MIN across the warp;
+//   rare    lanes whose minimum is within the slack re-read their keys and take the exact IEEE
+//           quotient of the (normally single) candidate, its mean re-read from global memory (L2).
+// Warps never synchronise with each other; the CTA only meets in scan_tail.
+template <typename T> struct InfKey;
+template <> struct InfKey<double> { static constexpr unsigned int value = 0x7ff00000u; };
+template <> struct InfKey<float> { static constexpr unsigned int value = 0x7f800000u; };
+
+constexpr int kRowWarps = 4;  // warps (rows in flight) per CTA
+
+template <typename T, int R, int NS>
+__global__ void __launch_bounds__(32 * kRowWarps, 6)
+ocba_scan_row_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n_c, int K,
                      int64_t ld, int arm_offset, const int32_t* __restrict__ ext_arm,
                      const T* __restrict__ ext_mean, const T* __restrict__ ext_var,
                      int32_t* __restrict__ best_arm, T* __restrict__ min_zeta,
                      int32_t* __restrict__ min_arm, int32_t* __restrict__ tie_cnt,
                      ScanPartial* partials, unsigned int* ticket, crs_decision* decision,
                      SelectArgs sel) {
-  constexpr int kThreads = 32 * NW;
-  constexpr int NS = NW == 1 ? 1 : 2;  // stages: a single warp re-fills its stage as soon as the row is in registers
-  constexpr int kpad = R * kThreads;
+  constexpr int kpad = R * 32;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
-  // dynamic smem: [select stage (kSelStageFused bytes, only if fused)] | stage0 {m[kpad], v[kpad]} | stage1 (NS = 2)
-  unsigned char* base = dyn_smem + (sel.do_select ? kSelStageFused : 0);
-  T* s_m[2] = {reinterpret_cast<T*>(base), reinterpret_cast<T*>(base) + (NS - 1) * 2 * kpad};
-  T* s_v[2] = {s_m[0] + kpad, s_m[1] + kpad};
-  __shared__ __align__(8) uint64_t bars[2];
-  __shared__ T s_xm[2][4], s_xv[2][4], s_zz[2][4], s_zmu[2][4];
-  __shared__ int s_xi[2][4], s_zc[2][4], s_zn[2][4], s_bi[2];
+  // dynamic smem: [select stage (kSelStageFused bytes, only if fused)] | per warp: NS x {m[kpad], v[kpad]}
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  T* wbase = reinterpret_cast<T*>(dyn_smem + (sel.do_select ? kSelStageFused : 0)) + (size_t)warp * NS * 2 * kpad;
+  __shared__ __align__(8) uint64_t bars[kRowWarps][2];
   const uint32_t row_bytes = (uint32_t)(K * sizeof(T));
   ScanPartial acc = empty_partial();
-
   for (int s = 0; s < NS; ++s)
-    for (int i = K + tid; i < kpad; i += kThreads) {  // sentinels behind the row: never best, never a candidate
-      s_m[s][i] = -pos_inf<T>();
-      s_v[s][i] = T(1);
+    for (int i = K + lane; i < kpad; i += 32) {  // sentinels behind the row: never best, key = +inf
+      wbase[s * 2 * kpad + i] = -pos_inf<T>();
+      wbase[s * 2 * kpad + kpad + i] = T(1);
     }
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+  if (lane == 0) {
+    mbar_init(&bars[warp][0], 1);
+    mbar_init(&bars[warp][1], 1);
     mbar_fence_init();
   }
-  __syncthreads();
-  auto issue = [&](int64_t c, int st) {
-    mbar_expect_tx(&bars[st], 2 * row_bytes);
-    tma_bulk_g2s(s_m[st], mean + c * ld, row_bytes, &bars[st]);
-    tma_bulk_g2s(s_v[st], var + c * ld, row_bytes, &bars[st]);
+  __syncwarp();
+  auto issue = [&](int64_t c, int st) {  // lane 0 only
+    T* sm = wbase + st * 2 * kpad;
+    mbar_expect_tx(&bars[warp][st], 2 * row_bytes);
+    tma_bulk_g2s(sm, mean + c * ld, row_bytes, &bars[warp][st]);
+    tma_bulk_g2s(sm + kpad, var + c * ld, row_bytes, &bars[warp][st]);
   };
-  // warp 0: fold the four per-warp minima of row `c` (exchange slot `par`) and emit the row
-  auto finish_row = [&](int64_t c, int par) {
-    ZMin<T> zm;
-    zm.z = s_zz[par][0]; zm.mu = s_zmu[par][0]; zm.col = s_zc[par][0]; zm.cnt = s_zn[par][0];
-#pragma unroll
-    for (int q = 1; q < NW; ++q) {
-      const T oz = s_zz[par][q], omu = s_zmu[par][q];
-      const int oi = s_zc[par][q], oc = s_zn[par][q];
-      if (oz < zm.z) { zm.z = oz; zm.mu = omu; zm.col = oi; zm.cnt = oc; }
-      else if (oz == zm.z) { zm.cnt += oc; if (omu > zm.mu || (omu == zm.mu && oi < zm.col)) { zm.mu = omu; zm.col = oi; } }
+  const int64_t row0 = (int64_t)blockIdx.x * kRowWarps + warp, step = (int64_t)gridDim.x * kRowWarps;
+  if (lane == 0)
+    for (int s = 0; s < NS; ++s)
+      if (row0 + s * step < n_c) issue(row0 + s * step, s);
+  int it = 0;
+  for (int64_t c = row0; c < n_c; c += step, ++it) {
+    const int st = NS == 2 ? (it & 1) : 0;
+    mbar_wait(&bars[warp][st], (uint32_t)(NS == 2 ? (it >> 1) : it) & 1u);
+    T* rm = wbase + st * 2 * kpad;
+    const T* rv = rm + kpad;
+    T bm, vb;
+    int bi;
+    if (ext_arm == nullptr) {
+      bm = -pos_inf<T>();
+      bi = INT_MAX;
+#pragma unroll 8
+      for (int j = 0; j < R; ++j) {
+        const T m = rm[j * 32 + lane];
+        if (m > bm) { bm = m; bi = j * 32 + lane; }
+      }
+      warp_argmax(bm, bi);
+      if (bi == INT_MAX) bi = 0;  // all-NaN row: arm 0 by convention
+      bm = rm[bi];
+      vb = rv[bi];
+    } else {
+      bi = ext_arm[c] - arm_offset;
+      bm = ext_mean[c];
+      vb = ext_var[c];
     }
-    const int gbest = s_bi[par] + arm_offset;
+    __syncwarp();
+    if (lane == 0 && bi >= 0 && bi < K) rm[bi] = -pos_inf<T>();  // the best arm never competes with itself
+    __syncwarp();
+    unsigned int* rk = reinterpret_cast<unsigned int*>(rm);  // key of entry a at word a * (sizeof(T) / 4)
+    constexpr int kw = sizeof(T) / 4;
+    unsigned int kmin = kKeyNone;
+#pragma unroll 8
+    for (int j = 0; j < R; ++j) {
+      const int a = j * 32 + lane;
+      const unsigned int key = zeta_key(bm, vb, rm[a], rv[a]);
+      rk[a * kw] = key;
+      kmin = min(kmin, key);
+    }
+    const unsigned int wmin = __reduce_min_sync(kFull, kmin);
+    // candidates: finite keys within the slack of the warp minimum (inf / NaN keys never qualify)
+    unsigned int thr = wmin + kKeySlack;
+    if (thr >= InfKey<T>::value || thr < wmin) thr = InfKey<T>::value - 1u;
+    ZMin<T> zm;
+    zm.init();
+    if (kmin <= thr) {
+      const T* grow = mean + c * ld;
+      for (int j = 0; j < R; ++j) {
+        const int a = j * 32 + lane;
+        if (rk[a * kw] <= thr) zm.add_exact(bm, vb, grow[a], rv[a], a);
+      }
+    }
+    const unsigned has = __ballot_sync(kFull, zm.cnt > 0);
+    if (__popc(has) == 1) {  // the common case: broadcast instead of a full reduction
+      const int src = __ffs(has) - 1;
+      zm.z = __shfl_sync(kFull, zm.z, src);
+      zm.mu = __shfl_sync(kFull, zm.mu, src);
+      zm.col = __shfl_sync(kFull, zm.col, src);
+      zm.cnt = __shfl_sync(kFull, zm.cnt, src);
+    } else if (has) {
+      zm.warp_reduce();
+    }
+    for (int i = K + lane; i < kpad; i += 32) rm[i] = -pos_inf<T>();  // the keys overwrote the sentinels too
+    __syncwarp();  // every lane is done with the stage
+    if (lane == 0 && c + NS * step < n_c) {
+      fence_proxy_async();
+      issue(c + NS * step, st);
+    }
+    const int gbest = bi + arm_offset;
     const int gz = zm.col == INT_MAX ? -1 : zm.col + arm_offset;
     if (lane == 0) {
       if (best_arm) best_arm[c] = gbest;
@@ -633,108 +697,7 @@ ocba_scan_tma_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
     p.best = gbest;
     p.pad = 0;
     if (zm.cnt > 0) combine(acc, p);
-  };
-  const int64_t step = gridDim.x;
-  if (tid == 0) {
-    if ((int64_t)blockIdx.x < n_c) issue(blockIdx.x, 0);
-    if (NS == 2 && (int64_t)blockIdx.x + step < n_c) issue(blockIdx.x + step, 1);
   }
-  int it = 0;
-  for (int64_t c = blockIdx.x; c < n_c; c += step, ++it) {
-    const int st = NS == 2 ? (it & 1) : 0, par = it & 1;
-    mbar_wait(&bars[st], (uint32_t)(NS == 2 ? (it >> 1) : it) & 1u);
-    T m[R], v[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      m[r] = s_m[st][r * kThreads + tid];
-      v[r] = s_v[st][r * kThreads + tid];
-    }
-    T bm, vb;
-    int bi;
-    if (ext_arm == nullptr) {
-      bm = m[0];
-      int br = 0;
-#pragma unroll
-      for (int r = 1; r < R; ++r)
-        if (m[r] > bm) { bm = m[r]; br = r; }
-      T vcand = v[0];
-#pragma unroll
-      for (int r = 1; r < R; ++r) vcand = br == r ? v[r] : vcand;
-      bi = br * kThreads + tid;
-      if (!(bm > -pos_inf<T>())) bi = INT_MAX;  // sentinel / NaN: not a candidate
-      const int mine = bi;
-      warp_argmax(bm, bi);
-      const unsigned own = __ballot_sync(kFull, mine == bi && bi != INT_MAX);
-      vb = __shfl_sync(kFull, vcand, own ? __ffs(own) - 1 : 0);  // the winner's variance sits in its owner lane
-      if (lane == 0) { s_xm[par][warp] = bm; s_xv[par][warp] = vb; s_xi[par][warp] = bi; }
-    }
-    __syncthreads();  // the only CTA barrier of the row: every thread holds its entries in registers
-    if (tid == 0 && c + NS * step < n_c) {
-      fence_proxy_async();
-      issue(c + NS * step, st);
-    }
-    if (warp == 0 && it > 0) finish_row(c - step, par ^ 1);
-    if (ext_arm == nullptr) {
-      bm = s_xm[par][0]; vb = s_xv[par][0]; bi = s_xi[par][0];
-#pragma unroll
-      for (int q = 1; q < NW; ++q) {
-        const T om = s_xm[par][q];
-        const int oi = s_xi[par][q];
-        if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; vb = s_xv[par][q]; }
-      }
-      if (bi == INT_MAX) {  // all-NaN row: arm 0 by convention
-        bi = 0;
-        bm = __shfl_sync(kFull, m[0], 0);
-        vb = __shfl_sync(kFull, v[0], 0);
-        if (warp != 0) { bm = mean[c * ld]; vb = var[c * ld]; }
-      }
-    } else {
-      bi = ext_arm[c] - arm_offset;
-      bm = ext_mean[c];
-      vb = ext_var[c];
-    }
-    if (tid == 0) s_bi[par] = bi;
-    // screening keys; the best arm's own entry is excluded
-    const int rb = (bi >= 0 && bi % kThreads == tid) ? bi / kThreads : -1;
-    unsigned int key[R], kmin = kKeyNone;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      key[r] = zeta_key(bm, vb, m[r], v[r]);
-      if (r == rb || !(m[r] > -pos_inf<T>())) key[r] = kKeyNone;
-      kmin = min(kmin, key[r]);
-    }
-    kmin = __reduce_min_sync(kFull, kmin);  // warp-local threshold: the row minimum lives in some warp
-    const unsigned int thr = kmin < kKeyNone - kKeySlack ? kmin + kKeySlack : kKeyNone - 1u;
-    unsigned cand = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) cand |= key[r] <= thr ? (1u << r) : 0u;
-    ZMin<T> zm;
-    zm.init();
-    while (cand) {  // typically one lane of the warp, one entry
-      const int r = __ffs(cand) - 1;
-      cand &= cand - 1;
-      T mm = m[0], vv = v[0];
-#pragma unroll
-      for (int q = 1; q < R; ++q) {
-        mm = q == r ? m[q] : mm;
-        vv = q == r ? v[q] : vv;
-      }
-      zm.add_exact(bm, vb, mm, vv, r * kThreads + tid);
-    }
-    const unsigned has = __ballot_sync(kFull, zm.cnt > 0);
-    if (__popc(has) == 1) {  // the common case: broadcast instead of a full reduction
-      const int src = __ffs(has) - 1;
-      zm.z = __shfl_sync(kFull, zm.z, src);
-      zm.mu = __shfl_sync(kFull, zm.mu, src);
-      zm.col = __shfl_sync(kFull, zm.col, src);
-      zm.cnt = __shfl_sync(kFull, zm.cnt, src);
-    } else if (has) {
-      zm.warp_reduce();
-    }
-    if (lane == 0) { s_zz[par][warp] = zm.z; s_zmu[par][warp] = zm.mu; s_zc[par][warp] = zm.col; s_zn[par][warp] = zm.cnt; }
-  }
-  __syncthreads();
-  if (warp == 0 && it > 0) finish_row(blockIdx.x + (int64_t)(it - 1) * step, (it - 1) & 1);
   scan_tail<T>(acc, partials, ticket, decision, sel, var, ld, arm_offset, dyn_smem);
 }
 
@@ -833,30 +796,29 @@ int scan_dispatch(const void* mean, const void* var, int64_t n_c, int K, int64_t
                                       decision, sel);
   };
   const size_t esz = sizeof(T);
-  const int seg = K <= 512 ? 4 : (K <= 768 ? 6 : 8);  // kpad = 128 seg >= K
-  // small fused problems: 4 warps per row, 2 stages (latency); otherwise one warp per row, 1 stage
-  // (measured, 65,536 rows: fp64 K = 1000 208 us with 4 warps vs 251 us with 1; fp32 175 vs 128 us)
-  const bool one_warp = !sel.do_select && !(esz == 8 && seg == 8);
-  const size_t tma_smem = dyn + (one_warp ? 2 : 4) * (size_t)seg * 128 * esz;  // stages of {mean row, var row}
+  const int seg = K <= 512 ? 4 : (K <= 768 ? 6 : 8);       // kpad = 128 seg >= K
+  const size_t stage = 2 * (size_t)seg * 128 * esz;         // one {mean row, var row} pair
+  const int ns = stage <= 4 * 1024 ? 2 : 1;                 // double-buffer a warp's rows only while >= 24 warps/SM still fit
+  const size_t tma_smem = dyn + (size_t)kRowWarps * ns * stage;
   const bool tma_ok = K > 256 && K <= 1024 && (K * esz) % 16 == 0 && (ld * esz) % 16 == 0 &&
                       ((uintptr_t)mean % 16 == 0) && ((uintptr_t)var % 16 == 0);
   if (tma_ok) {
     auto launch = [&](auto kern) -> int {
       if (tma_smem + 8 * 1024 > 48 * 1024)  // static shared memory (~4 KB) counts against the 48 KB default
         CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem), "scan attr");
-      int per_sm = (int)((220 * 1024) / (tma_smem + 1024 + 4096));
-      if (per_sm > 16) per_sm = 16;
-      if (!one_warp && per_sm > ((esz == 8 && seg == 8) ? 5 : 6)) per_sm = (esz == 8 && seg == 8) ? 5 : 6;
+      int per_sm = (int)((224 * 1024) / (tma_smem + 1024 + 4608));
+      if (per_sm > 8) per_sm = 8;
       if (per_sm < 1) per_sm = 1;
-      const int tblocks = (int)(n_c < 148 * per_sm ? n_c : 148 * per_sm);
-      kern<<<tblocks, one_warp ? 32 : 128, tma_smem, s>>>((const T*)mean, (const T*)var, n_c, K, ld, arm_offset, ext_best_arm,
+      const int64_t want_rows = (n_c + kRowWarps - 1) / kRowWarps;
+      const int tblocks = (int)(want_rows < 148 * per_sm ? want_rows : 148 * per_sm);
+      kern<<<tblocks, 32 * kRowWarps, tma_smem, s>>>((const T*)mean, (const T*)var, n_c, K, ld, arm_offset, ext_best_arm,
                                           (const T*)ext_best_mean, (const T*)ext_best_var, best_arm, (T*)min_zeta,
                                           min_arm, tie_cnt, partials, ticket, decision, sel);
       return CRS_OK;
     };
     int rc;
-    if (one_warp) rc = seg == 4 ? launch(ocba_scan_tma_kernel<T, 16, 1>) : (seg == 6 ? launch(ocba_scan_tma_kernel<T, 24, 1>) : launch(ocba_scan_tma_kernel<T, 32, 1>));
-    else rc = seg == 4 ? launch(ocba_scan_tma_kernel<T, 4, 4>) : (seg == 6 ? launch(ocba_scan_tma_kernel<T, 6, 4>) : launch(ocba_scan_tma_kernel<T, 8, 4>));
+    if (ns == 2) rc = seg == 4 ? launch(ocba_scan_row_kernel<T, 16, 2>) : (seg == 6 ? launch(ocba_scan_row_kernel<T, 24, 2>) : launch(ocba_scan_row_kernel<T, 32, 2>));
+    else rc = seg == 4 ? launch(ocba_scan_row_kernel<T, 16, 1>) : (seg == 6 ? launch(ocba_scan_row_kernel<T, 24, 1>) : launch(ocba_scan_row_kernel<T, 32, 1>));
     if (rc != CRS_OK) return rc;
   } else if (K <= 32) go(ocba_scan_kernel<T, 1, 1>);
   else if (K <= 64) go(ocba_scan_kernel<T, 2, 1>);
