@@ -42,6 +42,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner
+# to fd 1 when NCCL_DEBUG is set), so fd 1 is pointed at stderr for the whole run and the result line
+# goes to a private duplicate of the original stdout.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_RESULT_FD, (json.dumps(obj) + "\n").encode())
+
+
 import torch  # noqa: E402
 
 WORKLOADS = {
@@ -195,7 +206,7 @@ def run_reference(args, name):
     sample = (f"{steps} decisions on {sub}/{n_c} contexts x {K} arms, oracle '{variant}' variant "
               f"(PyTorch CPU, {cores} threads), time scaled x{n_c / sub:.0f}")
     val = 1.0 / dt_full
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "gp_c_ocba_decisions_per_sec", "value": val, "unit": "decisions/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt_full * 1e3,
         "higher_is_better": True, "scaling": "weak" if name == "c2" else "strong", "vs_baseline": None, "dtype": "f64",
@@ -405,7 +416,7 @@ def run_loop(args, dev, world, rank):
         peak = measure_pcs_draw_peak(dev)
         w = 8 if dtype == torch.float64 else 4
         val = steps / (tot_ms * 1e-3)
-        print(json.dumps({
+        emit(({
             "metric": "rs_loop_iterations_per_sec", "value": val, "unit": "iterations/s (decision + 2^16-sample PCS + update)",
             "n_gpus": world, "steps": steps, "warmup": W, "ms_per_step": tot_ms / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
@@ -640,7 +651,7 @@ def main():
             out["pcs"] = pcs
             out["headline"] = headline
             out["gpu_launches"] += pcs["gpu_launches"] + 4 * 4 * world  # headline: 4 kernels x (1 + 3) steps per rank
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
