@@ -87,6 +87,12 @@ CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32
   return launch_pcs_counts(mean, var, n_c, K, ld, dtype, num_samples, seed, offset, arm_offset, ctx_offset, counts, stats, (cudaStream_t)stream);
 }
 
+CRS_API int crs_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                                int32_t dtype, int64_t num_samples, uint64_t seed, uint32_t offset,
+                                int64_t ctx_offset, uint32_t* counts, uint64_t* stats, void* stream) {
+  return launch_pcs_counts_tree(mean, var, n_c, K, ld, dtype, num_samples, seed, offset, ctx_offset, counts, stats, (cudaStream_t)stream);
+}
+
 CRS_API int crs_levi_scan(const crs_gp_state* st, const void* mean, const void* var, int64_t n_c,
                           int64_t ld, const void* weights, void* ei_out, int64_t ld_ei, void* max_ei,
                           int32_t* max_arm, crs_levi_decision* decision, void* stream) {

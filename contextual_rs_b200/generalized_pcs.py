@@ -29,19 +29,43 @@ def _is_strict_indicator(func_I: Callable[[Tensor], Tensor]) -> bool:
     return out.shape == probe.shape and out.to(torch.float64).tolist() == [0.0, 0.0, 0.0, 1.0, 1.0]
 
 
+TREE_MAX_ARMS = 4098  # crs_pcs_counts_tree: top threat + 4^6 leaves + the best arm
+
+
 def pcs_counts(model: B200ModelListGP, mean: Tensor, var: Tensor, num_samples: int, seed: int,
                offset: int = 0, arm_offset: int = 0, ctx_offset: int = 0,
-               counts: Optional[Tensor] = None, stats: Optional[Tensor] = None) -> Tensor:
-    """Launch ``crs_pcs_counts`` on device tables ``[n_c, K]``; returns int32 counts ``[n_c]``."""
+               counts: Optional[Tensor] = None, stats: Optional[Tensor] = None,
+               sampler: str = "auto") -> Tensor:
+    """Correct-selection counts of device tables ``[n_c, K]``; returns int32 counts ``[n_c]``.
+
+    ``sampler``: ``"tree"`` = ``crs_pcs_counts_tree`` (max-tree stream: a sample is decided after a
+    few Philox calls; needs the full arm row, 2 <= K <= 4098), ``"flat"`` = ``crs_pcs_counts``
+    (one draw per arm, keyed by arm id — also serves arm slices via ``arm_offset``), ``"auto"`` =
+    tree whenever it applies.  Both are Monte-Carlo estimates of the same quantity; the two
+    streams are different, so counts agree within MC error, not draw for draw.
+    ``stats`` (``[2]`` int64, optional): flat -> {draws executed, nominal - executed};
+    tree -> {root tests, node expansions}."""
     n_c, K = mean.shape
+    if sampler not in ("auto", "tree", "flat"):
+        raise ValueError(f"unknown sampler {sampler!r}")
+    tree_ok = 2 <= K <= TREE_MAX_ARMS and arm_offset == 0
+    if sampler == "tree" and not tree_ok:
+        raise ValueError("the tree sampler needs the full arm row with 2 <= K <= 4098 and arm_offset = 0")
+    use_tree = tree_ok and sampler != "flat"
     if counts is None:
         counts = torch.empty(n_c, dtype=torch.int32, device=mean.device)
     with torch.cuda.device(mean.device):
-        rc = _lib.get().crs_pcs_counts(mean.data_ptr(), var.data_ptr(), n_c, K, mean.stride(0),
-                                       _lib.DTYPES[mean.dtype], int(num_samples), int(seed) & (2 ** 64 - 1),
-                                       int(offset) & 0xFFFFFFFF, int(arm_offset), int(ctx_offset),
-                                       counts.data_ptr(), _lib.ptr(stats), _lib.stream_ptr(mean.device))
-    _lib.check(rc, "crs_pcs_counts")
+        if use_tree:
+            rc = _lib.get().crs_pcs_counts_tree(mean.data_ptr(), var.data_ptr(), n_c, K, mean.stride(0),
+                                                _lib.DTYPES[mean.dtype], int(num_samples), int(seed) & (2 ** 64 - 1),
+                                                int(offset) & 0xFFFFFFFF, int(ctx_offset),
+                                                counts.data_ptr(), _lib.ptr(stats), _lib.stream_ptr(mean.device))
+        else:
+            rc = _lib.get().crs_pcs_counts(mean.data_ptr(), var.data_ptr(), n_c, K, mean.stride(0),
+                                           _lib.DTYPES[mean.dtype], int(num_samples), int(seed) & (2 ** 64 - 1),
+                                           int(offset) & 0xFFFFFFFF, int(arm_offset), int(ctx_offset),
+                                           counts.data_ptr(), _lib.ptr(stats), _lib.stream_ptr(mean.device))
+    _lib.check(rc, "crs_pcs_counts_tree" if use_tree else "crs_pcs_counts")
     return counts
 
 

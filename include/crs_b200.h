@@ -218,6 +218,23 @@ CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32
                    int32_t arm_offset, int64_t ctx_offset, uint32_t* counts, uint64_t* stats,
                    void* stream);
 
+/*
+ * Same estimate as crs_pcs_counts — counts[c] = number of the S posterior draws in which the
+ * predicted-best arm of context c beats every other arm (contextual_rs/generalized_pcs.py:441-475,
+ * func_I = strict indicator) — under the "max-tree" Philox stream: the K - 1 competitors are the
+ * leaves of a 4-ary tree in threat order, a node carries the largest standard normal among its
+ * leaves and the leaf that owns it, and children are drawn conditionally (truncated maxima), so a
+ * sample is decided after ~1-4 Philox calls instead of ~K/4 although the K - 1 leaf draws are iid
+ * N(0,1) exactly as before (stream definition + brute-force restatement: oracle/pcs_tree_ref.py).
+ * Counters (sample, context + ctx_offset, node, offset): counts do not depend on how contexts are
+ * sharded.  The full row of K arms must be passed (2 <= K <= 4098, else CRS_ERR_UNSUPPORTED).
+ * counts: [n_c] uint32.  stats (may be NULL): [2] uint64 = {root tests, node expansions} (one
+ * Philox call each).
+ */
+CRS_API int crs_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                                int32_t dtype, int64_t num_samples, uint64_t seed, uint32_t offset,
+                                int64_t ctx_offset, uint32_t* counts, uint64_t* stats, void* stream);
+
 /* Raw Philox4x32-10 words for known-answer tests: out[4*i..4*i+3] = philox(ctr[4*i..], key). */
 CRS_API int crs_philox_words(const uint32_t* ctr, int64_t n, uint32_t key0, uint32_t key1, uint32_t* out,
                      void* stream);
@@ -273,7 +290,8 @@ CRS_API int crs_debug_corr(const double* r2, int64_t n, int32_t kernel, int32_t 
  * 256 threads each run `iters` x 64 dependent-chain FMAs on 16 independent accumulators
  * (kind 0 = FP64, 1 = FP32): flops = blocks * 256 * iters * 64 * 2; kind 2 = FP64 mma.sync m8n8k4;
  * kind 5 = the bare PCS draw sequence (Philox4x32-10 + 2 Box-Muller + 4 FMA + max per iteration,
- * registers only): draws = blocks * 256 * iters * 4.  out: >= 8 bytes, device. */
+ * registers only): draws = blocks * 256 * iters * 4; kinds 6 / 7 = the bare root test / node
+ * expansion of the max-tree PCS kernel: steps = blocks * 256 * iters.  out: >= 8 bytes, device. */
 CRS_API int crs_peak_probe(int32_t kind, int32_t iters, int32_t blocks, void* out, void* stream);
 
 /*

@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import gp_oracle, levi_oracle, ocba_oracle, pcs_oracle, philox_ref
+from oracle import gp_oracle, levi_oracle, ocba_oracle, pcs_oracle, pcs_tree_ref, philox_ref
 
 pytestmark = pytest.mark.gpu
 
@@ -310,7 +310,7 @@ def test_pcs_counts_parity(crs, dtype, S):
     p = model.posterior(ctx.to(dtype))
     mean, var = p.mean.contiguous(), p.variance.contiguous()
     stats = torch.zeros(2, dtype=torch.int64, device=DEV)
-    cnt = pcs_counts(model, mean, var, S, seed=77, offset=3, stats=stats).cpu().numpy()
+    cnt = pcs_counts(model, mean, var, S, seed=77, offset=3, stats=stats, sampler="flat").cpu().numpy()
     want = philox_ref.pcs_counts_philox_ref(mean.cpu().numpy(), var.cpu().numpy(), S, seed=77, offset=3)
     # shared Philox stream: identical up to borderline draws (MUFU vs libm rounding of the normals)
     assert np.abs(cnt - want).max() <= 2 and (cnt != want).sum() <= 3
@@ -320,9 +320,9 @@ def test_pcs_counts_parity(crs, dtype, S):
     drawn, skipped = stats.cpu().tolist()
     assert drawn + skipped == S * 12 * 48  # executed + skipped = nominal S * K * n_c
     # sharding invariance: context / arm offsets only re-key the stream
-    half = pcs_counts(model, mean[24:], var[24:], S, seed=77, offset=3, ctx_offset=24).cpu().numpy()
+    half = pcs_counts(model, mean[24:], var[24:], S, seed=77, offset=3, ctx_offset=24, sampler="flat").cpu().numpy()
     assert np.array_equal(half, cnt[24:])
-    other = pcs_counts(model, mean, var, S, seed=78, offset=3).cpu().numpy()
+    other = pcs_counts(model, mean, var, S, seed=78, offset=3, sampler="flat").cpu().numpy()
     assert not np.array_equal(other, cnt)
 
 
@@ -335,7 +335,7 @@ def test_pcs_screening_is_exact(crs):
     mean[:, 20:] -= 50.0  # hopeless arms
     var = 0.05 + torch.rand(n_c, K, generator=gen, dtype=torch.float64)
     stats = torch.zeros(2, dtype=torch.int64, device=DEV)
-    cnt = pcs_counts(None, mean.to(DEV), var.to(DEV), S, seed=5, stats=stats).cpu().numpy()
+    cnt = pcs_counts(None, mean.to(DEV), var.to(DEV), S, seed=5, stats=stats, sampler="flat").cpu().numpy()
     want = philox_ref.pcs_counts_philox_ref(mean.numpy(), var.numpy(), S, seed=5)
     assert np.abs(cnt - want).max() <= 2
     drawn, skipped = stats.cpu().tolist()
@@ -343,8 +343,78 @@ def test_pcs_screening_is_exact(crs):
     # degenerate rows: a dominant best arm gives PCS = 1 exactly, equal arms give ~1/K
     mean2 = torch.zeros(4, 5, dtype=torch.float64); mean2[:2, 3] = 100.0
     var2 = torch.ones(4, 5, dtype=torch.float64)
-    c2 = pcs_counts(None, mean2.to(DEV), var2.to(DEV), S, seed=1).cpu().numpy()
-    assert c2[0] == S and c2[1] == S and abs(c2[2] / S - 0.2) < 0.04
+    for sampler in ("flat", "tree"):
+        c2 = pcs_counts(None, mean2.to(DEV), var2.to(DEV), S, seed=1, sampler=sampler).cpu().numpy()
+        assert c2[0] == S and c2[1] == S and abs(c2[2] / S - 0.2) < 0.04
+
+
+@pytest.mark.parametrize("dtype,S", [(torch.float64, 8192), (torch.float32, 5003)])
+def test_pcs_tree_parity(crs, dtype, S):
+    """Max-tree stream: the kernel's lazy walk reproduces the brute-force restatement
+    (oracle/pcs_tree_ref.py: every node and leaf generated) count for count, up to borderline
+    MUFU-vs-libm cases, and both estimate the quadrature value."""
+    from contextual_rs_b200.generalized_pcs import pcs_counts
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=12, n_c=48, d=2, n=10, seed=5)
+    model = crs.B200ModelListGP(desc, device=DEV, dtype=dtype)
+    p = model.posterior(ctx.to(dtype))
+    mean, var = p.mean.contiguous(), p.variance.contiguous()
+    stats = torch.zeros(2, dtype=torch.int64, device=DEV)
+    cnt = pcs_counts(model, mean, var, S, seed=77, offset=3, stats=stats, sampler="tree").cpu().numpy()
+    want = pcs_tree_ref.pcs_counts_tree_ref(mean.cpu().numpy(), var.cpu().numpy(), S, seed=77, offset=3)
+    assert np.abs(cnt - want).max() <= 2 and (cnt != want).sum() <= 3
+    exact = pcs_oracle.pcs_exact_quadrature(mean.double().cpu().numpy(), var.double().cpu().numpy())
+    se = np.sqrt(np.maximum(exact * (1 - exact), 1e-4) / S)
+    assert np.all(np.abs(cnt / S - exact) < 5 * se)
+    roots, expansions = stats.cpu().tolist()
+    assert roots == S * 48 and 0 < expansions < 12 * roots
+    half = pcs_counts(model, mean[24:], var[24:], S, seed=77, offset=3, ctx_offset=24, sampler="tree").cpu().numpy()
+    assert np.array_equal(half, cnt[24:])  # sharding invariance: context offsets only re-key the stream
+    other = pcs_counts(model, mean, var, S, seed=78, offset=3, sampler="tree").cpu().numpy()
+    assert not np.array_equal(other, cnt)
+    again = pcs_counts(model, mean, var, S, seed=77, offset=3).cpu().numpy()  # "auto" = tree; deterministic
+    assert np.array_equal(again, cnt)
+
+
+@pytest.mark.parametrize("K", [2, 3, 5, 6, 17, 18, 65, 70, 257, 258, 1000, 1025])
+def test_pcs_tree_shapes(crs, K):
+    """Every tree depth (1..6), full and ragged last levels, fp64 and fp32 tables, ragged sample
+    counts, rows with hopeless arms and exact mean ties."""
+    from contextual_rs_b200.generalized_pcs import pcs_counts
+    gen = torch.Generator().manual_seed(K)
+    n_c = 6
+    S = 3001 if K <= 300 else 700
+    mean = 0.6 * torch.randn(n_c, K, generator=gen, dtype=torch.float64)
+    var = 0.05 + 1.5 * torch.rand(n_c, K, generator=gen, dtype=torch.float64)
+    if K > 4:
+        mean[1, K // 2:] -= 40.0          # hopeless arms
+        mean[2, 1] = mean[2, 0] = mean[2].max() + 0.1  # tied best arms: first index is the predicted best
+        var[3] = 1e-10                    # variance floor: near-deterministic rows
+    for dtype in (torch.float64, torch.float32):
+        m, v = mean.to(dtype), var.to(dtype)
+        cnt = pcs_counts(None, m.to(DEV), v.to(DEV), S, seed=31 + K, offset=1, ctx_offset=7, sampler="tree").cpu().numpy()
+        want = pcs_tree_ref.pcs_counts_tree_ref(m.numpy(), v.numpy(), S, seed=31 + K, offset=1, ctx_offset=7)
+        assert np.abs(cnt - want).max() <= 2 and (cnt != want).sum() <= 2, (K, dtype, cnt, want)
+    exact = pcs_oracle.pcs_exact_quadrature(mean.numpy(), var.numpy())
+    se = np.sqrt(np.maximum(exact * (1 - exact), 1e-3) / S)
+    assert np.all(np.abs(want / S - exact) < 5 * se)
+
+
+def test_pcs_tree_limits(crs):
+    from contextual_rs_b200.generalized_pcs import pcs_counts
+    mean = torch.randn(2, 4100, dtype=torch.float64, device=DEV)
+    var = torch.ones(2, 4100, dtype=torch.float64, device=DEV)
+    with pytest.raises(ValueError):
+        pcs_counts(None, mean, var, 64, seed=1, sampler="tree")
+    a = pcs_counts(None, mean, var, 256, seed=1)          # auto -> flat stream beyond 4097 arms
+    b = pcs_counts(None, mean, var, 256, seed=1, sampler="flat")
+    assert torch.equal(a, b)
+    one = pcs_counts(None, mean[:, :1].contiguous(), var[:, :1].contiguous(), 100, seed=1)  # K = 1: no competitor
+    assert one.tolist() == [100, 100]
+    from contextual_rs_b200 import _lib
+    lib = _lib.get()
+    cnt = torch.zeros(2, dtype=torch.int32, device=DEV)
+    assert lib.crs_pcs_counts_tree(mean.data_ptr(), var.data_ptr(), 2, 4100, 4100, 0, 64, 1, 0, 0, cnt.data_ptr(), None, None) == 2
 
 
 def test_estimate_current_generalized_pcs_dropin(crs):
@@ -410,11 +480,12 @@ def test_full_size_properties(crs):
     c_star = int(zeta.min(dim=-1).values.argmin())
     assert torch.equal(x, ctx[c_star])
     S = 1024
-    full = pcs_counts(model, mean_d, var_d, S, seed=3)
-    parts = torch.cat([pcs_counts(model, mean_d[i:i + 2048], var_d[i:i + 2048], S, seed=3, ctx_offset=i)
-                       for i in range(0, 8192, 2048)])
-    assert torch.equal(full, parts)
-    assert int(full.min()) >= 0 and int(full.max()) <= S
+    for sampler in ("flat", "tree"):
+        full = pcs_counts(model, mean_d, var_d, S, seed=3, sampler=sampler)
+        parts = torch.cat([pcs_counts(model, mean_d[i:i + 2048], var_d[i:i + 2048], S, seed=3, ctx_offset=i, sampler=sampler)
+                           for i in range(0, 8192, 2048)])
+        assert torch.equal(full, parts)
+        assert int(full.min()) >= 0 and int(full.max()) <= S
 
 
 def test_fp64_kernel_math(crs):
@@ -786,6 +857,9 @@ def test_wide_model_decision_and_pcs(crs):
     mean = torch.randn(5, 1301, generator=g, dtype=torch.float64)
     var = 0.05 + torch.rand(5, 1301, generator=g, dtype=torch.float64)
     S = 512
-    cnt = pcs_counts(None, mean.to(DEV), var.to(DEV), S, seed=9).cpu().numpy()
+    cnt = pcs_counts(None, mean.to(DEV), var.to(DEV), S, seed=9, sampler="flat").cpu().numpy()
     want = philox_ref.pcs_counts_philox_ref(mean.numpy(), var.numpy(), S, seed=9)
+    assert np.abs(cnt - want).max() <= 2 and (cnt != want).sum() <= 2
+    cnt = pcs_counts(None, mean.to(DEV), var.to(DEV), S, seed=9, sampler="tree").cpu().numpy()  # depth 6
+    want = pcs_tree_ref.pcs_counts_tree_ref(mean.numpy(), var.numpy(), S, seed=9)
     assert np.abs(cnt - want).max() <= 2 and (cnt != want).sum() <= 2
