@@ -19,9 +19,10 @@
 //   expand   otherwise the node is expanded (one Philox call, three inverse-normal evaluations),
 //            each new child's arg-max leaf is tested, and only children whose bound reaches y_b
 //            are kept (per-lane stack in shared memory).  The bound of a node is the convex
-//            envelope g(z) = max_j (mu_j + sd_j z) of its leaves, tabulated at z = 0, 2.4, 4.8, 7.2
-//            and interpolated by chords (a chord of a convex function lies above it) — exact
-//            pruning, because zfun is non-increasing in t.  A success costs ~6-10 expansions at
+//            envelope g(z) = max_j (mu_j + sd_j z) of its leaves, tabulated at z = 0, 1.8, .. 7.2
+//            and interpolated by chords (a chord of a convex function lies above it; the
+//            interpolant is the max of the four chord lines: 4 FMA + 3 max) — exact pruning,
+//            because zfun is non-increasing in t.  A success costs ~6-10 expansions at
 //            K = 1,000 (30-60 with the cruder bound mu_max + sd_max z).
 //   pool     per warp: root tests run warp-wide (no divergence) and park their survivors in a
 //            shared-memory queue; lanes walk one survivor each and take the next one when done; when
@@ -40,7 +41,7 @@ constexpr int kTreeWarps = kTreeThreads / 32;
 constexpr int kTreeQueue = 96;          // root survivors parked per warp
 constexpr int kTreeMinActive = 20;      // fewer walking lanes than this (and fresh samples left): refill first
 constexpr int kTreeMaxLeaves = 4096;    // 10-bit arg-max fields per child: depth <= 6
-constexpr float kTreeGrid = 2.4f;       // spacing of the envelope table (zfun < 6.9 < 3 * 2.4)
+constexpr float kTreeGrid = 1.8f;       // spacing of the envelope table (zfun < 6.9 < 4 * 1.8)
 constexpr float kTreeEmpty = -1e30f;    // envelope of a node without leaves
 constexpr int kTreeSplitSamples = 8192; // smallest sample range worth a plan build of its own
 constexpr float kNegLn2 = -0.6931471805599453f;
@@ -55,10 +56,13 @@ __device__ __forceinline__ float approx_exp2(float x) {
 // mirrored by oracle/pcs_tree_ref.py::zfun32).  p = smaller tail probability (1 - e^-t by series for
 // small t), w = -ln(4 p (1 - p)), z = +-(1 - 2p) * poly, poly ~ sqrt(2) erfinv(x) / x in (w - 3.125)
 // for w < 6.25 and in (sqrt(w) - 3.848) up to w = 27 (|z| < 6.9).
+// kSmallT: the caller guarantees t < 0.25 (roots of trees with >= 128 leaves) — same values, fewer
+// instructions.
+template <bool kSmallT = false>
 __device__ __forceinline__ float zfun(float t) {
   t = fminf(t, 64.f);
-  const bool upper = t < 0.6931471805599453f;
-  const float P = approx_exp2(t * -1.4426950408889634f);
+  const bool upper = kSmallT || t < 0.6931471805599453f;
+  const float P = kSmallT ? 0.f : approx_exp2(t * -1.4426950408889634f);
   float qp = 0.000198412701f;
   qp = fmaf(qp, t, -0.00138888892f);
   qp = fmaf(qp, t, 0.00833333377f);
@@ -66,7 +70,7 @@ __device__ __forceinline__ float zfun(float t) {
   qp = fmaf(qp, t, 0.166666672f);
   qp = fmaf(qp, t, -0.5f);
   qp = fmaf(qp, t, 1.f);
-  const float q = t < 0.25f ? __fmul_rn(qp, t) : 1.f - P;
+  const float q = (kSmallT || t < 0.25f) ? __fmul_rn(qp, t) : 1.f - P;
   const float p = upper ? q : P;
   const float a = fmaf(-p, p, p);
   float w = fmaf(approx_log2(a), kNegLn2, -1.3862943611198906f);
@@ -95,14 +99,22 @@ __device__ __forceinline__ float zfun(float t) {
   return upper ? z : -z;
 }
 
-// chord interpolation of a node's envelope table g(0), g(2.4), g(4.8), g(7.2); z < 0: g(0)
-__device__ __forceinline__ float node_bound(const float4 g, float z) {
-  const float u = fmaxf(z, 0.f) * (1.f / kTreeGrid);
-  const int k = min((int)u, 2);
-  const float f = u - (float)k;
-  const float lo = k == 0 ? g.x : (k == 1 ? g.y : g.z);
-  const float hi = k == 0 ? g.y : (k == 1 ? g.z : g.w);
-  return fmaf(hi - lo, f, lo);
+// A node's bound: the four chord lines a_k + s_k z of its envelope table g(0), g(1.8), .. g(7.2).
+// The interpolant of a convex function is the maximum of its (extended) chords; z < 0: g(0).
+struct __align__(16) NodeLines { float4 a, s; };
+__device__ __forceinline__ float node_bound(const NodeLines& nd, float z) {
+  const float zp = fmaxf(z, 0.f);
+  return fmaxf(fmaxf(fmaf(nd.s.x, zp, nd.a.x), fmaf(nd.s.y, zp, nd.a.y)),
+               fmaxf(fmaf(nd.s.z, zp, nd.a.z), fmaf(nd.s.w, zp, nd.a.w)));
+}
+// lines from the table g[0..4] (grid spacing kTreeGrid)
+__device__ __forceinline__ NodeLines make_lines(const float g[5]) {
+  NodeLines nd;
+  const float inv = 1.f / kTreeGrid;
+  nd.s = make_float4((g[1] - g[0]) * inv, (g[2] - g[1]) * inv, (g[3] - g[2]) * inv, (g[4] - g[3]) * inv);
+  nd.a = make_float4(g[0], fmaf(-nd.s.y, kTreeGrid, g[1]), fmaf(-nd.s.z, 2.f * kTreeGrid, g[2]),
+                     fmaf(-nd.s.w, 3.f * kTreeGrid, g[3]));
+  return nd;
 }
 
 // index of the first node of level l: (4^l - 1) / 3 = 0b0101...01 (l ones)
@@ -131,10 +143,11 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // [ leaves (mu, sd) | nodes (envelope table) | sort scratch  ==alias==  stacks + queues ]
   float2* leaf = reinterpret_cast<float2*>(smem_raw);
-  float4* node = reinterpret_cast<float4*>(leaf + NL);
+  NodeLines* node = reinterpret_cast<NodeLines*>(leaf + NL);
   unsigned char* region = reinterpret_cast<unsigned char*>(node + NI);
   float* s_key = reinterpret_cast<float*>(region);
   int* s_ord = reinterpret_cast<int*>(s_key + n2);
+  float* s_g = reinterpret_cast<float*>(region);                    // [NI][5] envelope tables while the nodes are built
   uint32_t* stk_meta = reinterpret_cast<uint32_t*>(region);          // [slots][threads]: level<<24 | index<<12 | J
   float* stk_t = reinterpret_cast<float*>(stk_meta + slots * kTreeThreads);
   float* stk_z = stk_t + slots * kTreeThreads;
@@ -155,6 +168,7 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
   const int nleaf = K - 2;   // all but the most threatening one, which is drawn at the root
   const uint32_t jmask = (uint32_t)NL - 1u;
   const float c_root = neg_ln2_scaled(2 * D);
+  const bool small_root = D >= 4;  // t_root <= 16.7 / 256
   const unsigned int lt_mask = (1u << lane) - 1u;
   unsigned long long n_roots = 0, n_exp = 0;
 
@@ -245,36 +259,35 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
       const int nn = 1 << (2 * l);
       const uint32_t b0 = level_base(l), b1 = level_base(l + 1);
       for (int i = tid; i < nn; i += kTreeThreads) {
-        float4 g = make_float4(kTreeEmpty, kTreeEmpty, kTreeEmpty, kTreeEmpty);
+        float g[5] = {kTreeEmpty, kTreeEmpty, kTreeEmpty, kTreeEmpty, kTreeEmpty};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (l == D - 1) {
             const int p = 4 * i + k;
             if (p < nleaf) {
               const float2 lf = leaf[p];
-              g.x = fmaxf(g.x, lf.x);
-              g.y = fmaxf(g.y, fmaf(lf.y, kTreeGrid, lf.x));
-              g.z = fmaxf(g.z, fmaf(lf.y, 2.f * kTreeGrid, lf.x));
-              g.w = fmaxf(g.w, fmaf(lf.y, 3.f * kTreeGrid, lf.x));
+#pragma unroll
+              for (int q = 0; q < 5; ++q) g[q] = fmaxf(g[q], fmaf(lf.y, (float)q * kTreeGrid, lf.x));
             }
           } else {
-            const float4 nd = node[b1 + 4 * i + k];
-            g.x = fmaxf(g.x, nd.x);
-            g.y = fmaxf(g.y, nd.y);
-            g.z = fmaxf(g.z, nd.z);
-            g.w = fmaxf(g.w, nd.w);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) g[q] = fmaxf(g[q], s_g[5 * (b1 + 4 * i + k) + q]);
           }
         }
-        if (l == D - 1) {  // head-room for the rounding of the chord (g is non-decreasing: |g| <= max(|g0|, |g3|))
-          const float pad = fmaxf(fabsf(g.x), fabsf(g.w)) * 1.9073486328125e-06f;  // 2^-19
-          g.x += pad; g.y += pad; g.z += pad; g.w += pad;
+        if (l == D - 1) {  // head-room for the rounding of the lines (g is non-decreasing: |g| <= max(|g0|, |g4|))
+          const float pad = fmaxf(fabsf(g[0]), fabsf(g[4])) * 3.814697265625e-06f;  // 2^-18
+#pragma unroll
+          for (int q = 0; q < 5; ++q) g[q] += pad;
         }
-        node[b0 + i] = g;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) s_g[5 * (b0 + i) + q] = g[q];
+        node[b0 + i] = make_lines(g);
       }
       __syncthreads();
     }
     const uint32_t cw = (uint32_t)(c + ctx_offset);
-    const float4 root = node[0];
+    const NodeLines root = node[0];
+    __syncthreads();  // s_g (aliased by stacks and queues) is dead from here on
     const float2 top = s_top;
 
     // ---- sampling -------------------------------------------------------------------------------
@@ -298,7 +311,7 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
         const float ybs = __fmul_rn(sd_b, zb);
         const float t = __fmul_rn(log2_unit_open(w.z), c_root);
         const uint32_t J = w.w & jmask;
-        const float z = zfun(t);
+        const float z = small_root ? zfun<true>(t) : zfun<false>(t);
         const float2 lf = leaf[J];
         const bool fail = fmaf(top.y, ztop, top.x) >= ybs || fmaf(lf.y, z, lf.x) >= ybs;
         const bool open = node_bound(root, z) >= ybs;  // some other arm may still reach y_b
@@ -363,8 +376,7 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
             const float2 lf = leaf[Jc];
             fail = fail || fmaf(lf.y, zc, lf.x) >= yb;
             if (inner) {
-              const float4 nd = node[cbase + k];
-              if (node_bound(nd, zc) >= yb) {
+              if (node_bound(node[cbase + k], zc) >= yb) {
                 stk_meta[sp * kTreeThreads + tid] = lvl | (ci << 12) | Jc;
                 stk_t[sp * kTreeThreads + tid] = tc;
                 stk_z[sp * kTreeThreads + tid] = zc;
@@ -373,8 +385,7 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
             }
           }
           if (inner) {  // the child that inherits (t, J): its leaf J is already known to be below y_b
-            const float4 nd = node[cbase + kp];
-            if (node_bound(nd, z) >= yb) {
+            if (node_bound(node[cbase + kp], z) >= yb) {
               stk_meta[sp * kTreeThreads + tid] = lvl | ((4u * i + kp) << 12) | J;
               stk_t[sp * kTreeThreads + tid] = t;
               stk_z[sp * kTreeThreads + tid] = z;
@@ -416,10 +427,10 @@ tree_probe_kernel(int kind, int iters, const __grid_constant__ RoundKeys rk, flo
       float zb, ztop;
       box_muller(w.x, w.y, zb, ztop);
       const float yb = 0.9f * zb;
-      const float z = zfun(log2_unit_open(w.z) * c_m);
+      const float z = zfun<true>(log2_unit_open(w.z) * c_m);
       const float m2 = __uint_as_float((w.w & 0xffu) | 0x3f000000u);
       hits += (fmaf(sd, ztop, mu) >= yb || fmaf(m2, z, mu) >= yb) ? 1u : 0u;
-      hits += (node_bound(make_float4(mu, m2, 3.f, 5.f), z) >= yb) ? 2u : 0u;
+      hits += (node_bound(NodeLines{make_float4(mu, m2, -1.f, -3.f), make_float4(0.2f, 0.5f, 0.9f, 1.4f)}, z) >= yb) ? 2u : 0u;
     }
   } else {
     float t = 1e-3f;
@@ -431,7 +442,7 @@ tree_probe_kernel(int kind, int iters, const __grid_constant__ RoundKeys rk, flo
         const float zc = zfun(fmaf(log2_unit_open(word), c_m, t));
         const float m2 = __uint_as_float(((w.w >> (10 * r)) & 0xffu) | 0x3f000000u);
         hits += (fmaf(sd, zc, mu) >= 2.5f) ? 1u : 0u;
-        hits += (node_bound(make_float4(mu, m2, 3.f, 5.f), zc) >= 2.5f) ? 2u : 0u;
+        hits += (node_bound(NodeLines{make_float4(mu, m2, -1.f, -3.f), make_float4(0.2f, 0.5f, 0.9f, 1.4f)}, zc) >= 2.5f) ? 2u : 0u;
       }
       t = __uint_as_float((hits & 0xffu) | 0x3a000000u);
     }
@@ -457,8 +468,9 @@ int launch_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int K
   while (n2 < K - 1) n2 <<= 1;
   const int slots = D >= 2 ? 3 * (D - 1) + 1 : 1;
   const size_t walk = (size_t)slots * kTreeThreads * 12 + (size_t)kTreeWarps * kTreeQueue * 20;
-  const size_t sort = (size_t)n2 * 8;
-  const size_t smem = (size_t)NL * 8 + (size_t)NI * 16 + (walk > sort ? walk : sort);
+  size_t build = (size_t)n2 * 8;  // sort scratch, then the [NI][5] envelope tables — both dead before the walk
+  if (build < (size_t)NI * 20) build = (size_t)NI * 20;
+  const size_t smem = (size_t)NL * 8 + (size_t)NI * 32 + (walk > build ? walk : build);
   static unsigned long long* rings[64] = {nullptr};
   static unsigned int next_slot = 0;
   int dev = 0;

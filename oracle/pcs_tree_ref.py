@@ -96,7 +96,7 @@ def exp_log2(w: np.ndarray) -> np.ndarray:
     return np.log2(_unit(w) + F32(2.0 ** -24)).astype(F32)
 
 
-GRID = F32(2.4)          # spacing of the envelope table g(0), g(2.4), g(4.8), g(7.2)
+GRID = F32(1.8)          # spacing of the envelope table g(0), g(1.8), .. g(7.2)
 EMPTY = F32(-1e30)
 
 
@@ -109,8 +109,8 @@ def tree_depth(K: int) -> int:
 
 def tree_plan(mean_row: np.ndarray, var_row: np.ndarray):
     """Competitors in threat order and the per-node bounds.  Returns dict(best, sd_b, D, top_mu,
-    top_sd, leaf_mu, leaf_sd, order, levels) with levels[l] = ``[4^l, 4]`` envelope tables
-    g(z) = max over the node's leaves of mu_j + sd_j z at z = 0, 2.4, 4.8, 7.2 (EMPTY if none)."""
+    top_sd, leaf_mu, leaf_sd, order, levels) with levels[l] = ``[4^l, 5]`` envelope tables
+    g(z) = max over the node's leaves of mu_j + sd_j z at z = 0, 1.8, .. 7.2 (EMPTY if none)."""
     K = mean_row.shape[0]
     b = int(np.argmax(mean_row))
     mu = (mean_row - mean_row[b]).astype(F32)          # centred in the grid dtype, then fp32
@@ -127,24 +127,29 @@ def tree_plan(mean_row: np.ndarray, var_row: np.ndarray):
     leaf_mu[:K - 2] = mu[order[1:]]
     leaf_sd[:K - 2] = sd[order[1:]]
     real = (np.arange(NL) < K - 2).reshape(-1, 1)
-    zk = (np.arange(4, dtype=np.float64) * float(GRID)).astype(F32).reshape(1, -1)
-    g = np.where(real, _fma(leaf_sd.reshape(-1, 1), zk, leaf_mu.reshape(-1, 1)), EMPTY).astype(F32)  # [NL, 4]
+    zk = (np.arange(5, dtype=np.float64) * float(GRID)).astype(F32).reshape(1, -1)
+    g = np.where(real, _fma(leaf_sd.reshape(-1, 1), zk, leaf_mu.reshape(-1, 1)), EMPTY).astype(F32)  # [NL, 5]
     levels = [None] * D
     for l in range(D - 1, -1, -1):
-        g = g.reshape(-1, 4, 4).max(axis=1)
-        if l == D - 1:  # head-room for the rounding of the chord
-            g = (g + (np.maximum(np.abs(g[:, :1]), np.abs(g[:, 3:])) * F32(2.0 ** -19)).astype(F32)).astype(F32)
+        g = g.reshape(-1, 4, 5).max(axis=1)
+        if l == D - 1:  # head-room for the rounding of the chord lines
+            g = (g + (np.maximum(np.abs(g[:, :1]), np.abs(g[:, 4:])) * F32(2.0 ** -18)).astype(F32)).astype(F32)
         levels[l] = g
     return dict(best=b, sd_b=sd[b], D=D, top_mu=mu[order[0]], top_sd=sd[order[0]], leaf_mu=leaf_mu,
                 leaf_sd=leaf_sd, order=order, levels=levels)
 
 
 def node_bound(g: np.ndarray, z) -> float:
-    """Chord interpolation of one node's envelope table (the kernel's ``node_bound``)."""
-    u = F32(max(F32(z), F32(0))) * F32(1.0 / float(GRID))
-    k = min(int(u), 2)
-    f = F32(u - F32(k))
-    return float(_fma(F32(g[k + 1] - g[k]), f, g[k]))
+    """Upper bound of a node's envelope at z: the maximum of the four chord lines of its table
+    (the kernel's ``node_bound``; z < 0 -> g(0))."""
+    zp = F32(max(F32(z), F32(0)))
+    inv = F32(1.0 / float(GRID))
+    best = -np.inf
+    for k in range(4):
+        sl = F32(F32(g[k + 1] - g[k]) * inv)
+        a = g[0] if k == 0 else _fma(-sl, F32(k * float(GRID)), g[k])
+        best = max(best, float(_fma(sl, zp, a)))
+    return best
 
 
 def tree_leaf_normals(num_samples: int, context: int, D: int, seed: int, offset: int, first_sample: int = 0):

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "pcs" > gpurun_out/pytest_tree.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_tree.log
+FLAT=0 timeout 300 python scripts/pcs_tree_run.py 65536 c3 f32 2>&1 | tail -1
+FLAT=0 timeout 300 python scripts/pcs_tree_run.py 65536 c5 f32 2>&1 | tail -1
+FLAT=0 timeout 300 python scripts/pcs_tree_run.py 65536 c4 f32 16384 2>&1 | tail -1
+FLAT=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:pcs_tree_kernel -s 2 -c 1 -o gpurun_out/prof_tree_c4 -f python scripts/pcs_tree_run.py 65536 c4 f32 16384 > gpurun_out/ncu_tree.log 2>&1; echo "ncu rc=$?"
