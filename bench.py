@@ -224,9 +224,9 @@ PCS_CONFIG = "c3: generalized-PCS MC estimate, 2^16 samples, 256 arms x 8,192 co
 def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
     """PCS MC samples/s on config 3 (fp32).  Contexts are sharded over ranks; counts are combined
     with one all-reduce.  'value' counts the S*n_c*K nominal draws of the estimator ("equivalent
-    samples"); the draws actually executed — samples stop at their first failure / when no
-    remaining arm can win, which leaves every count identical — are reported beside it and are
-    what the roofline fraction is computed from."""
+    samples").  The max-tree kernel decides a sample with a root test plus a few node expansions
+    (one Philox call each) instead of K draws; the executed steps are reported beside the value
+    and are what the roofline fraction is computed from.  The flat per-arm stream is timed too."""
     import torch.distributed as dist
     import contextual_rs_b200 as crs
     from contextual_rs_b200.generalized_pcs import pcs_counts
@@ -241,8 +241,8 @@ def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
     stats = torch.zeros(2, dtype=torch.int64, device=dev)
     total = torch.zeros(1, dtype=torch.float64, device=dev)
 
-    def step(i):
-        c = pcs_counts(model, mean, var, num_samples, seed=0, offset=i, ctx_offset=b, stats=stats)
+    def step(i, sampler="tree"):
+        c = pcs_counts(model, mean, var, num_samples, seed=0, offset=i, ctx_offset=b, stats=stats, sampler=sampler)
         total[0] = c.sum(dtype=torch.int64).to(torch.float64)
         if world > 1:
             dist.all_reduce(total)
@@ -266,20 +266,33 @@ def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(st)
     t_step = float(tt)
-    drawn, skipped = st.tolist()
+    roots, expansions = st.tolist()
+    pcs_tree_mean = float(total) / (num_samples * n_c)
+    # the flat per-arm stream (crs_pcs_counts) on the same tables, for comparison
+    step(0, "flat")
+    torch.cuda.synchronize()
+    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    step(1, "flat")
+    t.record()
+    t.synchronize()
+    tf = torch.tensor([s.elapsed_time(t) * 1e-3], dtype=torch.float64, device=dev)
+    sf = stats.to(torch.float64)
+    if world > 1:
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sf)
     nominal = float(num_samples) * n_c * K
     out = {"metric": "pcs_mc_samples_per_sec", "value": nominal / t_step, "unit": "equivalent N(0,1) draws/s",
            "config": {"workload": PCS_CONFIG, "samples": num_samples, "arms": K, "contexts": n_c,
-                      "sharding": f"contexts/{world}" if world > 1 else "none"},
-           "ms_per_estimate": t_step * 1e3, "executed_draws_per_sec": drawn / t_step,
-           "executed_fraction": drawn / (drawn + skipped), "pcs_mean": float(total) / (num_samples * n_c),
-           "gpu_launches": reps + 1}
-    from contextual_rs_b200.peaks import measure_pcs_draw_peak
-    peak = measure_pcs_draw_peak(dev)  # live micro-kernel: the bare draw sequence on registers
-    out["roofline"] = {"kernel": "pcs_counts_kernel", "bound": "issue", "achieved": drawn / t_step / world / 1e9,
-                       "peak": peak / 1e9, "unit": "G draws/s", "frac": drawn / t_step / world / peak, "traffic": None,
-                       "peak_source": "measured in this run by crs_peak_probe kind 5 (Philox4x32-10 + 2 Box-Muller + 4 FMA + max "
-                                      "per 4 draws on registers, no memory, no control flow); achieved = EXECUTED draws/s"}
+                      "sharding": f"contexts/{world}" if world > 1 else "none", "sampler": "max-tree stream (crs_pcs_counts_tree)"},
+           "ms_per_estimate": t_step * 1e3, "sample_context_pairs_per_sec": float(num_samples) * n_c / t_step,
+           "philox_calls_per_sample": (roots + expansions) / (float(num_samples) * n_c),
+           "pcs_mean": pcs_tree_mean, "gpu_launches": reps + 3,
+           "flat_stream": {"ms_per_estimate": float(tf) * 1e3, "executed_draws_per_sec": float(sf[0]) / float(tf),
+                           "executed_fraction": float(sf[0]) / float(sf[0] + sf[1]),
+                           "pcs_mean": float(total) / (num_samples * n_c)}}
+    from contextual_rs_b200.peaks import measure_pcs_tree_rates, pcs_tree_roofline
+    out["roofline"] = pcs_tree_roofline(roots, expansions, t_step, world, measure_pcs_tree_rates(dev))
     if cpu and world == 1 and rank == 0:
         from oracle import pcs_oracle
         torch.set_num_threads(os.cpu_count() or 1)
@@ -355,7 +368,7 @@ def run_loop(args, dev, world, rank):
     all-reduce) -> condition the sampled arm on the new observation and refresh its grid column."""
     import torch.distributed as dist
     import contextual_rs_b200 as crs
-    from contextual_rs_b200.peaks import measure_pcs_draw_peak
+    from contextual_rs_b200.peaks import measure_pcs_tree_rates, pcs_tree_roofline
     from contextual_rs_b200.sharded import ShardedSequentialRS
     from contextual_rs_b200.synthetic import make_config
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
@@ -387,7 +400,7 @@ def run_loop(args, dev, world, rank):
     if rank == 0:
         sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
-    drawn = 0.0
+    drawn = torch.zeros(2, dtype=torch.float64)
     barrier()
     for i in range(steps):
         ev[i][0].record()
@@ -396,7 +409,7 @@ def run_loop(args, dev, world, rank):
         y = truth(out["next_arm"], out["next_context"])
         pcs = loop.pcs()
         ev[i][2].record()
-        drawn += float(stats[0])
+        drawn += stats.cpu().to(torch.float64)  # {root tests, node expansions} of this estimate
         loop.observe(out["next_arm"], out["next_context"].view(1, -1), y.reshape(1, 1))
         loop.iteration += 1
         it_box[0] += 1
@@ -404,16 +417,15 @@ def run_loop(args, dev, world, rank):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     parts = torch.tensor([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in ev], dtype=torch.float64).sum(dim=0)
-    t = torch.cat([parts, parts.sum().reshape(1), torch.tensor([drawn], dtype=torch.float64)]).to(dev)
+    t = torch.cat([parts, parts.sum().reshape(1), drawn]).to(dev)
     if world > 1:
         tmax = t[:4].clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dsum = t[4:].clone()
         dist.all_reduce(dsum)
         t = torch.cat([tmax, dsum])
-    dec_ms, pcs_ms, obs_ms, tot_ms, drawn_all = t.tolist()
+    dec_ms, pcs_ms, obs_ms, tot_ms, roots_all, exp_all = t.tolist()
     if rank == 0:
-        peak = measure_pcs_draw_peak(dev)
         w = 8 if dtype == torch.float64 else 4
         val = steps / (tot_ms * 1e-3)
         emit(({
@@ -427,9 +439,7 @@ def run_loop(args, dev, world, rank):
             "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": (d + 1) * 8 * world, "d2h_bytes_per_step": 64 * world,
                     "note": "the loop is host-driven: every iteration reads the decision back and uploads the new observation"},
             "gpu_launches": 5 * steps * world,
-            "roofline": {"kernel": "pcs_counts_kernel", "bound": "issue", "achieved": drawn_all / (pcs_ms * 1e-3) / world / 1e9,
-                         "peak": peak / 1e9, "unit": "G draws/s", "frac": drawn_all / (pcs_ms * 1e-3) / world / peak, "traffic": None,
-                         "peak_source": "crs_peak_probe kind 5 measured in this run; achieved = EXECUTED draws/s per GPU"},
+            "roofline": pcs_tree_roofline(roots_all, exp_all, pcs_ms * 1e-3, world, measure_pcs_tree_rates(dev)),
             "pcs_last": float(pcs), "clocks": clocks}))
     if world > 1:
         dist.barrier()

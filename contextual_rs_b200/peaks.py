@@ -45,3 +45,42 @@ def measure_pcs_draw_peak(device, iters: int = 4096, blocks: int = 148 * 8, reps
             if r:
                 best = max(best, blocks * 256.0 * iters * 4 / (s.elapsed_time(e) * 1e-3))
     return best
+
+
+def measure_pcs_tree_rates(device, iters: int = 2048, blocks: int = 148 * 8, reps: int = 4) -> dict:
+    """Steps/s of the bare arithmetic of the max-tree PCS kernel (``crs_pcs_counts_tree``) on
+    registers — ``crs_peak_probe`` kind 6: one root test (Philox4x32-10, Box-Muller pair, one
+    inverse normal, two leaf tests, one node bound); kind 7: one node expansion (Philox4x32-10,
+    three inverse normals, three leaf tests, three node bounds).  No memory, queueing or control
+    flow: the roofline denominators of that kernel."""
+    lib = _lib.get()
+    out = torch.zeros(2, dtype=torch.float32, device=device)
+    rates = {}
+    with torch.cuda.device(device):
+        stream = _lib.stream_ptr(torch.device(device))
+        for name, kind in (("root", 6), ("expand", 7)):
+            best = 0.0
+            for r in range(reps + 1):
+                s = torch.cuda.Event(enable_timing=True)
+                e = torch.cuda.Event(enable_timing=True)
+                s.record()
+                _lib.check(lib.crs_peak_probe(kind, iters, blocks, out.data_ptr(), stream), "crs_peak_probe")
+                e.record()
+                e.synchronize()
+                if r:
+                    best = max(best, blocks * 256.0 * iters / (s.elapsed_time(e) * 1e-3))
+            rates[name] = best
+    return rates
+
+
+def pcs_tree_roofline(roots: float, expansions: float, seconds: float, n_gpus: int, rates: dict) -> dict:
+    """Roofline entry of the tree kernel: the time the executed root tests and node expansions
+    would take as bare register arithmetic (``measure_pcs_tree_rates``) over the measured time."""
+    ideal = (roots / rates["root"] + expansions / rates["expand"]) / n_gpus
+    steps = roots + expansions
+    return {"kernel": "pcs_tree_kernel", "bound": "issue", "achieved": steps / seconds / n_gpus / 1e9,
+            "peak": steps / ideal / n_gpus / 1e9, "unit": "G steps/s", "frac": ideal / seconds, "traffic": None,
+            "root_tests": roots, "node_expansions": expansions,
+            "peak_source": "measured in this run by crs_peak_probe kinds 6 / 7: the bare root-test and node-expansion "
+                           "sequences on registers (%.1f / %.1f G steps/s per GPU), weighted by the executed mix; "
+                           "achieved = executed steps/s per GPU" % (rates["root"] / 1e9, rates["expand"] / 1e9)}
