@@ -52,29 +52,26 @@ __device__ __forceinline__ float approx_exp2(float x) {
   return r;
 }
 
-// z with Phi(z) = exp(-t), t >= 0 (|error| < 2e-6, non-increasing in t; fp32 operation sequence
+// z with Phi(z) = exp(-t), t >= 0 (|error| < 3e-6, non-increasing in t; fp32 operation sequence
 // mirrored by oracle/pcs_tree_ref.py::zfun32).  p = smaller tail probability (1 - e^-t by series for
-// small t), w = -ln(4 p (1 - p)), z = +-(1 - 2p) * poly, poly ~ sqrt(2) erfinv(x) / x in (w - 3.125)
+// t < 1/8), w = -ln(4 p (1 - p)), z = +-(1 - 2p) * poly, poly ~ sqrt(2) erfinv(x) / x in (w - 3.125)
 // for w < 6.25 and in (sqrt(w) - 3.848) up to w = 27 (|z| < 6.9).
-// kSmallT: the caller guarantees t < 0.25 (roots of trees with >= 128 leaves) — same values, fewer
+// kSmallT: the caller guarantees t < 0.125 (roots of trees with >= 256 leaves) — same values, fewer
 // instructions.
 template <bool kSmallT = false>
 __device__ __forceinline__ float zfun(float t) {
-  t = fminf(t, 64.f);
   const bool upper = kSmallT || t < 0.6931471805599453f;
   const float P = kSmallT ? 0.f : approx_exp2(t * -1.4426950408889634f);
-  float qp = 0.000198412701f;
-  qp = fmaf(qp, t, -0.00138888892f);
-  qp = fmaf(qp, t, 0.00833333377f);
+  float qp = 0.00833333377f;
   qp = fmaf(qp, t, -0.0416666679f);
   qp = fmaf(qp, t, 0.166666672f);
   qp = fmaf(qp, t, -0.5f);
   qp = fmaf(qp, t, 1.f);
-  const float q = (kSmallT || t < 0.25f) ? __fmul_rn(qp, t) : 1.f - P;
+  const float q = (kSmallT || t < 0.125f) ? __fmul_rn(qp, t) : 1.f - P;
   const float p = upper ? q : P;
   const float a = fmaf(-p, p, p);
   float w = fmaf(approx_log2(a), kNegLn2, -1.3862943611198906f);
-  w = fminf(fmaxf(w, 0.f), 27.f);
+  w = fminf(w, 27.f);  // w >= -1e-6 (rounding); a NaN square root below is never selected
   const float u = w - 3.125f;
   float ec = 4.58798354e-07f;
   ec = fmaf(ec, u, -2.39523933e-06f);

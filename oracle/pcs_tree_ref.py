@@ -41,7 +41,6 @@ from .philox_ref import philox4x32_10, box_muller, _unit
 F32 = np.float32
 LN2 = F32(0.6931471805599453)
 LOG2E = F32(1.4426950408889634)
-T_MAX = F32(64.0)
 W_MAX = F32(27.0)
 W_SPLIT = F32(6.25)
 CEN_MID = F32(3.125)
@@ -55,7 +54,7 @@ CEN = [F32(_SQ2 * c) for c in (1.6536552906036377, 0.24015966057777405, -0.00603
 TAIL = [F32(_SQ2 * c) for c in (3.6864500045776367, 1.0090477466583252, 0.0017072835471481085,
                                 -0.001114317448809743, 0.00042597835999913514, -0.00014658486179541796,
                                 0.00011464921408332884, -0.00010220367403235286, 3.313723573228344e-05)]
-EXPM1 = [F32(c) for c in (1.0, -1.0 / 2, 1.0 / 6, -1.0 / 24, 1.0 / 120, -1.0 / 720, 1.0 / 5040)]
+EXPM1 = [F32(c) for c in (1.0, -1.0 / 2, 1.0 / 6, -1.0 / 24, 1.0 / 120)]  # (1 - e^-t) / t, t < 1/8
 MAX_LEAVES = 4096
 
 
@@ -74,17 +73,19 @@ def _horner(coef, v):
 
 def zfun32(t) -> np.ndarray:
     """z with Phi(z) = exp(-t), t >= 0, evaluated with the kernel's fp32 operation sequence."""
-    t = np.minimum(np.asarray(t, dtype=F32), T_MAX)
+    t = np.asarray(t, dtype=F32)
     upper = t < LN2                                   # P > 1/2: z > 0
     P = np.exp2((t * -LOG2E).astype(F32)).astype(F32)
-    q = np.where(t < F32(0.25), (_horner(EXPM1, t) * t).astype(F32), (F32(1) - P).astype(F32))
+    with np.errstate(over="ignore", invalid="ignore"):  # the series is only selected for t < 1/8
+        q = np.where(t < F32(0.125), (_horner(EXPM1, t) * t).astype(F32), (F32(1) - P).astype(F32))
     p = np.where(upper, q, P).astype(F32)             # the smaller tail probability
     a = _fma(-p, p, p)                                # p (1 - p)
     with np.errstate(divide="ignore"):
         w = _fma(np.log2(a).astype(F32), -LN2, F32(-1.3862943611198906))  # -ln(4 p (1-p))
-    w = np.minimum(np.maximum(w, F32(0)), W_MAX)
+    w = np.minimum(w, W_MAX)  # w >= -1e-6 (rounding); the NaN square root of such a w is never selected
     ec = _horner(CEN, (w - CEN_MID).astype(F32))
-    et = _horner(TAIL, (np.sqrt(w).astype(F32) - TAIL_MID).astype(F32))
+    with np.errstate(invalid="ignore"):
+        et = _horner(TAIL, (np.sqrt(w).astype(F32) - TAIL_MID).astype(F32))
     e = np.where(w < W_SPLIT, ec, et)
     x = _fma(F32(-2), p, F32(1))
     z = (e * x).astype(F32)

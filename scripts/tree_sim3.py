@@ -16,7 +16,7 @@ mean, var = posterior_grid_batched(desc, ctx[sel])
 mean, var = mean.numpy(), var.numpy()
 rng = np.random.default_rng(1)
 STEP = float(os.environ.get("STEP", "1")); ZG = np.arange(0, 7.0 + STEP, STEP)
-tot_exp = 0; tot_n = 0; tot_succ = 0; exp_succ = 0; exp_fail = 0; root_fail = 0
+pre_pass = 0; pre_tot = 0; exp_nophx = 0; tot_exp = 0; tot_n = 0; tot_succ = 0; exp_succ = 0; exp_fail = 0; root_fail = 0
 for c in range(n_ctx):
     mu, sd = mean[c], np.sqrt(var[c])
     K = len(mu); b = int(np.argmax(mu)); mu = mu - mu[b]
@@ -50,6 +50,14 @@ for c in range(n_ctx):
         while stack and not fail:
             l, n, L, J, z = stack.pop(); cnt += 1
             mch = A ** (depth - l - 1); jpath = (J // mch) % A; new = []
+            npass = 0
+            for k in range(A):
+                cn = n * A + k
+                if k != jpath:
+                    pre_tot += 1
+                    pv = node_bound(l + 1, cn, z) if l + 1 < depth else (mt[cn] + st[cn] * z)
+                    if pv >= yb: pre_pass += 1; npass += 1
+            if npass == 0: exp_nophx += 1
             for k in range(A):
                 cn = n * A + k
                 if k == jpath: Lc, Jc, zc = L, J, z
@@ -61,4 +69,5 @@ for c in range(n_ctx):
         tot_exp += cnt; tot_n += 1
         if fail: exp_fail += cnt
         else: tot_succ += 1; exp_succ += cnt
+print(f"pretest: {pre_pass/max(pre_tot,1):.3f} of non-path children pass; {pre_pass/max(tot_exp,1):.2f} per expansion; expansions without any passing child {exp_nophx/max(tot_exp,1):.3f}")
 print(f"{cfgname} bound={BOUND} T={T}: expansions/sample {tot_exp/tot_n:.2f} | PCS {tot_succ/tot_n:.4f} | per success {exp_succ/max(tot_succ,1):.1f} | per failure {exp_fail/max(tot_n-tot_succ,1):.2f} | failed at root {root_fail/max(tot_n-tot_succ,1):.3f}")

@@ -12,7 +12,7 @@ def test_zfun32_accuracy_and_monotonicity():
     t = np.concatenate([10 ** rng.uniform(-11, -3, 100000), rng.uniform(1e-3, 0.7, 100000),
                         rng.uniform(0.6, 5, 100000), rng.uniform(5, 25, 100000)]).astype(np.float32)
     err = np.abs(pcs_tree_ref.zfun32(t) - ndtri_exp(-t.astype(np.float64)))
-    assert err.max() < 2.5e-6  # |z| up to 6.7: a few fp32 ulps
+    assert err.max() < 3e-6  # |z| up to 6.7: a few fp32 ulps
     grid = (10 ** np.linspace(-11, 1.8, 1000001)).astype(np.float32)
     assert not (np.diff(pcs_tree_ref.zfun32(grid)) > 0).any()  # pruning relies on this
     assert np.isfinite(pcs_tree_ref.zfun32(np.array([0.0, 1e-30, 64.0, 1e9], dtype=np.float32))).all()
