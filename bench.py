@@ -126,8 +126,8 @@ class ClockSampler:
 
 def ncu_traffic(workload, kernel, dtype):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
-    capture of the same workload (profiles/r01c_traffic.json; fp64 captures only), else None."""
-    path = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    capture of the same workload (profiles/r01d_traffic.json; fp64 captures only), else None."""
+    path = os.path.join(ROOT, "profiles", "r01d_traffic.json")
     if dtype != "f64" or not os.path.exists(path):
         return None
     with open(path) as f:
