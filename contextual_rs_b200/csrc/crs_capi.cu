@@ -93,6 +93,10 @@ CRS_API int crs_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, 
   return launch_pcs_counts_tree(mean, var, n_c, K, ld, dtype, num_samples, seed, offset, ctx_offset, counts, stats, (cudaStream_t)stream);
 }
 
+CRS_API int crs_debug_zfun(const float* t, int64_t n, float* out, void* stream) {
+  return launch_tree_zfun(t, n, out, (cudaStream_t)stream);
+}
+
 CRS_API int crs_levi_scan(const crs_gp_state* st, const void* mean, const void* var, int64_t n_c,
                           int64_t ld, const void* weights, void* ei_out, int64_t ld_ei, void* max_ei,
                           int32_t* max_arm, crs_levi_decision* decision, void* stream) {

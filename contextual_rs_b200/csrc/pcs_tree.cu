@@ -38,8 +38,14 @@ using namespace rng;
 
 constexpr int kTreeThreads = 256;
 constexpr int kTreeWarps = kTreeThreads / 32;
-constexpr int kTreeQueue = 96;          // root survivors parked per warp
-constexpr int kTreeMinActive = 20;      // fewer walking lanes than this (and fresh samples left): refill first
+#ifndef CRS_TREE_QUEUE
+#define CRS_TREE_QUEUE 96
+#endif
+#ifndef CRS_TREE_MIN_ACTIVE
+#define CRS_TREE_MIN_ACTIVE 28
+#endif
+constexpr int kTreeQueue = CRS_TREE_QUEUE;            // root survivors parked per warp
+constexpr int kTreeMinActive = CRS_TREE_MIN_ACTIVE;   // fewer walking lanes than this (and fresh samples left): refill first
 constexpr int kTreeMaxLeaves = 4096;    // 10-bit arg-max fields per child: depth <= 6
 constexpr float kTreeGrid = 1.8f;       // spacing of the envelope table (zfun < 6.9 < 4 * 1.8)
 constexpr float kTreeEmpty = -1e30f;    // envelope of a node without leaves
@@ -447,7 +453,20 @@ tree_probe_kernel(int kind, int iters, const __grid_constant__ RoundKeys rk, flo
   if (hits == 0xffffffffu) out[0] = 1.f;  // keep the loop alive
 }
 
+__global__ void tree_zfun_kernel(const float* __restrict__ t, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = t[i] < 0.125f && (i & 1) ? zfun<true>(t[i]) : zfun<false>(t[i]);
+}
+
 }  // namespace
+
+int launch_tree_zfun(const float* t, int64_t n, float* out, cudaStream_t s) {
+  if (!t || !out || n < 0) return CRS_ERR_INVALID_ARG;
+  if (n == 0) return CRS_OK;
+  tree_zfun_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t, n, out);
+  CRS_CUDA_TRY(cudaGetLastError(), "tree_zfun launch");
+  return CRS_OK;
+}
 
 int launch_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int K, int64_t ld, int dtype,
                            int64_t num_samples, uint64_t seed, uint32_t offset, int64_t ctx_offset,

@@ -235,6 +235,10 @@ CRS_API int crs_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, 
                                 int32_t dtype, int64_t num_samples, uint64_t seed, uint32_t offset,
                                 int64_t ctx_offset, uint32_t* counts, uint64_t* stats, void* stream);
 
+/* The tree sampler's fp32 inverse normal for tests: out[i] = z with Phi(z) = exp(-t[i]), t[i] >= 0
+ * (odd i with t < 1/8 take the small-t variant used at the root — same values by construction). */
+CRS_API int crs_debug_zfun(const float* t, int64_t n, float* out, void* stream);
+
 /* Raw Philox4x32-10 words for known-answer tests: out[4*i..4*i+3] = philox(ctr[4*i..], key). */
 CRS_API int crs_philox_words(const uint32_t* ctr, int64_t n, uint32_t key0, uint32_t key1, uint32_t* out,
                      void* stream);

@@ -400,6 +400,29 @@ def test_pcs_tree_shapes(crs, K):
     assert np.all(np.abs(want / S - exact) < 5 * se)
 
 
+def test_pcs_tree_inverse_normal(crs):
+    """The kernel's fp32 inverse normal zfun(t), Phi(z) = exp(-t): equal to the oracle's restatement
+    of the same operation sequence up to the MUFU approximations (lg2 / ex2 / sqrt), within 3e-6 of
+    scipy over the whole range the sampler produces, and non-increasing (exact pruning relies on it)."""
+    from contextual_rs_b200 import _lib
+    from scipy.special import ndtri_exp
+    rng = np.random.default_rng(0)
+    t = np.concatenate([10 ** rng.uniform(-11, -3, 200000), rng.uniform(1e-3, 0.7, 200000),
+                        rng.uniform(0.6, 5, 200000), rng.uniform(5, 25, 200000),
+                        np.sort(10 ** rng.uniform(-11, 1.8, 400000))]).astype(np.float32)
+    td = torch.from_numpy(t).to(DEV)
+    out = torch.empty_like(td)
+    _lib.check(_lib.get().crs_debug_zfun(td.data_ptr(), td.numel(), out.data_ptr(), None))
+    z = out.cpu().numpy()
+    assert np.isfinite(z).all()
+    assert np.abs(z - pcs_tree_ref.zfun32(t)).max() < 2e-6
+    ok = t <= 25.0  # beyond w = 27 (z < -7.1) the function saturates by design
+    assert np.abs(z - ndtri_exp(-t.astype(np.float64)))[ok].max() < 3.5e-6
+    zs = z[800000:]
+    assert (np.diff(zs[0::2]) <= 0).all() and (np.diff(zs[1::2]) <= 0).all()  # both variants, sorted t
+    assert (np.diff(zs) <= 2e-7).all()  # and they agree where both apply
+
+
 def test_pcs_tree_limits(crs):
     from contextual_rs_b200.generalized_pcs import pcs_counts
     mean = torch.randn(2, 4100, dtype=torch.float64, device=DEV)
