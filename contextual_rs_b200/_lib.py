@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libcrs_b200.so")
 CRS_OK, CRS_ERR_INVALID_ARG, CRS_ERR_UNSUPPORTED, CRS_ERR_CUDA, CRS_ERR_NOT_PSD, CRS_TIES_PENDING = range(6)
 CRS_F64, CRS_F32 = 0, 1
 CRS_MATERN52, CRS_RBF = 0, 1
-CRS_LEARN_NORMALIZE, CRS_LEARN_STANDARDIZE = 1, 2
+CRS_LEARN_NORMALIZE, CRS_LEARN_STANDARDIZE, CRS_TRAIN_INPUTS_RAW = 1, 2, 4
 CRS_P_COUNT, CRS_P_KDE, CRS_P_INFER = 0, 1, 2
 CRS_MAX_DIM, CRS_MAX_OBS = 16, 160
 CRS_HEAD_ELEMS = 2 * CRS_MAX_DIM + 8

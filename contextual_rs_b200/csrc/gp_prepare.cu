@@ -95,8 +95,8 @@ gp_prepare_kernel(crs_gp_state st, int arm_begin, int arm_end) {
       const double x = X[(size_t)i * d + dd];
       const double xn = (x - tr[dd]) / tr[CRS_MAX_DIM + dd];
       v = xn / st.lengthscale[(size_t)k * d + dd];
-      // eval-mode model.train_inputs: normalised in the model dtype's own arithmetic
-      xn_out[(size_t)i * d + dd] = (T(x) - T(tr[dd])) / T(tr[CRS_MAX_DIM + dd]);
+      // model.train_inputs: raw, or normalised in the model dtype's own arithmetic (eval-mode BoTorch >= 0.4)
+      xn_out[(size_t)i * d + dd] = (st.flags & CRS_TRAIN_INPUTS_RAW) ? T(x) : (T(x) - T(tr[dd])) / T(tr[CRS_MAX_DIM + dd]);
     } else if (dd < d) {
       xn_out[(size_t)i * d + dd] = T(0);
     }
@@ -344,7 +344,7 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
       const double x = s_x[i * d + dd];
       const double xn = (x - tr[dd]) / tr[CRS_MAX_DIM + dd];
       v = xn / s_ls[dd];
-      xn_out[(size_t)i * d + dd] = (T(x) - T(tr[dd])) / T(tr[CRS_MAX_DIM + dd]);
+      xn_out[(size_t)i * d + dd] = (st.flags & CRS_TRAIN_INPUTS_RAW) ? T(x) : (T(x) - T(tr[dd])) / T(tr[CRS_MAX_DIM + dd]);
     } else if (dd < d) {
       xn_out[(size_t)i * d + dd] = T(0);
     }

@@ -497,14 +497,19 @@ int launch_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int K
   CRS_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s), "pcs_tree memset ticket");
   const RoundKeys rk = round_keys((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
   auto go = [&](auto kern, auto* m, auto* v) -> int {
-    if (smem > 40 * 1024)
-      CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pcs_tree attr");
-    int per_sm = 0;
-    CRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTreeThreads, smem), "pcs_tree occupancy");
-    if (per_sm < 1) return CRS_ERR_UNSUPPORTED;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t resident = (int64_t)sms * per_sm;
+    // resident CTAs of this (device, dtype, depth): queried once, the answers do not change
+    static int cached_resident[64][2][8] = {};
+    int& resident_c = cached_resident[dev][dtype == CRS_F64 ? 0 : 1][D];
+    if (resident_c == 0) {
+      if (smem > 40 * 1024)
+        CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "pcs_tree attr");
+      int per_sm = 0, sms = 148;
+      CRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTreeThreads, smem), "pcs_tree occupancy");
+      if (per_sm < 1) return CRS_ERR_UNSUPPORTED;
+      CRS_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "pcs_tree sm count");
+      resident_c = sms * per_sm;
+    }
+    const int64_t resident = resident_c;
     // ~12 work items per resident CTA so that the dynamic hand-out evens out their different costs;
     // a work item re-builds the plan of its context, so sample ranges are not split too finely
     const int64_t max_splits = (num_samples + kTreeSplitSamples - 1) / kTreeSplitSamples;

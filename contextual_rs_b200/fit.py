@@ -223,7 +223,10 @@ def _transforms(Xk: Tensor, Yk: Tensor):
 def fit_modellist_with_reuse(X: Tensor, Y: Tensor, num_arms: int, old_model: Optional[B200ModelListGP] = None,
                              device="cuda", dtype: torch.dtype = torch.float64, kernel: str = "matern52") -> B200ModelListGP:
     r"""Fit one GP per arm; arms whose number of observations did not change since ``old_model``
-    keep its hyper-parameters and transforms (``contextual_rs/experiment_utils.py:68-121``).
+    keep its hyper-parameters and transforms (``contextual_rs/experiment_utils.py:68-121``).  As in
+    the reference (``num_last_train_inputs``, ``:66, 93-97, 113-117``) "did not change" refers to the
+    arm's last FIT: observations appended by ``condition_on_observations`` since then make the arm
+    due for a re-fit (``model.n_at_fit`` carries the counts).
 
     Args:
         X: all evaluated arm-context pairs, first column = arm index.
@@ -240,6 +243,8 @@ def fit_modellist_with_reuse(X: Tensor, Y: Tensor, num_arms: int, old_model: Opt
     mc = torch.zeros(num_arms, dtype=torch.float64)
     refit: List[int] = []
     old = old_model.description() if old_model is not None and old_model.num_arms == num_arms else None
+    old_n_fit = getattr(old_model, "n_at_fit", None) if old is not None else None
+    n_at_fit: List[int] = []
     for i in range(num_arms):
         mask = X64[..., 0] == i
         Xi, Yi = X64[mask][..., 1:], Y64[mask]
@@ -247,7 +252,9 @@ def fit_modellist_with_reuse(X: Tensor, Y: Tensor, num_arms: int, old_model: Opt
             raise RuntimeError("Missing data!")  # experiment_utils.py:98-100
         tx.append(Xi)
         ty.append(Yi.reshape(-1, 1))
-        if old is not None and old["train_X"][i].shape[0] == Yi.numel():  # :93-97 reuse
+        n_old = old_n_fit[i] if old_n_fit is not None else (old["train_X"][i].shape[0] if old is not None else -1)
+        n_at_fit.append(int(Yi.numel()))
+        if old is not None and n_old == Yi.numel():  # :93-97 reuse
             ls[i], osc[i], noise[i], mc[i] = old["lengthscale"][i], old["outputscale"][i], old["noise"][i], old["mean_const"][i]
             mins.append(old["norm_mins"][i]); rngs.append(old["norm_ranges"][i])
             ym.append(old["y_mean"][i]); ys.append(old["y_std"][i])
@@ -258,7 +265,10 @@ def fit_modellist_with_reuse(X: Tensor, Y: Tensor, num_arms: int, old_model: Opt
     desc = {"train_X": tx, "train_Y": ty, "lengthscale": ls, "outputscale": osc, "noise": noise, "mean_const": mc,
             "kernel": kernel, "normalize": True, "standardize": True, "norm_mins": torch.stack(mins),
             "norm_ranges": torch.stack(rngs), "y_mean": torch.stack(ym), "y_std": torch.stack(ys)}
+    if old_model is not None and old is not None:
+        desc["train_inputs"] = old_model.train_inputs_mode
     model = B200ModelListGP(desc, device=device, dtype=dtype)
+    model.n_at_fit = n_at_fit
     if refit:
         model.fit_info = fit_hyperparameters(model, arms=refit)
     print(f"Skipped model fitting for {num_arms - len(refit)} out of {num_arms}.")  # :120

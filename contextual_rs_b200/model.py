@@ -79,10 +79,18 @@ class B200ModelListGP:
     ``standardize`` and optionally frozen transform constants ``norm_mins/norm_ranges [K, d]``,
     ``y_mean/y_std [K]``.  ``dtype`` is the compute dtype of every table (fp64 as the
     reference's default, ``experiments/wsc_experiments/main.py:184``, or fp32).
+
+    ``train_inputs`` (or ``desc["train_inputs"]``) selects what ``model.train_inputs`` holds — the
+    tensors OCBA step 2(b) compares with the chosen context (exact-match counts / KDE weights,
+    ``contextual_rs_strategies.py:168-193``): ``"raw"`` (default) = the raw inputs, which is what the
+    reference's own recorded runs show (replaying ``experiments/wsc_experiments/config_b_3_mean/
+    0000_ML_Gao.pt`` reproduces 90 of its first 100 decisions with raw inputs, 15 with transformed
+    ones — ``tests/golden/reference_trace_ml_gao.json``); ``"transformed"`` = the Normalize-d inputs
+    a BoTorch >= 0.4 model exposes in eval mode.
     """
 
     def __init__(self, desc: Dict, device="cuda", dtype: torch.dtype = torch.float64,
-                 n_cap: Optional[int] = None, headroom: int = 8):
+                 n_cap: Optional[int] = None, headroom: int = 8, train_inputs: Optional[str] = None):
         self.device = torch.device(device)
         if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -103,6 +111,9 @@ class B200ModelListGP:
             raise ValueError("n_cap smaller than the largest arm")
         self.normalize = bool(desc.get("normalize", True))
         self.standardize = bool(desc.get("standardize", True))
+        self.train_inputs_mode = train_inputs if train_inputs is not None else desc.get("train_inputs", "raw")
+        if self.train_inputs_mode not in ("raw", "transformed"):
+            raise ValueError(f"train_inputs must be 'raw' or 'transformed', got {self.train_inputs_mode!r}")
         self._alloc(desc)
         self.models: List[B200ArmView] = [B200ArmView(self, k) for k in range(K)]
         self._ws_cache: Dict[int, dict] = {}
@@ -151,8 +162,9 @@ class B200ModelListGP:
         self.linv_t = torch.zeros(K, int(_lib.get().crs_linv_stride(ncap, _lib.DTYPES[T])), dtype=T, device=dev)
         self.arm_head = torch.zeros(K, _lib.CRS_HEAD_ELEMS, dtype=T, device=dev)
         self.status = torch.zeros(K, dtype=torch.int32, device=dev)
-        self._state = self._make_state(flags)
-        self._state_frozen = self._make_state(0)
+        raw = _lib.CRS_TRAIN_INPUTS_RAW if self.train_inputs_mode == "raw" else 0
+        self._state = self._make_state(flags | raw)
+        self._state_frozen = self._make_state(raw)
 
     def _make_state(self, flags: int) -> _lib.GPState:
         p = _lib.ptr
@@ -248,13 +260,15 @@ class B200ModelListGP:
             "norm_ranges": self.norm_ranges.cpu() if self.normalize else None,
             "y_mean": self.y_mean.cpu() if self.standardize else None,
             "y_std": self.y_std.cpu() if self.standardize else None,
+            "train_inputs": self.train_inputs_mode,
         }
 
     # ------------------------------------------------------------------ duck-typed surface
     @property
     def train_inputs(self) -> List[Tuple[Tensor]]:
-        """Eval-mode BoTorch semantics: the *normalised* training inputs, one 1-tuple per arm —
-        what ``gao_modellist`` reads at strategies.py:176/188 after ``model.posterior`` ran."""
+        """One 1-tuple per arm — what ``gao_modellist`` reads at strategies.py:176/188 after
+        ``model.posterior`` ran: the raw inputs (``train_inputs="raw"``, the behaviour of the
+        reference's recorded runs) or the normalised ones (``"transformed"``, BoTorch >= 0.4 eval mode)."""
         return [(self.xn[k, :n],) for k, n in enumerate(self._n_host)]
 
     def num_observations(self) -> List[int]:

@@ -50,6 +50,10 @@ typedef enum crs_kernel { CRS_MATERN52 = 0, CRS_RBF = 1 } crs_kernel;
 /* flags for crs_gp_state.flags */
 #define CRS_LEARN_NORMALIZE 1   /* learn Normalize bounds from each arm's train_x (else use norm_*) */
 #define CRS_LEARN_STANDARDIZE 2 /* learn Standardize mean/std from each arm's train_y (else use y_*) */
+#define CRS_TRAIN_INPUTS_RAW 4  /* `xn` (= model.train_inputs, read by OCBA step 2(b): exact-match counts / KDE,
+                                   contextual_rs_strategies.py:168-193) holds the RAW inputs — what the reference's
+                                   recorded runs show (tests/golden/reference_trace_ml_gao.json) — instead of the
+                                   Normalize-transformed ones (BoTorch >= 0.4 eval mode) */
 
 /* p-surrogate of OCBA step 2(b): contextual_rs/contextual_rs_strategies.py:158-193 */
 typedef enum crs_p_mode {
@@ -72,7 +76,7 @@ typedef struct crs_gp_state {
   int32_t dim_pad;    /* padded d used by the prepared arrays */
   int32_t kernel;     /* crs_kernel */
   int32_t dtype;      /* crs_dtype of the prepared arrays and of all tables */
-  int32_t flags;      /* CRS_LEARN_* */
+  int32_t flags;      /* CRS_LEARN_* | CRS_TRAIN_INPUTS_RAW */
   int32_t n_max;      /* caller's bound on max n_obs (sizes the kernels' tiles); 0 = use n_cap */
   /* fitted description */
   const double* train_x;      /* [K, n_cap, d]  raw inputs */
@@ -87,7 +91,7 @@ typedef struct crs_gp_state {
   double* y_mean;             /* [K] */
   double* y_std;              /* [K] */
   /* prepared */
-  void* xn;        /* [K, n_cap, d]        T  normalised inputs == eval-mode model.train_inputs */
+  void* xn;        /* [K, n_cap, d]        T  model.train_inputs: raw (CRS_TRAIN_INPUTS_RAW) or normalised inputs */
   void* xs;        /* [K, n_cap, dim_pad]  T  normalised / lengthscale */
   void* alpha;     /* [K, n_cap]           T  o * K^-1 (y~ - m) */
   void* linv_t;    /* [K, crs_linv_stride(n_cap, dtype)] T  o * L^-T in 32-column panels */

@@ -103,7 +103,10 @@ class OracleSingleTaskGP:
     def __init__(self, train_X: Tensor, train_Y: Tensor, lengthscale: Tensor, outputscale,
                  noise, mean_const, kernel: str = "matern52", normalize: bool = True,
                  standardize: bool = True, norm_mins: Optional[Tensor] = None,
-                 norm_ranges: Optional[Tensor] = None, y_mean=None, y_std=None):
+                 norm_ranges: Optional[Tensor] = None, y_mean=None, y_std=None,
+                 train_inputs_mode: str = "raw"):
+        assert train_inputs_mode in ("raw", "transformed")
+        self.train_inputs_mode = train_inputs_mode
         dt = train_X.dtype
         self.dtype = dt
         self.kernel = kernel
@@ -144,9 +147,14 @@ class OracleSingleTaskGP:
 
     @property
     def train_inputs(self) -> Tuple[Tensor]:
-        """Eval-mode BoTorch semantics: the *transformed* (normalised) training inputs — what
-        ``model.train_inputs`` holds when ``gao_modellist`` reads it after ``model.posterior``
-        (``contextual_rs/contextual_rs_strategies.py:133`` then ``:176/:188``)."""
+        """What ``gao_modellist`` reads after ``model.posterior`` (``contextual_rs/
+        contextual_rs_strategies.py:133`` then ``:176/:188``).  ``train_inputs_mode == "raw"``
+        (default): the raw inputs — the behaviour of the reference's recorded runs (replaying
+        ``experiments/wsc_experiments/config_b_3_mean/0000_ML_Gao.pt`` reproduces 90 of its first
+        100 decisions this way and 15 with transformed inputs); ``"transformed"``: the Normalize-d
+        inputs of a BoTorch >= 0.4 model in eval mode."""
+        if self.train_inputs_mode == "raw":
+            return (self.raw_X,)
         return (self.transform_inputs(self.raw_X),)
 
     # ---- exact GP ---------------------------------------------------------------------
@@ -198,7 +206,7 @@ class OracleSingleTaskGP:
             torch.cat([self.raw_Y, Y.reshape(-1, 1)], dim=0),
             self.lengthscale, self.outputscale, self.noise, self.mean_const, self.kernel,
             self.normalize, self.standardize, self.norm_mins, self.norm_ranges,
-            self.y_mean, self.y_std)
+            self.y_mean, self.y_std, train_inputs_mode=self.train_inputs_mode)
 
 
 class OracleModelListGP:
@@ -237,7 +245,7 @@ def model_from_description(desc: Dict, dtype: torch.dtype = torch.float64) -> Or
             desc["lengthscale"][k].to(dtype), desc["outputscale"][k].to(dtype),
             desc["noise"][k].to(dtype), desc["mean_const"][k].to(dtype),
             kernel=desc.get("kernel", "matern52"), normalize=desc.get("normalize", True),
-            standardize=desc.get("standardize", True), **kw))
+            standardize=desc.get("standardize", True), train_inputs_mode=desc.get("train_inputs", "raw"), **kw))
     return OracleModelListGP(*models)
 
 

@@ -15,6 +15,10 @@ Fixtures
                           experiments/wsc_experiments/config_b_3_mean/0000_ML_Gao.pt (first 200 rows =
                           initial design, next 200 = the reference's own decision sequence).
   philox_kat.json         Random123 Philox4x32-10 known-answer vectors.
+  reference_trace_ml_gao.json  the first 100 decisions the reference recorded in 0000_ML_Gao.pt next to
+                          the decisions of the CPU oracle replaying the same run (oracle/trace_replay.py)
+                          with raw and with transformed ``model.train_inputs`` — the measured pinning of
+                          the oracle on outputs of the reference itself.
 """
 import json
 import os
@@ -29,6 +33,28 @@ def dump(name, obj):
     with open(os.path.join(HERE, name), "w") as f:
         json.dump(obj, f, indent=1)
     print("wrote", name)
+
+
+def reference_trace(iterations=100):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import trace_replay
+    d = torch.load(os.path.join(REF, "experiments/wsc_experiments/config_b_3_mean/0000_ML_Gao.pt"), weights_only=False)
+    X, Y = d["X"].double(), d["Y"].double()
+    torch.manual_seed(0)
+    context_map = torch.rand(10, 1, dtype=torch.float64)  # experiments/wsc_experiments/main.py:237-240
+    torch.manual_seed(0)
+    dec = trace_replay.replay_decisions(X, Y, context_map, 10, 200, iterations, modes=("raw", "transformed"))
+    dump("reference_trace_ml_gao.json", {
+        "source": "experiments/wsc_experiments/config_b_3_mean/0000_ML_Gao.pt (X[200 + i] = decision of iteration i)",
+        "generator": "tests/golden/make_golden.py::reference_trace -> oracle/trace_replay.py (re-fit with oracle/fit_oracle.py)",
+        "iterations": iterations,
+        "reference": [[int(X[200 + i, 0]), float(X[200 + i, 1])] for i in range(iterations)],
+        "oracle_raw_train_inputs": dec["raw"],
+        "oracle_transformed_train_inputs": dec["transformed"],
+        "match_raw": trace_replay.match_counts(dec["raw"], X, 200),
+        "match_transformed": trace_replay.match_counts(dec["transformed"], X, 200),
+    })
 
 
 def mock_tables():
@@ -96,3 +122,4 @@ if __name__ == "__main__":
     gao_iid()
     wsc_branin()
     philox()
+    reference_trace()

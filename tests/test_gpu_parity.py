@@ -64,7 +64,7 @@ def test_posterior_and_decision_fp64(crs, K, n_c, d, n, kernel, train):
     # batch x 1 x d input (MinZeta's shape) gives batch x 1 x K
     p3 = model.posterior(ctx.unsqueeze(1))
     assert p3.mean.shape == (n_c, 1, K) and torch.equal(p3.mean.squeeze(1), p.mean)
-    # normalised train inputs are bit-identical to the oracle's (needed by the exact-match count)
+    # model.train_inputs are bit-identical to the oracle's (needed by the exact-match count)
     for (a,), (b,) in zip(model.train_inputs, ref.train_inputs):
         assert torch.equal(a.cpu(), b)
     assert torch.equal(crs.empirical_best_arms(model, ctx).cpu(), ocba_oracle.best_arms_ref(ref, ctx))
@@ -130,6 +130,62 @@ def test_wsc_fixture_replay(crs, golden):
             arm, x = crs.gao_modellist(model, ctx, **kw)
             rarm, rx = ocba_oracle.gao_modellist_ref(ref, ctx, **kw)
             assert int(arm) == int(rarm) and torch.equal(x, rx)
+
+
+def test_reference_recorded_run_through_the_product(crs, golden):
+    """The reference's recorded run (0000_ML_Gao.pt) replayed END TO END through the product, the
+    way ``experiments/wsc_experiments/main.py:345-402`` drives it: ``fit_modellist_with_reuse``
+    every 10 iterations (batched device L-BFGS on ``crs_gp_mll``), ``condition_on_observations`` in
+    between, ``gao_modellist(model, context_map, randomize_ties, kernel_scale=1.0)``.  The decisions
+    must track both the reference's recorded ones and the CPU oracle's replay."""
+    from contextual_rs_b200.fit import fit_modellist_with_reuse
+    g = golden("wsc_branin_seed0.json")
+    trace = golden("reference_trace_ml_gao.json")
+    X = torch.tensor(g["X"], dtype=torch.float64)
+    Y = torch.tensor(g["Y"], dtype=torch.float64).view(-1, 1)
+    ctx = torch.tensor(g["context_map"], dtype=torch.float64)
+    n0, K, N = g["num_init"], g["num_arms"], 40
+    torch.manual_seed(0)
+    model, hits_ref, hits_oracle = None, 0, 0
+    for i in range(N):
+        Xi, Yi = X[: n0 + i], Y[: n0 + i]
+        if i % 10 == 0:
+            model = fit_modellist_with_reuse(Xi, Yi, K, model, device=DEV)
+        else:
+            model.condition_on_observations(int(Xi[-1, 0]), Xi[-1:, 1:], Yi[-1:])
+        assert model.num_observations() == [int((Xi[:, 0] == k).sum()) for k in range(K)]
+        arm, x = crs.gao_modellist(model, ctx, True, kernel_scale=1.0)
+        got = (int(arm), float(x.reshape(-1)[0]))
+        ref = (int(X[n0 + i, 0]), float(X[n0 + i, 1]))
+        hits_ref += got[0] == ref[0] and abs(got[1] - ref[1]) < 1e-12
+        hits_oracle += got == tuple(trace["oracle_raw_train_inputs"][i])
+    assert hits_ref >= 30, (hits_ref, N)        # the CPU oracle reproduces 35 of these 40
+    assert hits_oracle >= 34, (hits_oracle, N)  # same pipeline, two optimisers (device L-BFGS vs scipy L-BFGS-B)
+
+
+def test_transformed_train_inputs_mode(crs):
+    """``train_inputs="transformed"`` (BoTorch >= 0.4 eval mode): step 2(b) sees the Normalize-d
+    inputs; ``"raw"`` (default) the raw ones.  Both equal the oracle in the same mode."""
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=10, n_c=10, d=1, n=20, kernel="matern52", train="full", seed=4)
+    for mode in ("raw", "transformed"):
+        d2 = dict(desc)
+        d2["train_inputs"] = mode
+        model = crs.B200ModelListGP(d2, device=DEV)
+        ref = gp_oracle.model_from_description(d2)
+        assert model.train_inputs_mode == mode and model.description()["train_inputs"] == mode
+        for (a,), (b,) in zip(model.train_inputs, ref.train_inputs):
+            assert torch.equal(a.cpu(), b)
+        raw_equal = all(torch.equal(a.cpu(), x.to(torch.float64)) for (a,), x in zip(model.train_inputs, desc["train_X"]))
+        assert raw_equal == (mode == "raw")
+        for kw in ({}, {"use_kde": True, "kernel_scale": 1.0}):
+            arm, x = crs.gao_modellist(model, ctx, **kw)
+            rarm, rx = ocba_oracle.gao_modellist_ref(ref, ctx, **kw)
+            assert int(arm) == int(rarm) and torch.equal(x, rx), (mode, kw)
+        m32 = crs.B200ModelListGP(d2, device=DEV, dtype=torch.float32, train_inputs=mode)
+        ref32 = gp_oracle.model_from_description(d2, dtype=torch.float32)
+        for (a,), (b,) in zip(m32.train_inputs, ref32.train_inputs):
+            assert torch.equal(a.cpu(), b)
 
 
 def _run_tables(crs, mean, var, model, ctx, p_mode=0, kernel_scale=2.0):
