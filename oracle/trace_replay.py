@@ -20,16 +20,19 @@ from typing import Dict, List, Tuple
 import torch
 from torch import Tensor
 
-from . import fit_oracle, gp_oracle, ocba_oracle
+from . import fit_oracle, gp_oracle, levi_oracle, ocba_oracle
 
 HP_KEYS = ("lengthscale", "outputscale", "noise", "mean_const", "norm_mins", "norm_ranges", "y_mean", "y_std")
 
 
 def replay_decisions(X: Tensor, Y: Tensor, context_map: Tensor, num_arms: int, num_init: int, iterations: int,
                      fit_frequency: int = 10, kernel_scale: float = 1.0,
-                     modes: Tuple[str, ...] = ("raw",)) -> Dict[str, List[Tuple[int, float]]]:
+                     modes: Tuple[str, ...] = ("raw",), policy: str = "gao",
+                     weights: Tensor = None) -> Dict[str, List[Tuple[int, float]]]:
     """Decisions of the oracle at iterations 0..iterations-1 of the recorded run, for each
-    ``train_inputs`` mode (the fits are shared).  Returns ``{mode: [(arm, context value), ...]}``."""
+    ``train_inputs`` mode (the fits are shared).  ``policy``: "gao" = ``gao_modellist`` (label
+    ML_Gao, main.py:391-402), "levi" = ``discrete_levi(model, context_map, weights)`` (label LEVI,
+    main.py:406-413).  Returns ``{mode: [(arm, context value), ...]}``."""
     X, Y = X.to(torch.float64), Y.to(torch.float64).reshape(-1, 1)
     hp = [None] * num_arms
     n_at_fit = [0] * num_arms          # experiment_utils.py:66 ``num_last_train_inputs``
@@ -49,7 +52,10 @@ def replay_decisions(X: Tensor, Y: Tensor, context_map: Tensor, num_arms: int, n
         for mode in modes:
             desc["train_inputs"] = mode
             model = gp_oracle.model_from_description(desc)  # conditioning keeps hyper-parameters and transforms
-            arm, ctx = ocba_oracle.gao_modellist_ref(model, context_map, True, kernel_scale=kernel_scale)
+            if policy == "levi":
+                arm, ctx = levi_oracle.discrete_levi_ref(model, context_map, weights)
+            else:
+                arm, ctx = ocba_oracle.gao_modellist_ref(model, context_map, True, kernel_scale=kernel_scale)
             out[mode].append((int(arm), float(ctx.reshape(-1)[0])))
     return out
 
