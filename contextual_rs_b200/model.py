@@ -338,19 +338,29 @@ class B200ModelListGP:
         return ws
 
 
-def from_botorch(model, device="cuda", dtype: Optional[torch.dtype] = None) -> B200ModelListGP:
+def from_botorch(model, device="cuda", dtype: Optional[torch.dtype] = None,
+                 train_inputs: Optional[str] = None) -> B200ModelListGP:
     """Extract a fitted BoTorch ``ModelListGP`` of ``SingleTaskGP`` sub-models by attribute path
     (SURVEY.md §8b).  BoTorch is not installed in this image, so this function is written against
-    the documented attribute names and is NOT exercised by the test-suite."""
+    the documented attribute names and is NOT exercised by the test-suite.
+
+    ``train_inputs=None`` detects what ``model.train_inputs`` holds in eval mode under the installed
+    BoTorch (raw inputs, or Normalize-transformed ones from 0.4 on) so that OCBA step 2(b) sees what
+    the reference's ``gao_modellist`` would see with the same model; pass "raw" / "transformed" to force."""
     tx, ty, ls, osc, noise, mc, mins, rngs, ym, ys = [], [], [], [], [], [], [], [], [], []
     kernel = None
+    detected = "raw"
     for m in model.models:
         was_training = m.training
         m.train()  # expose the raw (untransformed) train_inputs
         X = m.train_inputs[0].detach()
         Yt = m.train_targets.detach()
-        if not was_training:
-            m.eval()
+        m.eval()
+        X_eval = m.train_inputs[0].detach()
+        if X_eval.shape != X.shape or not torch.equal(X_eval, X):
+            detected = "transformed"
+        if was_training:
+            m.train()
         cov = m.covar_module
         base = getattr(cov, "base_kernel", cov)
         name = type(base).__name__.lower()
@@ -388,4 +398,4 @@ def from_botorch(model, device="cuda", dtype: Optional[torch.dtype] = None) -> B
             "noise": torch.stack(noise), "mean_const": torch.stack(mc), "kernel": kernel,
             "normalize": True, "standardize": True, "norm_mins": torch.stack(mins),
             "norm_ranges": torch.stack(rngs), "y_mean": torch.stack(ym), "y_std": torch.stack(ys)}
-    return B200ModelListGP(desc, device=device, dtype=dtype or tx[0].dtype)
+    return B200ModelListGP(desc, device=device, dtype=dtype or tx[0].dtype, train_inputs=train_inputs or detected)
