@@ -6,15 +6,19 @@ one hot path this repository accelerates.  It is *the checker*: only ``tests/``,
 import it.  Nothing under ``contextual_rs_b200/`` imports it and the product path has no CPU
 fallback: it fails loudly when the CUDA library is missing.
 
-Parity status: **parity unpinned at the BoTorch/GPyTorch boundary**.  The reference's
-arithmetic for ``model.posterior`` / ``posterior.rsample`` lives in BoTorch (>=0.4) / GPyTorch
-(>=1.4) (``/root/reference/setup.py:3-11``, not version-pinned, no lock file), neither of which
-is vendored in the reference tree nor importable in this image, and no reference test pins a
-numeric posterior value.  ``gp_oracle.py`` therefore restates the *published* exact-GP
-algorithm of those libraries (SingleTaskGP = Normalize -> ScaleKernel(Matern-5/2 ARD | RBF ARD)
-+ ConstantMean + homoskedastic noise -> Standardize), anchored on the reference's own call sites.
+Parity status.  The reference's arithmetic for ``model.posterior`` / ``posterior.rsample`` lives in
+BoTorch (>=0.4) / GPyTorch (>=1.4) (``/root/reference/setup.py:3-11``, not version-pinned, no lock
+file), neither of which is vendored in the reference tree nor importable in this image, and no
+reference TEST pins a numeric posterior value.  ``gp_oracle.py`` therefore restates the *published*
+exact-GP algorithm of those libraries (SingleTaskGP = Normalize -> ScaleKernel(Matern-5/2 ARD | RBF
+ARD) + ConstantMean + homoskedastic noise -> Standardize), anchored on the reference's own call
+sites — and the whole chain (transforms, fit, posterior, zeta table, OCBA step 2(b)) is pinned on
+OUTPUTS OF THE REFERENCE ITSELF: the recorded run ``experiments/wsc_experiments/config_b_3_mean/
+0000_ML_Gao.pt`` is replayed by ``trace_replay.py`` and 90 of its first 100 recorded decisions are
+reproduced from re-fitted hyper-parameters (fixture ``tests/golden/reference_trace_ml_gao.json``).
+Still unpinned: bit-level agreement of posterior VALUES with GPyTorch (not observable here).
 
-What IS pinned (see ``tests/test_oracle_golden.py``):
+What else is pinned (see ``tests/test_oracle_golden.py``):
   * the decision logic (sort / zeta / argmin / OCBA ratio) against the mock posterior tables of
     ``test/test_contextual_rs_strategies.py:169-176`` and the ``(arm 2, context 1)`` known answer
     of ``test/test_contextual_rs_strategies.py:22-62``;

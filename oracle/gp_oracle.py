@@ -4,8 +4,9 @@ that the reference builds at ``contextual_rs/experiment_utils.py:29-40`` and que
 ``contextual_rs/contextual_rs_strategies.py:133-136``, ``contextual_rs/generalized_pcs.py:441-451``,
 ``contextual_rs/continuous_context.py:68,96``.  TEST INFRASTRUCTURE ONLY (see ``oracle/__init__``).
 
-PARITY UNPINNED: BoTorch/GPyTorch are absent from this image, so the arithmetic below restates
-their published exact-GP prediction equations:
+BoTorch/GPyTorch are absent from this image, so the arithmetic below restates their published
+exact-GP prediction equations (posterior VALUES are unpinned at the bit level; the decisions they
+lead to are pinned on the reference's recorded run, see ``trace_replay.py``):
 
     x~  = (x - mins) / ranges                          Normalize, bounds learnt from train X
     y~  = (y - ybar) / s                               Standardize(m=1), unbiased std
