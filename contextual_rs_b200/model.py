@@ -194,6 +194,8 @@ class B200ModelListGP:
             rc = _lib.get().crs_gp_prepare(C.byref(st), arm_begin, arm_end, _lib.stream_ptr(self.device))
         _lib.check(rc, "crs_gp_prepare")
         self._prepared = True
+        for ws in self._ws_cache.values():  # cached grids (reuse_grid=True) describe the old state
+            ws["valid_for"] = None
 
     def check_status(self) -> None:
         """Synchronising check of the per-arm Cholesky status."""

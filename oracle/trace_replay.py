@@ -32,11 +32,17 @@ def replay_decisions(X: Tensor, Y: Tensor, context_map: Tensor, num_arms: int, n
     """Decisions of the oracle at iterations 0..iterations-1 of the recorded run, for each
     ``train_inputs`` mode (the fits are shared).  ``policy``: "gao" = ``gao_modellist`` (label
     ML_Gao, main.py:391-402), "levi" = ``discrete_levi(model, context_map, weights)`` (label LEVI,
-    main.py:406-413).  Returns ``{mode: [(arm, context value), ...]}``."""
+    main.py:406-413).  Returns ``{mode: [(arm, context value), ...]}`` plus, under the keys
+    ``"best_arms"`` and ``"pcs_exact"``, the per-context arg-max of the posterior mean (what the
+    reference stores in ``all_maximizers``, main.py:459-466) and the exact per-context PCS of the
+    same posterior (quadrature; the reference stores a 64-sample MC estimate of ``rho`` of it in
+    ``pcs_estimates``, main.py:447-455)."""
+    from . import pcs_oracle
     X, Y = X.to(torch.float64), Y.to(torch.float64).reshape(-1, 1)
     hp = [None] * num_arms
     n_at_fit = [0] * num_arms          # experiment_utils.py:66 ``num_last_train_inputs``
-    out: Dict[str, List[Tuple[int, float]]] = {m: [] for m in modes}
+    out: Dict[str, List] = {m: [] for m in modes}
+    out["best_arms"], out["pcs_exact"] = [], []
     for i in range(iterations):
         Xi, Yi = X[: num_init + i], Y[: num_init + i]
         masks = [Xi[:, 0] == k for k in range(num_arms)]
@@ -49,6 +55,9 @@ def replay_decisions(X: Tensor, Y: Tensor, context_map: Tensor, num_arms: int, n
         desc = {"train_X": [Xi[m][:, 1:] for m in masks], "train_Y": [Yi[m] for m in masks],
                 "kernel": "matern52", "normalize": True, "standardize": True}
         desc.update({key: torch.stack([hp[k][key] for k in range(num_arms)]) for key in HP_KEYS})
+        post = gp_oracle.model_from_description(desc).posterior(context_map)
+        out["best_arms"].append(post.mean.argmax(dim=-1).tolist())
+        out["pcs_exact"].append(pcs_oracle.pcs_exact_quadrature(post.mean.numpy(), post.variance.numpy()).tolist())
         for mode in modes:
             desc["train_inputs"] = mode
             model = gp_oracle.model_from_description(desc)  # conditioning keeps hyper-parameters and transforms

@@ -52,6 +52,11 @@ def reference_trace(iterations=100):
         "reference": [[int(X[200 + i, 0]), float(X[200 + i, 1])] for i in range(iterations)],
         "oracle_raw_train_inputs": dec["raw"],
         "oracle_transformed_train_inputs": dec["transformed"],
+        "reference_best_arms": d["all_maximizers"][:iterations].long().tolist(),   # main.py:459-466
+        "reference_pcs_estimates": d["pcs_estimates"][:iterations].tolist(),       # main.py:447-455, 64 samples
+        "pcs_weights": [0.03, 0.07, 0.2, 0.1, 0.15, 0.2, 0.02, 0.08, 0.1, 0.05],     # config_b_3_mean/config.json
+        "oracle_best_arms": dec["best_arms"],
+        "oracle_pcs_exact": dec["pcs_exact"],
         "match_raw": trace_replay.match_counts(dec["raw"], X, 200),
         "match_transformed": trace_replay.match_counts(dec["transformed"], X, 200),
     })

@@ -146,7 +146,10 @@ def test_reference_recorded_run_through_the_product(crs, golden):
     ctx = torch.tensor(g["context_map"], dtype=torch.float64)
     n0, K, N = g["num_init"], g["num_arms"], 40
     torch.manual_seed(0)
-    model, hits_ref, hits_oracle = None, 0, 0
+    model, hits_ref, hits_oracle, best_hits, pcs_dev = None, 0, 0, 0, []
+    w = torch.tensor(trace["pcs_weights"], dtype=torch.float64)
+    rho = lambda P: (P * w.to(P.device).view(-1, 1).expand_as(P)).mean(dim=-2)  # main.py:245-249
+    arm_set = torch.arange(K, dtype=torch.float64).view(-1, 1)
     for i in range(N):
         Xi, Yi = X[: n0 + i], Y[: n0 + i]
         if i % 10 == 0:
@@ -159,6 +162,17 @@ def test_reference_recorded_run_through_the_product(crs, golden):
         ref = (int(X[n0 + i, 0]), float(X[n0 + i, 1]))
         hits_ref += got[0] == ref[0] and abs(got[1] - ref[1]) < 1e-12
         hits_oracle += got == tuple(trace["oracle_raw_train_inputs"][i])
+        # best-arm readout (main.py:459-466) against the recorded all_maximizers
+        best = crs.empirical_best_arms(model, ctx).cpu()
+        best_hits += int((best == torch.tensor(trace["reference_best_arms"][i])).sum())
+        if i % 5 == 0:  # PCS estimate (main.py:447-455): 2^16 samples here, 64 in the recorded run
+            est = crs.estimate_current_generalized_pcs(model, arm_set, ctx, 1 << 16, None,
+                                                       lambda V: (V > 0).to(torch.float64), rho, seed=i, reuse_grid=True)
+            p_c = np.array(trace["oracle_pcs_exact"][i])
+            se64 = np.sqrt((w.numpy() ** 2 * p_c * (1 - p_c) / 64).sum()) / K
+            pcs_dev.append((trace["reference_pcs_estimates"][i] - float(est)) / se64)
+    assert best_hits >= 0.93 * N * 10, best_hits
+    assert abs(np.mean(pcs_dev)) < 1.5 and np.abs(pcs_dev).max() < 4.0, pcs_dev
     assert hits_ref >= 30, (hits_ref, N)        # the CPU oracle reproduces 35 of these 40
     assert hits_oracle >= 34, (hits_oracle, N)  # same pipeline, two optimisers (device L-BFGS vs scipy L-BFGS-B)
 
