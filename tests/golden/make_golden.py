@@ -19,6 +19,8 @@ Fixtures
                           the decisions of the CPU oracle replaying the same run (oracle/trace_replay.py)
                           with raw and with transformed ``model.train_inputs`` — the measured pinning of
                           the oracle on outputs of the reference itself.
+  reference_trace_levi_new.json  the same for the recorded LEVI run (0000_LEVI_new.pt, discrete_levi):
+                          training data, recorded decisions and the oracle's replay.
 """
 import json
 import os
@@ -59,6 +61,29 @@ def reference_trace(iterations=100):
         "oracle_pcs_exact": dec["pcs_exact"],
         "match_raw": trace_replay.match_counts(dec["raw"], X, 200),
         "match_transformed": trace_replay.match_counts(dec["transformed"], X, 200),
+    })
+
+
+def reference_trace_levi(iterations=100):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import trace_replay
+    d = torch.load(os.path.join(REF, "experiments/wsc_experiments/config_b_3_mean/0000_LEVI_new.pt"), weights_only=False)
+    X, Y = d["X"].double(), d["Y"].double()
+    weights = [0.03, 0.07, 0.2, 0.1, 0.15, 0.2, 0.02, 0.08, 0.1, 0.05]  # config_b_3_mean/config.json
+    torch.manual_seed(0)
+    context_map = torch.rand(10, 1, dtype=torch.float64)
+    dec = trace_replay.replay_decisions(X, Y, context_map, 10, 200, iterations, policy="levi",
+                                        weights=torch.tensor(weights, dtype=torch.float64))
+    dump("reference_trace_levi_new.json", {
+        "source": "experiments/wsc_experiments/config_b_3_mean/0000_LEVI_new.pt (label LEVI_new = discrete_levi with "
+                  "_compute_all_EI_reviewer, contextual_rs/levi.py:132-227; X[200 + i] = decision of iteration i)",
+        "generator": "tests/golden/make_golden.py::reference_trace_levi -> oracle/trace_replay.py",
+        "iterations": iterations, "num_arms": 10, "num_init": 200, "weights": weights,
+        "context_map": context_map.reshape(-1).tolist(),
+        "X": X[: 200 + iterations].tolist(), "Y": Y[: 200 + iterations].reshape(-1).tolist(),
+        "oracle": dec["raw"],
+        "match": trace_replay.match_counts(dec["raw"], X, 200),
     })
 
 
@@ -128,3 +153,4 @@ if __name__ == "__main__":
     wsc_branin()
     philox()
     reference_trace()
+    reference_trace_levi()

@@ -177,6 +177,32 @@ def test_reference_recorded_run_through_the_product(crs, golden):
     assert hits_oracle >= 34, (hits_oracle, N)  # same pipeline, two optimisers (device L-BFGS vs scipy L-BFGS-B)
 
 
+def test_reference_recorded_levi_run_through_the_product(crs, golden):
+    """Row f2 end to end: the recorded LEVI run replayed through the product (device fit +
+    conditioning + ``discrete_levi`` on ``crs_levi_scan``) tracks the recorded decisions and the
+    oracle's replay."""
+    from contextual_rs_b200.fit import fit_modellist_with_reuse
+    g = golden("reference_trace_levi_new.json")
+    X = torch.tensor(g["X"], dtype=torch.float64)
+    Y = torch.tensor(g["Y"], dtype=torch.float64).view(-1, 1)
+    ctx = torch.tensor(g["context_map"], dtype=torch.float64).view(-1, 1)
+    w = torch.tensor(g["weights"], dtype=torch.float64)
+    n0, K, N = g["num_init"], g["num_arms"], 40
+    model, hits_ref, hits_oracle = None, 0, 0
+    for i in range(N):
+        Xi, Yi = X[: n0 + i], Y[: n0 + i]
+        if i % 10 == 0:
+            model = fit_modellist_with_reuse(Xi, Yi, K, model, device=DEV)
+        else:
+            model.condition_on_observations(int(Xi[-1, 0]), Xi[-1:, 1:], Yi[-1:])
+        arm, x = crs.discrete_levi(model, ctx, w)
+        got = (int(arm), float(x.reshape(-1)[0]))
+        hits_ref += got[0] == int(X[n0 + i, 0]) and abs(got[1] - float(X[n0 + i, 1])) < 1e-12
+        hits_oracle += got == tuple(g["oracle"][i])
+    assert hits_ref >= 23, (hits_ref, N)        # the CPU oracle reproduces 29 of these 40
+    assert hits_oracle >= 32, (hits_oracle, N)  # two optimisers (device L-BFGS vs scipy L-BFGS-B)
+
+
 def test_transformed_train_inputs_mode(crs):
     """``train_inputs="transformed"`` (BoTorch >= 0.4 eval mode): step 2(b) sees the Normalize-d
     inputs; ``"raw"`` (default) the raw ones.  Both equal the oracle in the same mode."""

@@ -352,3 +352,21 @@ def test_reference_recorded_run_is_reproduced(golden):
     dev = (np.array(trace["reference_pcs_estimates"]) - rho) / se
     assert abs(dev.mean()) < 1.0 and 0.7 < np.sqrt((dev ** 2).mean()) < 1.3, (dev.mean(), np.sqrt((dev ** 2).mean()))
     assert np.allclose(dec["pcs_exact"], pcs_c[:N], atol=1e-9)
+
+
+def test_reference_recorded_levi_run_is_reproduced(golden):
+    """Row f2: the recorded LEVI run (``0000_LEVI_new.pt`` = ``discrete_levi`` with the reviewer EI,
+    ``contextual_rs/levi.py:132-227``, weights of ``config_b_3_mean``) replayed through the oracle:
+    77 of its first 100 recorded decisions are reproduced (fixture); 30 iterations re-run here."""
+    from oracle import trace_replay
+    g = golden("reference_trace_levi_new.json")
+    assert g["match"]["both"] >= 70
+    X = torch.tensor(g["X"], dtype=torch.float64)
+    Y = torch.tensor(g["Y"], dtype=torch.float64).view(-1, 1)
+    ctx = torch.tensor(g["context_map"], dtype=torch.float64).view(-1, 1)
+    w = torch.tensor(g["weights"], dtype=torch.float64)
+    N = 30
+    dec = trace_replay.replay_decisions(X, Y, ctx, g["num_arms"], g["num_init"], N, policy="levi", weights=w)
+    assert dec["raw"] == [tuple(d) for d in g["oracle"][:N]]
+    m = trace_replay.match_counts(dec["raw"], X, g["num_init"])
+    assert m["both"] >= 17 and m["arm"] >= 19, m  # 19 of the first 30 (the later part of the trace agrees more often)
