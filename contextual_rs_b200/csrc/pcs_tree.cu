@@ -150,6 +150,8 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
   unsigned char* region = reinterpret_cast<unsigned char*>(node + NI);
   float* s_key = reinterpret_cast<float*>(region);
   int* s_ord = reinterpret_cast<int*>(s_key + n2);
+  float* s_mu = reinterpret_cast<float*>(s_ord + n2);                // centred mean / std-dev of competitor e
+  float* s_sd = s_mu + n2;
   float* s_g = reinterpret_cast<float*>(region);                    // [NI][5] envelope tables while the nodes are built
   uint32_t* stk_meta = reinterpret_cast<uint32_t*>(region);          // [slots][threads]: level<<24 | index<<12 | J
   float* stk_t = reinterpret_cast<float*>(stk_meta + slots * kTreeThreads);
@@ -221,9 +223,13 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
       if (e < nsort) {
         arm = e + (e >= best ? 1 : 0);
         const float mu = (float)(mrow[arm] - mu_b);  // centred in the grid dtype, then fp32
-        const float sd = (float)sqrt((double)vrow[arm]);
+        float sd;
+        if constexpr (sizeof(T) == 4) sd = __fsqrt_rn((float)vrow[arm]);  // == (float)sqrt((double)v)
+        else sd = (float)sqrt((double)vrow[arm]);
         const float s = __fadd_rn(__fadd_rn(__fmul_rn(sd, sd), sdb2), 1e-30f);
         key = __fdiv_rn(mu, __fsqrt_rn(s));
+        s_mu[e] = mu;
+        s_sd[e] = sd;
       }
       s_key[e] = key;
       s_ord[e] = arm;
@@ -251,8 +257,9 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
       float2 lf = make_float2(-CUDART_INF_F, 0.f);
       if (p < nsort) {
         const int arm = s_ord[p];
-        lf.x = (float)(mrow[arm] - mu_b);
-        lf.y = (float)sqrt((double)vrow[arm]);
+        const int e = arm - (arm > best ? 1 : 0);
+        lf.x = s_mu[e];
+        lf.y = s_sd[e];
       }
       if (p == 0) s_top = lf;
       else leaf[p - 1] = lf;
@@ -484,7 +491,7 @@ int launch_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int K
   while (n2 < K - 1) n2 <<= 1;
   const int slots = D >= 2 ? 3 * (D - 1) + 1 : 1;
   const size_t walk = (size_t)slots * kTreeThreads * 12 + (size_t)kTreeWarps * kTreeQueue * 20;
-  size_t build = (size_t)n2 * 8;  // sort scratch, then the [NI][5] envelope tables — both dead before the walk
+  size_t build = (size_t)n2 * 16;  // sort scratch + competitor table, then the [NI][5] envelope tables — dead before the walk
   if (build < (size_t)NI * 20) build = (size_t)NI * 20;
   const size_t smem = (size_t)NL * 8 + (size_t)NI * 32 + (walk > build ? walk : build);
   static unsigned long long* rings[64] = {nullptr};
