@@ -238,7 +238,7 @@ def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
     b, e = shard_bounds(n_c, world, rank)
     post = model.posterior(ctx[b:e].float())
     mean, var = post.mean.contiguous(), post.variance.contiguous()
-    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
     total = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def step(i, sampler="tree"):
@@ -266,7 +266,7 @@ def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(st)
     t_step = float(tt)
-    roots, expansions = st.tolist()
+    roots, expansions, directs = st.tolist()[:3]
     pcs_tree_mean = float(total) / (num_samples * n_c)
     # the flat per-arm stream (crs_pcs_counts) on the same tables, for comparison
     step(0, "flat")
@@ -286,13 +286,13 @@ def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
            "config": {"workload": PCS_CONFIG, "samples": num_samples, "arms": K, "contexts": n_c,
                       "sharding": f"contexts/{world}" if world > 1 else "none", "sampler": "max-tree stream (crs_pcs_counts_tree)"},
            "ms_per_estimate": t_step * 1e3, "sample_context_pairs_per_sec": float(num_samples) * n_c / t_step,
-           "philox_calls_per_sample": (roots + expansions) / (float(num_samples) * n_c),
+           "philox_calls_per_sample": (roots + expansions + directs) / (float(num_samples) * n_c),
            "pcs_mean": pcs_tree_mean, "gpu_launches": reps + 3,
            "flat_stream": {"ms_per_estimate": float(tf) * 1e3, "executed_draws_per_sec": float(sf[0]) / float(tf),
                            "executed_fraction": float(sf[0]) / float(sf[0] + sf[1]),
                            "pcs_mean": float(total) / (num_samples * n_c)}}
     from contextual_rs_b200.peaks import measure_pcs_tree_rates, pcs_tree_roofline
-    out["roofline"] = pcs_tree_roofline(roots, expansions, t_step, world, measure_pcs_tree_rates(dev))
+    out["roofline"] = pcs_tree_roofline(roots, expansions, t_step, world, measure_pcs_tree_rates(dev), directs)
     if cpu and world == 1 and rank == 0:
         from oracle import pcs_oracle
         torch.set_num_threads(os.cpu_count() or 1)
@@ -400,7 +400,7 @@ def run_loop(args, dev, world, rank):
     if rank == 0:
         sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
-    drawn = torch.zeros(2, dtype=torch.float64)
+    drawn = torch.zeros(3, dtype=torch.float64)
     barrier()
     for i in range(steps):
         ev[i][0].record()
@@ -409,7 +409,7 @@ def run_loop(args, dev, world, rank):
         y = truth(out["next_arm"], out["next_context"])
         pcs = loop.pcs()
         ev[i][2].record()
-        drawn += stats.cpu().to(torch.float64)  # {root tests, node expansions} of this estimate
+        drawn += stats[:3].cpu().to(torch.float64)  # {root tests, node expansions, direct-arm tests} of this estimate
         loop.observe(out["next_arm"], out["next_context"].view(1, -1), y.reshape(1, 1))
         loop.iteration += 1
         it_box[0] += 1
@@ -424,7 +424,7 @@ def run_loop(args, dev, world, rank):
         dsum = t[4:].clone()
         dist.all_reduce(dsum)
         t = torch.cat([tmax, dsum])
-    dec_ms, pcs_ms, obs_ms, tot_ms, roots_all, exp_all = t.tolist()
+    dec_ms, pcs_ms, obs_ms, tot_ms, roots_all, exp_all, dir_all = t.tolist()
     if rank == 0:
         w = 8 if dtype == torch.float64 else 4
         val = steps / (tot_ms * 1e-3)
@@ -439,7 +439,7 @@ def run_loop(args, dev, world, rank):
             "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": (d + 1) * 8 * world, "d2h_bytes_per_step": 64 * world,
                     "note": "the loop is host-driven: every iteration reads the decision back and uploads the new observation"},
             "gpu_launches": 5 * steps * world,
-            "roofline": pcs_tree_roofline(roots_all, exp_all, pcs_ms * 1e-3, world, measure_pcs_tree_rates(dev)),
+            "roofline": pcs_tree_roofline(roots_all, exp_all, pcs_ms * 1e-3, world, measure_pcs_tree_rates(dev), dir_all),
             "pcs_last": float(pcs), "clocks": clocks}))
     if world > 1:
         dist.barrier()

@@ -7,15 +7,17 @@
 // K = 1,000 diffuse posteriors almost every sample fails.  The flat stream (pcs_philox.cu) has to
 // draw arms until it meets a winner (3-4 Philox calls) and all K of them to certify a success
 // (250 calls).  This kernel samples the same law top-down instead: the competitors are the leaves of
-// a 4-ary tree (threat order); a node covering m leaves carries t = -ln Phi(z_max)^... of the
+// a 4-ary tree (threat order; the five most threatening ones are drawn directly); a node covering m leaves carries t = -ln Phi(z_max)^... of the
 // maximum of its m iid N(0,1) draws (Exp(1)/m, one uniform) and the leaf J that attains it
 // (uniform).  Children of a node: the one containing J inherits (t, J), the others draw the maximum
 // of m/4 normals truncated at the parent's value, t_c = t + Exp(1)/(m/4), and their own J_c.
 // Stream definition and brute-force restatement: oracle/pcs_tree_ref.py.
 //   root     one Philox call per sample: y_b, the draw of the most threatening competitor (the
-//            second Box-Muller variate, free), the largest of the other K-2 standard normals and
-//            the arm that owns it.  If either arm reaches y_b the sample has failed (60-90 % of
-//            the samples at 1,000 arms end here); if no leaf can reach y_b it has succeeded.
+//            second Box-Muller variate, free), the largest of the K-6 standard normals of the
+//            tree and the leaf that owns it.  If either arm reaches y_b the sample has failed
+//            (60-90 % of the samples at 1,000 arms end here).
+//   direct   samples that survive draw the next four threats directly (one more Philox call, two
+//            Box-Muller pairs): most failures the root missed end here, before any tree work.
 //   expand   otherwise the node is expanded (one Philox call, three inverse-normal evaluations),
 //            each new child's arg-max leaf is tested, and only children whose bound reaches y_b
 //            are kept (per-lane stack in shared memory).  The bound of a node is the convex
@@ -47,6 +49,8 @@ constexpr int kTreeWarps = kTreeThreads / 32;
 constexpr int kTreeQueue = CRS_TREE_QUEUE;            // root survivors parked per warp
 constexpr int kTreeMinActive = CRS_TREE_MIN_ACTIVE;   // fewer walking lanes than this (and fresh samples left): refill first
 constexpr int kTreeMaxLeaves = 4096;    // 10-bit arg-max fields per child: depth <= 6
+constexpr int kTreeDirect = 5;          // most threatening competitors, drawn outside the tree
+constexpr uint32_t kTreeDirectNode = 0xffffffffu;  // Philox counter word of the call that draws direct arms 1..4
 constexpr float kTreeGrid = 1.8f;       // spacing of the envelope table (zfun < 6.9 < 4 * 1.8)
 constexpr float kTreeEmpty = -1e30f;    // envelope of a node without leaves
 constexpr int kTreeSplitSamples = 8192; // smallest sample range worth a plan build of its own
@@ -165,17 +169,17 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
   __shared__ int s_bi[kTreeWarps];
   __shared__ int s_best;
   __shared__ float s_sdb;
-  __shared__ float2 s_top;
+  __shared__ float2 s_top[kTreeDirect];
   __shared__ unsigned int s_hits;
   __shared__ long long s_item;
   const int64_t items = n_c * splits;
-  const int nsort = K - 1;   // competitors
-  const int nleaf = K - 2;   // all but the most threatening one, which is drawn at the root
+  const int nsort = K - 1;                                        // competitors
+  const int nleaf = nsort > kTreeDirect ? nsort - kTreeDirect : 0;  // all but the five most threatening ones
   const uint32_t jmask = (uint32_t)NL - 1u;
   const float c_root = neg_ln2_scaled(2 * D);
   const bool small_root = D >= 4;  // t_root <= 16.7 / 256
   const unsigned int lt_mask = (1u << lane) - 1u;
-  unsigned long long n_roots = 0, n_exp = 0;
+  unsigned long long n_roots = 0, n_exp = 0, n_direct = 0;
 
   for (;;) {
     if (tid == 0) s_item = (long long)atomicAdd(ticket, 1ull);
@@ -253,7 +257,7 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
         __syncthreads();
       }
     }
-    for (int p = tid; p < NL + 1; p += kTreeThreads) {  // sorted position 0 = top threat, p >= 1 = leaf p - 1
+    for (int p = tid; p < NL + kTreeDirect; p += kTreeThreads) {  // sorted positions 0..4 = direct arms, then the leaves
       float2 lf = make_float2(-CUDART_INF_F, 0.f);
       if (p < nsort) {
         const int arm = s_ord[p];
@@ -261,8 +265,8 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
         lf.x = s_mu[e];
         lf.y = s_sd[e];
       }
-      if (p == 0) s_top = lf;
-      else leaf[p - 1] = lf;
+      if (p < kTreeDirect) s_top[p] = lf;
+      else leaf[p - kTreeDirect] = lf;
     }
     __syncthreads();  // the sort scratch is dead from here on (aliased by stacks and queues)
     for (int l = D - 1; l >= 0; --l) {
@@ -298,43 +302,77 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
     const uint32_t cw = (uint32_t)(c + ctx_offset);
     const NodeLines root = node[0];
     __syncthreads();  // s_g (aliased by stacks and queues) is dead from here on
-    const float2 top = s_top;
+    const float2 top = s_top[0];
 
     // ---- sampling -------------------------------------------------------------------------------
     const unsigned int n_item = (unsigned int)(s_hi - s_lo);
     const unsigned int w_hi = (unsigned int)((uint64_t)n_item * (warp + 1) / kTreeWarps);
     unsigned int wnext = (unsigned int)((uint64_t)n_item * warp / kTreeWarps);
-    unsigned int hits = 0, steps = 0;
-    int sp = 0, qn = 0;
+    unsigned int hits = 0, steps = 0, directs = 0;
+    int sp = 0, qn = 0, qdone = 0;  // queue entries [0, qdone) have passed the direct-arm test
     uint32_t smp = 0;
     float yb = 0.f;
     for (;;) {
-      // root tests, warp-wide: y_b, the top threat's draw, the largest other normal and its owner
-      __syncwarp();  // queue slots read by the walk below are rewritten here
-      while (qn <= kTreeQueue - 32 && wnext < w_hi) {
-        const unsigned int my = wnext + lane;
-        const bool valid = my < w_hi;
-        const uint32_t s = (uint32_t)(s_lo + (valid ? my : w_hi - 1));
-        const Words w = philox4x32_10(s, cw, 0u, offset, rk);
-        float zb, ztop;
-        box_muller(w.x, w.y, zb, ztop);
-        const float ybs = __fmul_rn(sd_b, zb);
-        const float t = __fmul_rn(log2_unit_open(w.z), c_root);
-        const uint32_t J = w.w & jmask;
-        const float z = small_root ? zfun<true>(t) : zfun<false>(t);
-        const float2 lf = leaf[J];
-        const bool fail = fmaf(top.y, ztop, top.x) >= ybs || fmaf(lf.y, z, lf.x) >= ybs;
-        const bool open = node_bound(root, z) >= ybs;  // some other arm may still reach y_b
-        const bool surv = valid && !fail && open;
-        hits += (valid && !fail && !open) ? 1u : 0u;
-        const unsigned bal = __ballot_sync(kFull, surv);
-        if (surv) {
-          const int pos = qn + __popc(bal & lt_mask);
-          q_s[pos] = s; q_yb[pos] = ybs; q_t[pos] = t; q_J[pos] = J; q_z[pos] = z;
+      // Root tests, warp-wide: y_b, the top threat's draw, the largest tree normal and its owner.
+      // Samples that survive are parked; the parked ones then draw direct arms 1..4 (second Philox
+      // call, again warp-wide) and only those that still stand — and whose root bound reaches y_b —
+      // stay in the queue for the tree walk.
+      for (;;) {
+        __syncwarp();  // queue slots read by the walk below are rewritten here
+        while (qn <= kTreeQueue - 32 && wnext < w_hi) {
+          const unsigned int my = wnext + lane;
+          const bool valid = my < w_hi;
+          const uint32_t s = (uint32_t)(s_lo + (valid ? my : w_hi - 1));
+          const Words w = philox4x32_10(s, cw, 0u, offset, rk);
+          float zb, ztop;
+          box_muller(w.x, w.y, zb, ztop);
+          const float ybs = __fmul_rn(sd_b, zb);
+          const float t = __fmul_rn(log2_unit_open(w.z), c_root);
+          const uint32_t J = w.w & jmask;
+          const float z = small_root ? zfun<true>(t) : zfun<false>(t);
+          const float2 lf = leaf[J];
+          const bool fail = fmaf(top.y, ztop, top.x) >= ybs || fmaf(lf.y, z, lf.x) >= ybs;
+          const bool open = node_bound(root, z) >= ybs;  // some leaf may still reach y_b
+          const bool surv = valid && !fail;
+          const unsigned bal = __ballot_sync(kFull, surv);
+          if (surv) {
+            const int pos = qn + __popc(bal & lt_mask);
+            q_s[pos] = s; q_yb[pos] = ybs; q_t[pos] = t; q_J[pos] = J | (open ? 0u : 0x80000000u); q_z[pos] = z;
+          }
+          qn += __popc(bal);
+          n_roots += lane == 0 ? (unsigned long long)min(32u, w_hi - wnext) : 0ull;
+          wnext += 32;
         }
-        qn += __popc(bal);
-        n_roots += lane == 0 ? (unsigned long long)min(32u, w_hi - wnext) : 0ull;
-        wnext += 32;
+        // direct arms 1..4 of the newly parked samples; the queue is compacted in place
+        int wq = qdone;
+        for (int base = qdone; base < qn; base += 32) {
+          __syncwarp();
+          const int idx = base + lane;
+          const bool v = idx < qn;
+          const int ri = v ? idx : qn - 1;
+          const uint32_t s = q_s[ri], Jf = q_J[ri];
+          const float ybs = q_yb[ri], t = q_t[ri], z = q_z[ri];
+          __syncwarp();  // every lane holds its entry: slots may be overwritten now
+          const Words w = philox4x32_10(s, cw, kTreeDirectNode, offset, rk);
+          float z1, z2, z3, z4;
+          box_muller(w.x, w.y, z1, z2);
+          box_muller(w.z, w.w, z3, z4);
+          const float2 d1 = s_top[1], d2 = s_top[2], d3 = s_top[3], d4 = s_top[4];
+          const float ymax = fmaxf(fmaxf(fmaf(d1.y, z1, d1.x), fmaf(d2.y, z2, d2.x)),
+                                   fmaxf(fmaf(d3.y, z3, d3.x), fmaf(d4.y, z4, d4.x)));
+          const bool ok = v && !(ymax >= ybs);
+          hits += (ok && (Jf >> 31)) ? 1u : 0u;  // no leaf can reach y_b either: success
+          const bool keep = ok && !(Jf >> 31);
+          const unsigned bal = __ballot_sync(kFull, keep);
+          if (keep) {
+            const int pos = wq + __popc(bal & lt_mask);
+            q_s[pos] = s; q_yb[pos] = ybs; q_t[pos] = t; q_J[pos] = Jf; q_z[pos] = z;
+          }
+          wq += __popc(bal);
+          directs += v ? 1u : 0u;
+        }
+        qn = qdone = wq;
+        if (qn > kTreeQueue - 64 || wnext >= w_hi) break;  // enough parked work, or no fresh samples left
       }
       __syncwarp();
       if (qn == 0 && !__any_sync(kFull, sp > 0)) break;  // no fresh samples left either
@@ -358,6 +396,7 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
         }
         if (act == 0) break;
         if (qn == 0 && wnext < w_hi && __popc(act) < kTreeMinActive) break;  // refill the queue first
+
         if (sp > 0) {
           --sp;
           const uint32_t meta = stk_meta[sp * kTreeThreads + tid];
@@ -406,8 +445,10 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
           else if (sp == 0) ++hits;
         }
       }
+      qdone = qn;  // what is left in the queue has passed the direct-arm test
     }
     n_exp += steps;
+    n_direct += directs;
     hits = warp_sum(hits);
     if (lane == 0 && hits) atomicAdd(&s_hits, hits);
     __syncthreads();
@@ -416,9 +457,11 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
   if (stats) {
     n_roots = warp_sum(n_roots);
     n_exp = warp_sum(n_exp);
+    n_direct = warp_sum(n_direct);
     if (lane == 0) {
       atomicAdd(stats, n_roots);
       atomicAdd(stats + 1, n_exp);
+      atomicAdd(stats + 2, n_direct);
     }
   }
 }
@@ -479,13 +522,13 @@ int launch_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int K
                            int64_t num_samples, uint64_t seed, uint32_t offset, int64_t ctx_offset,
                            uint32_t* counts, uint64_t* stats, cudaStream_t s) {
   if (!mean || !var || !counts || n_c < 0 || K < 1 || ld < K || num_samples < 0) return CRS_ERR_INVALID_ARG;
-  if (num_samples > 0xffffffffLL || K < 2 || K - 2 > kTreeMaxLeaves) return CRS_ERR_UNSUPPORTED;
+  if (num_samples > 0xffffffffLL || K < 2 || K - 1 - kTreeDirect > kTreeMaxLeaves) return CRS_ERR_UNSUPPORTED;
   if (n_c == 0) return CRS_OK;
   CRS_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)n_c, s), "pcs_tree memset");
-  if (stats) CRS_CUDA_TRY(cudaMemsetAsync(stats, 0, 2 * sizeof(uint64_t), s), "pcs_tree memset stats");
+  if (stats) CRS_CUDA_TRY(cudaMemsetAsync(stats, 0, 3 * sizeof(uint64_t), s), "pcs_tree memset stats");
   if (num_samples == 0) return CRS_OK;
   int D = 1;
-  while ((1 << (2 * D)) < K - 2) ++D;
+  while ((1 << (2 * D)) < K - 1 - kTreeDirect) ++D;
   const int NL = 1 << (2 * D), NI = (NL - 1) / 3;
   int n2 = 1;
   while (n2 < K - 1) n2 <<= 1;

@@ -29,7 +29,7 @@ def _is_strict_indicator(func_I: Callable[[Tensor], Tensor]) -> bool:
     return out.shape == probe.shape and out.to(torch.float64).tolist() == [0.0, 0.0, 0.0, 1.0, 1.0]
 
 
-TREE_MAX_ARMS = 4098  # crs_pcs_counts_tree: top threat + 4^6 leaves + the best arm
+TREE_MAX_ARMS = 4102  # crs_pcs_counts_tree: 5 direct arms + 4^6 leaves + the best arm
 
 
 def pcs_counts(model: B200ModelListGP, mean: Tensor, var: Tensor, num_samples: int, seed: int,
@@ -39,21 +39,23 @@ def pcs_counts(model: B200ModelListGP, mean: Tensor, var: Tensor, num_samples: i
     """Correct-selection counts of device tables ``[n_c, K]``; returns int32 counts ``[n_c]``.
 
     ``sampler``: ``"tree"`` = ``crs_pcs_counts_tree`` (max-tree stream: a sample is decided after a
-    few Philox calls; needs the full arm row, 2 <= K <= 4098), ``"flat"`` = ``crs_pcs_counts``
+    few Philox calls; needs the full arm row, 2 <= K <= 4102), ``"flat"`` = ``crs_pcs_counts``
     (one draw per arm, keyed by arm id — also serves arm slices via ``arm_offset``), ``"auto"`` =
     tree whenever it applies.  Both are Monte-Carlo estimates of the same quantity; the two
     streams are different, so counts agree within MC error, not draw for draw.
-    ``stats`` (``[2]`` int64, optional): flat -> {draws executed, nominal - executed};
-    tree -> {root tests, node expansions}."""
+    ``stats`` (``[>= 3]`` int64, optional): flat -> {draws executed, nominal - executed, -};
+    tree -> {root tests, node expansions, direct-arm tests}."""
     n_c, K = mean.shape
     if sampler not in ("auto", "tree", "flat"):
         raise ValueError(f"unknown sampler {sampler!r}")
     tree_ok = 2 <= K <= TREE_MAX_ARMS and arm_offset == 0
     if sampler == "tree" and not tree_ok:
-        raise ValueError("the tree sampler needs the full arm row with 2 <= K <= 4098 and arm_offset = 0")
+        raise ValueError("the tree sampler needs the full arm row with 2 <= K <= 4102 and arm_offset = 0")
     use_tree = tree_ok and sampler != "flat"
     if counts is None:
         counts = torch.empty(n_c, dtype=torch.int32, device=mean.device)
+    if stats is not None and stats.numel() < 3:
+        raise ValueError("stats needs room for 3 int64 values")
     with torch.cuda.device(mean.device):
         if use_tree:
             rc = _lib.get().crs_pcs_counts_tree(mean.data_ptr(), var.data_ptr(), n_c, K, mean.stride(0),

@@ -327,7 +327,7 @@ class B200ModelListGP:
                 "scan_ws": torch.zeros(int(_lib.get().crs_scan_workspace_bytes()), dtype=torch.uint8, device=dev),
                 "decision_host": torch.zeros(64, dtype=torch.uint8).pin_memory(),
                 "counts": torch.empty(n_c, dtype=torch.int32, device=dev),
-                "stats": torch.zeros(2, dtype=torch.int64, device=dev),
+                "stats": torch.zeros(4, dtype=torch.int64, device=dev),
             }
             p = _lib.ptr
             ws["struct"] = _lib.DecideWS(p(ws["ctx"]), p(ws["mean"]), p(ws["var"]), p(ws["best_arm"]),

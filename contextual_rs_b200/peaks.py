@@ -58,7 +58,7 @@ def measure_pcs_tree_rates(device, iters: int = 2048, blocks: int = 148 * 8, rep
     rates = {}
     with torch.cuda.device(device):
         stream = _lib.stream_ptr(torch.device(device))
-        for name, kind in (("root", 6), ("expand", 7)):
+        for name, kind in (("root", 6), ("expand", 7), ("direct", 5)):
             best = 0.0
             for r in range(reps + 1):
                 s = torch.cuda.Event(enable_timing=True)
@@ -73,14 +73,16 @@ def measure_pcs_tree_rates(device, iters: int = 2048, blocks: int = 148 * 8, rep
     return rates
 
 
-def pcs_tree_roofline(roots: float, expansions: float, seconds: float, n_gpus: int, rates: dict) -> dict:
-    """Roofline entry of the tree kernel: the time the executed root tests and node expansions
-    would take as bare register arithmetic (``measure_pcs_tree_rates``) over the measured time."""
-    ideal = (roots / rates["root"] + expansions / rates["expand"]) / n_gpus
-    steps = roots + expansions
+def pcs_tree_roofline(roots: float, expansions: float, seconds: float, n_gpus: int, rates: dict,
+                      directs: float = 0.0) -> dict:
+    """Roofline entry of the tree kernel: the time the executed root tests, direct-arm tests and node
+    expansions would take as bare register arithmetic (``measure_pcs_tree_rates``) over the measured time."""
+    ideal = (roots / rates["root"] + expansions / rates["expand"] + directs / rates["direct"]) / n_gpus
+    steps = roots + expansions + directs
     return {"kernel": "pcs_tree_kernel", "bound": "issue", "achieved": steps / seconds / n_gpus / 1e9,
             "peak": steps / ideal / n_gpus / 1e9, "unit": "G steps/s", "frac": ideal / seconds, "traffic": None,
-            "root_tests": roots, "node_expansions": expansions,
-            "peak_source": "measured in this run by crs_peak_probe kinds 6 / 7: the bare root-test and node-expansion "
-                           "sequences on registers (%.1f / %.1f G steps/s per GPU), weighted by the executed mix; "
-                           "achieved = executed steps/s per GPU" % (rates["root"] / 1e9, rates["expand"] / 1e9)}
+            "root_tests": roots, "direct_arm_tests": directs, "node_expansions": expansions,
+            "peak_source": "measured in this run by crs_peak_probe kinds 6 / 5 / 7: the bare root-test, direct-arm-test "
+                           "(Philox + 2 Box-Muller + 4 FMA + max) and node-expansion sequences on registers "
+                           "(%.1f / %.1f / %.1f G steps/s per GPU), weighted by the executed mix; achieved = executed "
+                           "steps/s per GPU" % (rates["root"] / 1e9, rates["direct"] / 1e9, rates["expand"] / 1e9)}

@@ -226,14 +226,15 @@ CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32
  * Same estimate as crs_pcs_counts — counts[c] = number of the S posterior draws in which the
  * predicted-best arm of context c beats every other arm (contextual_rs/generalized_pcs.py:441-475,
  * func_I = strict indicator) — under the "max-tree" Philox stream: the K - 1 competitors are the
- * leaves of a 4-ary tree in threat order, a node carries the largest standard normal among its
- * leaves and the leaf that owns it, and children are drawn conditionally (truncated maxima), so a
- * sample is decided after ~1-4 Philox calls instead of ~K/4 although the K - 1 leaf draws are iid
- * N(0,1) exactly as before (stream definition + brute-force restatement: oracle/pcs_tree_ref.py).
+ * five most threatening ones, drawn directly, plus the leaves of a 4-ary tree in threat order; a
+ * node carries the largest standard normal among its leaves and the leaf that owns it, and children
+ * are drawn conditionally (truncated maxima), so a sample is decided after ~1-3 Philox calls instead
+ * of ~K/4 although the K - 1 competitor draws are iid N(0,1) exactly as before (stream definition +
+ * brute-force restatement: oracle/pcs_tree_ref.py).
  * Counters (sample, context + ctx_offset, node, offset): counts do not depend on how contexts are
- * sharded.  The full row of K arms must be passed (2 <= K <= 4098, else CRS_ERR_UNSUPPORTED).
- * counts: [n_c] uint32.  stats (may be NULL): [2] uint64 = {root tests, node expansions} (one
- * Philox call each).
+ * sharded.  The full row of K arms must be passed (2 <= K <= 4102, else CRS_ERR_UNSUPPORTED).
+ * counts: [n_c] uint32.  stats (may be NULL): [3] uint64 = {root tests, node expansions, direct-arm
+ * tests} (one Philox call each).
  */
 CRS_API int crs_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
                                 int32_t dtype, int64_t num_samples, uint64_t seed, uint32_t offset,

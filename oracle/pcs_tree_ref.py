@@ -10,9 +10,9 @@ definition (kernel: ``contextual_rs_b200/csrc/pcs_tree.cu``), equal in law to K 
 N(0,1) draws per (sample, context):
 
   * The K - 1 competitors are ordered by decreasing threat (mu_j - mu_b) / sqrt(sd_j^2 + sd_b^2)
-    (IEEE fp32, ties by arm id).  The first one ("top") is drawn directly; the other K - 2 are the
-    leaves of a complete 4-ary tree of depth D (4^D >= K - 2) in that order; unused leaves have
-    mu = -inf.
+    (IEEE fp32, ties by arm id).  The first five ("direct" arms) are drawn directly; the other
+    K - 6 are the leaves of a complete 4-ary tree of depth D (4^D >= K - 6) in that order; unused
+    leaves (and unused direct slots when K < 6) have mu = -inf.
   * A node that covers m leaves carries (t, J): t = -ln P(max of its m iid normals <= its value),
     J = the leaf that attains the maximum.  The maximum of m iid N(0,1) has CDF Phi(z)^m, so
     t_root = E / m with E ~ Exp(1) and J_root uniform.  Given a node's (t, J), the child that
@@ -20,8 +20,9 @@ N(0,1) draws per (sample, context):
     truncated at the parent's value, t_c = t + E' / m_c, and a uniform J_c among its leaves.
     At the leaves m = 1 and z_leaf = zfun(t_leaf), Phi(zfun(t)) = exp(-t).
   * Philox4x32-10 (``philox_ref``), key = seed, counters
-        (sample, context, 0, offset)            -> w0, w1: Box-Muller (z_b, z_top), y_b = sd_b z_b;
+        (sample, context, 0, offset)            -> w0, w1: Box-Muller (z_b, z of direct arm 0), y_b = sd_b z_b;
                                                   w2: E of the root, w3 & (4^D - 1): J of the root
+        (sample, context, 0xffffffff, offset)   -> Box-Muller (w0, w1), (w2, w3): z of direct arms 1, 2, 3, 4
         (sample, context, 1 + node id, offset)  -> w0, w1, w2: E' of the three children that do not
                                                   contain J (in child order); 10-bit fields of w3: their J
     node id = (4^level - 1) / 3 + index;  E(w) = -ln u(w), u(w) = ((w >> 9) + 1/2) 2^-23.
@@ -97,20 +98,22 @@ def exp_log2(w: np.ndarray) -> np.ndarray:
     return np.log2(_unit(w) + F32(2.0 ** -24)).astype(F32)
 
 
+NUM_DIRECT = 5           # most threatening competitors, drawn outside the tree
+DIRECT_NODE = 0xFFFFFFFF  # Philox counter word of the call that draws direct arms 1..4
 GRID = F32(1.8)          # spacing of the envelope table g(0), g(1.8), .. g(7.2)
 EMPTY = F32(-1e30)
 
 
 def tree_depth(K: int) -> int:
     D = 1
-    while 4 ** D < K - 2:
+    while 4 ** D < K - 1 - NUM_DIRECT:
         D += 1
     return D
 
 
 def tree_plan(mean_row: np.ndarray, var_row: np.ndarray):
-    """Competitors in threat order and the per-node bounds.  Returns dict(best, sd_b, D, top_mu,
-    top_sd, leaf_mu, leaf_sd, order, levels) with levels[l] = ``[4^l, 5]`` envelope tables
+    """Competitors in threat order and the per-node bounds.  Returns dict(best, sd_b, D, top_mu [5],
+    top_sd [5], leaf_mu, leaf_sd, order, levels) with levels[l] = ``[4^l, 5]`` envelope tables
     g(z) = max over the node's leaves of mu_j + sd_j z at z = 0, 1.8, .. 7.2 (EMPTY if none)."""
     K = mean_row.shape[0]
     b = int(np.argmax(mean_row))
@@ -125,9 +128,15 @@ def tree_plan(mean_row: np.ndarray, var_row: np.ndarray):
     NL = 4 ** D
     leaf_mu = np.full(NL, -np.inf, dtype=F32)
     leaf_sd = np.zeros(NL, dtype=F32)
-    leaf_mu[:K - 2] = mu[order[1:]]
-    leaf_sd[:K - 2] = sd[order[1:]]
-    real = (np.arange(NL) < K - 2).reshape(-1, 1)
+    nleaf = max(K - 1 - NUM_DIRECT, 0)
+    leaf_mu[:nleaf] = mu[order[NUM_DIRECT:]]
+    leaf_sd[:nleaf] = sd[order[NUM_DIRECT:]]
+    real = (np.arange(NL) < nleaf).reshape(-1, 1)
+    top_mu = np.full(NUM_DIRECT, -np.inf, dtype=F32)
+    top_sd = np.zeros(NUM_DIRECT, dtype=F32)
+    nd = min(NUM_DIRECT, K - 1)
+    top_mu[:nd] = mu[order[:nd]]
+    top_sd[:nd] = sd[order[:nd]]
     zk = (np.arange(5, dtype=np.float64) * float(GRID)).astype(F32).reshape(1, -1)
     g = np.where(real, _fma(leaf_sd.reshape(-1, 1), zk, leaf_mu.reshape(-1, 1)), EMPTY).astype(F32)  # [NL, 5]
     levels = [None] * D
@@ -136,7 +145,7 @@ def tree_plan(mean_row: np.ndarray, var_row: np.ndarray):
         if l == D - 1:  # head-room for the rounding of the chord lines
             g = (g + (np.maximum(np.abs(g[:, :1]), np.abs(g[:, 4:])) * F32(2.0 ** -18)).astype(F32)).astype(F32)
         levels[l] = g
-    return dict(best=b, sd_b=sd[b], D=D, top_mu=mu[order[0]], top_sd=sd[order[0]], leaf_mu=leaf_mu,
+    return dict(best=b, sd_b=sd[b], D=D, top_mu=top_mu, top_sd=top_sd, leaf_mu=leaf_mu,
                 leaf_sd=leaf_sd, order=order, levels=levels)
 
 
@@ -154,12 +163,14 @@ def node_bound(g: np.ndarray, z) -> float:
 
 
 def tree_leaf_normals(num_samples: int, context: int, D: int, seed: int, offset: int, first_sample: int = 0):
-    """Brute force: (z_b [S], z_top [S], z_leaf [S, 4^D]) of the stream for one context."""
+    """Brute force: (z_b [S], z_direct [S, 5], z_leaf [S, 4^D]) of the stream for one context."""
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
     NL = 4 ** D
     smp = (np.arange(num_samples, dtype=np.uint64) + np.uint64(first_sample)).astype(np.uint32).reshape(-1, 1)
     w0, w1, w2, w3 = philox4x32_10(smp, np.uint32(context), np.uint32(0), np.uint32(offset), k0, k1)
-    zb, ztop = (z.reshape(-1) for z in box_muller(w0, w1))
+    zb, zd0 = (z.reshape(-1) for z in box_muller(w0, w1))
+    v0, v1, v2, v3 = philox4x32_10(smp, np.uint32(context), np.uint32(DIRECT_NODE), np.uint32(offset), k0, k1)
+    zd = np.stack([zd0] + [z.reshape(-1) for z in box_muller(v0, v1) + box_muller(v2, v3)], axis=1)
     t = (exp_log2(w2) * F32(-float(LN2) / NL)).astype(F32)       # [S, 1]
     J = (w3 & np.uint32(NL - 1)).astype(np.int64)
     for l in range(D):
@@ -184,24 +195,24 @@ def tree_leaf_normals(num_samples: int, context: int, D: int, seed: int, offset:
             Jc[:, :, k] = np.where(own, J, J_new)
         t = tc.reshape(num_samples, nn * 4)
         J = Jc.reshape(num_samples, nn * 4)
-    return zb, ztop, zfun32(t)
+    return zb, zd, zfun32(t)
 
 
 def pcs_counts_tree_ref(mean: np.ndarray, variance: np.ndarray, num_samples: int, seed: int,
                         offset: int = 0, ctx_offset: int = 0, chunk: int = 4096) -> np.ndarray:
     """Correct-selection counts per context under the max-tree stream.  mean/variance: ``[n_c, K]``."""
     n_c, K = mean.shape
-    assert 2 <= K <= MAX_LEAVES + 2
+    assert 2 <= K <= MAX_LEAVES + 1 + NUM_DIRECT
     counts = np.zeros(n_c, dtype=np.int64)
     for c in range(n_c):
         pl = tree_plan(mean[c], variance[c])
         for s0 in range(0, num_samples, chunk):
             S = min(chunk, num_samples - s0)
-            zb, ztop, z = tree_leaf_normals(S, c + ctx_offset, pl["D"], seed, offset, first_sample=s0)
+            zb, zd, z = tree_leaf_normals(S, c + ctx_offset, pl["D"], seed, offset, first_sample=s0)
             yb = (pl["sd_b"] * zb).astype(F32)
-            ytop = _fma(pl["top_sd"], ztop, pl["top_mu"])
+            ytop = _fma(pl["top_sd"].reshape(1, -1), zd, pl["top_mu"].reshape(1, -1))
             y = _fma(pl["leaf_sd"].reshape(1, -1), z, pl["leaf_mu"].reshape(1, -1))
-            counts[c] += int(((y.max(axis=1) < yb) & (ytop < yb)).sum())
+            counts[c] += int(((y.max(axis=1) < yb) & (ytop.max(axis=1) < yb)).sum())
     return counts
 
 
@@ -223,9 +234,9 @@ def pcs_counts_tree_lazy(mean: np.ndarray, variance: np.ndarray, num_samples: in
 
         smp = np.arange(num_samples, dtype=np.uint32)
         w0, w1, w2, w3 = philox4x32_10(smp, ctx, np.uint32(0), np.uint32(offset), k0, k1)
-        zb, ztop = box_muller(w0, w1)
+        zb, zd0 = box_muller(w0, w1)
         yb_all = (pl["sd_b"] * zb).astype(F32)
-        ytop_all = _fma(pl["top_sd"], ztop, pl["top_mu"])
+        ytop_all = _fma(pl["top_sd"][0], zd0, pl["top_mu"][0])
         t_all = (exp_log2(w2) * F32(-float(LN2) / NL)).astype(F32)
         z_all = zfun32(t_all)
         J_all = (w3 & np.uint32(NL - 1)).astype(np.int64)
@@ -233,6 +244,11 @@ def pcs_counts_tree_lazy(mean: np.ndarray, variance: np.ndarray, num_samples: in
         for s in range(num_samples):
             yb, t, J, z = float(yb_all[s]), t_all[s], int(J_all[s]), z_all[s]
             fail = float(ytop_all[s]) >= yb or float(_fma(ls[J], z, lm[J])) >= yb
+            if not fail:  # direct arms 1..4: one more Philox call for every sample that survives the root test
+                calls += 1
+                v = philox4x32_10(np.uint32(s), ctx, np.uint32(DIRECT_NODE), np.uint32(offset), k0, k1)
+                zd = np.array([z_[0] for z_ in box_muller(v[0].reshape(1), v[1].reshape(1)) + box_muller(v[2].reshape(1), v[3].reshape(1))])
+                fail = bool((_fma(pl["top_sd"][1:], zd, pl["top_mu"][1:]) >= yb).any())
             stack = []
             if not fail and bound(0, 0, z) >= yb:
                 stack.append((0, 0, t, J, z))

@@ -75,7 +75,7 @@ ref = gp_oracle.model_from_description(desc)
 rp = ref.posterior(ctx)
 p = model.posterior(ctx)
 S = 8192
-stats = torch.zeros(2, dtype=torch.int64, device=dev)
+stats = torch.zeros(4, dtype=torch.int64, device=dev)
 cnt = pcs_counts(model, p.mean.contiguous(), p.variance.contiguous(), S, seed=77, offset=3, stats=stats).cpu().numpy()
 rc = philox_ref.pcs_counts_philox_ref(p.mean.cpu().numpy(), p.variance.cpu().numpy(), S, seed=77, offset=3)
 exact = pcs_oracle.pcs_exact_quadrature(rp.mean.numpy(), rp.variance.numpy())
@@ -104,7 +104,7 @@ for name in ("c2", "c3", "c5", "c4"):
               f"({2*K*n_c*w/t_scan/1e6:.0f} GB/s) decide(dev ctx) {t_dec*1e3:.1f}us decide(host ctx) {t_dec_h*1e3:.1f}us")
         if name in ("c3", "c5") and dt == torch.float32:
             for S in (4096, 65536):
-                st = torch.zeros(2, dtype=torch.int64, device=dev)
+                st = torch.zeros(4, dtype=torch.int64, device=dev)
                 t_pcs = ev_time(lambda: pcs_counts(model, ws["mean"], ws["var"], S, seed=1, stats=st), iters=2, warm=1)
                 d_, s_ = st.cpu().tolist()
                 print(f"   pcs S={S}: {t_pcs:.2f} ms; drawn {d_:.3e} skipped {s_:.3e} ({d_/(d_+s_):.3f} executed); "

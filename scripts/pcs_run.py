@@ -13,12 +13,12 @@ desc, ctx = make_config(name)
 model = crs.B200ModelListGP(desc, device="cuda:0", dtype=dt)
 p = model.posterior(ctx.to(dt))
 mean, var = p.mean.contiguous(), p.variance.contiguous()
-st = torch.zeros(2, dtype=torch.int64, device="cuda:0")
+st = torch.zeros(4, dtype=torch.int64, device="cuda:0")
 for _ in range(2):
     c = pcs_counts(model, mean, var, S, seed=1, stats=st)
 torch.cuda.synchronize()
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record(); c = pcs_counts(model, mean, var, S, seed=1, stats=st); e.record(); torch.cuda.synchronize()
-d, k = st.cpu().tolist()
+d, k = st.cpu().tolist()[:2]
 print(f"{name} {dt} S={S}: {s.elapsed_time(e):.3f} ms, executed {d:.3e} draws ({d/(d+k):.4f}), {d/s.elapsed_time(e)/1e6:.1f} G draws/s, "
       f"pcs mean {float(c.float().mean())/S:.4f} min {float(c.min())/S:.4f}")

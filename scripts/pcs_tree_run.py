@@ -17,7 +17,7 @@ if lim:
 model = crs.B200ModelListGP(desc, device="cuda:0", dtype=dt)
 p = model.posterior(ctx.to(dt))
 mean, var = p.mean.contiguous(), p.variance.contiguous()
-st = torch.zeros(2, dtype=torch.int64, device="cuda:0")
+st = torch.zeros(4, dtype=torch.int64, device="cuda:0")
 res = {}
 for sampler in (("tree", "flat") if flat else ("tree",)):
     for _ in range(2):
@@ -25,12 +25,12 @@ for sampler in (("tree", "flat") if flat else ("tree",)):
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record(); c = pcs_counts(model, mean, var, S, seed=1, stats=st, sampler=sampler); e.record(); torch.cuda.synchronize()
-    a, b = st.cpu().tolist()
+    a, b, dct = st.cpu().tolist()[:3]
     ms = s.elapsed_time(e)
     res[sampler] = c.double() / S
     n = S * mean.shape[0]
     if sampler == "tree":
-        print(f"{name} {dt} S={S} n_c={mean.shape[0]} K={mean.shape[1]} tree: {ms:.3f} ms, roots {a:.3e} expansions {b:.3e} ({b/a:.3f}/sample), "
+        print(f"{name} {dt} S={S} n_c={mean.shape[0]} K={mean.shape[1]} tree: {ms:.3f} ms, roots {a:.3e} direct {dct:.3e} expansions {b:.3e} ({b/a:.3f}/sample), "
               f"{n/ms/1e6:.2f} G samples/s, pcs mean {float(res[sampler].mean()):.5f}")
     else:
         print(f"{name} {dt} S={S} flat: {ms:.3f} ms, executed {a:.3e} draws ({a/4/n:.2f} calls/sample), pcs mean {float(res[sampler].mean()):.5f}")

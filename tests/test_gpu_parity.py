@@ -405,7 +405,7 @@ def test_pcs_counts_parity(crs, dtype, S):
     model = crs.B200ModelListGP(desc, device=DEV, dtype=dtype)
     p = model.posterior(ctx.to(dtype))
     mean, var = p.mean.contiguous(), p.variance.contiguous()
-    stats = torch.zeros(2, dtype=torch.int64, device=DEV)
+    stats = torch.zeros(4, dtype=torch.int64, device=DEV)
     cnt = pcs_counts(model, mean, var, S, seed=77, offset=3, stats=stats, sampler="flat").cpu().numpy()
     want = philox_ref.pcs_counts_philox_ref(mean.cpu().numpy(), var.cpu().numpy(), S, seed=77, offset=3)
     # shared Philox stream: identical up to borderline draws (MUFU vs libm rounding of the normals)
@@ -413,7 +413,7 @@ def test_pcs_counts_parity(crs, dtype, S):
     exact = pcs_oracle.pcs_exact_quadrature(mean.double().cpu().numpy(), var.double().cpu().numpy())
     se = np.sqrt(np.maximum(exact * (1 - exact), 1e-4) / S)
     assert np.all(np.abs(cnt / S - exact) < 5 * se)
-    drawn, skipped = stats.cpu().tolist()
+    drawn, skipped = stats.cpu().tolist()[:2]
     assert drawn + skipped == S * 12 * 48  # executed + skipped = nominal S * K * n_c
     # sharding invariance: context / arm offsets only re-key the stream
     half = pcs_counts(model, mean[24:], var[24:], S, seed=77, offset=3, ctx_offset=24, sampler="flat").cpu().numpy()
@@ -430,11 +430,11 @@ def test_pcs_screening_is_exact(crs):
     mean = torch.randn(n_c, K, generator=gen, dtype=torch.float64)
     mean[:, 20:] -= 50.0  # hopeless arms
     var = 0.05 + torch.rand(n_c, K, generator=gen, dtype=torch.float64)
-    stats = torch.zeros(2, dtype=torch.int64, device=DEV)
+    stats = torch.zeros(4, dtype=torch.int64, device=DEV)
     cnt = pcs_counts(None, mean.to(DEV), var.to(DEV), S, seed=5, stats=stats, sampler="flat").cpu().numpy()
     want = philox_ref.pcs_counts_philox_ref(mean.numpy(), var.numpy(), S, seed=5)
     assert np.abs(cnt - want).max() <= 2
-    drawn, skipped = stats.cpu().tolist()
+    drawn, skipped = stats.cpu().tolist()[:2]
     assert skipped >= S * n_c * 20 and drawn + skipped == S * n_c * K
     # degenerate rows: a dominant best arm gives PCS = 1 exactly, equal arms give ~1/K
     mean2 = torch.zeros(4, 5, dtype=torch.float64); mean2[:2, 3] = 100.0
@@ -455,15 +455,15 @@ def test_pcs_tree_parity(crs, dtype, S):
     model = crs.B200ModelListGP(desc, device=DEV, dtype=dtype)
     p = model.posterior(ctx.to(dtype))
     mean, var = p.mean.contiguous(), p.variance.contiguous()
-    stats = torch.zeros(2, dtype=torch.int64, device=DEV)
+    stats = torch.zeros(4, dtype=torch.int64, device=DEV)
     cnt = pcs_counts(model, mean, var, S, seed=77, offset=3, stats=stats, sampler="tree").cpu().numpy()
     want = pcs_tree_ref.pcs_counts_tree_ref(mean.cpu().numpy(), var.cpu().numpy(), S, seed=77, offset=3)
     assert np.abs(cnt - want).max() <= 2 and (cnt != want).sum() <= 3
     exact = pcs_oracle.pcs_exact_quadrature(mean.double().cpu().numpy(), var.double().cpu().numpy())
     se = np.sqrt(np.maximum(exact * (1 - exact), 1e-4) / S)
     assert np.all(np.abs(cnt / S - exact) < 5 * se)
-    roots, expansions = stats.cpu().tolist()
-    assert roots == S * 48 and 0 < expansions < 12 * roots
+    roots, expansions, directs = stats.cpu().tolist()[:3]
+    assert roots == S * 48 and 0 < directs < roots and 0 < expansions < 12 * roots
     half = pcs_counts(model, mean[24:], var[24:], S, seed=77, offset=3, ctx_offset=24, sampler="tree").cpu().numpy()
     assert np.array_equal(half, cnt[24:])  # sharding invariance: context offsets only re-key the stream
     other = pcs_counts(model, mean, var, S, seed=78, offset=3, sampler="tree").cpu().numpy()
@@ -472,7 +472,7 @@ def test_pcs_tree_parity(crs, dtype, S):
     assert np.array_equal(again, cnt)
 
 
-@pytest.mark.parametrize("K", [2, 3, 5, 6, 17, 18, 65, 70, 257, 258, 1000, 1025])
+@pytest.mark.parametrize("K", [2, 3, 5, 6, 7, 10, 21, 22, 69, 70, 261, 262, 1000, 1029, 1030])
 def test_pcs_tree_shapes(crs, K):
     """Every tree depth (1..6), full and ragged last levels, fp64 and fp32 tables, ragged sample
     counts, rows with hopeless arms and exact mean ties."""
@@ -521,11 +521,11 @@ def test_pcs_tree_inverse_normal(crs):
 
 def test_pcs_tree_limits(crs):
     from contextual_rs_b200.generalized_pcs import pcs_counts
-    mean = torch.randn(2, 4100, dtype=torch.float64, device=DEV)
-    var = torch.ones(2, 4100, dtype=torch.float64, device=DEV)
+    mean = torch.randn(2, 4110, dtype=torch.float64, device=DEV)
+    var = torch.ones(2, 4110, dtype=torch.float64, device=DEV)
     with pytest.raises(ValueError):
         pcs_counts(None, mean, var, 64, seed=1, sampler="tree")
-    a = pcs_counts(None, mean, var, 256, seed=1)          # auto -> flat stream beyond 4097 arms
+    a = pcs_counts(None, mean, var, 256, seed=1)          # auto -> flat stream beyond 4102 arms
     b = pcs_counts(None, mean, var, 256, seed=1, sampler="flat")
     assert torch.equal(a, b)
     one = pcs_counts(None, mean[:, :1].contiguous(), var[:, :1].contiguous(), 100, seed=1)  # K = 1: no competitor
@@ -533,7 +533,7 @@ def test_pcs_tree_limits(crs):
     from contextual_rs_b200 import _lib
     lib = _lib.get()
     cnt = torch.zeros(2, dtype=torch.int32, device=DEV)
-    assert lib.crs_pcs_counts_tree(mean.data_ptr(), var.data_ptr(), 2, 4100, 4100, 0, 64, 1, 0, 0, cnt.data_ptr(), None, None) == 2
+    assert lib.crs_pcs_counts_tree(mean.data_ptr(), var.data_ptr(), 2, 4110, 4110, 0, 64, 1, 0, 0, cnt.data_ptr(), None, None) == 2
 
 
 def test_estimate_current_generalized_pcs_dropin(crs):

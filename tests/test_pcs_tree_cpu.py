@@ -31,20 +31,24 @@ def test_tree_plan_order_and_bounds():
     assert np.all(np.diff(key[pl["order"]]) <= 1e-6)
     i3, i7 = list(pl["order"]).index(3), list(pl["order"]).index(7)
     assert i7 == i3 + 1  # ties: lower arm id first
-    top = pl["order"][0]
-    assert pl["top_mu"] == np.float32(mean[top] - mean[b]) and pl["leaf_mu"][0] == np.float32(mean[pl["order"][1]] - mean[b])
+    nd = pcs_tree_ref.NUM_DIRECT
+    assert np.array_equal(pl["top_mu"], (mean[pl["order"][:nd]] - mean[b]).astype(np.float32))
+    assert pl["leaf_mu"][0] == np.float32(mean[pl["order"][nd]] - mean[b])
     # the chord table bounds the envelope max_j (mu_j + sd_j z) of every node from above
-    lm, ls = pl["leaf_mu"][:21].astype(np.float64), pl["leaf_sd"][:21].astype(np.float64)
+    nl = 22 - nd
+    lm, ls = pl["leaf_mu"][:nl].astype(np.float64), pl["leaf_sd"][:nl].astype(np.float64)
     for z in np.linspace(-3, 6.9, 100):
-        assert pcs_tree_ref.node_bound(pl["levels"][0][0], z) >= (lm + ls * min(z, max(z, 0))).max() - 0  # root
+        assert pcs_tree_ref.node_bound(pl["levels"][0][0], z) >= (lm + ls * max(z, 0)).max()  # root
         for i in range(4):
-            seg = slice(16 * i, min(16 * i + 16, 21))
-            if seg.start < 21:
+            seg = slice(16 * i, min(16 * i + 16, nl))
+            if seg.start < nl:
                 assert pcs_tree_ref.node_bound(pl["levels"][1][i], z) >= (lm[seg] + ls[seg] * z).max()
-    assert (pl["levels"][2][6:] < -9e29).all()  # nodes without a real leaf can never win
+    assert (pl["levels"][2][5:] < -9e29).all()  # nodes without a real leaf can never win
+    small = pcs_tree_ref.tree_plan(mean[:4], var[:4])  # K - 1 = 3 competitors: all direct, the tree is empty
+    assert np.isneginf(small["top_mu"][3:]).all() and np.isneginf(small["leaf_mu"]).all() and small["D"] == 1
 
 
-@pytest.mark.parametrize("K", [2, 5, 6, 17, 40])
+@pytest.mark.parametrize("K", [2, 5, 6, 7, 17, 40])
 def test_lazy_walk_equals_brute_force(K):
     rng = np.random.default_rng(K)
     mean = rng.normal(size=(2, K))
@@ -53,7 +57,7 @@ def test_lazy_walk_equals_brute_force(K):
     brute = pcs_tree_ref.pcs_counts_tree_ref(mean, var, S, seed=12345, offset=2, ctx_offset=5)
     lazy, calls = pcs_tree_ref.pcs_counts_tree_lazy(mean, var, S, seed=12345, offset=2, ctx_offset=5)
     assert np.array_equal(brute, lazy)
-    assert 2 * S <= calls <= 2 * S * (1 + (4 ** pcs_tree_ref.tree_depth(K) - 1) // 3)
+    assert 2 * S <= calls <= 2 * S * (2 + (4 ** pcs_tree_ref.tree_depth(K) - 1) // 3)
 
 
 def test_tree_stream_is_unbiased():
