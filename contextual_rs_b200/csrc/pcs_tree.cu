@@ -6,11 +6,12 @@
 // A sample fails as soon as ONE competitor beats y_b and succeeds only if NONE does, and with
 // K = 1,000 diffuse posteriors almost every sample fails.  The flat stream (pcs_philox.cu) has to
 // draw arms until it meets a winner (3-4 Philox calls) and all K of them to certify a success
-// (250 calls).  This kernel samples the same law top-down instead: the competitors are the leaves of
-// a 4-ary tree (threat order; the five most threatening ones are drawn directly); a node covering m leaves carries t = -ln Phi(z_max)^... of the
-// maximum of its m iid N(0,1) draws (Exp(1)/m, one uniform) and the leaf J that attains it
-// (uniform).  Children of a node: the one containing J inherits (t, J), the others draw the maximum
-// of m/4 normals truncated at the parent's value, t_c = t + Exp(1)/(m/4), and their own J_c.
+// (250 calls).  This kernel samples the same law top-down instead: the competitors are sorted by
+// threat, the five most threatening ones are drawn directly and the others are the leaves of a
+// 4-ary tree.  A node covering m leaves carries t = -ln P(max of its m iid N(0,1) draws <= its
+// value) (Exp(1)/m at the root, one uniform) and the leaf J that attains the maximum (uniform).
+// Children of a node: the one containing J inherits (t, J), the others draw the maximum of m/4
+// normals truncated at the parent's value, t_c = t + Exp(1)/(m/4), and their own J_c.
 // Stream definition and brute-force restatement: oracle/pcs_tree_ref.py.
 //   root     one Philox call per sample: y_b, the draw of the most threatening competitor (the
 //            second Box-Muller variate, free), the largest of the K-6 standard normals of the
