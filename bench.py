@@ -309,6 +309,34 @@ def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
         out["cpu_baseline"] = {"value": sub_s * sub_c * K / dt, "unit": "N(0,1) draws/s", "cores": torch.get_num_threads(),
                                "kind": "port", "sample": f"{n_rep} x marginal sampler (oracle.pcs_marginal_ref) on {sub_c} contexts x {K} arms x "
                                f"{sub_s} samples, fp64, PyTorch CPU; the reference's joint sampler is O(n_c^3) and cannot run at this size"}
+        # the reference-faithful JOINT sampler at config 1 (10 arms x 10 contexts), the case of the
+        # reference's notebooks/pcs_sampling_overhead.ipynb, next to the kernel on the same posterior
+        from oracle import gp_oracle
+        d1, c1 = make_config("c1")
+        ref1 = gp_oracle.model_from_description(d1)
+        arm_set = torch.arange(10, dtype=torch.float64).view(-1, 1)
+        f_I, rho = pcs_oracle.strict_indicator(), (lambda P: P.mean(dim=-2))
+        for S1 in (64, 1024):
+            pcs_oracle.estimate_current_generalized_pcs_ref(ref1, arm_set, c1, S1, None, f_I, rho)
+        t0, n_rep = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 2.0:
+            v_ref = pcs_oracle.estimate_current_generalized_pcs_ref(ref1, arm_set, c1, 1024, None, f_I, rho)
+            n_rep += 1
+        dt_ref = (time.perf_counter() - t0) / n_rep
+        m1 = crs.B200ModelListGP(d1, device=dev)
+        c1d = c1.to(dev)
+        crs.estimate_current_generalized_pcs(m1, arm_set, c1d, 1024, None, f_I, rho, seed=1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(50):
+            v_gpu = crs.estimate_current_generalized_pcs(m1, arm_set, c1d, 1024, None, f_I, rho, seed=2 + i)
+        torch.cuda.synchronize()
+        dt_gpu = (time.perf_counter() - t0) / 50
+        out["c1_joint_sampler"] = {"workload": "c1: estimate_current_generalized_pcs, 10 arms x 10 contexts, 1,024 samples, posterior included",
+                                   "reference_port_ms": dt_ref * 1e3, "b200_ms": dt_gpu * 1e3, "cores": torch.get_num_threads(),
+                                   "pcs_reference_port": float(v_ref), "pcs_b200": float(v_gpu),
+                                   "note": "oracle.estimate_current_generalized_pcs_ref = the reference's joint MVN sampler "
+                                           "(generalized_pcs.py:441-479) restated; the B200 number is the host API call (wall clock)"}
     return out
 
 
