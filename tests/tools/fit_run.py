@@ -1,6 +1,6 @@
 """Time the hyper-parameter fit (fit_modellist) on config-2-shaped data: 100 arms x 20 obs, 4-D."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from contextual_rs_b200.fit import fit_modellist
 from contextual_rs_b200.synthetic import make_config

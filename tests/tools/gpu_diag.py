@@ -1,6 +1,6 @@
 """First-contact GPU diagnostics: parity numbers and rough kernel timings.  Run under gpurun."""
 import sys, os, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import contextual_rs_b200 as crs

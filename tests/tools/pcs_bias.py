@@ -1,7 +1,7 @@
 """Bias check of the two PCS streams against exact quadrature: many samples on a few hundred contexts.
 usage: pcs_bias.py [config] [n_ctx] [log2 S]"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import contextual_rs_b200 as crs
 from contextual_rs_b200.generalized_pcs import pcs_counts

@@ -1,6 +1,6 @@
 """Replay the first iterations of several recorded ML_Gao runs of the reference through the oracle."""
 import sys, os, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import trace_replay
 ROOT = "/root/reference/experiments/wsc_experiments"

@@ -9,7 +9,7 @@ the replay re-fits with the oracle's restatement of BoTorch's fit (`oracle/fit_o
 recorded data and asks the oracle's `gao_modellist_ref` for the decision.
 usage: replay_reference_trace.py [iterations] [out.json]"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import fit_oracle, gp_oracle, ocba_oracle
 

@@ -1,6 +1,6 @@
 """Design aid: expansions per sample of the max-tree walk under different node bounds."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from scipy.special import ndtri_exp
 from contextual_rs_b200.synthetic import make_config
