@@ -17,8 +17,8 @@
 // context tile in and the two tables out.  Tables are [n_c, ld] arm-fastest, so each thread buffers
 // its results in shared memory and writes them as one contiguous run per arm tile.
 //
-// fp64 transcendental cost dominates at n ~ 20, so exp() is a 16-entry-table + degree-7 polynomial
-// (12 FP64 ops) and sqrt() is rsqrt.approx + coupled Newton steps + one correction (branch-free).
+// fp64 transcendental cost dominates at n ~ 20, so exp() is a 64-entry-table + degree-5 polynomial
+// (10 FP64 ops) and sqrt() is rsqrt.approx + one coupled Newton step + one correction (branch-free).
 #include <type_traits>
 #include <utility>
 #include <cstdlib>
@@ -38,31 +38,41 @@ constexpr int kMinBlocks = CRS_GRID_MIN_BLOCKS;
 #endif
 constexpr int kPhaseAUnroll = CRS_PHASE_A_UNROLL;  // divides 4 (rows are padded to a multiple of 4)
 
-// ---- fp64 exp(x), x <= 0: x = (16 k + i) ln2/16 + r, exp(x) = 2^k * 2^(i/16) * e^r ------------
-__constant__ double kExpTable[16] = {
-    1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721,
-    1.241857812073484, 1.2968395546510096, 1.3542555469368927, 1.4142135623730951,
-    1.4768261459394993, 1.5422108254079407, 1.6104903319492543, 1.681792830507429,
-    1.7562521603732995, 1.8340080864093424, 1.9152065613971474};
+// ---- fp64 exp(x), x <= 0: x = (64 k + i) ln2/64 + r, exp(x) = 2^k * 2^(i/64) * e^r ------------
+__constant__ double kExpTable[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
 
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ s_tab) {
-  // t = x * 16/ln2 + 1.5*2^52: the integer n = 16 k + i lands in the low mantissa bits of t
-  const double t = fma(x, 23.083120654223414, 6755399441055744.0);
+  // t = x * 64/ln2 + 1.5*2^52: the integer n = 64 k + i lands in the low mantissa bits of t
+  const double t = fma(x, 92.33248261689366, 6755399441055744.0);
   const double nd = t - 6755399441055744.0;
-  double r = fma(nd, -0.04332169878499658, x);   // ln2/16 (high part)
-  r = fma(nd, -1.4494042586539372e-18, r);       // ln2/16 (low part)
+  double r = fma(nd, -0.010830424696249145, x);   // ln2/64 (high part)
+  r = fma(nd, -3.623510646634843e-19, r);       // ln2/64 (low part)
   int n = __double2loint(t);
-  n = max(n, -16000);                             // exp(-693) ~ 1e-301: clamp instead of underflow
-  double p = 1.0 / 5040.0;                        // e^r, |r| <= ln2/32: degree 7, error 1.2e-18
-  p = fma(p, r, 1.0 / 720.0);
-  p = fma(p, r, 1.0 / 120.0);
+  n = max(n, -64000);                             // exp(-693) ~ 1e-301: clamp instead of underflow
+  double p = 1.0 / 120.0;                         // e^r, |r| <= ln2/128: degree 5, error 3.5e-17
   p = fma(p, r, 1.0 / 24.0);
   p = fma(p, r, 1.0 / 6.0);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  const double y = s_tab[n & 15] * p;
-  return __hiloint2double(__double2hiint(y) + ((n >> 4) << 20), __double2loint(y));
+  const double y = s_tab[n & 63] * p;
+  return __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
 }
 
 // sqrt(x) for x > 0 (callers add 1e-290, harmless: the result only enters s and exp(-s)).
@@ -75,7 +85,7 @@ __device__ __forceinline__ double sqrt_pos(double x) {
   for (int it = 0; it < ITERS; ++it) {
     const double r = fma(-h, g, 0.5);
     g = fma(g, r, g);
-    h = fma(h, r, h);
+    if (it + 1 < ITERS) h = fma(h, r, h);  // the last h only scales the 2^-44 residual below: 22 bits suffice
   }
   const double e = fma(-g, g, x);
   return fma(e, h, g);
@@ -272,11 +282,11 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
   constexpr int CS = CStride<T>::value;   // row stride of the parked correlations
   const int tid = threadIdx.x;
   const int ncap = st.n_cap, d = st.dim;
-  // shared layout: bars[4] u64 | tab[16] T | q[128] T | stage[2] { head[40] | alpha[n_rows] |
+  // shared layout: bars[4] u64 | tab[64] T | q[128] T | stage[2] { head[40] | alpha[n_rows] |
   //                xs[n_rows][D] | panel[n_rows][LD] } | c[n_rows][CS] | out[2][arm_tile][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   T* s_tab = reinterpret_cast<T*>(smem_raw + 32);
-  T* s_q = s_tab + 16;
+  T* s_q = s_tab + 64;
   T* s_stage = s_q + kGridThreads;
   const int stage_elems = kHeadElems + n_rows + n_rows * D + n_rows * LD;
   T* s_c = s_stage + 2 * stage_elems;
@@ -318,7 +328,7 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
     mbar_init(&bars[2], 1);
     mbar_fence_init();
   }
-  if (tid < 16) s_tab[tid] = (T)kExpTable[tid];
+  if (tid < 64) s_tab[tid] = (T)kExpTable[tid];
   __syncthreads();
   if (tid == 0) {
     issue(0);
@@ -427,7 +437,7 @@ int launch_variant(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm
   while (arm_tile > 1 && ctx_tiles * ((narms + arm_tile - 1) / arm_tile) < min_ctas) arm_tile >>= 1;
   auto smem_for = [&](int at) {
     const size_t stage = kHeadElems + (size_t)n_rows + (size_t)n_rows * D + (size_t)n_rows * PanelLd<T>::value;
-    return 32 + sizeof(T) * (16 + kGridThreads + 2 * stage + (size_t)n_rows * CStride<T>::value +
+    return 32 + sizeof(T) * (64 + kGridThreads + 2 * stage + (size_t)n_rows * CStride<T>::value +
                              2 * (size_t)at * kGridThreads);
   };
   while (arm_tile > 1 && smem_for(arm_tile) > 227 * 1024) arm_tile >>= 1;
@@ -473,8 +483,8 @@ int dispatch_vb(const crs_gp_state* st, const void* ctx, int64_t n_c, int a0, in
 
 __global__ void debug_corr_kernel(const double* __restrict__ r2, int64_t n, int kernel, int variant,
                                   double* __restrict__ out) {
-  __shared__ double s_tab[16];
-  if (threadIdx.x < 16) s_tab[threadIdx.x] = kExpTable[threadIdx.x];
+  __shared__ double s_tab[64];
+  if (threadIdx.x < 64) s_tab[threadIdx.x] = kExpTable[threadIdx.x];
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
