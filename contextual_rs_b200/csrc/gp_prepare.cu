@@ -253,6 +253,7 @@ constexpr int kSmallCap = 32;
 template <typename T>
 __global__ void __launch_bounds__(kSmallThreads)
 gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
+  griddep_launch_dependents();  // the grid kernel may become resident now; it waits for this grid before reading
   const int k = arm_begin + blockIdx.x;
   if (k >= arm_end) return;
   constexpr int lda = kSmallCap + 1;

@@ -366,6 +366,7 @@ ocba_scan_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t 
                  int32_t* __restrict__ min_arm, int32_t* __restrict__ tie_cnt,
                  ScanPartial* partials, unsigned int* ticket, crs_decision* decision,
                  SelectArgs sel) {
+  griddep_wait();  // the posterior grid of the same decision may still be running (PDL)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   ScanPartial acc = empty_partial();
@@ -586,6 +587,7 @@ ocba_scan_row_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
                      ScanPartial* partials, unsigned int* ticket, crs_decision* decision,
                      SelectArgs sel) {
   constexpr int kpad = R * 32;
+  griddep_wait();  // the posterior grid of the same decision may still be running (PDL)
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   // dynamic smem: [select stage (kSelStageFused bytes, only if fused)] | per warp: NS x {m[kpad], v[kpad]}
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -790,10 +792,9 @@ int scan_dispatch(const void* mean, const void* var, int64_t n_c, int K, int64_t
   ScanPartial* partials = workspace ? reinterpret_cast<ScanPartial*>(reinterpret_cast<char*>(workspace) + 64) : nullptr;
   const size_t dyn = sel.do_select ? kSelStageFused : 0;
   auto go = [&](auto kern) {
-    kern<<<blocks, threads, dyn, s>>>((const T*)mean, (const T*)var, n_c, K, ld, arm_offset,
-                                      ext_best_arm, (const T*)ext_best_mean, (const T*)ext_best_var,
-                                      best_arm, (T*)min_zeta, min_arm, tie_cnt, partials, ticket,
-                                      decision, sel);
+    (void)launch_pdl(kern, dim3(blocks), dim3(threads), dyn, s, (const T*)mean, (const T*)var, n_c, K, ld, arm_offset,
+                     ext_best_arm, (const T*)ext_best_mean, (const T*)ext_best_var, best_arm, (T*)min_zeta,
+                     min_arm, tie_cnt, partials, ticket, decision, sel);
   };
   const size_t esz = sizeof(T);
   const int seg = K <= 512 ? 4 : (K <= 768 ? 6 : 8);       // kpad = 128 seg >= K
@@ -811,9 +812,9 @@ int scan_dispatch(const void* mean, const void* var, int64_t n_c, int K, int64_t
       if (per_sm < 1) per_sm = 1;
       const int64_t want_rows = (n_c + kRowWarps - 1) / kRowWarps;
       const int tblocks = (int)(want_rows < 148 * per_sm ? want_rows : 148 * per_sm);
-      kern<<<tblocks, 32 * kRowWarps, tma_smem, s>>>((const T*)mean, (const T*)var, n_c, K, ld, arm_offset, ext_best_arm,
-                                          (const T*)ext_best_mean, (const T*)ext_best_var, best_arm, (T*)min_zeta,
-                                          min_arm, tie_cnt, partials, ticket, decision, sel);
+      CRS_CUDA_TRY(launch_pdl(kern, dim3(tblocks), dim3(32 * kRowWarps), tma_smem, s, (const T*)mean, (const T*)var, n_c, K, ld,
+                              arm_offset, ext_best_arm, (const T*)ext_best_mean, (const T*)ext_best_var, best_arm,
+                              (T*)min_zeta, min_arm, tie_cnt, partials, ticket, decision, sel), "ocba_scan launch");
       return CRS_OK;
     };
     int rc;

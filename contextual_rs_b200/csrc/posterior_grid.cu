@@ -330,6 +330,8 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
   }
   if (tid < 64) s_tab[tid] = (T)kExpTable[tid];
   __syncthreads();
+  griddep_wait();                // crs_gp_prepare of the same decision may still be running (PDL)
+  griddep_launch_dependents();   // every CTA of this grid is resident by the time the scan may start
   if (tid == 0) {
     issue(0);
     if (na > 1) issue(1);
@@ -449,10 +451,9 @@ int launch_variant(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm
   if (smem > 40 * 1024)
     CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "grid attr");
   dim3 grid((unsigned)ctx_tiles, (unsigned)arm_tiles);
-  kern<<<grid, kGridThreads, smem, s>>>(*st, reinterpret_cast<const T*>(ctx), n_c, arm_begin,
-                                         arm_end, arm_tile, n_rows, reinterpret_cast<T*>(mean),
-                                         reinterpret_cast<T*>(var), ld, col_offset);
-  CRS_CUDA_TRY(cudaGetLastError(), "posterior_grid launch");
+  CRS_CUDA_TRY(launch_pdl(kern, grid, dim3(kGridThreads), smem, s, *st, reinterpret_cast<const T*>(ctx), n_c, arm_begin,
+                          arm_end, arm_tile, n_rows, reinterpret_cast<T*>(mean), reinterpret_cast<T*>(var), ld,
+                          col_offset), "posterior_grid launch");
   return CRS_OK;
 }
 
