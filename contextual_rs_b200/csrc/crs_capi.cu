@@ -155,9 +155,26 @@ CRS_API int crs_gao_decide_host(const crs_gp_state* st, const void* ctx_host, in
   const int seq = (++seq_counter == 0) ? ++seq_counter : seq_counter;
   if (mirror) reinterpret_cast<volatile int32_t*>(decision_host->reserved)[1] = 0;
 
-  CRS_CUDA_TRY(cudaMemcpyAsync(ws->ctx, ctx_host, (size_t)n_c * st->dim * w, cudaMemcpyHostToDevice, s), "ctx H2D");
+  // Context set: if the caller's buffer is mapped pinned memory (and small), the prepare launch itself
+  // pulls it over PCIe with a few extra CTAs — the H2D copy overlaps prepare instead of preceding it.
+  const size_t ctx_bytes = (size_t)n_c * st->dim * w;
+  void* ctx_alias = nullptr;
+  if (prep_end > prep_begin && ctx_bytes <= (1u << 20) && (ctx_bytes & 15) == 0 &&
+      ((uintptr_t)ws->ctx & 15) == 0) {
+    if (cudaHostGetDevicePointer(&ctx_alias, const_cast<void*>(ctx_host), 0) != cudaSuccess) {
+      (void)cudaGetLastError();  // pageable memory: plain copy below
+      ctx_alias = nullptr;
+    } else if ((uintptr_t)ctx_alias & 15) {
+      ctx_alias = nullptr;
+    }
+  }
   int rc;
-  if (prep_end > prep_begin && (rc = launch_gp_prepare(st, prep_begin, prep_end, s)) != CRS_OK) return rc;
+  if (ctx_alias) {
+    if ((rc = launch_gp_prepare_copy(st, prep_begin, prep_end, ctx_alias, ws->ctx, ctx_bytes, s)) != CRS_OK) return rc;
+  } else {
+    CRS_CUDA_TRY(cudaMemcpyAsync(ws->ctx, ctx_host, ctx_bytes, cudaMemcpyHostToDevice, s), "ctx H2D");
+    if (prep_end > prep_begin && (rc = launch_gp_prepare(st, prep_begin, prep_end, s)) != CRS_OK) return rc;
+  }
   if ((rc = launch_posterior_grid(st, ws->ctx, n_c, 0, K, ws->mean, ws->var, K, 0, s)) != CRS_OK) return rc;
   if ((rc = launch_ocba_scan_select(ws->mean, ws->var, n_c, K, K, st->dtype, 0, nullptr, nullptr, nullptr,
                                     ws->best_arm, ws->min_zeta, ws->min_arm, ws->tie_cnt, ws->decision,

@@ -150,6 +150,8 @@ void set_cuda_error(cudaError_t e, const char* where);
 
 // Kernel launchers (one translation unit each).
 int launch_gp_prepare(const crs_gp_state* st, int arm_begin, int arm_end, cudaStream_t s);
+int launch_gp_prepare_copy(const crs_gp_state* st, int arm_begin, int arm_end, const void* cp_src, void* cp_dst,
+                           size_t cp_bytes, cudaStream_t s);
 int launch_posterior_grid(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm_begin,
                           int arm_end, void* mean, void* var, int64_t ld, int col_offset,
                           cudaStream_t s);

@@ -252,10 +252,18 @@ constexpr int kSmallCap = 32;
 
 template <typename T>
 __global__ void __launch_bounds__(kSmallThreads)
-gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
+gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end, const uint4* __restrict__ cp_src,
+                        uint4* __restrict__ cp_dst, int cp_n16) {
   griddep_launch_dependents();  // the grid kernel may become resident now; it waits for this grid before reading
   const int k = arm_begin + blockIdx.x;
-  if (k >= arm_end) return;
+  if (k >= arm_end) {
+    // extra CTAs (crs_gao_decide_host): bring the caller's context set from mapped pinned host memory
+    // into HBM while the arms are being prepared — the H2D copy of a decision overlaps prepare
+    const int narms = arm_end - arm_begin;
+    const int stride = ((int)gridDim.x - narms) * kSmallThreads;
+    for (int i = ((int)blockIdx.x - narms) * kSmallThreads + (int)threadIdx.x; i < cp_n16; i += stride) cp_dst[i] = cp_src[i];
+    return;
+  }
   constexpr int lda = kSmallCap + 1;
   __shared__ double A[kSmallCap * lda];   // K^ then L (lower)
   __shared__ double B[kSmallCap * lda];   // L^-1 (lower)
@@ -476,18 +484,32 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end) {
 }  // namespace
 
 int launch_gp_prepare(const crs_gp_state* st, int arm_begin, int arm_end, cudaStream_t s) {
+  return launch_gp_prepare_copy(st, arm_begin, arm_end, nullptr, nullptr, 0, s);
+}
+
+// cp_src != nullptr: also copy cp_bytes (multiple of 16) from device-visible cp_src (mapped pinned host
+// memory) to cp_dst, inside the prepare launch when the small-arm kernel is used, else by a plain copy.
+int launch_gp_prepare_copy(const crs_gp_state* st, int arm_begin, int arm_end, const void* cp_src, void* cp_dst,
+                           size_t cp_bytes, cudaStream_t s) {
   if (!st || arm_begin < 0 || arm_end > st->num_arms || arm_begin > arm_end) return CRS_ERR_INVALID_ARG;
+  if (cp_src && (!cp_dst || (cp_bytes & 15) || arm_begin == arm_end)) return CRS_ERR_INVALID_ARG;
   if (st->dim < 1 || st->dim > CRS_MAX_DIM || st->dim_pad != dim_pad_of(st->dim)) return CRS_ERR_UNSUPPORTED;
   if (st->n_cap < 1 || st->n_cap > CRS_MAX_OBS || (st->n_cap & 7)) return CRS_ERR_UNSUPPORTED;
   if (st->dtype != CRS_F64 && st->dtype != CRS_F32) return CRS_ERR_INVALID_ARG;
   if (arm_begin == arm_end) return CRS_OK;
   const int narms = arm_end - arm_begin;
   if (st->n_cap <= kSmallCap) {
-    if (st->dtype == CRS_F64) gp_prepare_small_kernel<double><<<narms, kSmallThreads, 0, s>>>(*st, arm_begin, arm_end);
-    else gp_prepare_small_kernel<float><<<narms, kSmallThreads, 0, s>>>(*st, arm_begin, arm_end);
+    const int n16 = cp_src ? (int)(cp_bytes >> 4) : 0;
+    int cp_blocks = (n16 + 2 * kSmallThreads - 1) / (2 * kSmallThreads);
+    if (cp_blocks > 48) cp_blocks = 48;
+    const auto* src = reinterpret_cast<const uint4*>(cp_src);
+    auto* dst = reinterpret_cast<uint4*>(cp_dst);
+    if (st->dtype == CRS_F64) gp_prepare_small_kernel<double><<<narms + cp_blocks, kSmallThreads, 0, s>>>(*st, arm_begin, arm_end, src, dst, n16);
+    else gp_prepare_small_kernel<float><<<narms + cp_blocks, kSmallThreads, 0, s>>>(*st, arm_begin, arm_end, src, dst, n16);
     CRS_CUDA_TRY(cudaGetLastError(), "gp_prepare launch");
     return CRS_OK;
   }
+  if (cp_src) CRS_CUDA_TRY(cudaMemcpyAsync(cp_dst, cp_src, cp_bytes, cudaMemcpyDefault, s), "ctx copy");
   const size_t smem = prep_group_doubles(st->n_cap, st->dim_pad) * sizeof(double);
   auto go = [&](auto kern) -> int {
     if (smem > 40 * 1024)

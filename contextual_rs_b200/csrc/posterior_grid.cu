@@ -329,16 +329,17 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
     mbar_fence_init();
   }
   if (tid < 64) s_tab[tid] = (T)kExpTable[tid];
-  T xraw[D];  // the context row: not written by prepare, so it is fetched before the dependency wait
-#pragma unroll
-  for (int dd = 0; dd < D; ++dd) xraw[dd] = (live && dd < d) ? ctx[c * d + dd] : T(0);
   __syncthreads();
-  griddep_wait();                // crs_gp_prepare of the same decision may still be running (PDL)
+  griddep_wait();                // crs_gp_prepare of the same decision may still be running (PDL); its
+                                 // launch may also carry the H2D copy of `ctx` (crs_gao_decide_host)
   griddep_launch_dependents();   // every CTA of this grid is resident by the time the scan may start
   if (tid == 0) {
     issue(0);
     if (na > 1) issue(1);
   }
+  T xraw[D];
+#pragma unroll
+  for (int dd = 0; dd < D; ++dd) xraw[dd] = (live && dd < d) ? ctx[c * d + dd] : T(0);
   uint32_t xphase = 0;
 
   for (int t = 0; t < na; ++t) {
