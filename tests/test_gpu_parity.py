@@ -203,6 +203,29 @@ def test_reference_recorded_levi_run_through_the_product(crs, golden):
     assert hits_oracle >= 32, (hits_oracle, N)  # two optimisers (device L-BFGS vs scipy L-BFGS-B)
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_decide_host_with_pinned_contexts(crs, dtype):
+    """``crs_gao_decide_host`` with a mapped pinned context buffer and a prepare range: the H2D copy of
+    the context set rides in the prepare launch (extra CTAs) and the grid kernel's dependency wait
+    covers it.  Same decision as with pageable memory (plain copy) and as the oracle, also after the
+    host buffer is rewritten in place between calls."""
+    from contextual_rs_b200.contextual_rs_strategies import decide
+    from contextual_rs_b200.synthetic import make_problem
+    desc, ctx = make_problem(K=24, n_c=700, d=4, n=14, seed=9)
+    model = crs.B200ModelListGP(desc, device=DEV, dtype=dtype)
+    ref = gp_oracle.model_from_description(desc, dtype=dtype)
+    host = ctx.to(dtype).pin_memory()
+    for trial in range(3):
+        rarm, rx = ocba_oracle.gao_modellist_ref(ref, host.clone(), randomize_ties=False)
+        d_pin = decide(model, host, False, 0, 2.0, prepare_arms=(0, 24))
+        got_pin = (d_pin.next_arm, d_pin.context)
+        d_page = decide(model, host.clone(), False, 0, 2.0, prepare_arms=(0, 24))  # pageable: cudaMemcpyAsync path
+        assert got_pin == (d_page.next_arm, d_page.context)
+        if dtype == torch.float64:  # fp32 tables may break near-ties differently from torch's fp32 arithmetic
+            assert got_pin[0] == int(rarm) and torch.equal(host[got_pin[1]], rx)
+        host.copy_(torch.rand(700, 4, generator=torch.Generator().manual_seed(trial), dtype=torch.float64).to(dtype))
+
+
 def test_transformed_train_inputs_mode(crs):
     """``train_inputs="transformed"`` (BoTorch >= 0.4 eval mode): step 2(b) sees the Normalize-d
     inputs; ``"raw"`` (default) the raw ones.  Both equal the oracle in the same mode."""
