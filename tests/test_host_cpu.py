@@ -95,3 +95,31 @@ def test_strict_indicator_probe():
     assert not _is_strict_indicator(lambda X: (X >= 0).to(torch.float64))
     assert not _is_strict_indicator(lambda X: torch.sigmoid(X))
     assert not _is_strict_indicator(lambda X: X.sum())
+
+
+def test_pcs_sampler_argument_handling(built_library):
+    """Host-side validation of ``pcs_counts`` happens before any launch (no GPU needed): unknown
+    sampler, tree sampler on an arm slice or beyond 4,102 arms, too small a ``stats`` tensor."""
+    from contextual_rs_b200.generalized_pcs import TREE_MAX_ARMS, pcs_counts
+    mean, var = torch.zeros(2, 6), torch.ones(2, 6)
+    with pytest.raises(ValueError):
+        pcs_counts(None, mean, var, 8, seed=0, sampler="bogus")
+    with pytest.raises(ValueError):
+        pcs_counts(None, mean, var, 8, seed=0, arm_offset=4, sampler="tree")
+    wide = torch.zeros(1, TREE_MAX_ARMS + 1)
+    with pytest.raises(ValueError):
+        pcs_counts(None, wide, wide + 1, 8, seed=0, sampler="tree")
+    with pytest.raises(ValueError):
+        pcs_counts(None, mean, var, 8, seed=0, stats=torch.zeros(2, dtype=torch.int64))
+    # the C entry validates too: NULL tables / too many arms / K = 1 (no competitor: use the flat stream)
+    lib = built_library
+    assert lib.crs_pcs_counts_tree(None, None, 4, 3, 3, 0, 16, 0, 0, 0, None, None, None) == 1
+    assert lib.crs_debug_zfun(None, 4, None, None) == 1
+
+
+def test_model_rejects_unknown_train_inputs_mode():
+    from contextual_rs_b200.model import B200ModelListGP
+    with pytest.raises((ValueError, RuntimeError)):
+        B200ModelListGP({"train_X": [torch.zeros(2, 1)], "train_Y": [torch.zeros(2, 1)], "train_inputs": "bogus",
+                         "lengthscale": torch.ones(1, 1), "outputscale": torch.ones(1), "noise": torch.ones(1),
+                         "mean_const": torch.zeros(1)}, device="cuda")
