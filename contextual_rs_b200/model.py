@@ -340,15 +340,13 @@ class B200ModelListGP:
         return ws
 
 
-def from_botorch(model, device="cuda", dtype: Optional[torch.dtype] = None,
-                 train_inputs: Optional[str] = None) -> B200ModelListGP:
-    """Extract a fitted BoTorch ``ModelListGP`` of ``SingleTaskGP`` sub-models by attribute path
-    (SURVEY.md §8b).  BoTorch is not installed in this image, so this function is written against
-    the documented attribute names and is NOT exercised by the test-suite.
-
-    ``train_inputs=None`` detects what ``model.train_inputs`` holds in eval mode under the installed
-    BoTorch (raw inputs, or Normalize-transformed ones from 0.4 on) so that OCBA step 2(b) sees what
-    the reference's ``gao_modellist`` would see with the same model; pass "raw" / "transformed" to force."""
+def description_from_botorch(model) -> Dict:
+    """The *fitted model description* dict of a BoTorch ``ModelListGP`` of ``SingleTaskGP`` sub-models,
+    read by attribute path (pure host code).  BoTorch is not installed in this image:
+    the function is written against the documented attribute names and exercised with a duck-typed
+    stand-in (``tests/test_host_cpu.py``).  ``desc["train_inputs"]`` records what ``model.train_inputs``
+    holds in eval mode under the installed BoTorch (raw inputs, or Normalize-transformed ones from
+    0.4 on), i.e. what the reference's ``gao_modellist`` would see with the same model."""
     tx, ty, ls, osc, noise, mc, mins, rngs, ym, ys = [], [], [], [], [], [], [], [], [], []
     kernel = None
     detected = "raw"
@@ -399,5 +397,15 @@ def from_botorch(model, device="cuda", dtype: Optional[torch.dtype] = None,
     desc = {"train_X": tx, "train_Y": ty, "lengthscale": torch.stack(ls), "outputscale": torch.stack(osc),
             "noise": torch.stack(noise), "mean_const": torch.stack(mc), "kernel": kernel,
             "normalize": True, "standardize": True, "norm_mins": torch.stack(mins),
-            "norm_ranges": torch.stack(rngs), "y_mean": torch.stack(ym), "y_std": torch.stack(ys)}
-    return B200ModelListGP(desc, device=device, dtype=dtype or tx[0].dtype, train_inputs=train_inputs or detected)
+            "norm_ranges": torch.stack(rngs), "y_mean": torch.stack(ym), "y_std": torch.stack(ys),
+            "train_inputs": detected}
+    return desc
+
+
+def from_botorch(model, device="cuda", dtype: Optional[torch.dtype] = None,
+                 train_inputs: Optional[str] = None) -> B200ModelListGP:
+    """Pack a fitted BoTorch ``ModelListGP`` for the B200 kernels (:func:`description_from_botorch`).
+    ``train_inputs=None`` keeps the detected eval-mode semantics; pass "raw" / "transformed" to force."""
+    desc = description_from_botorch(model)
+    return B200ModelListGP(desc, device=device, dtype=dtype or desc["train_X"][0].dtype,
+                           train_inputs=train_inputs or desc["train_inputs"])

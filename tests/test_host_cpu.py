@@ -123,3 +123,72 @@ def test_model_rejects_unknown_train_inputs_mode():
         B200ModelListGP({"train_X": [torch.zeros(2, 1)], "train_Y": [torch.zeros(2, 1)], "train_inputs": "bogus",
                          "lengthscale": torch.ones(1, 1), "outputscale": torch.ones(1), "noise": torch.ones(1),
                          "mean_const": torch.zeros(1)}, device="cuda")
+
+
+class _FakeParam:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class MaternKernel:  # the extractor keys on the class name, as with gpytorch.kernels.MaternKernel
+    def __init__(self, lengthscale):
+        self.lengthscale, self.nu = lengthscale, 2.5
+
+
+class _FakeSingleTaskGP:
+    """Duck-typed stand-in for a fitted BoTorch SingleTaskGP(Normalize, Standardize): the attribute
+    paths of SURVEY.md §8b.  ``transformed_in_eval`` mimics BoTorch >= 0.4 (eval mode exposes the
+    Normalize-d train inputs); False mimics the behaviour of the reference's recorded runs."""
+
+    def __init__(self, X, Y, ls, osc, noise, mean, transformed_in_eval):
+        self._X, self.training, self._tie = X, False, transformed_in_eval
+        mins, rng = X.min(dim=0).values, X.max(dim=0).values - X.min(dim=0).values
+        ym, ys = Y.mean(), Y.std()
+        self.train_targets = ((Y - ym) / ys).reshape(-1)
+        self.covar_module = _FakeParam(base_kernel=MaternKernel(ls.reshape(1, -1)), outputscale=osc)
+        self.likelihood = _FakeParam(noise=noise.reshape(1))
+        self.mean_module = _FakeParam(constant=mean)
+        self.input_transform = _FakeParam(bounds=torch.stack([mins, mins + rng]))
+        self.outcome_transform = _FakeParam(means=ym.reshape(1, 1), stdvs=ys.reshape(1, 1))
+        self._mins, self._rng = mins, rng
+
+    def train(self):
+        self.training = True
+
+    def eval(self):
+        self.training = False
+
+    @property
+    def train_inputs(self):
+        if not self.training and self._tie:
+            return ((self._X - self._mins) / self._rng,)
+        return (self._X,)
+
+
+@pytest.mark.parametrize("transformed_in_eval", [False, True])
+def test_description_from_botorch_attribute_paths(transformed_in_eval):
+    """``description_from_botorch`` against a duck-typed BoTorch model: hyper-parameters, transform
+    constants and raw data come out right, the eval-mode semantics of ``train_inputs`` are detected,
+    and the description drives the oracle to the same posterior as a directly built one."""
+    from contextual_rs_b200.model import description_from_botorch
+    from oracle import gp_oracle
+    gen = torch.Generator().manual_seed(0)
+    subs, want = [], []
+    for k in range(3):
+        X = torch.rand(7 + k, 2, generator=gen, dtype=torch.float64)
+        Y = torch.randn(7 + k, 1, generator=gen, dtype=torch.float64) * 3 + 5
+        ls = 0.2 + torch.rand(2, generator=gen, dtype=torch.float64)
+        osc, noise, mean = torch.tensor(1.3 + k), torch.tensor(0.01 * (k + 1)), torch.tensor(0.1 * k)
+        subs.append(_FakeSingleTaskGP(X, Y, ls, osc.double(), noise.double(), mean.double(), transformed_in_eval))
+        want.append(gp_oracle.OracleSingleTaskGP(X, Y, ls, osc.double(), noise.double(), mean.double()))
+    desc = description_from_botorch(_FakeParam(models=subs))
+    assert desc["train_inputs"] == ("transformed" if transformed_in_eval else "raw")
+    assert desc["kernel"] == "matern52" and all(not m.training for m in subs)  # modes restored
+    got = gp_oracle.model_from_description(desc)
+    ctx = torch.rand(11, 2, generator=gen, dtype=torch.float64)
+    pw = gp_oracle.OracleModelListGP(*want).posterior(ctx)
+    pg = got.posterior(ctx)
+    torch.testing.assert_close(pg.mean, pw.mean, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(pg.variance, pw.variance, rtol=1e-12, atol=1e-12)
+    for (a,), m in zip(got.train_inputs, subs):  # what OCBA step 2(b) will see == what the model shows in eval mode
+        torch.testing.assert_close(a, m.train_inputs[0], rtol=0, atol=1e-15)
