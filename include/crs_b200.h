@@ -308,7 +308,10 @@ CRS_API int crs_peak_probe(int32_t kind, int32_t iters, int32_t blocks, void* ou
  * stands in for `gao_modellist(model, context_set, ...)` when context_set lives on the CPU, as it
  * does in the reference's driver (experiments/wsc_experiments/main.py:226-228).
  * Copies ctx_host (pinned or pageable, [n_c, d] T) to ws->ctx, optionally re-prepares arms
- * [prep_begin, prep_end) and runs grid -> fused scan + select on `stream`.  If decision_host is
+ * [prep_begin, prep_end) and runs grid -> fused scan + select on `stream`.  A mapped pinned ctx_host
+ * of <= 1 MiB is pulled over PCIe by extra CTAs of the prepare launch (the copy overlaps prepare);
+ * otherwise a cudaMemcpyAsync precedes the kernels.  The three kernels are chained by programmatic
+ * dependent launch.  If decision_host is
  * pinned memory the last kernel writes the decision straight into it (mapped, zero-copy) and the
  * call spins on a completion tag (decision_host->reserved[1]); otherwise it copies the decision
  * back and synchronises the stream.  Either way the decision is complete on return.  Returns CRS_TIES_PENDING if randomize_ties and
