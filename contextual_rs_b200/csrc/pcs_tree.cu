@@ -30,6 +30,7 @@
 //   pool     per warp: root tests run warp-wide (no divergence) and park their survivors in a
 //            shared-memory queue; lanes walk one survivor each and take the next one when done; when
 //            the queue is empty and few lanes are still walking, the warp goes back to root tests.
+#include <atomic>
 #include <math_constants.h>
 #include "crs_common.cuh"
 #include "pcs_rng.cuh"
@@ -539,12 +540,12 @@ int launch_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int K
   if (build < (size_t)NI * 20) build = (size_t)NI * 20;
   const size_t smem = (size_t)NL * 8 + (size_t)NI * 32 + (walk > build ? walk : build);
   static unsigned long long* rings[64] = {nullptr};
-  static unsigned int next_slot = 0;
+  static std::atomic<unsigned int> next_slot{0};  // launches from several host threads take distinct tickets
   int dev = 0;
   CRS_CUDA_TRY(cudaGetDevice(&dev), "pcs_tree get device");
   if (dev < 0 || dev >= 64) return CRS_ERR_UNSUPPORTED;
   if (!rings[dev]) CRS_CUDA_TRY(cudaGetSymbolAddress((void**)&rings[dev], g_tree_tickets), "pcs_tree ticket symbol");
-  unsigned long long* ticket = rings[dev] + (next_slot++ % kTreeTicketRing);
+  unsigned long long* ticket = rings[dev] + (next_slot.fetch_add(1u, std::memory_order_relaxed) % kTreeTicketRing);
   CRS_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s), "pcs_tree memset ticket");
   const RoundKeys rk = round_keys((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
   auto go = [&](auto kern, auto* m, auto* v) -> int {
