@@ -9,8 +9,9 @@ The model only has to expose what the reference reads: ``model.posterior(X)`` ->
 ``.mean/.variance`` (``batch x 1 x K``), ``model.models[i].noise`` (``model.likelihood.
 likelihoods[i].noise``) and ``model.models[i].y_std`` (``outcome_transform._stdvs_sq`` = its
 square).  The reference has no test of LEVI, so the known answers in tests/test_oracle_golden.py
-are hand-derived from the formulas with scalar ``math.erf`` arithmetic (**parity unpinned** at
-the BoTorch boundary like the rest of the posterior path).
+are hand-derived from the formulas with scalar ``math.erf`` arithmetic; on top of that the
+reference's recorded LEVI run (``0000_LEVI_new.pt``) is replayed by ``trace_replay.py``: 77 of its
+first 100 decisions are reproduced (``tests/golden/reference_trace_levi_new.json``).
 """
 from __future__ import annotations
 
