@@ -48,7 +48,7 @@ def test_tree_plan_order_and_bounds():
     assert np.isneginf(small["top_mu"][3:]).all() and np.isneginf(small["leaf_mu"]).all() and small["D"] == 1
 
 
-@pytest.mark.parametrize("K", [2, 5, 6, 7, 17, 40])
+@pytest.mark.parametrize("K", [2, 5, 6, 7, 17, 40, 300])
 def test_lazy_walk_equals_brute_force(K):
     rng = np.random.default_rng(K)
     mean = rng.normal(size=(2, K))
