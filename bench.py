@@ -424,7 +424,7 @@ def run_loop(args, dev, world, rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    stats = model.workspace(max(loop.n_loc, 1))["stats"]
+    stats = loop.dec.ws["stats"]
     for _ in range(W):
         loop.step(truth)
         it_box[0] += 1

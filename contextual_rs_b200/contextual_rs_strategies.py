@@ -12,20 +12,24 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from .model import B200ModelListGP, from_botorch
+from .model import B200ModelListGP, botorch_fingerprint, from_botorch
 
 
 def _as_b200(model) -> B200ModelListGP:
+    """A :class:`B200ModelListGP` is used as is; a BoTorch ``ModelListGP`` is converted once and the
+    handle cached on the object, keyed on :func:`botorch_fingerprint` so that in-place changes of the
+    model (new data, re-fit, ``load_state_dict``) are seen."""
     if isinstance(model, B200ModelListGP):
         return model
+    fp = botorch_fingerprint(model)
     cached = getattr(model, "_crs_b200_handle", None)
-    if cached is None:
-        cached = from_botorch(model)
+    if cached is None or cached[0] != fp:
+        cached = (fp, from_botorch(model))
         try:
             model._crs_b200_handle = cached
         except Exception:  # pragma: no cover
             pass
-    return cached
+    return cached[1]
 
 
 def _p_mode(infer_p: bool, use_kde: bool) -> int:
@@ -85,7 +89,7 @@ def decide(model: B200ModelListGP, context_set: Tensor, randomize_ties: bool, p_
                        "crs_ocba_select")
             ws["decision_host"].copy_(ws["decision"], non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
-    ws["valid_for"] = (ctx2.data_ptr(), n_c)
+    ws["valid_for"] = model.grid_key(ctx2)
     return dec
 
 

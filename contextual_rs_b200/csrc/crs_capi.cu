@@ -93,6 +93,12 @@ CRS_API int crs_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, 
   return launch_pcs_counts_tree(mean, var, n_c, K, ld, dtype, num_samples, seed, offset, ctx_offset, counts, stats, (cudaStream_t)stream);
 }
 
+CRS_API int crs_pcs_counts_base(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                                int32_t dtype, const void* base, int64_t num_samples, uint32_t* counts,
+                                void* stream) {
+  return launch_pcs_counts_base(mean, var, n_c, K, ld, dtype, base, num_samples, counts, (cudaStream_t)stream);
+}
+
 CRS_API int crs_debug_zfun(const float* t, int64_t n, float* out, void* stream) {
   return launch_tree_zfun(t, n, out, (cudaStream_t)stream);
 }
@@ -138,20 +144,19 @@ CRS_API int crs_gao_decide_host(const crs_gp_state* st, const void* ctx_host, in
   const int K = st->num_arms;
   // If decision_host is pinned (mapped under UVA) the last kernel writes the decision straight
   // into it and the host spins on a sequence tag instead of paying a D2H copy + stream sync.
-  static thread_local const void* cached_host = nullptr;
-  static thread_local crs_decision* cached_dev = nullptr;
+  // The mapping is queried on every call (one driver call, no device work): a cache keyed on the raw
+  // host address would go stale when the caller frees a pinned buffer and the allocator hands the same
+  // address out again as pageable memory.
   static thread_local int seq_counter = 0;
-  if (cached_host != decision_host) {
+  crs_decision* mirror = nullptr;
+  {
     void* dptr = nullptr;
     if (cudaHostGetDevicePointer(&dptr, decision_host, 0) == cudaSuccess) {
-      cached_dev = reinterpret_cast<crs_decision*>(dptr);
+      mirror = reinterpret_cast<crs_decision*>(dptr);
     } else {
       (void)cudaGetLastError();  // pageable memory: fall back to the copy path
-      cached_dev = nullptr;
     }
-    cached_host = decision_host;
   }
-  crs_decision* mirror = cached_dev;
   const int seq = (++seq_counter == 0) ? ++seq_counter : seq_counter;
   if (mirror) reinterpret_cast<volatile int32_t*>(decision_host->reserved)[1] = 0;
 

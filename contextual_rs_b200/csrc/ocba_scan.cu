@@ -174,7 +174,7 @@ __device__ void select_block(const crs_gp_state& st, const T* __restrict__ ctx,
   __shared__ T s_x[CRS_MAX_DIM];
   __shared__ T s_v[256];
   __shared__ int s_n[256];
-  __shared__ T s_red[32];
+  __shared__ double s_red[32][2];
   __shared__ T s_best;
   __shared__ int s_bad;
   T* s_stage = reinterpret_cast<T*>(s_stage_raw);
@@ -196,7 +196,11 @@ __device__ void select_block(const crs_gp_state& st, const T* __restrict__ ctx,
   }
   __syncthreads();
   const T* g_xn = reinterpret_cast<const T*>(st.xn);
-  T rest = T(0);
+  // y_s_2 (strategies.py:196) is a sum of K - 1 terms whose order the reference leaves to torch's
+  // vectorised CPU reduction (machine-dependent in the last ulp).  Here it is accumulated in
+  // double-double (error ~2^-104) and rounded ONCE to T: the result does not depend on the order,
+  // on the warp layout or — arm-sharded runs — on how the arms are split over ranks.
+  double rest_hi = 0.0, rest_lo = 0.0;
   uint32_t phase = 0;
   for (int c0 = 0; c0 < K; c0 += chunk) {
     const int na = min(chunk, K - c0);
@@ -243,16 +247,31 @@ __device__ void select_block(const crs_gp_state& st, const T* __restrict__ ctx,
       }
       if (lane == 0) {
         const T y = p / vr;
-        if (c0 + a == best) s_best = y; else rest += y;
+        if (c0 + a == best) {
+          s_best = y;
+        } else {  // TwoSum
+          const double yd = (double)y;
+          const double sh = rest_hi + yd;
+          const double bb = sh - rest_hi;
+          rest_lo += (rest_hi - (sh - bb)) + (yd - bb);
+          rest_hi = sh;
+        }
       }
     }
     __syncthreads();  // the stage buffer is free for the next chunk
   }
-  if (lane == 0) s_red[warp] = rest;
+  if (lane == 0) { s_red[warp][0] = rest_hi; s_red[warp][1] = rest_lo; }
   __syncthreads();
   if (tid == 0) {
-    T tot = T(0);
-    for (int w = 0; w < nw; ++w) tot += s_red[w];
+    double th = 0.0, tl = 0.0;
+    for (int w = 0; w < nw; ++w) {
+      const double yd = s_red[w][0];
+      const double sh = th + yd;
+      const double bb = sh - th;
+      tl += (th - (sh - bb)) + (yd - bb) + s_red[w][1];
+      th = sh;
+    }
+    const T tot = (T)(th + tl);
     const T yb = s_best;
     decision->psi_best = (double)yb;
     decision->psi_rest = (double)tot;

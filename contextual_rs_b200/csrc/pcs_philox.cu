@@ -21,6 +21,7 @@
 //            per-lane plan reads are shared-memory gathers of 40 bytes per block).
 // Executed and skipped draws are reported in `stats`.
 #include <atomic>
+#include <mutex>
 #include <math_constants.h>
 #include "crs_common.cuh"
 #include "pcs_rng.cuh"
@@ -57,7 +58,7 @@ struct Plan {
 #ifndef CRS_PCS_MIN_BLOCKS
 #define CRS_PCS_MIN_BLOCKS 4
 #endif
-constexpr int kPcsTicketRing = 64;
+constexpr int kPcsTicketRing = 1024;
 __device__ unsigned long long g_pcs_tickets[kPcsTicketRing];
 template <typename T>
 __global__ void __launch_bounds__(kPcsThreads, CRS_PCS_MIN_BLOCKS)
@@ -367,12 +368,18 @@ int launch_pcs_counts(const void* mean, const void* var, int64_t n_c, int K, int
   // ticket of this launch: a small ring of device counters, so that launches in flight on different
   // streams do not share one
   static unsigned long long* rings[64] = {nullptr};  // per device: the symbol lives in each context
+  static std::mutex rings_mutex;                     // the library may be entered from several host threads
   static std::atomic<unsigned int> next_slot{0};  // launches from several host threads take distinct tickets
   int dev = 0;
   CRS_CUDA_TRY(cudaGetDevice(&dev), "pcs get device");
   if (dev < 0 || dev >= 64) return CRS_ERR_UNSUPPORTED;
-  if (!rings[dev]) CRS_CUDA_TRY(cudaGetSymbolAddress((void**)&rings[dev], g_pcs_tickets), "pcs ticket symbol");
-  unsigned long long* ticket = rings[dev] + (next_slot.fetch_add(1u, std::memory_order_relaxed) % kPcsTicketRing);
+  unsigned long long* ring;
+  {
+    std::lock_guard<std::mutex> lock(rings_mutex);
+    if (!rings[dev]) CRS_CUDA_TRY(cudaGetSymbolAddress((void**)&rings[dev], g_pcs_tickets), "pcs ticket symbol");
+    ring = rings[dev];
+  }
+  unsigned long long* ticket = ring + (next_slot.fetch_add(1u, std::memory_order_relaxed) % kPcsTicketRing);
   CRS_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s), "pcs memset ticket");
   const RoundKeys rk = round_keys((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
   auto go = [&](auto kern, auto* m, auto* v) -> int {

@@ -31,6 +31,7 @@
 //            shared-memory queue; lanes walk one survivor each and take the next one when done; when
 //            the queue is empty and few lanes are still walking, the warp goes back to root tests.
 #include <atomic>
+#include <mutex>
 #include <math_constants.h>
 #include "crs_common.cuh"
 #include "pcs_rng.cuh"
@@ -133,8 +134,12 @@ __device__ __forceinline__ float neg_ln2_scaled(int sh) {
   return __uint_as_float(__float_as_uint(kNegLn2) - ((uint32_t)sh << 23));
 }
 
-constexpr int kTreeTicketRing = 64;
-__device__ unsigned long long g_tree_tickets[kTreeTicketRing];
+// Work-item tickets: one 16-byte slot {next item, CTAs done} per launch, taken round-robin from a
+// ring.  The last CTA to leave a launch zeroes its slot, so a slot is clean whenever the previous
+// launch that used it has finished; two launches could only share a slot if kTreeTicketRing launches
+// of this kernel were in flight on one device at once.
+constexpr int kTreeTicketRing = 1024;
+__device__ unsigned long long g_tree_tickets[2 * kTreeTicketRing];
 
 #ifndef CRS_TREE_MIN_BLOCKS
 #define CRS_TREE_MIN_BLOCKS 3
@@ -456,6 +461,16 @@ pcs_tree_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n
     __syncthreads();
     if (tid == 0 && s_hits) atomicAdd(counts + c, s_hits);
   }
+  // leave the ticket slot clean for the next launch that draws it (no per-launch memset)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(ticket + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+      ticket[0] = 0ull;
+      ticket[1] = 0ull;
+      __threadfence();
+    }
+  }
   if (stats) {
     n_roots = warp_sum(n_roots);
     n_exp = warp_sum(n_exp);
@@ -539,27 +554,40 @@ int launch_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int K
   size_t build = (size_t)n2 * 16;  // sort scratch + competitor table, then the [NI][5] envelope tables — dead before the walk
   if (build < (size_t)NI * 20) build = (size_t)NI * 20;
   const size_t smem = (size_t)NL * 8 + (size_t)NI * 32 + (walk > build ? walk : build);
-  static unsigned long long* rings[64] = {nullptr};
+  // per-device facts, looked up once under a lock (the library may be entered from several host threads)
+  struct DevInfo { unsigned long long* ring = nullptr; int sms = 0; int resident[2][8] = {}; };
+  static DevInfo info[64];
+  static std::mutex info_mutex;
   static std::atomic<unsigned int> next_slot{0};  // launches from several host threads take distinct tickets
   int dev = 0;
   CRS_CUDA_TRY(cudaGetDevice(&dev), "pcs_tree get device");
   if (dev < 0 || dev >= 64) return CRS_ERR_UNSUPPORTED;
-  if (!rings[dev]) CRS_CUDA_TRY(cudaGetSymbolAddress((void**)&rings[dev], g_tree_tickets), "pcs_tree ticket symbol");
-  unsigned long long* ticket = rings[dev] + (next_slot.fetch_add(1u, std::memory_order_relaxed) % kTreeTicketRing);
-  CRS_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s), "pcs_tree memset ticket");
+  unsigned long long* ring;
+  {
+    std::lock_guard<std::mutex> lock(info_mutex);
+    if (!info[dev].ring) {
+      CRS_CUDA_TRY(cudaGetSymbolAddress((void**)&info[dev].ring, g_tree_tickets), "pcs_tree ticket symbol");
+      CRS_CUDA_TRY(cudaDeviceGetAttribute(&info[dev].sms, cudaDevAttrMultiProcessorCount, dev), "pcs_tree sm count");
+    }
+    ring = info[dev].ring;
+  }
+  unsigned long long* ticket = ring + 2 * (next_slot.fetch_add(1u, std::memory_order_relaxed) % kTreeTicketRing);
   const RoundKeys rk = round_keys((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
   auto go = [&](auto kern, auto* m, auto* v) -> int {
     // resident CTAs of this (device, dtype, depth): queried once, the answers do not change
-    static int cached_resident[64][2][8] = {};
-    int& resident_c = cached_resident[dev][dtype == CRS_F64 ? 0 : 1][D];
-    if (resident_c == 0) {
-      if (smem > 40 * 1024)
-        CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "pcs_tree attr");
-      int per_sm = 0, sms = 148;
-      CRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTreeThreads, smem), "pcs_tree occupancy");
-      if (per_sm < 1) return CRS_ERR_UNSUPPORTED;
-      CRS_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "pcs_tree sm count");
-      resident_c = sms * per_sm;
+    int resident_c;
+    {
+      std::lock_guard<std::mutex> lock(info_mutex);
+      int& slot = info[dev].resident[dtype == CRS_F64 ? 0 : 1][D];
+      if (slot == 0) {
+        if (smem > 40 * 1024)
+          CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "pcs_tree attr");
+        int per_sm = 0;
+        CRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTreeThreads, smem), "pcs_tree occupancy");
+        if (per_sm < 1) return CRS_ERR_UNSUPPORTED;
+        slot = info[dev].sms * per_sm;
+      }
+      resident_c = slot;
     }
     const int64_t resident = resident_c;
     // ~12 work items per resident CTA so that the dynamic hand-out evens out their different costs;

@@ -71,6 +71,25 @@ def pcs_counts(model: B200ModelListGP, mean: Tensor, var: Tensor, num_samples: i
     return counts
 
 
+def pcs_counts_base(mean: Tensor, var: Tensor, base_samples: Tensor, counts: Optional[Tensor] = None) -> Tensor:
+    """Correct-selection counts from caller-supplied standard normals (``crs_pcs_counts_base``):
+    ``base_samples`` is ``[S, n_c, K]`` (the shape the reference hands to ``posterior.rsample``,
+    ``generalized_pcs.py:449-451``); entry (s, c, k) is the marginal draw of arm k at context c."""
+    n_c, K = mean.shape
+    S = int(base_samples.shape[0])
+    if tuple(base_samples.shape[-2:]) != (n_c, K) or base_samples.numel() != S * n_c * K:
+        raise ValueError(f"base_samples must have shape [num_samples, {n_c}, {K}], got {tuple(base_samples.shape)}")
+    z = base_samples.reshape(S, n_c, K).to(device=mean.device, dtype=mean.dtype).contiguous()
+    if counts is None:
+        counts = torch.empty(n_c, dtype=torch.int32, device=mean.device)
+    with torch.cuda.device(mean.device):
+        rc = _lib.get().crs_pcs_counts_base(mean.data_ptr(), var.data_ptr(), n_c, K, mean.stride(0),
+                                            _lib.DTYPES[mean.dtype], z.data_ptr(), S, counts.data_ptr(),
+                                            _lib.stream_ptr(mean.device))
+    _lib.check(rc, "crs_pcs_counts_base")
+    return counts
+
+
 def estimate_current_generalized_pcs(
     model,
     arm_set: Tensor,
@@ -88,7 +107,10 @@ def estimate_current_generalized_pcs(
     r"""Estimate of the generalized PCS implied by the current model
     (``contextual_rs/generalized_pcs.py:318-479``; argument meaning as in the reference).
 
-    Extra keyword-only arguments (not in the reference): ``seed``/``offset`` pin the Philox
+    ``base_samples`` (``num_samples x n_c x K`` standard normals, the tensor the reference passes to
+    ``posterior.rsample``) are honoured as the MARGINAL draws of their (sample, context, arm) —
+    ``crs_pcs_counts_base``; with ``None`` the draws come from the in-kernel Philox stream and nothing
+    sample-sized exists.  Extra keyword-only arguments (not in the reference): ``seed``/``offset`` pin the Philox
     stream (by default a seed is drawn from the global torch RNG, which the reference also
     consumes through ``posterior.rsample``); ``reuse_grid`` skips the posterior launch when the
     model's workspace already holds the grid of this ``context_set`` (same iteration's decision).
@@ -102,10 +124,6 @@ def estimate_current_generalized_pcs(
         raise NotImplementedError
     if use_approximation:  # :396-399
         raise NotImplementedError
-    if base_samples is not None:
-        raise NotImplementedError(
-            "base_samples cannot be honoured: samples are generated inside the kernel from a "
-            "Philox stream and never materialised (pass seed=/offset= to pin the stream)")
     if not _is_strict_indicator(func_I):
         raise NotImplementedError(
             "only the strict indicator func_I = (X > 0) is fused into the PCS kernel "
@@ -114,14 +132,21 @@ def estimate_current_generalized_pcs(
         raise ValueError("arm_set must list one row per arm of the model")
     n_c = context_set.shape[0]
     ws = m.workspace(n_c)
-    if not (reuse_grid and ws.get("valid_for") == (context_set.data_ptr(), n_c)):
+    if not (reuse_grid and ws.get("valid_for") == m.grid_key(context_set)):
         ws["ctx"].copy_(context_set.to(dtype=m.dtype), non_blocking=True)
         m.posterior_tables(ws["ctx"], ws["mean"], ws["var"], arms=(0, m.num_arms))
-        ws["valid_for"] = (context_set.data_ptr(), n_c)
-    if seed is None:
-        seed = int(torch.randint(2 ** 62, (1,)))
-    counts = pcs_counts(m, ws["mean"], ws["var"], num_samples, seed, offset,
-                        counts=ws["counts"], stats=ws["stats"])
+        ws["valid_for"] = m.grid_key(context_set)
+    if base_samples is not None:
+        # generalized_pcs.py:449-451: caller-supplied standard normals, sample_shape x n_c x K, used as
+        # the marginal draws of their (sample, context, arm); num_samples must agree with their count
+        if base_samples.dim() < 3 or base_samples.numel() != num_samples * n_c * m.num_arms:
+            raise ValueError(f"base_samples must hold num_samples x {n_c} x {m.num_arms} standard normals")
+        counts = pcs_counts_base(ws["mean"], ws["var"], base_samples, counts=ws["counts"])
+    else:
+        if seed is None:
+            seed = int(torch.randint(2 ** 62, (1,)))
+        counts = pcs_counts(m, ws["mean"], ws["var"], num_samples, seed, offset,
+                            counts=ws["counts"], stats=ws["stats"])
     pcs_c_est = (counts.to(m.dtype) / float(num_samples)).unsqueeze(-1)  # n_c x 1, :475
     rho_vals = rho(pcs_c_est)  # :477
     return rho_vals.squeeze(-1).to(context_set.device)  # :479
@@ -230,10 +255,10 @@ def empirical_best_arms(model, context_set: Tensor, reuse_grid: bool = False) ->
     K = m.num_arms
     with torch.cuda.device(m.device):
         stream = _lib.stream_ptr(m.device)
-        if not (reuse_grid and ws.get("valid_for") == (context_set.data_ptr(), n_c)):
+        if not (reuse_grid and ws.get("valid_for") == m.grid_key(context_set)):
             ws["ctx"].copy_(context_set.to(dtype=m.dtype), non_blocking=True)
             m.posterior_tables(ws["ctx"], ws["mean"], ws["var"], arms=(0, K))
-            ws["valid_for"] = (context_set.data_ptr(), n_c)
+            ws["valid_for"] = m.grid_key(context_set)
         _lib.check(lib.crs_ocba_scan(ws["mean"].data_ptr(), ws["var"].data_ptr(), n_c, K, K,
                                      _lib.DTYPES[m.dtype], 0, None, None, None,
                                      ws["best_arm"].data_ptr(), None, None, None, None, None, stream),

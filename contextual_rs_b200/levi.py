@@ -39,10 +39,10 @@ def _levi_launch(m: B200ModelListGP, ctx2: Tensor, weights: Optional[Tensor], wa
             raise ValueError("weights must hold one entry per context")
     with torch.cuda.device(m.device):
         stream = _lib.stream_ptr(m.device)
-        if not (reuse_grid and ws.get("valid_for") == (ctx2.data_ptr(), n_c)):
+        if not (reuse_grid and ws.get("valid_for") == m.grid_key(ctx2)):
             ws["ctx"].copy_(ctx2.to(dtype=m.dtype), non_blocking=True)
             m.posterior_tables(ws["ctx"], ws["mean"], ws["var"], arms=(0, K))
-            ws["valid_for"] = (ctx2.data_ptr(), n_c)
+            ws["valid_for"] = m.grid_key(ctx2)
         _lib.check(lib.crs_levi_scan(C.byref(m.state), ws["mean"].data_ptr(), ws["var"].data_ptr(), n_c, K,
                                      _lib.ptr(w_dev), ws["levi_ei"].data_ptr() if want_table else None, K,
                                      ws["levi_max"].data_ptr(), ws["levi_arm"].data_ptr(),
@@ -60,7 +60,9 @@ def _compute_all_EI_reviewer(X: Tensor, model) -> Tensor:
     """
     m = _as_b200(model)
     ws = _levi_launch(m, X.reshape(X.shape[0], -1), None, want_table=True)
-    return ws["levi_ei"].to(device=X.device, dtype=X.dtype)
+    # a NEW tensor, like the reference: `.to` alone would alias the workspace buffer when X already
+    # lives on the model's GPU in the model's dtype, and the next call would overwrite the result
+    return ws["levi_ei"].to(device=X.device, dtype=X.dtype, copy=True)
 
 
 class PredictiveEI:
@@ -74,7 +76,7 @@ class PredictiveEI:
         r"""``X``: ``batch x 1 x d_c`` -> ``batch`` max-EI values (on ``X.device``)."""
         assert X.shape[-2] == 1 and X.ndim == 3
         ws = _levi_launch(self.model, X.reshape(X.shape[0], -1), None, want_table=False)
-        return ws["levi_max"].to(device=X.device, dtype=X.dtype)
+        return ws["levi_max"].to(device=X.device, dtype=X.dtype, copy=True)  # never an alias of the workspace
 
     __call__ = forward
 

@@ -38,10 +38,22 @@ class B200Posterior:
         self.mean = mean
         self.variance = variance
 
-    def rsample(self, *args, **kwargs):
-        raise NotImplementedError(
-            "posterior samples are drawn inside the PCS kernel (crs_pcs_counts) and never "
-            "materialised; use estimate_current_generalized_pcs")
+    MAX_RSAMPLE_ELEMS = 1 << 28
+
+    def rsample(self, sample_shape=torch.Size([1]), base_samples: Optional[Tensor] = None) -> Tensor:
+        """``sample_shape x [..., K]`` draws like ``posterior.rsample`` (``generalized_pcs.py:449-451``),
+        from the MARGINALS: ``mean + sqrt(variance) * z`` with ``z = base_samples`` or fresh standard
+        normals.  Materialising samples is only meant for the reference's small call shapes — the PCS
+        kernels draw in registers — so anything above 2^28 elements is refused."""
+        shape = torch.Size(sample_shape) + self.mean.shape
+        if shape.numel() > self.MAX_RSAMPLE_ELEMS:
+            raise NotImplementedError(
+                "a sample tensor of this size is what the PCS kernels exist to avoid; "
+                "use estimate_current_generalized_pcs")
+        if base_samples is None:
+            base_samples = torch.randn(shape, dtype=self.mean.dtype, device=self.mean.device)
+        z = base_samples.reshape(shape).to(device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.variance.sqrt() * z
 
 
 class _Prior:
@@ -117,6 +129,7 @@ class B200ModelListGP:
         self._alloc(desc)
         self.models: List[B200ArmView] = [B200ArmView(self, k) for k in range(K)]
         self._ws_cache: Dict[int, dict] = {}
+        self._update_count = 0
         self.prepare()
 
     # ------------------------------------------------------------------ storage
@@ -194,7 +207,8 @@ class B200ModelListGP:
             rc = _lib.get().crs_gp_prepare(C.byref(st), arm_begin, arm_end, _lib.stream_ptr(self.device))
         _lib.check(rc, "crs_gp_prepare")
         self._prepared = True
-        for ws in self._ws_cache.values():  # cached grids (reuse_grid=True) describe the old state
+        self._update_count += 1  # cached grids (reuse_grid=True, grid_key) describe the old state
+        for ws in self._ws_cache.values():
             ws["valid_for"] = None
 
     def check_status(self) -> None:
@@ -246,7 +260,6 @@ class B200ModelListGP:
         desc = self.description()
         self.n_cap = new_cap
         self._alloc(desc)
-        self._ws_cache.clear()
         self._prepared = True  # transforms come frozen from description()
         self.prepare(relearn=False)
 
@@ -311,56 +324,93 @@ class B200ModelListGP:
         return B200Posterior(mean.reshape(shape), var.reshape(shape))
 
     # ------------------------------------------------------------------ decision workspace
-    def workspace(self, n_c: int) -> dict:
-        ws = self._ws_cache.get(n_c)
-        if ws is None:
-            dev, T, K = self.device, self.dtype, self.num_arms
-            ws = {
-                "ctx": torch.empty(n_c, self.dim, dtype=T, device=dev),
-                "mean": torch.empty(n_c, K, dtype=T, device=dev),
-                "var": torch.empty(n_c, K, dtype=T, device=dev),
-                "best_arm": torch.empty(n_c, dtype=torch.int32, device=dev),
-                "min_zeta": torch.empty(n_c, dtype=T, device=dev),
-                "min_arm": torch.empty(n_c, dtype=torch.int32, device=dev),
-                "tie_cnt": torch.empty(n_c, dtype=torch.int32, device=dev),
-                "decision": torch.zeros(64, dtype=torch.uint8, device=dev),
-                "scan_ws": torch.zeros(int(_lib.get().crs_scan_workspace_bytes()), dtype=torch.uint8, device=dev),
-                "decision_host": torch.zeros(64, dtype=torch.uint8).pin_memory(),
-                "counts": torch.empty(n_c, dtype=torch.int32, device=dev),
-                "stats": torch.zeros(4, dtype=torch.int64, device=dev),
-            }
-            p = _lib.ptr
-            ws["struct"] = _lib.DecideWS(p(ws["ctx"]), p(ws["mean"]), p(ws["var"]), p(ws["best_arm"]),
-                                         p(ws["min_zeta"]), p(ws["min_arm"]), p(ws["tie_cnt"]),
-                                         p(ws["decision"]), p(ws["scan_ws"]))
-            ws["decision_view"] = _lib.Decision.from_address(ws["decision_host"].data_ptr())
-            if len(self._ws_cache) >= 4:
-                self._ws_cache.pop(next(iter(self._ws_cache)))
-            self._ws_cache[n_c] = ws
+    WS_CACHE_SIZE = 4
+
+    def _make_workspace(self, n_c: int) -> dict:
+        dev, T, K = self.device, self.dtype, self.num_arms
+        ws = {
+            "ctx": torch.empty(n_c, self.dim, dtype=T, device=dev),
+            "mean": torch.empty(n_c, K, dtype=T, device=dev),
+            "var": torch.empty(n_c, K, dtype=T, device=dev),
+            "best_arm": torch.empty(n_c, dtype=torch.int32, device=dev),
+            "min_zeta": torch.empty(n_c, dtype=T, device=dev),
+            "min_arm": torch.empty(n_c, dtype=torch.int32, device=dev),
+            "tie_cnt": torch.empty(n_c, dtype=torch.int32, device=dev),
+            "decision": torch.zeros(64, dtype=torch.uint8, device=dev),
+            "scan_ws": torch.zeros(int(_lib.get().crs_scan_workspace_bytes()), dtype=torch.uint8, device=dev),
+            "decision_host": torch.zeros(64, dtype=torch.uint8).pin_memory(),
+            "counts": torch.empty(n_c, dtype=torch.int32, device=dev),
+            "stats": torch.zeros(4, dtype=torch.int64, device=dev),
+            "valid_for": None,  # a fresh workspace holds no grid yet
+        }
+        p = _lib.ptr
+        ws["struct"] = _lib.DecideWS(p(ws["ctx"]), p(ws["mean"]), p(ws["var"]), p(ws["best_arm"]),
+                                     p(ws["min_zeta"]), p(ws["min_arm"]), p(ws["tie_cnt"]),
+                                     p(ws["decision"]), p(ws["scan_ws"]))
+        ws["decision_view"] = _lib.Decision.from_address(ws["decision_host"].data_ptr())
         return ws
+
+    def workspace(self, n_c: int) -> dict:
+        """Shared per-``n_c`` device buffers of a stateless call (context copy, ``[n_c, K]`` tables,
+        scan outputs, counts): a true LRU over the last ``WS_CACHE_SIZE`` batch sizes.  Whether its
+        tables hold the grid of a given context set is recorded in ``ws["valid_for"]``
+        (:meth:`grid_key`); consumers that keep a grid ACROSS calls must not use this cache — see
+        :meth:`private_workspace`."""
+        ws = self._ws_cache.pop(n_c, None)
+        if ws is None:
+            ws = self._make_workspace(n_c)
+            while len(self._ws_cache) >= self.WS_CACHE_SIZE:
+                self._ws_cache.pop(next(iter(self._ws_cache)))  # least recently used first
+        self._ws_cache[n_c] = ws  # most recently used last
+        return ws
+
+    def private_workspace(self, n_c: int) -> dict:
+        """Buffers owned by ONE long-lived consumer (sequential loops, sharded deciders): never
+        shared with, evicted by or overwritten through the stateless entry points, whatever batch
+        sizes those are called with on the same model."""
+        return self._make_workspace(n_c)
+
+    def grid_key(self, context_set: Tensor) -> tuple:
+        """Identity of "the grid of this context set under the current model state": storage address,
+        shape, the tensor's in-place version counter and the model's own update counter — an in-place
+        edit of the contexts or any re-prepare invalidates a cached grid (``reuse_grid=True``)."""
+        return (context_set.data_ptr(), tuple(context_set.shape), int(context_set._version), self._update_count)
 
 
 def description_from_botorch(model) -> Dict:
     """The *fitted model description* dict of a BoTorch ``ModelListGP`` of ``SingleTaskGP`` sub-models,
-    read by attribute path (pure host code).  BoTorch is not installed in this image:
-    the function is written against the documented attribute names and exercised with a duck-typed
-    stand-in (``tests/test_host_cpu.py``).  ``desc["train_inputs"]`` records what ``model.train_inputs``
-    holds in eval mode under the installed BoTorch (raw inputs, or Normalize-transformed ones from
-    0.4 on), i.e. what the reference's ``gao_modellist`` would see with the same model."""
+    read by attribute path (pure host code).  The caller's model is NOT touched: no
+    ``train()`` / ``eval()`` toggling (that would drop GPyTorch's prediction caches and, on a model
+    produced by ``condition_on_observations``, revert ``train_inputs`` to the stale pre-conditioning
+    copy).  ``train_inputs[0]`` is read as the model shows it now; if BoTorch holds the
+    Normalize-transformed copy (``_has_transformed_inputs``, eval mode of BoTorch >= 0.4) the raw inputs
+    are recovered from ``_original_train_inputs`` when its length still matches ``train_targets``
+    (not the case after conditioning) and otherwise by ``input_transform.untransform``.
+    ``desc["train_inputs"]`` records what ``model.train_inputs`` holds in eval mode under the
+    installed BoTorch (raw, or transformed), i.e. what the reference's ``gao_modellist`` sees.
+
+    BoTorch is not installed in this image: the function is written against the documented attribute
+    names and has only been exercised with a duck-typed stand-in (``tests/test_host_cpu.py``)."""
     tx, ty, ls, osc, noise, mc, mins, rngs, ym, ys = [], [], [], [], [], [], [], [], [], []
     kernel = None
     detected = "raw"
-    for m in model.models:
-        was_training = m.training
-        m.train()  # expose the raw (untransformed) train_inputs
-        X = m.train_inputs[0].detach()
+    for k, m in enumerate(model.models):
+        X_seen = m.train_inputs[0].detach()
         Yt = m.train_targets.detach()
-        m.eval()
-        X_eval = m.train_inputs[0].detach()
-        if X_eval.shape != X.shape or not torch.equal(X_eval, X):
-            detected = "transformed"
-        if was_training:
-            m.train()
+        it = getattr(m, "input_transform", None)
+        holds_transformed = it is not None and bool(getattr(m, "_has_transformed_inputs", False))
+        if it is not None and (holds_transformed or hasattr(m, "_set_transformed_inputs")):
+            detected = "transformed"  # eval mode swaps in the transformed inputs under this BoTorch
+        if holds_transformed:
+            orig = getattr(m, "_original_train_inputs", None)
+            if orig is not None and orig.shape == X_seen.shape:
+                X = orig.detach()
+            else:
+                X = it.untransform(X_seen).detach()
+        else:
+            X = X_seen
+        if X.shape[0] != Yt.reshape(-1).shape[0]:
+            raise ValueError(f"arm {k}: {X.shape[0]} training inputs but {Yt.reshape(-1).shape[0]} targets")
         cov = m.covar_module
         base = getattr(cov, "base_kernel", cov)
         name = type(base).__name__.lower()
@@ -375,7 +425,6 @@ def description_from_botorch(model) -> Dict:
         osc.append(cov.outputscale.detach().reshape(()).cpu() if hasattr(cov, "outputscale") else torch.ones(()))
         noise.append(m.likelihood.noise.detach().reshape(-1)[0].cpu())
         mc.append(m.mean_module.constant.detach().reshape(()).cpu())
-        it = getattr(m, "input_transform", None)
         if it is not None:
             b = it.bounds.detach() if hasattr(it, "bounds") else torch.stack([it.mins, it.mins + it.ranges]).squeeze(1)
             mins.append(b[0].reshape(-1).cpu())
@@ -400,6 +449,28 @@ def description_from_botorch(model) -> Dict:
             "norm_ranges": torch.stack(rngs), "y_mean": torch.stack(ym), "y_std": torch.stack(ys),
             "train_inputs": detected}
     return desc
+
+
+def botorch_fingerprint(model) -> tuple:
+    """Cheap identity of a BoTorch model's data and hyper-parameters: object ids, shapes and the
+    in-place version counters of the training tensors and of every parameter / buffer.  Used to
+    invalidate the cached B200 handle when the caller mutates the model in place
+    (``load_state_dict``, ``set_train_data``, a re-fit)."""
+    parts = []
+    for m in model.models:
+        X, Y = m.train_inputs[0], m.train_targets
+        item = [id(m), tuple(X.shape), int(getattr(X, "_version", 0)), X.data_ptr(),
+                tuple(Y.shape), int(getattr(Y, "_version", 0)), Y.data_ptr(), bool(getattr(m, "training", False))]
+        params = getattr(m, "parameters", None)
+        if callable(params):
+            for prm in params():
+                item.append((prm.data_ptr(), int(prm._version)))
+        buffers = getattr(m, "buffers", None)
+        if callable(buffers):
+            for b in buffers():
+                item.append((b.data_ptr(), int(b._version)))
+        parts.append(tuple(item))
+    return tuple(parts)
 
 
 def from_botorch(model, device="cuda", dtype: Optional[torch.dtype] = None,

@@ -41,7 +41,7 @@ class SequentialRS:
         self.pcs_seed = pcs_seed
         self.rho = rho if rho is not None else (lambda x: x.mean(dim=-2))
         self.iteration = 0
-        self.ws = model.workspace(self.n_c)
+        self.ws = model.private_workspace(self.n_c)  # owned: not shared with the stateless entry points
         self.ws["ctx"].copy_(self.ctx)
         self._dirty: Optional[int] = None
         # full grid once; afterwards only dirty columns
@@ -53,9 +53,7 @@ class SequentialRS:
         m = self.model
         cap_before = m.n_cap
         m.condition_on_observations(int(arm), x, y)
-        if m.n_cap != cap_before:  # storage was regrown: workspace buffers were re-created
-            self.ws = m.workspace(self.n_c)
-            self.ws["ctx"].copy_(self.ctx)
+        if m.n_cap != cap_before:  # storage was regrown: every arm was re-prepared
             m.posterior_tables(self.ws["ctx"], self.ws["mean"], self.ws["var"], arms=(0, m.num_arms))
         else:
             m.posterior_tables(self.ws["ctx"], self.ws["mean"], self.ws["var"], arms=(int(arm), int(arm) + 1))

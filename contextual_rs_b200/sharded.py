@@ -131,6 +131,10 @@ class ContextShardedDecider:
         self._empty = torch.frombuffer(bytearray(bytes(empty)), dtype=torch.uint8).to(model.device)
         self._gather = torch.zeros(self.world, 64, dtype=torch.uint8, device=model.device)
         self._gather_host = torch.zeros(self.world, 64, dtype=torch.uint8).pin_memory()
+        # the decider OWNS its workspace: the cached local grid must survive any number of stateless
+        # calls of any batch size passing through the same model
+        self.n_loc = self.end - self.begin
+        self.ws = model.private_workspace(max(self.n_loc, 1))
 
     def decide(self, p_mode: int = _lib.CRS_P_COUNT, kernel_scale: float = 2.0,
                prepare_arms: Optional[Tuple[int, int]] = None) -> Tensor:
@@ -139,7 +143,7 @@ class ContextShardedDecider:
         m, lib = self.model, _lib.get()
         n_loc = self.end - self.begin
         if n_loc > 0:
-            ws = m.workspace(n_loc)
+            ws = self.ws
             K = m.num_arms
             with torch.cuda.device(m.device):
                 stream = _lib.stream_ptr(m.device)
@@ -165,7 +169,7 @@ class ContextShardedDecider:
         depend on the number of ranks); call ``all_gather_counts`` to assemble the full vector."""
         from .generalized_pcs import pcs_counts
         n_loc = self.end - self.begin
-        ws = self.model.workspace(max(n_loc, 1))
+        ws = self.ws
         return pcs_counts(self.model, ws["mean"][:n_loc], ws["var"][:n_loc], num_samples, seed, offset,
                           ctx_offset=self.begin, counts=ws["counts"][:n_loc], stats=ws["stats"])
 
@@ -212,7 +216,7 @@ class ArmShardedDecider:
         m = self.model
         self.n_c = context_set.shape[0]
         self.ctx = context_set.to(device=m.device, dtype=m.dtype).contiguous()
-        self.ws = m.workspace(self.n_c)
+        self.ws = m.private_workspace(self.n_c)
         self.ws["ctx"].copy_(self.ctx)
         self._ext_arm = torch.zeros(self.n_c, dtype=torch.int32, device=m.device)
         self._pack = torch.zeros(3, self.n_c, dtype=torch.float64, device=m.device)
@@ -333,7 +337,7 @@ class ShardedSequentialRS:
 
     def _refresh(self, a0: int, a1: int) -> None:
         if self.n_loc:
-            ws = self.model.workspace(self.n_loc)
+            ws = self.dec.ws
             self.model.posterior_tables(self.dec.local_ctx, ws["mean"], ws["var"], arms=(a0, a1))
 
     def decide(self) -> dict:
@@ -341,7 +345,7 @@ class ShardedSequentialRS:
         from .contextual_rs_strategies import _scan_select
         m, d = self.model, self.dec
         if self.n_loc:
-            ws = m.workspace(self.n_loc)
+            ws = d.ws
             with torch.cuda.device(m.device):
                 _scan_select(_lib.get(), m, ws, self.n_loc, self.p_mode, self.kernel_scale,
                              _lib.stream_ptr(m.device), ctx_ptr=d.local_ctx.data_ptr())

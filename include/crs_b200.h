@@ -240,6 +240,19 @@ CRS_API int crs_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, 
                                 int32_t dtype, int64_t num_samples, uint64_t seed, uint32_t offset,
                                 int64_t ctx_offset, uint32_t* counts, uint64_t* stats, void* stream);
 
+/*
+ * The same counts from CALLER-SUPPLIED standard normals — the `base_samples` argument of
+ * estimate_current_generalized_pcs (contextual_rs/generalized_pcs.py:325, 449-451; the tensor the
+ * reference passes to `posterior.rsample`, shape num_samples x n_c x K).  base: [S, n_c, K] T,
+ * contiguous; element (s, c, k) is used as the marginal draw of arm k at context c in sample s:
+ * y = mean + sqrt(var) * z (IEEE sqrt, mul, add — no FMA contraction, so a torch restatement of the
+ * same formula gives identical counts), counts[c] = #{s : y_best - max_rest > 0}
+ * (generalized_pcs.py:464-473).  Reads S * n_c * K normals: for the reference's call shapes.
+ */
+CRS_API int crs_pcs_counts_base(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                                int32_t dtype, const void* base, int64_t num_samples, uint32_t* counts,
+                                void* stream);
+
 /* The tree sampler's fp32 inverse normal for tests: out[i] = z with Phi(z) = exp(-t[i]), t[i] >= 0
  * (odd i with t < 1/8 take the small-t variant used at the root — same values by construction). */
 CRS_API int crs_debug_zfun(const float* t, int64_t n, float* out, void* stream);

@@ -13,7 +13,11 @@ lead to are pinned on the reference's recorded run, see ``trace_replay.py``):
     K^  = o * c(X~, X~) + noise * I,  L = chol(K^),  alpha = K^-1 (y~ - m)
     mu~(x*)  = m + k* . alpha,        k* = o * c(x~*, X~)
     var~(x*) = o - || L^-1 k* ||^2                     (latent f, observation_noise=False)
-    mu = ybar + s * mu~,  var = s^2 * max(var~, floor) floor = 1e-10 (fp64) / 1e-6 (fp32)
+    mu = ybar + s * mu~,  var = max(s^2 * var~, floor) floor = 1e-10 (fp64) / 1e-6 (fp32)
+                                                       [clamped AFTER un-standardising: the floor
+                                                        lives in gpytorch's MultivariateNormal.variance,
+                                                        which BoTorch reads on the posterior that
+                                                        Standardize.untransform_posterior returns]
 
 with c = Matern-5/2 ARD (reference-era SingleTaskGP default, mirrored in-tree at
 ``contextual_rs/models/lce_gp.py:117-129``) or RBF ARD.  Scaled distances are computed by
@@ -185,9 +189,10 @@ class OracleSingleTaskGP:
     def posterior(self, X: Tensor) -> OraclePosterior:
         shape = X.shape[:-1]
         mu, var = self._latent(X.reshape(-1, X.shape[-1]))
-        var = var.clamp_min(variance_floor(self.dtype))
         mean = self.y_mean + self.y_std * mu
-        variance = self.y_std * self.y_std * var
+        # [3P] the floor is applied by MultivariateNormal.variance, i.e. on the un-standardised
+        # posterior (Standardize.untransform_posterior rescales the covariance first)
+        variance = (self.y_std * self.y_std * var).clamp_min(variance_floor(self.dtype))
         return OraclePosterior(mean.reshape(*shape, 1), variance.reshape(*shape, 1))
 
     def joint_covariance(self, X: Tensor) -> Tensor:
@@ -298,7 +303,7 @@ def posterior_grid_batched(desc: Dict, X: Tensor, dtype: torch.dtype = torch.flo
         kstar = o * correlation(scaled_sq_dist(xs, Xs), kernel)  # [K, q, n]
         mu = m.reshape(K, 1) + torch.bmm(kstar, alpha).squeeze(-1)  # [K, q]
         V = torch.linalg.solve_triangular(L, kstar.transpose(1, 2), upper=False)  # [K, n, q]
-        var = (o.reshape(K, 1) - (V * V).sum(dim=1)).clamp_min(floor)
+        var = o.reshape(K, 1) - (V * V).sum(dim=1)
         means.append((ybar.reshape(K, 1) + sd.reshape(K, 1) * mu).t())
-        variances.append((sd.reshape(K, 1) ** 2 * var).t())
+        variances.append((sd.reshape(K, 1) ** 2 * var).clamp_min(floor).t())
     return torch.cat(means, dim=0).contiguous(), torch.cat(variances, dim=0).contiguous()

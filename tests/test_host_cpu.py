@@ -135,12 +135,23 @@ class MaternKernel:  # the extractor keys on the class name, as with gpytorch.ke
         self.lengthscale, self.nu = lengthscale, 2.5
 
 
-class _FakeSingleTaskGP:
-    """Duck-typed stand-in for a fitted BoTorch SingleTaskGP(Normalize, Standardize): the attribute
-    paths of SURVEY.md §8b.  ``transformed_in_eval`` mimics BoTorch >= 0.4 (eval mode exposes the
-    Normalize-d train inputs); False mimics the behaviour of the reference's recorded runs."""
+class _FakeNormalize:
+    def __init__(self, mins, rng):
+        self.bounds, self._mins, self._rng = torch.stack([mins, mins + rng]), mins, rng
 
-    def __init__(self, X, Y, ls, osc, noise, mean, transformed_in_eval):
+    def untransform(self, X):
+        return X * self._rng + self._mins
+
+
+class _FakeSingleTaskGP:
+    """Duck-typed stand-in for a fitted BoTorch SingleTaskGP(Normalize, Standardize) in eval mode: the
+    attribute paths of SURVEY.md §8b.  ``transformed_in_eval`` mimics BoTorch >= 0.4 (eval mode holds
+    the Normalize-d train inputs, ``_has_transformed_inputs``, raw copy in ``_original_train_inputs``);
+    False mimics the behaviour of the reference's recorded runs.  ``conditioned`` mimics a model
+    returned by ``condition_on_observations``: ``_original_train_inputs`` is the STALE pre-conditioning
+    copy (one row short).  Switching modes is forbidden: the extractor must not touch the model."""
+
+    def __init__(self, X, Y, ls, osc, noise, mean, transformed_in_eval, conditioned=False):
         self._X, self.training, self._tie = X, False, transformed_in_eval
         mins, rng = X.min(dim=0).values, X.max(dim=0).values - X.min(dim=0).values
         ym, ys = Y.mean(), Y.std()
@@ -148,29 +159,37 @@ class _FakeSingleTaskGP:
         self.covar_module = _FakeParam(base_kernel=MaternKernel(ls.reshape(1, -1)), outputscale=osc)
         self.likelihood = _FakeParam(noise=noise.reshape(1))
         self.mean_module = _FakeParam(constant=mean)
-        self.input_transform = _FakeParam(bounds=torch.stack([mins, mins + rng]))
+        self.input_transform = _FakeNormalize(mins, rng)
         self.outcome_transform = _FakeParam(means=ym.reshape(1, 1), stdvs=ys.reshape(1, 1))
         self._mins, self._rng = mins, rng
+        if transformed_in_eval:
+            self._has_transformed_inputs = True
+            self._set_transformed_inputs = lambda: None
+            self._original_train_inputs = X[:-1] if conditioned else X
 
     def train(self):
-        self.training = True
+        raise AssertionError("description_from_botorch must not switch the caller's model to train mode")
 
     def eval(self):
-        self.training = False
+        raise AssertionError("description_from_botorch must not toggle the caller's model")
 
     @property
     def train_inputs(self):
-        if not self.training and self._tie:
-            return ((self._X - self._mins) / self._rng,)
+        if self._tie:
+            if not hasattr(self, "_Xt"):  # BoTorch stores the transformed copy; it is not rebuilt per access
+                self._Xt = (self._X - self._mins) / self._rng
+            return (self._Xt,)
         return (self._X,)
 
 
-@pytest.mark.parametrize("transformed_in_eval", [False, True])
-def test_description_from_botorch_attribute_paths(transformed_in_eval):
+@pytest.mark.parametrize("transformed_in_eval,conditioned", [(False, False), (True, False), (True, True)])
+def test_description_from_botorch_attribute_paths(transformed_in_eval, conditioned):
     """``description_from_botorch`` against a duck-typed BoTorch model: hyper-parameters, transform
-    constants and raw data come out right, the eval-mode semantics of ``train_inputs`` are detected,
-    and the description drives the oracle to the same posterior as a directly built one."""
-    from contextual_rs_b200.model import description_from_botorch
+    constants and raw data come out right WITHOUT touching the model (no train()/eval()), the
+    eval-mode semantics of ``train_inputs`` are detected, a conditioned model's stale
+    ``_original_train_inputs`` is not trusted, and the description drives the oracle to the same
+    posterior as a directly built one."""
+    from contextual_rs_b200.model import botorch_fingerprint, description_from_botorch
     from oracle import gp_oracle
     gen = torch.Generator().manual_seed(0)
     subs, want = [], []
@@ -179,16 +198,28 @@ def test_description_from_botorch_attribute_paths(transformed_in_eval):
         Y = torch.randn(7 + k, 1, generator=gen, dtype=torch.float64) * 3 + 5
         ls = 0.2 + torch.rand(2, generator=gen, dtype=torch.float64)
         osc, noise, mean = torch.tensor(1.3 + k), torch.tensor(0.01 * (k + 1)), torch.tensor(0.1 * k)
-        subs.append(_FakeSingleTaskGP(X, Y, ls, osc.double(), noise.double(), mean.double(), transformed_in_eval))
+        subs.append(_FakeSingleTaskGP(X, Y, ls, osc.double(), noise.double(), mean.double(), transformed_in_eval, conditioned))
         want.append(gp_oracle.OracleSingleTaskGP(X, Y, ls, osc.double(), noise.double(), mean.double()))
-    desc = description_from_botorch(_FakeParam(models=subs))
+    fake = _FakeParam(models=subs)
+    desc = description_from_botorch(fake)
     assert desc["train_inputs"] == ("transformed" if transformed_in_eval else "raw")
-    assert desc["kernel"] == "matern52" and all(not m.training for m in subs)  # modes restored
+    assert desc["kernel"] == "matern52"
+    for k in range(3):  # raw inputs recovered (exactly, or through untransform for the conditioned model)
+        torch.testing.assert_close(desc["train_X"][k], subs[k]._X, rtol=0, atol=1e-15)
     got = gp_oracle.model_from_description(desc)
     ctx = torch.rand(11, 2, generator=gen, dtype=torch.float64)
     pw = gp_oracle.OracleModelListGP(*want).posterior(ctx)
     pg = got.posterior(ctx)
     torch.testing.assert_close(pg.mean, pw.mean, rtol=1e-12, atol=1e-12)
-    torch.testing.assert_close(pg.variance, pw.variance, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(pg.variance, pw.variance, rtol=1e-10, atol=1e-12)
     for (a,), m in zip(got.train_inputs, subs):  # what OCBA step 2(b) will see == what the model shows in eval mode
         torch.testing.assert_close(a, m.train_inputs[0], rtol=0, atol=1e-15)
+    # the cached-handle key changes when the caller mutates the model in place, and only then
+    fp0 = botorch_fingerprint(fake)
+    assert botorch_fingerprint(fake) == fp0
+    subs[1].train_targets.mul_(1.0)  # in-place edit bumps the tensor's version counter
+    assert botorch_fingerprint(fake) != fp0
+    # inconsistent model (targets one short of inputs): refuse instead of packing garbage
+    subs[0].train_targets = subs[0].train_targets[:-1]
+    with pytest.raises(ValueError):
+        description_from_botorch(fake)

@@ -370,3 +370,27 @@ def test_reference_recorded_levi_run_is_reproduced(golden):
     assert dec["raw"] == [tuple(d) for d in g["oracle"][:N]]
     m = trace_replay.match_counts(dec["raw"], X, g["num_init"])
     assert m["both"] >= 17 and m["arm"] >= 19, m  # 19 of the first 30 (the later part of the trace agrees more often)
+
+
+def test_oracle_variance_floor_order():
+    """[3P] gpytorch's min_variance floor (1e-10 fp64) lives in ``MultivariateNormal.variance``, which
+    BoTorch reads on the posterior ``Standardize.untransform_posterior`` returns: the clamp applies to
+    s^2 * var~, not to var~.  Both oracle paths (per-arm and batched) must agree on that order."""
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.rand(1, 2, dtype=torch.float64, generator=g)
+    X = torch.cat([x0.repeat(20, 1), torch.rand(4, 2, dtype=torch.float64, generator=g)])
+    Y = 1e-4 * (torch.sin(7 * X).sum(-1, keepdim=True) + 0.01 * torch.randn(24, 1, dtype=torch.float64, generator=g))
+    desc = {"train_X": [X, X + 0.0], "train_Y": [Y, 2 * Y], "lengthscale": torch.full((2, 2), 0.5, dtype=torch.float64),
+            "outputscale": torch.ones(2, dtype=torch.float64), "noise": torch.full((2,), 1e-4, dtype=torch.float64),
+            "mean_const": torch.zeros(2, dtype=torch.float64), "kernel": "matern52", "normalize": True, "standardize": True}
+    model = gp_oracle.model_from_description(desc)
+    ctx = torch.cat([x0, torch.rand(3, 2, dtype=torch.float64, generator=g)])
+    post = model.posterior(ctx)
+    latent = model.models[0]._latent(ctx)[1]
+    s2 = float(model.models[0].y_std) ** 2
+    assert 1e-10 < float(latent[0]) < 1e-4 and s2 * float(latent[0]) < 1e-10  # above the floor before, below after the rescale
+    assert float(post.variance[0, 0]) == 1e-10                                 # clamped AFTER un-standardising
+    assert float(post.variance[1, 0]) == s2 * float(latent[1]) > 1e-10         # untouched elsewhere
+    mean_b, var_b = gp_oracle.posterior_grid_batched(desc, ctx)
+    torch.testing.assert_close(var_b, post.variance, rtol=1e-9, atol=0)
+    assert float(var_b[0, 0]) == 1e-10
