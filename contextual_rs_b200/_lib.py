@@ -79,6 +79,8 @@ _SIGNATURES = {
     "crs_ocba_scan_select": (C.c_int, [C.POINTER(GPState), vp, vp, vp, i64, i64, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp]),
     "crs_pcs_counts": (C.c_int, [vp, vp, i64, i32, i64, i32, i64, u64, u32, i32, i64, vp, vp, vp]),
     "crs_pcs_counts_tree": (C.c_int, [vp, vp, i64, i32, i64, i32, i64, u64, u32, i64, vp, vp, vp]),
+    "crs_pcs_cdf_workspace_bytes": (i64, [i64]),
+    "crs_pcs_counts_cdf": (C.c_int, [vp, vp, i64, i32, i64, i32, i64, u64, u32, i64, vp, vp, vp, vp]),
     "crs_pcs_counts_base": (C.c_int, [vp, vp, i64, i32, i64, i32, vp, i64, vp, vp]),
     "crs_debug_zfun": (C.c_int, [vp, i64, vp, vp]),
     "crs_levi_scan": (C.c_int, [C.POINTER(GPState), vp, vp, i64, i64, vp, vp, i64, vp, vp, vp, vp]),

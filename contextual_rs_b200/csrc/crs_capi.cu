@@ -93,6 +93,16 @@ CRS_API int crs_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, 
   return launch_pcs_counts_tree(mean, var, n_c, K, ld, dtype, num_samples, seed, offset, ctx_offset, counts, stats, (cudaStream_t)stream);
 }
 
+CRS_API int64_t crs_pcs_cdf_workspace_bytes(int64_t n_c) { return pcs_cdf_workspace_bytes(n_c); }
+
+CRS_API int crs_pcs_counts_cdf(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                               int32_t dtype, int64_t num_samples, uint64_t seed, uint32_t offset,
+                               int64_t ctx_offset, uint32_t* counts, uint64_t* stats, void* workspace,
+                               void* stream) {
+  return launch_pcs_counts_cdf(mean, var, n_c, K, ld, dtype, num_samples, seed, offset, ctx_offset, counts, stats,
+                               workspace, (cudaStream_t)stream);
+}
+
 CRS_API int crs_pcs_counts_base(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
                                 int32_t dtype, const void* base, int64_t num_samples, uint32_t* counts,
                                 void* stream) {

@@ -188,6 +188,11 @@ int launch_pcs_counts(const void* mean, const void* var, int64_t n_c, int K, int
 int launch_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int K, int64_t ld, int dtype,
                            int64_t num_samples, uint64_t seed, uint32_t offset, int64_t ctx_offset,
                            uint32_t* counts, uint64_t* stats, cudaStream_t s);
+int64_t pcs_cdf_workspace_bytes(int64_t n_c);
+int launch_pcs_counts_cdf(const void* mean, const void* var, int64_t n_c, int K, int64_t ld, int dtype,
+                          int64_t num_samples, uint64_t seed, uint32_t offset, int64_t ctx_offset,
+                          uint32_t* counts, uint64_t* stats, void* workspace, cudaStream_t s);
+int launch_cdf_probe(int kind, int iters, int blocks, void* out, cudaStream_t s);
 int launch_pcs_counts_base(const void* mean, const void* var, int64_t n_c, int K, int64_t ld, int dtype,
                            const void* base, int64_t num_samples, uint32_t* counts, cudaStream_t s);
 int launch_tree_zfun(const float* t, int64_t n, float* out, cudaStream_t s);

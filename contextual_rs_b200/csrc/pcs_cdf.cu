@@ -1,0 +1,479 @@
+// crs_pcs_counts_cdf (K3, "cdf" stream, default): Monte-Carlo correct-selection counts per context —
+// the sampling half of estimate_current_generalized_pcs for a ModelListGP
+// (contextual_rs/generalized_pcs.py:441-475): in how many of the S posterior draws does the
+// predicted-best arm b beat every other arm (func_I = (delta > 0), experiments/wsc_experiments/main.py:453)?
+//
+// Arms are independent, so given the best arm's draw y_b = mu_b + sd_b z the other K - 1 draws are
+// still independent normals and
+//     P(success | z) = F_c(z) = prod_{j != b} Phi(a_j z + b_j),   a_j = sd_b / sd_j,  b_j = (mu_b - mu_j) / sd_j.
+// One sample of the indicator is therefore: z ~ N(0,1), u ~ U(0,1), success iff u < F_c(z) — the SAME
+// Bernoulli law as drawing all K normals and comparing (counts[c] ~ Binomial(S, PCS(c)) either way), at
+// the cost of one normal and one uniform instead of K normals.  Two kernels:
+//   build   one warp per context: arg-max, the range [lo, hi] of z outside which F is 0 / 1 to 1e-9
+//           (lo = max_j (-6 - b_j) / a_j, hi = max_j (7 - b_j) / a_j, clipped to the Box-Muller range),
+//           ln F at 128 grid points (ln Phi from a 1,024-cell cubic table in shared memory: 13
+//           instructions per term, terms with a_j z + b_j > 7 skipped warp-uniformly), then the 4-point
+//           Lagrange cubic of F on each of the G = 125 cells as one float4 -> workspace.  Competitors
+//           whose factor is too sharp for the grid (a_j h > 1: the best arm's posterior is much wider
+//           than theirs) are kept OUT of the table, listed in the context's header and evaluated exactly
+//           per sample (up to 8 per context; beyond that the context is flagged in stats).
+//   sample  one warp per (context, sample range): the 2 KB table goes to shared memory; one
+//           Philox4x32-10 call per TWO samples — Box-Muller pair (z1, z2) from words 0, 1, the uniforms
+//           are words 2, 3 compared as integers with F * 2^32 — so a sample costs ~45 instructions,
+//           independent of K, with no divergence and no queues.
+// Philox counters (call, global context, 0xCDF00001, offset): counts do not depend on how contexts are
+// sharded.  Stream definition and CPU restatement: oracle/pcs_cdf_ref.py.  Interpolation bias of F,
+// integrated against the normal density: < 2e-7 on all BASELINE configurations (tests/tools/cdf_design.py),
+// three orders of magnitude below the Monte-Carlo standard error of a 2^16-sample estimate.
+#include <math_constants.h>
+#include <atomic>
+#include <climits>
+#include <mutex>
+#include "crs_common.cuh"
+#include "pcs_rng.cuh"
+
+namespace crs {
+namespace {
+
+using namespace rng;
+
+constexpr int kCdfThreads = 256;
+constexpr int kCdfWarps = kCdfThreads / 32;
+constexpr int kCdfCells = 125;          // cells of the F table (grid points -1 .. 126: 4 per lane)
+constexpr int kCdfStride = 128;         // float4 per context in the workspace
+constexpr int kCdfHdr = 24;             // floats per context header: lo, inv_h, n_sharp, flags, pad[4], sharp[8] (a, b)
+constexpr int kCdfMaxSharp = 8;
+constexpr float kCdfZMax = 5.8f;        // Box-Muller on 24-bit uniforms: |z| <= 5.77
+constexpr float kCdfXLo = 6.0f;         // Phi(-6) = 1e-9: F = 0 below lo
+constexpr float kCdfXHi = 7.0f;         // K * (1 - Phi(7)) < 1e-8 for K < 8,000: F = 1 above hi
+constexpr float kCdfSharp = 1.0f;       // a_j h above this: the factor is evaluated exactly per sample
+constexpr uint32_t kCdfTag = 0xCDF00001u;
+
+// ---- ln Phi(x) on [-9, 7]: 1,024 cells of width 1/64, 4-point Lagrange cubic per cell ----------
+constexpr int kLnPhiCells = 1024;
+constexpr float kLnPhiX0 = -9.0f, kLnPhiScale = 64.0f;
+__device__ float4 g_lnphi[kLnPhiCells];
+
+__global__ void lnphi_init_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kLnPhiCells) return;
+  double p[4];
+  for (int k = 0; k < 4; ++k) {
+    const double x = (double)kLnPhiX0 + (double)(i - 1 + k) / (double)kLnPhiScale;
+    // ln Phi(x): log of the lower tail for x < 0, log1p of minus the upper tail for x >= 0
+    p[k] = x < 0.0 ? log(0.5 * erfc(-x * 0.70710678118654752440)) : log1p(-0.5 * erfc(x * 0.70710678118654752440));
+  }
+  const double c1 = -p[0] / 3.0 - p[1] / 2.0 + p[2] - p[3] / 6.0;
+  const double c2 = p[0] / 2.0 - p[1] + p[2] / 2.0;
+  const double c3 = -p[0] / 6.0 + p[1] / 2.0 - p[2] / 2.0 + p[3] / 6.0;
+  g_lnphi[i] = make_float4((float)p[1], (float)c1, (float)c2, (float)c3);
+}
+
+__device__ __forceinline__ float lnphi(float x, const float4* __restrict__ tab) {
+  float t = fmaf(x, kLnPhiScale, -kLnPhiX0 * kLnPhiScale);
+  t = fminf(fmaxf(t, 0.f), (float)kLnPhiCells - 0.001f);  // x <= -9: ln Phi = -43.6 (F = 0 anyway); x >= 7: -1.3e-12
+  const int i = (int)t;
+  const float f = t - (float)i;
+  const float4 c = tab[i];
+  return fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x);
+}
+
+__device__ __forceinline__ float exp_approx(float x) {  // e^x, x <= 0
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+
+template <typename T> __device__ __forceinline__ float sd_of(T v);
+template <> __device__ __forceinline__ float sd_of<float>(float v) { return __fsqrt_rn(v); }
+template <> __device__ __forceinline__ float sd_of<double>(double v) { return (float)sqrt(v); }
+
+// (a_j, b_j) of competitor `arm` against the best arm (mu_b in the grid dtype, sd_b fp32); the means
+// are centred in the grid dtype and only then rounded to fp32, like the other PCS kernels do.
+template <typename T>
+__device__ __forceinline__ void competitor(const T* __restrict__ mrow, const T* __restrict__ vrow, int arm,
+                                           T mu_b, float sd_b, float& a, float& b, float& r) {
+  const float mu = (float)(mrow[arm] - mu_b);
+  const float sd = sd_of<T>(vrow[arm]);
+  r = __fdiv_rn(sd, sd_b);          // 1 / a_j
+  a = __fdiv_rn(sd_b, sd);
+  b = __fdiv_rn(-mu, sd);
+}
+
+// ---- build ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kCdfThreads)
+pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n_c, int K, int64_t ld,
+                     float4* __restrict__ tables, float* __restrict__ headers, uint32_t* __restrict__ counts,
+                     unsigned long long* __restrict__ ticket, unsigned long long* __restrict__ stats) {
+  __shared__ float4 s_lnphi[kLnPhiCells];
+  __shared__ float s_F[kCdfWarps][kCdfStride];
+  __shared__ float2 s_sharp[kCdfWarps][kCdfMaxSharp];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kLnPhiCells; i += kCdfThreads) s_lnphi[i] = g_lnphi[i];
+  __syncthreads();
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned long long n_terms = 0, n_sharp_ctx = 0, n_over_ctx = 0;
+  for (;;) {
+    // contexts are handed out one at a time (their cost depends on how many terms can be skipped)
+    long long cc = 0;
+    if (lane == 0) cc = (long long)atomicAdd(ticket, 1ull);
+    const int64_t c = __shfl_sync(kFull, cc, 0);
+    if (c >= n_c) break;
+    const T* mrow = mean + c * ld;
+    const T* vrow = var + c * ld;
+    // predicted best arm: first arg-max of the mean row (generalized_pcs.py:464)
+    T bm = -(T)CUDART_INF;
+    int bi = INT_MAX;
+    for (int a = lane; a < K; a += 32) {
+      const T m = mrow[a];
+      if (m > bm) { bm = m; bi = a; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const T om = __shfl_xor_sync(kFull, bm, o);
+      const int oi = __shfl_xor_sync(kFull, bi, o);
+      if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
+    }
+    if (bi == INT_MAX) bi = 0;
+    const T mu_b = mrow[bi];
+    const float sd_b = sd_of<T>(vrow[bi]);
+    // range of z outside which F is 0 / 1
+    float zlo = -CUDART_INF_F, zhi = -CUDART_INF_F;
+    for (int a = lane; a < K; a += 32) {
+      if (a == bi) continue;
+      float aj, bj, rj;
+      competitor<T>(mrow, vrow, a, mu_b, sd_b, aj, bj, rj);
+      zlo = fmaxf(zlo, __fmul_rn(-kCdfXLo - bj, rj));
+      zhi = fmaxf(zhi, __fmul_rn(kCdfXHi - bj, rj));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      zlo = fmaxf(zlo, __shfl_xor_sync(kFull, zlo, o));
+      zhi = fmaxf(zhi, __shfl_xor_sync(kFull, zhi, o));
+    }
+    const float lo = fmaxf(zlo, -kCdfZMax);
+    float hi = fminf(zhi, kCdfZMax);
+    if (!(hi > lo + 1e-3f)) hi = lo + 1e-3f;  // F is 0 (or 1) over the whole sampled range
+    const float h = __fdiv_rn(hi - lo, (float)kCdfCells);
+    const float inv_h = __fdiv_rn((float)kCdfCells, hi - lo);
+    // grid points g = 32 r + lane <-> z = lo + (g - 1) h
+    float z[4], acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      z[r] = fmaf((float)(32 * r + lane - 1), h, lo);
+      acc[r] = 0.f;
+    }
+    float zq[4];  // lowest z of each quarter: warp-uniform skip of terms that are 0 there and above
+#pragma unroll
+    for (int r = 0; r < 4; ++r) zq[r] = fmaf((float)(32 * r - 1), h, lo);
+    int n_sharp = 0;
+    bool overflow = false;
+    for (int base = 0; base < K; base += 32) {
+      const int a = base + lane;
+      float aj = 0.f, bj = 1e30f, rj = 0.f;
+      if (a < K && a != bi) competitor<T>(mrow, vrow, a, mu_b, sd_b, aj, bj, rj);
+      // too sharp for the grid and alive somewhere in [lo, hi]: exact per sample, not tabulated
+      const bool sharp = aj * h > kCdfSharp && fmaf(aj, lo, bj) < kCdfXHi;
+      const unsigned sb = __ballot_sync(kFull, sharp);
+      if (sb) {
+        const int pos = n_sharp + __popc(sb & lt_mask);
+        if (sharp && pos < kCdfMaxSharp) {
+          s_sharp[warp][pos] = make_float2(aj, bj);
+          bj = 1e30f;  // out of the table
+          aj = 0.f;
+        }
+        overflow = overflow || n_sharp + __popc(sb) > kCdfMaxSharp;
+        n_sharp = min(n_sharp + __popc(sb), kCdfMaxSharp);
+      }
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const float ai = __shfl_sync(kFull, aj, i);
+        const float bb = __shfl_sync(kFull, bj, i);
+        if (fmaf(ai, zq[0], bb) < kCdfXHi) {
+          acc[0] += lnphi(fmaf(ai, z[0], bb), s_lnphi);
+          n_terms += 1;
+          if (fmaf(ai, zq[1], bb) < kCdfXHi) {
+            acc[1] += lnphi(fmaf(ai, z[1], bb), s_lnphi);
+            n_terms += 1;
+            if (fmaf(ai, zq[2], bb) < kCdfXHi) {
+              acc[2] += lnphi(fmaf(ai, z[2], bb), s_lnphi);
+              n_terms += 1;
+              if (fmaf(ai, zq[3], bb) < kCdfXHi) {
+                acc[3] += lnphi(fmaf(ai, z[3], bb), s_lnphi);
+                n_terms += 1;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s_F[warp][32 * r + lane] = exp_approx(fmaxf(acc[r], -80.f));
+    __syncwarp();
+    float4* tab = tables + c * kCdfStride;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = 32 * r + lane;
+      float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < kCdfCells) {
+        const float p0 = s_F[warp][i], p1 = s_F[warp][i + 1], p2 = s_F[warp][i + 2], p3 = s_F[warp][i + 3];
+        cf.x = p1;
+        cf.y = fmaf(-1.f / 3.f, p0, fmaf(-0.5f, p1, fmaf(-1.f / 6.f, p3, p2)));
+        cf.z = fmaf(0.5f, p0 + p2, -p1);
+        cf.w = fmaf(1.f / 6.f, p3 - p0, 0.5f * (p1 - p2));
+      }
+      tab[i] = cf;
+    }
+    float* hdr = headers + c * kCdfHdr;
+    if (lane == 0) {
+      hdr[0] = lo;
+      hdr[1] = inv_h;
+      hdr[2] = __int_as_float(n_sharp);
+      hdr[3] = __int_as_float(overflow ? 1 : 0);
+      counts[c] = 0u;  // the sampling kernel adds to it
+    }
+    if (lane < kCdfMaxSharp) {
+      const float2 sh = lane < n_sharp ? s_sharp[warp][lane] : make_float2(0.f, 1e30f);
+      hdr[8 + 2 * lane] = sh.x;
+      hdr[9 + 2 * lane] = sh.y;
+    }
+    n_sharp_ctx += (lane == 0 && n_sharp > 0) ? 1 : 0;
+    n_over_ctx += (lane == 0 && overflow) ? 1 : 0;
+    __syncwarp();  // s_F / s_sharp are rewritten by the next context
+  }
+  if (stats) {
+    n_terms = warp_sum(n_terms);
+    n_sharp_ctx = warp_sum(n_sharp_ctx);
+    n_over_ctx = warp_sum(n_over_ctx);
+    if (lane == 0) {
+      if (n_terms) atomicAdd(stats + 1, n_terms);
+      if (n_sharp_ctx) atomicAdd(stats + 2, n_sharp_ctx);
+      if (n_over_ctx) atomicAdd(stats + 3, n_over_ctx);
+    }
+  }
+}
+
+// ---- sample --------------------------------------------------------------------------------------
+struct CdfCtx {
+  float lo, inv_h;
+  int n_sharp;
+};
+
+__device__ __forceinline__ float cdf_eval(float z, const CdfCtx& cx, const float4* __restrict__ tab,
+                                          const float2* __restrict__ sharp, const float4* __restrict__ s_lnphi) {
+  const float t = (z - cx.lo) * cx.inv_h;
+  const float tc = fminf(fmaxf(t, 0.f), (float)kCdfCells - 0.001f);
+  const int i = (int)tc;
+  const float f = tc - (float)i;
+  const float4 c = tab[i];
+  float F = fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x);
+  F = t < 0.f ? 0.f : (t >= (float)kCdfCells ? 1.f : F);
+  for (int k = 0; k < cx.n_sharp; ++k) {  // warp-uniform trip count
+    const float2 ab = sharp[k];
+    F *= exp_approx(lnphi(fmaf(ab.x, z, ab.y), s_lnphi));
+  }
+  return F;
+}
+
+__device__ __forceinline__ uint32_t prob_to_u32(float F) {
+  uint32_t r;  // floor(F 2^32), saturating: F >= 1 -> 0xffffffff, F <= 0 (or NaN) -> 0
+  asm("cvt.rzi.sat.u32.f32 %0, %1;" : "=r"(r) : "f"(F * 4294967296.f));
+  return r;
+}
+
+__global__ void __launch_bounds__(kCdfThreads)
+pcs_cdf_sample_kernel(const float4* __restrict__ tables, const float* __restrict__ headers, int64_t n_c,
+                      int64_t num_samples, const __grid_constant__ RoundKeys rk, uint32_t offset,
+                      int64_t ctx_offset, int splits, uint32_t* __restrict__ counts,
+                      unsigned long long* __restrict__ stats) {
+  __shared__ float4 s_lnphi[kLnPhiCells];
+  __shared__ float4 s_tab[kCdfWarps][kCdfStride];
+  __shared__ float2 s_sharp[kCdfWarps][kCdfMaxSharp];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kLnPhiCells; i += kCdfThreads) s_lnphi[i] = g_lnphi[i];
+  __syncthreads();
+  const int64_t ncalls = (num_samples + 1) >> 1;
+  const int64_t items = n_c * splits;
+  const int64_t gw = (int64_t)blockIdx.x * kCdfWarps + warp, nw = (int64_t)gridDim.x * kCdfWarps;
+  unsigned long long total = 0, calls = 0;
+  for (int64_t item = gw; item < items; item += nw) {
+    const int64_t c = item / splits;
+    const int sp = (int)(item - c * splits);
+    const int64_t i_lo = ncalls * sp / splits, i_hi = ncalls * (sp + 1) / splits;
+    const float* hdr = headers + c * kCdfHdr;
+    CdfCtx cx;
+    cx.lo = hdr[0];
+    cx.inv_h = hdr[1];
+    cx.n_sharp = __float_as_int(hdr[2]);
+    const float4* gt = tables + c * kCdfStride;
+    __syncwarp();  // the previous item's reads of this warp's stage are done
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s_tab[warp][32 * r + lane] = gt[32 * r + lane];
+    if (lane < kCdfMaxSharp) s_sharp[warp][lane] = make_float2(hdr[8 + 2 * lane], hdr[9 + 2 * lane]);
+    __syncwarp();
+    const uint32_t cw = (uint32_t)(c + ctx_offset);
+    const float4* tab = s_tab[warp];
+    const float2* sharp = s_sharp[warp];
+    unsigned int hits = 0;
+    for (int64_t i = i_lo + lane; i < i_hi; i += 32) {
+      const Words w = philox4x32_10((uint32_t)i, cw, kCdfTag, offset, rk);
+      float z1, z2;
+      box_muller(w.x, w.y, z1, z2);
+      const float F1 = cdf_eval(z1, cx, tab, sharp, s_lnphi);
+      const float F2 = cdf_eval(z2, cx, tab, sharp, s_lnphi);
+      hits += w.z < prob_to_u32(F1) ? 1u : 0u;
+      hits += (w.w < prob_to_u32(F2) && 2 * i + 1 < num_samples) ? 1u : 0u;
+    }
+    calls += lane == 0 ? (unsigned long long)(i_hi - i_lo) : 0ull;
+    hits = warp_sum(hits);
+    if (lane == 0 && hits) {
+      atomicAdd(counts + c, hits);  // zeroed by the build kernel
+      total += hits;
+    }
+  }
+  if (stats && lane == 0) {
+    if (calls) atomicAdd(stats, calls);
+    if (total) atomicAdd(stats + 4, total);
+  }
+}
+
+// Peak probes (crs_peak_probe kinds 8 / 9): the bare arithmetic of one sampling call (Philox4x32-10,
+// one Box-Muller pair, two cubic evaluations on register coefficients, two integer compares) and of
+// one table term of the build (one FMA, one ln Phi lookup in shared memory, one add) — no global
+// memory, no control flow besides the loop.
+__global__ void __launch_bounds__(kCdfThreads)
+cdf_probe_kernel(int kind, int iters, const __grid_constant__ RoundKeys rk, float* out) {
+  __shared__ float4 s_lnphi[kLnPhiCells];
+  for (int i = threadIdx.x; i < kLnPhiCells; i += kCdfThreads) s_lnphi[i] = g_lnphi[i];
+  __syncthreads();
+  const uint32_t smp = blockIdx.x * kCdfThreads + threadIdx.x;
+  unsigned int hits = 0;
+  if (kind == 8) {
+    const float4 c = make_float4(0.3f, 0.2f, -0.05f, 0.01f);
+    for (int it = 0; it < iters; ++it) {
+      const Words w = philox4x32_10(smp, 7u, (uint32_t)it, 0u, rk);
+      float z1, z2;
+      box_muller(w.x, w.y, z1, z2);
+      float F[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float t = ((k ? z2 : z1) + 5.f) * 12.5f;
+        const float tc = fminf(fmaxf(t, 0.f), 124.999f);
+        const int i = (int)tc;
+        const float f = tc - (float)i;
+        const float v = fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x + 1e-3f * (float)i);
+        F[k] = t < 0.f ? 0.f : (t >= 125.f ? 1.f : v);
+      }
+      hits += w.z < prob_to_u32(F[0]) ? 1u : 0u;
+      hits += w.w < prob_to_u32(F[1]) ? 1u : 0u;
+    }
+  } else {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float a = 1.f + 1e-3f * (float)(smp & 31), b = 0.5f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] += lnphi(fmaf(a, -2.f + 1.3f * (float)r, b), s_lnphi);
+      b += 1e-3f;
+    }
+    hits = (acc[0] + acc[1] + acc[2] + acc[3]) < -1e30f ? 1u : 0u;
+  }
+  if (hits == 0xffffffffu) out[0] = 1.f;  // keep the loop alive
+}
+
+struct CdfDevInfo { bool ready = false; int sms = 0; int build_ctas[2] = {0, 0}; int sample_ctas = 0; };
+CdfDevInfo g_cdf_info[64];
+std::mutex g_cdf_mutex;
+
+// one-off per device: fill the ln Phi table (a 4-block kernel, synchronised once under the lock)
+int cdf_device_ready(CdfDevInfo& info) {
+  int dev = 0;
+  CRS_CUDA_TRY(cudaGetDevice(&dev), "pcs_cdf get device");
+  if (dev < 0 || dev >= 64) return CRS_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> lock(g_cdf_mutex);
+  if (!g_cdf_info[dev].ready) {
+    cudaStream_t s0;
+    CRS_CUDA_TRY(cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking), "pcs_cdf init stream");
+    lnphi_init_kernel<<<kLnPhiCells / 256, 256, 0, s0>>>();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
+    cudaStreamDestroy(s0);
+    CRS_CUDA_TRY(e, "pcs_cdf ln Phi table");
+    CRS_CUDA_TRY(cudaDeviceGetAttribute(&g_cdf_info[dev].sms, cudaDevAttrMultiProcessorCount, dev), "pcs_cdf sm count");
+    // resident CTAs of each kernel: the grids are sized to exactly one wave
+    int per_sm = 0;
+    CRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcs_cdf_build_kernel<double>, kCdfThreads, 0), "pcs_cdf occupancy");
+    g_cdf_info[dev].build_ctas[0] = g_cdf_info[dev].sms * (per_sm > 0 ? per_sm : 1);
+    CRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcs_cdf_build_kernel<float>, kCdfThreads, 0), "pcs_cdf occupancy");
+    g_cdf_info[dev].build_ctas[1] = g_cdf_info[dev].sms * (per_sm > 0 ? per_sm : 1);
+    CRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcs_cdf_sample_kernel, kCdfThreads, 0), "pcs_cdf occupancy");
+    g_cdf_info[dev].sample_ctas = g_cdf_info[dev].sms * (per_sm > 0 ? per_sm : 1);
+    g_cdf_info[dev].ready = true;
+  }
+  info = g_cdf_info[dev];
+  return CRS_OK;
+}
+
+}  // namespace
+
+int64_t pcs_cdf_workspace_bytes(int64_t n_c) {  // tables | headers | work ticket
+  return n_c <= 0 ? 0 : n_c * (int64_t)(kCdfStride * sizeof(float4) + kCdfHdr * sizeof(float)) + 64;
+}
+
+int launch_pcs_counts_cdf(const void* mean, const void* var, int64_t n_c, int K, int64_t ld, int dtype,
+                          int64_t num_samples, uint64_t seed, uint32_t offset, int64_t ctx_offset,
+                          uint32_t* counts, uint64_t* stats, void* workspace, cudaStream_t s) {
+  if (!mean || !var || !counts || n_c < 0 || K < 2 || ld < K || num_samples < 0) return CRS_ERR_INVALID_ARG;
+  if (n_c > 0 && (!workspace || ((uintptr_t)workspace & 15))) return CRS_ERR_INVALID_ARG;
+  if (num_samples > 0x1fffffffeLL) return CRS_ERR_UNSUPPORTED;  // 32-bit call counter, two samples per call
+  if (n_c == 0) return CRS_OK;
+  CdfDevInfo info;
+  int rc;
+  if ((rc = cdf_device_ready(info)) != CRS_OK) return rc;
+  if (stats) CRS_CUDA_TRY(cudaMemsetAsync(stats, 0, 6 * sizeof(uint64_t), s), "pcs_cdf memset stats");
+  float4* tables = reinterpret_cast<float4*>(workspace);
+  float* headers = reinterpret_cast<float*>(tables + n_c * kCdfStride);
+  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(headers + n_c * kCdfHdr);
+  CRS_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s), "pcs_cdf memset ticket");
+  const int64_t want_b = (n_c + kCdfWarps - 1) / kCdfWarps;
+  const int64_t res_b = info.build_ctas[dtype == CRS_F64 ? 0 : 1];
+  const int blocks_b = (int)(want_b < res_b ? want_b : res_b);
+  if (dtype == CRS_F64)
+    pcs_cdf_build_kernel<double><<<blocks_b, kCdfThreads, 0, s>>>((const double*)mean, (const double*)var, n_c, K, ld, tables,
+                                                                  headers, counts, ticket, (unsigned long long*)stats);
+  else if (dtype == CRS_F32)
+    pcs_cdf_build_kernel<float><<<blocks_b, kCdfThreads, 0, s>>>((const float*)mean, (const float*)var, n_c, K, ld, tables,
+                                                                 headers, counts, ticket, (unsigned long long*)stats);
+  else
+    return CRS_ERR_INVALID_ARG;
+  CRS_CUDA_TRY(cudaGetLastError(), "pcs_cdf build launch");
+  if (num_samples == 0) return CRS_OK;
+  // sampling: every (context, range) item costs the same, so a static round-robin over warps is
+  // balanced as soon as each warp holds a few items; contexts are split only when they are few
+  const int64_t ncalls = (num_samples + 1) >> 1;
+  const int64_t warps = (int64_t)info.sample_ctas * kCdfWarps;
+  int64_t splits = 1;
+  if (n_c < 4 * warps) splits = (4 * warps + n_c - 1) / n_c;
+  const int64_t max_splits = ncalls / 64 > 0 ? ncalls / 64 : 1;  // >= 2 calls per lane and item
+  if (splits > max_splits) splits = max_splits;
+  const int64_t items = n_c * splits;
+  const int64_t want_s = (items + kCdfWarps - 1) / kCdfWarps;
+  const int blocks_s = (int)(want_s < info.sample_ctas ? want_s : info.sample_ctas);
+  const RoundKeys rk = round_keys((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+  pcs_cdf_sample_kernel<<<blocks_s, kCdfThreads, 0, s>>>(tables, headers, n_c, num_samples, rk, offset, ctx_offset,
+                                                         (int)splits, counts, (unsigned long long*)stats);
+  CRS_CUDA_TRY(cudaGetLastError(), "pcs_cdf sample launch");
+  return CRS_OK;
+}
+
+int launch_cdf_probe(int kind, int iters, int blocks, void* out, cudaStream_t s) {
+  CdfDevInfo info;
+  int rc;
+  if ((rc = cdf_device_ready(info)) != CRS_OK) return rc;
+  cdf_probe_kernel<<<blocks, kCdfThreads, 0, s>>>(kind, iters, round_keys(1u, 2u), (float*)out);
+  CRS_CUDA_TRY(cudaGetLastError(), "cdf_probe launch");
+  return CRS_OK;
+}
+
+}  // namespace crs

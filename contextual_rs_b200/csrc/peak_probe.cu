@@ -60,6 +60,7 @@ int launch_peak_probe(int kind, int iters, int blocks, void* out, cudaStream_t s
   else if (kind == 2) dmma_probe_kernel<<<blocks, 256, 0, s>>>(iters, 1.0, (double*)out);  // 16 DMMA / iter / warp
   else if (kind == 5) return launch_pcs_probe(iters, blocks, out, s);  // Philox + Box-Muller + FMA + max
   else if (kind == 6 || kind == 7) return launch_tree_probe(kind, iters, blocks, out, s);  // max-tree PCS: root test / expansion
+  else if (kind == 8 || kind == 9) return launch_cdf_probe(kind, iters, blocks, out, s);  // cdf PCS: sampling call / 4 table terms
   else return CRS_ERR_INVALID_ARG;
   CRS_CUDA_TRY(cudaGetLastError(), "peak_probe launch");
   return CRS_OK;

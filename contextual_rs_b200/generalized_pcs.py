@@ -35,39 +35,55 @@ TREE_MAX_ARMS = 4102  # crs_pcs_counts_tree: 5 direct arms + 4^6 leaves + the be
 def pcs_counts(model: B200ModelListGP, mean: Tensor, var: Tensor, num_samples: int, seed: int,
                offset: int = 0, arm_offset: int = 0, ctx_offset: int = 0,
                counts: Optional[Tensor] = None, stats: Optional[Tensor] = None,
-               sampler: str = "auto") -> Tensor:
+               sampler: str = "auto", workspace: Optional[Tensor] = None) -> Tensor:
     """Correct-selection counts of device tables ``[n_c, K]``; returns int32 counts ``[n_c]``.
 
-    ``sampler``: ``"tree"`` = ``crs_pcs_counts_tree`` (max-tree stream: a sample is decided after a
-    few Philox calls; needs the full arm row, 2 <= K <= 4102), ``"flat"`` = ``crs_pcs_counts``
-    (one draw per arm, keyed by arm id — also serves arm slices via ``arm_offset``), ``"auto"`` =
-    tree whenever it applies.  Both are Monte-Carlo estimates of the same quantity; the two
-    streams are different, so counts agree within MC error, not draw for draw.
-    ``stats`` (``[>= 3]`` int64, optional): flat -> {draws executed, nominal - executed, -};
-    tree -> {root tests, node expansions, direct-arm tests}."""
+    ``sampler``: ``"cdf"`` = ``crs_pcs_counts_cdf`` (default: one normal + one uniform per sample
+    against the tabulated conditional success probability F_c(z); any K >= 2, full arm row),
+    ``"tree"`` = ``crs_pcs_counts_tree`` (max-tree stream: K - 1 competitor normals sampled lazily;
+    2 <= K <= 4102), ``"flat"`` = ``crs_pcs_counts`` (one draw per arm, keyed by arm id — also serves
+    arm slices via ``arm_offset``), ``"auto"`` = cdf whenever the full row is given.  All three are
+    Monte-Carlo estimates of the same quantity with the same per-sample law; the streams differ, so
+    counts agree within MC error, not draw for draw.
+    ``stats`` (int64, optional): cdf (>= 6) -> {Philox calls, table terms, contexts with exact sharp
+    competitors, contexts over the sharp limit, total successes, 0}; flat (>= 3) -> {draws executed,
+    nominal - executed, -}; tree (>= 3) -> {root tests, node expansions, direct-arm tests}.
+    ``workspace`` (cdf): uint8 tensor of ``crs_pcs_cdf_workspace_bytes(n_c)`` bytes; allocated per
+    call (torch's caching allocator) when omitted."""
     n_c, K = mean.shape
-    if sampler not in ("auto", "tree", "flat"):
+    if sampler not in ("auto", "cdf", "tree", "flat"):
         raise ValueError(f"unknown sampler {sampler!r}")
-    tree_ok = 2 <= K <= TREE_MAX_ARMS and arm_offset == 0
+    full_row = arm_offset == 0
+    tree_ok = 2 <= K <= TREE_MAX_ARMS and full_row
     if sampler == "tree" and not tree_ok:
         raise ValueError("the tree sampler needs the full arm row with 2 <= K <= 4102 and arm_offset = 0")
-    use_tree = tree_ok and sampler != "flat"
+    if sampler == "cdf" and not (full_row and K >= 2):
+        raise ValueError("the cdf sampler needs the full arm row (arm_offset = 0) and K >= 2")
+    if sampler == "auto":
+        sampler = "cdf" if (full_row and K >= 2) else "flat"
     if counts is None:
         counts = torch.empty(n_c, dtype=torch.int32, device=mean.device)
-    if stats is not None and stats.numel() < 3:
-        raise ValueError("stats needs room for 3 int64 values")
+    need = 6 if sampler == "cdf" else 3
+    if stats is not None and stats.numel() < need:
+        raise ValueError(f"stats needs room for {need} int64 values")
+    lib = _lib.get()
+    args = (mean.data_ptr(), var.data_ptr(), n_c, K, mean.stride(0), _lib.DTYPES[mean.dtype], int(num_samples),
+            int(seed) & (2 ** 64 - 1), int(offset) & 0xFFFFFFFF)
     with torch.cuda.device(mean.device):
-        if use_tree:
-            rc = _lib.get().crs_pcs_counts_tree(mean.data_ptr(), var.data_ptr(), n_c, K, mean.stride(0),
-                                                _lib.DTYPES[mean.dtype], int(num_samples), int(seed) & (2 ** 64 - 1),
-                                                int(offset) & 0xFFFFFFFF, int(ctx_offset),
-                                                counts.data_ptr(), _lib.ptr(stats), _lib.stream_ptr(mean.device))
+        stream = _lib.stream_ptr(mean.device)
+        if sampler == "cdf":
+            nbytes = int(lib.crs_pcs_cdf_workspace_bytes(n_c))
+            if workspace is None:
+                workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=mean.device)
+            elif workspace.numel() * workspace.element_size() < nbytes:
+                raise ValueError(f"cdf workspace needs {nbytes} bytes")
+            rc = lib.crs_pcs_counts_cdf(*args, int(ctx_offset), counts.data_ptr(), _lib.ptr(stats),
+                                        workspace.data_ptr(), stream)
+        elif sampler == "tree":
+            rc = lib.crs_pcs_counts_tree(*args, int(ctx_offset), counts.data_ptr(), _lib.ptr(stats), stream)
         else:
-            rc = _lib.get().crs_pcs_counts(mean.data_ptr(), var.data_ptr(), n_c, K, mean.stride(0),
-                                           _lib.DTYPES[mean.dtype], int(num_samples), int(seed) & (2 ** 64 - 1),
-                                           int(offset) & 0xFFFFFFFF, int(arm_offset), int(ctx_offset),
-                                           counts.data_ptr(), _lib.ptr(stats), _lib.stream_ptr(mean.device))
-    _lib.check(rc, "crs_pcs_counts_tree" if use_tree else "crs_pcs_counts")
+            rc = lib.crs_pcs_counts(*args, int(arm_offset), int(ctx_offset), counts.data_ptr(), _lib.ptr(stats), stream)
+    _lib.check(rc, {"cdf": "crs_pcs_counts_cdf", "tree": "crs_pcs_counts_tree", "flat": "crs_pcs_counts"}[sampler])
     return counts
 
 

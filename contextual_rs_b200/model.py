@@ -340,7 +340,7 @@ class B200ModelListGP:
             "scan_ws": torch.zeros(int(_lib.get().crs_scan_workspace_bytes()), dtype=torch.uint8, device=dev),
             "decision_host": torch.zeros(64, dtype=torch.uint8).pin_memory(),
             "counts": torch.empty(n_c, dtype=torch.int32, device=dev),
-            "stats": torch.zeros(4, dtype=torch.int64, device=dev),
+            "stats": torch.zeros(8, dtype=torch.int64, device=dev),
             "valid_for": None,  # a fresh workspace holds no grid yet
         }
         p = _lib.ptr

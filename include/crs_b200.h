@@ -241,6 +241,28 @@ CRS_API int crs_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, 
                                 int64_t ctx_offset, uint32_t* counts, uint64_t* stats, void* stream);
 
 /*
+ * Same estimate again — counts[c] = number of the S posterior draws in which the predicted-best arm of
+ * context c beats every other arm (contextual_rs/generalized_pcs.py:441-475, func_I = strict
+ * indicator) — under the "cdf" Philox stream, the default sampler: arms are independent, so given the
+ * best arm's draw y_b = mu_b + sd_b z the sample succeeds with probability
+ * F_c(z) = prod_{j != b} Phi((y_b - mu_j) / sd_j); one sample is z ~ N(0,1), u ~ U(0,1), success iff
+ * u < F_c(z) — the same Bernoulli law as drawing all K normals, for one normal and one uniform.  A
+ * build kernel tabulates F_c per context (cubic on 125 cells, competitors too sharp for the grid kept
+ * exact), a sampling kernel spends one Philox4x32-10 call per two samples.  Stream definition and CPU
+ * restatement: oracle/pcs_cdf_ref.py.  Counters (call, context + ctx_offset, 0xCDF00001, offset):
+ * counts do not depend on how contexts are sharded.  Any K >= 2.
+ * workspace: crs_pcs_cdf_workspace_bytes(n_c) bytes of device memory, 16-byte aligned, no
+ * initialisation needed.  counts: [n_c] uint32.  stats (may be NULL): [6] uint64 = {Philox calls,
+ * ln Phi terms evaluated by the build, contexts with exactly-evaluated sharp competitors, contexts
+ * with more than 8 of them (table accuracy not guaranteed), total successes, 0}.
+ */
+CRS_API int64_t crs_pcs_cdf_workspace_bytes(int64_t n_c);
+CRS_API int crs_pcs_counts_cdf(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
+                               int32_t dtype, int64_t num_samples, uint64_t seed, uint32_t offset,
+                               int64_t ctx_offset, uint32_t* counts, uint64_t* stats, void* workspace,
+                               void* stream);
+
+/*
  * The same counts from CALLER-SUPPLIED standard normals — the `base_samples` argument of
  * estimate_current_generalized_pcs (contextual_rs/generalized_pcs.py:325, 449-451; the tensor the
  * reference passes to `posterior.rsample`, shape num_samples x n_c x K).  base: [S, n_c, K] T,

@@ -1,0 +1,71 @@
+"""CPU tests of the cdf PCS stream's restatement (oracle/pcs_cdf_ref.py): its counts estimate the same
+PCS(c) as exact quadrature, the cubic table changes only a handful of borderline samples against the
+exact conditional probability on the same draws, sharp competitors are taken out of the table, and the
+counts are invariant to how contexts are sharded."""
+import numpy as np
+import torch
+
+from contextual_rs_b200.synthetic import make_problem
+from oracle import gp_oracle, pcs_cdf_ref, pcs_oracle
+
+
+def _tables(K, n_c, d, n, seed):
+    desc, ctx = make_problem(K=K, n_c=n_c, d=d, n=n, seed=seed)
+    mu, var = gp_oracle.posterior_grid_batched(desc, ctx)
+    return mu.numpy(), var.numpy()
+
+
+def test_cdf_stream_estimates_pcs():
+    mu, var = _tables(40, 24, 3, 12, seed=5)
+    S = 8192
+    counts, _ = pcs_cdf_ref.pcs_counts_cdf_ref(mu, var, S, seed=11)
+    exact = pcs_oracle.pcs_exact_quadrature(mu, var)
+    se = np.sqrt(np.maximum(exact * (1 - exact), 1e-4) / S)
+    assert np.all(np.abs(counts / S - exact) < 5 * se)
+    assert abs(np.mean(counts / S - exact)) < 4 * np.sqrt(np.mean(se ** 2) / len(se))
+
+
+def test_table_against_exact_conditional_probability():
+    """Same draws, table interpolant vs exact product: the counts differ by far less than the MC
+    error, and the interpolant's bias integrated against the normal density is < 1e-6."""
+    mu, var = _tables(100, 12, 4, 20, seed=3)
+    S = 16384
+    tab, _ = pcs_cdf_ref.pcs_counts_cdf_ref(mu, var, S, seed=2)
+    exa, _ = pcs_cdf_ref.pcs_counts_cdf_ref(mu, var, S, seed=2, exact=True)
+    assert np.abs(tab - exa).max() <= 3 and np.abs(tab - exa).sum() <= 8
+    z = np.linspace(-5.8, 5.8, 8001)
+    w = np.exp(-0.5 * z * z) / np.sqrt(2 * np.pi) * (z[1] - z[0])
+    for c in range(12):
+        plan = pcs_cdf_ref.context_plan(mu[c], var[c])
+        bias = np.sum(w * (pcs_cdf_ref.success_probability(plan, z) - pcs_cdf_ref.exact_success_probability(plan, z)))
+        assert abs(bias) < 1e-6, (c, bias)
+
+
+def test_sharp_competitors_are_exact_not_tabulated():
+    """Best arm 300x wider than its closest competitor: the competitor's factor is a near-step that a
+    125-cell grid cannot follow; it must be listed as sharp and the estimate must stay unbiased."""
+    mu = np.array([[1.0, 0.949, 0.2, -0.5, 0.95]])
+    var = np.array([[9e-2, 1e-6, 4e-2, 1e-1, 2e-7]])
+    plan = pcs_cdf_ref.context_plan(mu[0], var[0])
+    assert len(plan["sharp_a"]) == 2 and not plan["overflow"]
+    assert float(plan["sharp_a"].min()) > 100
+    z = np.linspace(-5.8, 5.8, 200001)
+    w = np.exp(-0.5 * z * z) / np.sqrt(2 * np.pi) * (z[1] - z[0])
+    bias = np.sum(w * (pcs_cdf_ref.success_probability(plan, z) - pcs_cdf_ref.exact_success_probability(plan, z)))
+    assert abs(bias) < 1e-6
+    counts, _ = pcs_cdf_ref.pcs_counts_cdf_ref(mu, var, 65536, seed=4)
+    exact = pcs_oracle.pcs_exact_quadrature(mu, var)
+    assert abs(counts[0] / 65536 - exact[0]) < 5 * np.sqrt(exact[0] * (1 - exact[0]) / 65536)
+
+
+def test_degenerate_ranges_and_shard_invariance():
+    # a hopeless best arm (F = 0 wherever z is sampled) and a certain one (F = 1 everywhere)
+    mu = np.array([[0.0, -1e-9, -2.0], [5.0, -50.0, -60.0]])
+    var = np.array([[1e-8, 1e2, 1.0], [1.0, 1.0, 1.0]])
+    counts, _ = pcs_cdf_ref.pcs_counts_cdf_ref(mu, var, 4001, seed=1)
+    assert 1500 < counts[0] < 2500   # best arm ~ tie with a very wide competitor: ~1/2
+    assert counts[1] == 4001
+    mu2, var2 = _tables(9, 10, 2, 8, seed=7)
+    full, _ = pcs_cdf_ref.pcs_counts_cdf_ref(mu2, var2, 1001, seed=9, offset=3)
+    part, _ = pcs_cdf_ref.pcs_counts_cdf_ref(mu2[4:], var2[4:], 1001, seed=9, offset=3, ctx_offset=4)
+    assert np.array_equal(full[4:], part)
