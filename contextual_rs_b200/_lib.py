@@ -57,6 +57,11 @@ class DecideWS(C.Structure):
                 ("min_arm", vp), ("tie_cnt", vp), ("decision", vp), ("scan_ws", vp)]
 
 
+class PeerExchange(C.Structure):
+    """``crs_peer_exchange``"""
+    _fields_ = [("mailboxes", vp), ("rank", i32), ("world", i32), ("seq", i32), ("reserved", i32), ("ctx_begin", i64)]
+
+
 class LeviDecision(C.Structure):
     """``crs_levi_decision``"""
     _fields_ = [("value", f64), ("context", i32), ("arm", i32), ("reserved", i64)]
@@ -77,6 +82,15 @@ _SIGNATURES = {
     "crs_ocba_resolve_tie": (C.c_int, [vp, vp, i64, i32, i64, i32, vp, vp, vp, i64, vp, vp]),
     "crs_ocba_select": (C.c_int, [C.POINTER(GPState), vp, vp, vp, i64, i32, i32, f64, vp, vp]),
     "crs_ocba_scan_select": (C.c_int, [C.POINTER(GPState), vp, vp, vp, i64, i64, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp]),
+    "crs_ocba_scan_select_sharded": (C.c_int, [C.POINTER(GPState), vp, vp, vp, i64, i64, i32, f64, vp, vp, vp, vp, vp, vp,
+                                               C.POINTER(PeerExchange), vp, vp]),
+    "crs_wait_decision": (C.c_int, [vp, i32, i32]),
+    "crs_mailbox_bytes": (i64, [i32]),
+    "crs_device_alloc": (C.c_int, [i64, C.POINTER(vp)]),
+    "crs_device_free": (C.c_int, [vp]),
+    "crs_ipc_export": (C.c_int, [vp, vp]),
+    "crs_ipc_open": (C.c_int, [vp, C.POINTER(vp)]),
+    "crs_ipc_close": (C.c_int, [vp]),
     "crs_pcs_counts": (C.c_int, [vp, vp, i64, i32, i64, i32, i64, u64, u32, i32, i64, vp, vp, vp]),
     "crs_pcs_counts_tree": (C.c_int, [vp, vp, i64, i32, i64, i32, i64, u64, u32, i64, vp, vp, vp]),
     "crs_pcs_cdf_workspace_bytes": (i64, [i64]),

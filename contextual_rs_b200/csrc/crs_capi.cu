@@ -66,7 +66,7 @@ CRS_API int crs_ocba_resolve_tie(const void* mean, const void* var, int64_t n_c,
 CRS_API int crs_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
                     int64_t ld, int32_t arm_offset, int32_t p_mode, double kernel_scale,
                     crs_decision* decision, void* stream) {
-  return launch_ocba_select(st, ctx, mean, var, ld, arm_offset, p_mode, kernel_scale, decision, nullptr, 0, (cudaStream_t)stream);
+  return launch_ocba_select(st, ctx, mean, var, ld, arm_offset, p_mode, kernel_scale, decision, nullptr, 0, nullptr, (cudaStream_t)stream);
 }
 
 CRS_API int crs_ocba_scan_select(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
@@ -77,7 +77,87 @@ CRS_API int crs_ocba_scan_select(const crs_gp_state* st, const void* ctx, const 
   if (!st) return CRS_ERR_INVALID_ARG;
   return launch_ocba_scan_select(mean, var, n_c, st->num_arms, ld, st->dtype, arm_offset, nullptr, nullptr,
                                  nullptr, best_arm, min_zeta, min_arm, tie_cnt, decision, workspace, st, ctx,
-                                 p_mode, kernel_scale, nullptr, 0, (cudaStream_t)stream);
+                                 p_mode, kernel_scale, nullptr, 0, nullptr, (cudaStream_t)stream);
+}
+
+CRS_API int crs_ocba_scan_select_sharded(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
+                                         int64_t n_c, int64_t ld, int32_t p_mode, double kernel_scale,
+                                         int32_t* best_arm, void* min_zeta, int32_t* min_arm, int32_t* tie_cnt,
+                                         crs_decision* decision, void* workspace, const crs_peer_exchange* px,
+                                         crs_decision* decision_host, void* stream) {
+  if (!st || !px || !decision) return CRS_ERR_INVALID_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  crs_decision* mirror = nullptr;
+  if (decision_host) {
+    void* dptr = nullptr;
+    if (cudaHostGetDevicePointer(&dptr, decision_host, 0) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return CRS_ERR_INVALID_ARG;  // the zero-copy read-back needs mapped pinned memory
+    }
+    mirror = reinterpret_cast<crs_decision*>(dptr);
+  }
+  if (n_c == 0) return launch_peer_exchange_only(decision, mirror, px->seq, px, s);
+  return launch_ocba_scan_select(mean, var, n_c, st->num_arms, ld, st->dtype, 0, nullptr, nullptr, nullptr, best_arm,
+                                 min_zeta, min_arm, tie_cnt, decision, workspace, st, ctx, p_mode, kernel_scale, mirror,
+                                 px->seq, px, s);
+}
+
+CRS_API int crs_wait_decision(const crs_decision* decision_host, int32_t seq, int32_t timeout_ms) {
+  if (!decision_host) return CRS_ERR_INVALID_ARG;
+  const volatile int32_t* tag = reinterpret_cast<const volatile int32_t*>(decision_host->reserved) + 1;
+  struct timespec t0;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  unsigned long long spins = 0;
+  while (*tag != seq) {
+    __builtin_ia32_pause();
+    if ((++spins & 0xfff) == 0) {
+      struct timespec t1;
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if ((t1.tv_sec - t0.tv_sec) * 1e3 + 1e-6 * (t1.tv_nsec - t0.tv_nsec) > timeout_ms) {
+        set_cuda_error(cudaErrorTimeout, "crs_wait_decision");
+        return CRS_ERR_CUDA;
+      }
+    }
+  }
+  __sync_synchronize();
+  return CRS_OK;
+}
+
+CRS_API int64_t crs_mailbox_bytes(int32_t world) { return world < 1 ? 0 : (int64_t)2 * world * 128; }
+
+CRS_API int crs_device_alloc(int64_t bytes, void** dev_ptr) {
+  if (!dev_ptr || bytes <= 0) return CRS_ERR_INVALID_ARG;
+  CRS_CUDA_TRY(cudaMalloc(dev_ptr, (size_t)bytes), "crs_device_alloc");
+  CRS_CUDA_TRY(cudaMemset(*dev_ptr, 0, (size_t)bytes), "crs_device_alloc memset");
+  CRS_CUDA_TRY(cudaDeviceSynchronize(), "crs_device_alloc sync");
+  return CRS_OK;
+}
+
+CRS_API int crs_device_free(void* dev_ptr) {
+  if (dev_ptr) CRS_CUDA_TRY(cudaFree(dev_ptr), "crs_device_free");
+  return CRS_OK;
+}
+
+CRS_API int crs_ipc_export(void* dev_ptr, unsigned char handle[64]) {
+  if (!dev_ptr || !handle) return CRS_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CRS_CUDA_TRY(cudaIpcGetMemHandle(&h, dev_ptr), "crs_ipc_export");
+  memcpy(handle, &h, 64);
+  return CRS_OK;
+}
+
+CRS_API int crs_ipc_open(const unsigned char handle[64], void** dev_ptr) {
+  if (!dev_ptr || !handle) return CRS_ERR_INVALID_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CRS_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess), "crs_ipc_open");
+  return CRS_OK;
+}
+
+CRS_API int crs_ipc_close(void* dev_ptr) {
+  if (dev_ptr) CRS_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr), "crs_ipc_close");
+  return CRS_OK;
 }
 
 CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
@@ -193,7 +273,7 @@ CRS_API int crs_gao_decide_host(const crs_gp_state* st, const void* ctx_host, in
   if ((rc = launch_posterior_grid(st, ws->ctx, n_c, 0, K, ws->mean, ws->var, K, 0, s)) != CRS_OK) return rc;
   if ((rc = launch_ocba_scan_select(ws->mean, ws->var, n_c, K, K, st->dtype, 0, nullptr, nullptr, nullptr,
                                     ws->best_arm, ws->min_zeta, ws->min_arm, ws->tie_cnt, ws->decision,
-                                    ws->scan_ws, st, ws->ctx, p_mode, kernel_scale, mirror, seq, s)) != CRS_OK)
+                                    ws->scan_ws, st, ws->ctx, p_mode, kernel_scale, mirror, seq, nullptr, s)) != CRS_OK)
     return rc;
   if (mirror) {
     volatile int32_t* tag = reinterpret_cast<volatile int32_t*>(decision_host->reserved) + 1;

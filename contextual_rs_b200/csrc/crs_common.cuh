@@ -165,14 +165,17 @@ int launch_ocba_resolve_tie(const void* mean, const void* var, int64_t n_c, int 
                             cudaStream_t s);
 int launch_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
                        int64_t ld, int arm_offset, int p_mode, double kernel_scale,
-                       crs_decision* decision, crs_decision* host_mirror, int seq, cudaStream_t s);
+                       crs_decision* decision, crs_decision* host_mirror, int seq, const crs_peer_exchange* px,
+                       cudaStream_t s);
+int launch_peer_exchange_only(crs_decision* decision, crs_decision* host_mirror, int seq, const crs_peer_exchange* px,
+                              cudaStream_t s);
 int launch_ocba_scan_select(const void* mean, const void* var, int64_t n_c, int K, int64_t ld,
                             int dtype, int arm_offset, const int32_t* ext_best_arm,
                             const void* ext_best_mean, const void* ext_best_var, int32_t* best_arm,
                             void* min_zeta, int32_t* min_arm, int32_t* tie_cnt,
                             crs_decision* decision, void* workspace, const crs_gp_state* st,
                             const void* ctx, int p_mode, double kernel_scale,
-                            crs_decision* host_mirror, int seq, cudaStream_t s);
+                            crs_decision* host_mirror, int seq, const crs_peer_exchange* px, cudaStream_t s);
 int64_t scan_workspace_bytes();
 int launch_gp_mll(const crs_gp_state* st, int arm_begin, int arm_end, double* value, double* grad,
                   cudaStream_t s);

@@ -42,6 +42,7 @@ struct SelectArgs {
   int do_select;
   crs_decision* host_mirror;  // mapped pinned host copy of the decision (may be null)
   int seq;                    // written to reserved[1] of the mirror LAST: completion tag
+  crs_peer_exchange px;       // world > 1: combine the ranks' local decisions through peer mailboxes
 };
 
 __device__ __forceinline__ void combine(ScanPartial& a, const ScanPartial& b) {
@@ -280,6 +281,90 @@ __device__ void select_block(const crs_gp_state& st, const T* __restrict__ ctx,
   }
 }
 
+// ---- multi-GPU combine of a context-sharded decision, device side ------------------------------
+// Every rank owns a mailbox of 2 x world slots of 128 bytes in ITS memory, peer-mapped by all ranks
+// (CUDA IPC).  The rank's finishing CTA stores its 64-byte record (context made global) straight into
+// slot [seq & 1][rank] of EVERY rank's mailbox over NVLink, flags it with the exchange number
+// (release, system scope), waits until the world slots of its own mailbox carry that number
+// (acquire) and folds them with the single-GPU rule: smallest zeta, then lowest global context; tie
+// counts of the ranks that attain the minimum are added.  No NCCL launch, no host in the loop; the
+// double buffer is enough because a rank cannot post exchange s + 2 before every peer posted s + 1,
+// i.e. finished reading s.  A peer that never shows up ends the wait after ~2 s with status -2.
+constexpr int kMailSlot = 128;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ void peer_exchange_fold(crs_decision* dec, const crs_peer_exchange& px) {
+  __shared__ int s_timeout;
+  const int t = threadIdx.x;
+  if (t == 0) s_timeout = 0;
+  __syncthreads();  // the local decision is complete and visible to the CTA
+  const size_t half = (size_t)(px.seq & 1) * (size_t)px.world * kMailSlot;
+  if (t < px.world) {
+    unsigned char* slot = reinterpret_cast<unsigned char*>(px.mailboxes[t]) + half + (size_t)px.rank * kMailSlot;
+    crs_decision rec = *dec;
+    if (rec.context >= 0) rec.context += (int32_t)px.ctx_begin;
+    else rec.min_zeta = CUDART_INF;
+    const int4* src = reinterpret_cast<const int4*>(&rec);
+    int4* dst = reinterpret_cast<int4*>(slot);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = src[i];
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<int*>(slot + 64), px.seq);
+    // and wait for rank t's record in my own mailbox
+    const unsigned char* mine = reinterpret_cast<const unsigned char*>(px.mailboxes[px.rank]) + half + (size_t)t * kMailSlot;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(reinterpret_cast<const int*>(mine + 64)) != px.seq) {
+      __nanosleep(64);
+      if (global_ns() - t0 > 2000000000ull) { atomicExch(&s_timeout, 1); break; }
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(px.mailboxes[px.rank]) + half;
+    crs_decision out;
+    out.min_zeta = CUDART_INF;
+    out.tie_count = 0;
+    out.context = -1;
+    out.zeta_arm = out.best_arm = out.next_arm = -1;
+    out.psi_best = out.psi_rest = 0.0;
+    int bad = 0;
+    for (int r = 0; r < px.world; ++r) {
+      const int4* src = reinterpret_cast<const int4*>(base + (size_t)r * kMailSlot);
+      crs_decision q;
+      int4* qd = reinterpret_cast<int4*>(&q);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qd[i] = __ldcv(src + i);
+      if (q.reserved[0] != 0 && bad == 0) bad = q.reserved[0];
+      if (q.context < 0) continue;  // an empty shard
+      if (q.min_zeta < out.min_zeta || (q.min_zeta == out.min_zeta && out.context < 0)) {
+        const long long ties = q.tie_count;
+        out = q;
+        out.tie_count = ties;
+      } else if (q.min_zeta == out.min_zeta) {
+        const long long ties = out.tie_count + q.tie_count;
+        if (q.context < out.context) out = q;
+        out.tie_count = ties;
+      }
+    }
+    out.reserved[0] = s_timeout ? -2 : bad;
+    out.reserved[1] = out.reserved[2] = out.reserved[3] = 0;
+    *dec = out;
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void publish(const crs_decision* dec, crs_decision* mirror, int seq) {
   // thread 0 only: copy the finished decision to mapped host memory; the tag goes last
   mirror->min_zeta = dec->min_zeta;
@@ -368,6 +453,7 @@ __device__ void scan_tail(ScanPartial acc, ScanPartial* partials, unsigned int* 
     select_block<T>(sel.st, reinterpret_cast<const T*>(sel.ctx), var, ld, arm_offset, sel.p_mode,
                     (T)sel.kernel_scale, decision, sel_smem ? sel_smem : dyn_smem, kSelStageFused);
   }
+  if (sel.px.world > 1) peer_exchange_fold(decision, sel.px);  // set only when this launch finishes the decision
   if (sel.host_mirror && threadIdx.x == 0) publish(decision, sel.host_mirror, sel.seq);
 }
 
@@ -787,9 +873,24 @@ template <typename T>
 __global__ void __launch_bounds__(1024)
 ocba_select_kernel(crs_gp_state st, const T* __restrict__ ctx, const T* __restrict__ var,
                    int64_t ld, int arm_offset, int p_mode, T kernel_scale, crs_decision* decision,
-                   crs_decision* host_mirror, int seq, int stage_bytes) {
+                   crs_decision* host_mirror, int seq, int stage_bytes, crs_peer_exchange px) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   select_block<T>(st, ctx, var, ld, arm_offset, p_mode, kernel_scale, decision, dyn_smem, stage_bytes);
+  if (px.world > 1) peer_exchange_fold(decision, px);
+  if (host_mirror && threadIdx.x == 0) publish(decision, host_mirror, seq);
+}
+
+// An empty shard (a rank without contexts) still takes part in the exchange.
+__global__ void __launch_bounds__(64)
+peer_exchange_only_kernel(crs_decision* decision, crs_decision* host_mirror, int seq, crs_peer_exchange px) {
+  if (threadIdx.x == 0) {
+    decision->min_zeta = CUDART_INF;
+    decision->psi_best = decision->psi_rest = 0.0;
+    decision->tie_count = 0;
+    decision->context = decision->zeta_arm = decision->best_arm = decision->next_arm = -1;
+    decision->reserved[0] = decision->reserved[1] = decision->reserved[2] = decision->reserved[3] = 0;
+  }
+  if (px.world > 1) peer_exchange_fold(decision, px);
   if (host_mirror && threadIdx.x == 0) publish(decision, host_mirror, seq);
 }
 
@@ -861,8 +962,10 @@ int launch_ocba_scan_select(const void* mean, const void* var, int64_t n_c, int 
                             void* min_zeta, int32_t* min_arm, int32_t* tie_cnt,
                             crs_decision* decision, void* workspace, const crs_gp_state* st,
                             const void* ctx, int p_mode, double kernel_scale,
-                            crs_decision* host_mirror, int seq, cudaStream_t s) {
+                            crs_decision* host_mirror, int seq, const crs_peer_exchange* px, cudaStream_t s) {
   if (!mean || !var || n_c < 0 || n_c > INT_MAX || K < 1 || ld < K) return CRS_ERR_INVALID_ARG;
+  if (px && (px->world < 1 || px->rank < 0 || px->rank >= px->world || px->world > 64 || px->seq == 0 ||
+             (px->world > 1 && (!px->mailboxes || !st)))) return CRS_ERR_INVALID_ARG;
   if (decision && !workspace) return CRS_ERR_INVALID_ARG;
   if (ext_best_arm && (!ext_best_mean || !ext_best_var)) return CRS_ERR_INVALID_ARG;
   if (st && (!ctx || !decision || p_mode < 0 || p_mode > 2 || st->num_arms != K)) return CRS_ERR_INVALID_ARG;
@@ -881,6 +984,7 @@ int launch_ocba_scan_select(const void* mean, const void* var, int64_t n_c, int 
     sel.do_select = 1;
     sel.host_mirror = host_mirror;
     sel.seq = seq;
+    if (px && px->world > 1) sel.px = *px;
   } else if (!st) {
     sel.host_mirror = host_mirror;
     sel.seq = seq;
@@ -895,7 +999,17 @@ int launch_ocba_scan_select(const void* mean, const void* var, int64_t n_c, int 
   else
     return CRS_ERR_INVALID_ARG;
   if (rc != CRS_OK || !st || fuse) return rc;
-  return launch_ocba_select(st, ctx, mean, var, ld, arm_offset, p_mode, kernel_scale, decision, host_mirror, seq, s);
+  return launch_ocba_select(st, ctx, mean, var, ld, arm_offset, p_mode, kernel_scale, decision, host_mirror, seq, px, s);
+}
+
+int launch_peer_exchange_only(crs_decision* decision, crs_decision* host_mirror, int seq, const crs_peer_exchange* px,
+                              cudaStream_t s) {
+  if (!decision || !px || px->world < 1 || px->world > 64 || px->rank < 0 || px->rank >= px->world || px->seq == 0 ||
+      (px->world > 1 && !px->mailboxes))
+    return CRS_ERR_INVALID_ARG;
+  peer_exchange_only_kernel<<<1, 64, 0, s>>>(decision, host_mirror, seq, *px);
+  CRS_CUDA_TRY(cudaGetLastError(), "peer_exchange launch");
+  return CRS_OK;
 }
 
 int launch_ocba_scan(const void* mean, const void* var, int64_t n_c, int K, int64_t ld, int dtype,
@@ -904,7 +1018,7 @@ int launch_ocba_scan(const void* mean, const void* var, int64_t n_c, int K, int6
                      int32_t* tie_cnt, crs_decision* decision, void* workspace, cudaStream_t s) {
   return launch_ocba_scan_select(mean, var, n_c, K, ld, dtype, arm_offset, ext_best_arm, ext_best_mean,
                                  ext_best_var, best_arm, min_zeta, min_arm, tie_cnt, decision, workspace,
-                                 nullptr, nullptr, 0, 0.0, nullptr, 0, s);
+                                 nullptr, nullptr, 0, 0.0, nullptr, 0, nullptr, s);
 }
 
 int launch_ocba_resolve_tie(const void* mean, const void* var, int64_t n_c, int K, int64_t ld,
@@ -924,9 +1038,13 @@ int launch_ocba_resolve_tie(const void* mean, const void* var, int64_t n_c, int 
 
 int launch_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
                        int64_t ld, int arm_offset, int p_mode, double kernel_scale,
-                       crs_decision* decision, crs_decision* host_mirror, int seq, cudaStream_t s) {
+                       crs_decision* decision, crs_decision* host_mirror, int seq, const crs_peer_exchange* px,
+                       cudaStream_t s) {
   (void)mean;
   if (!st || !ctx || !var || !decision || p_mode < 0 || p_mode > 2) return CRS_ERR_INVALID_ARG;
+  crs_peer_exchange pxv;
+  memset(&pxv, 0, sizeof(pxv));
+  if (px && px->world > 1) pxv = *px;
   const int threads = st->num_arms >= 32 ? 1024 : (st->num_arms >= 8 ? 256 : 64);
   const size_t blk = (size_t)st->n_cap * st->dim * (st->dtype == CRS_F64 ? 8 : 4);
   size_t stage = blk * (size_t)(st->num_arms < 256 ? st->num_arms : 256);
@@ -935,11 +1053,11 @@ int launch_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean
   if (st->dtype == CRS_F64) {
     auto kern = ocba_select_kernel<double>;
     if (stage > 40 * 1024) CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage), "select attr");
-    kern<<<1, threads, stage, s>>>(*st, (const double*)ctx, (const double*)var, ld, arm_offset, p_mode, kernel_scale, decision, host_mirror, seq, (int)stage);
+    kern<<<1, threads, stage, s>>>(*st, (const double*)ctx, (const double*)var, ld, arm_offset, p_mode, kernel_scale, decision, host_mirror, seq, (int)stage, pxv);
   } else if (st->dtype == CRS_F32) {
     auto kern = ocba_select_kernel<float>;
     if (stage > 40 * 1024) CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage), "select attr");
-    kern<<<1, threads, stage, s>>>(*st, (const float*)ctx, (const float*)var, ld, arm_offset, p_mode, (float)kernel_scale, decision, host_mirror, seq, (int)stage);
+    kern<<<1, threads, stage, s>>>(*st, (const float*)ctx, (const float*)var, ld, arm_offset, p_mode, (float)kernel_scale, decision, host_mirror, seq, (int)stage, pxv);
   } else {
     return CRS_ERR_INVALID_ARG;
   }

@@ -113,6 +113,22 @@ typedef struct crs_decision {
   int32_t reserved[4]; /* [0] = (first arm whose Cholesky failed)+1 or 0; [1] = completion tag */
 } crs_decision;
 
+/*
+ * Multi-GPU combine of a context-sharded decision without NCCL or the host (one process per GPU).
+ * Every rank owns a MAILBOX of crs_mailbox_bytes(world) bytes of device memory that all ranks have
+ * mapped (crs_ipc_export / crs_ipc_open).  `mailboxes` is a DEVICE array of the world base pointers as
+ * seen from this rank.  The kernel that finishes a rank's local decision stores its 64-byte record
+ * (context + ctx_begin) into every rank's mailbox, waits for the world records of exchange `seq` in its
+ * own and folds them (smallest zeta, then lowest global context; tie counts added).  `seq` must be the
+ * same non-zero number on every rank and change by one per exchange.
+ */
+typedef struct crs_peer_exchange {
+  void* const* mailboxes;  /* device array [world] */
+  int32_t rank, world;
+  int32_t seq, reserved;
+  int64_t ctx_begin;       /* global index of this rank's first context */
+} crs_peer_exchange;
+
 /* Result of crs_levi_scan; device memory, 24 bytes. */
 typedef struct crs_levi_decision {
   double value;      /* max over contexts of (weight *) max over arms of EI  (levi.py:220-224) */
@@ -239,6 +255,30 @@ CRS_API int crs_pcs_counts(const void* mean, const void* var, int64_t n_c, int32
 CRS_API int crs_pcs_counts_tree(const void* mean, const void* var, int64_t n_c, int32_t K, int64_t ld,
                                 int32_t dtype, int64_t num_samples, uint64_t seed, uint32_t offset,
                                 int64_t ctx_offset, uint32_t* counts, uint64_t* stats, void* stream);
+
+/*
+ * crs_ocba_scan_select for ONE decision sharded over `px->world` GPUs by contexts — the multi-GPU form
+ * of gao_modellist's scan (contextual_rs/contextual_rs_strategies.py:137-202): the local scan + step
+ * 2(b) run as in crs_ocba_scan_select, then the ranks' records are combined on the device through the
+ * peer mailboxes (crs_peer_exchange) and the GLOBAL decision (global context index) lands in `decision`
+ * and, if decision_host is mapped pinned memory, in *decision_host with reserved[1] = px->seq written
+ * last (poll it with crs_wait_decision).  n_c = 0 (a rank without contexts) takes part with an empty
+ * record.  reserved[0] = -2 reports a peer that did not post within 2 s.
+ */
+CRS_API int crs_ocba_scan_select_sharded(const crs_gp_state* st, const void* ctx, const void* mean, const void* var,
+                                         int64_t n_c, int64_t ld, int32_t p_mode, double kernel_scale,
+                                         int32_t* best_arm, void* min_zeta, int32_t* min_arm, int32_t* tie_cnt,
+                                         crs_decision* decision, void* workspace, const crs_peer_exchange* px,
+                                         crs_decision* decision_host, void* stream);
+/* Spin (GIL-free for ctypes callers) until decision_host->reserved[1] == seq; CRS_ERR_CUDA after timeout_ms. */
+CRS_API int crs_wait_decision(const crs_decision* decision_host, int32_t seq, int32_t timeout_ms);
+/* Mailbox plumbing: plain cudaMalloc'd (zeroed) memory + CUDA IPC handles (64 bytes) to map it in peers. */
+CRS_API int64_t crs_mailbox_bytes(int32_t world);
+CRS_API int crs_device_alloc(int64_t bytes, void** dev_ptr);
+CRS_API int crs_device_free(void* dev_ptr);
+CRS_API int crs_ipc_export(void* dev_ptr, unsigned char handle[64]);
+CRS_API int crs_ipc_open(const unsigned char handle[64], void** dev_ptr);
+CRS_API int crs_ipc_close(void* dev_ptr);
 
 /*
  * Same estimate again — counts[c] = number of the S posterior draws in which the predicted-best arm of

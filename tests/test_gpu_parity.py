@@ -491,7 +491,7 @@ def test_pcs_tree_parity(crs, dtype, S):
     assert np.array_equal(half, cnt[24:])  # sharding invariance: context offsets only re-key the stream
     other = pcs_counts(model, mean, var, S, seed=78, offset=3, sampler="tree").cpu().numpy()
     assert not np.array_equal(other, cnt)
-    again = pcs_counts(model, mean, var, S, seed=77, offset=3).cpu().numpy()  # "auto" = tree; deterministic
+    again = pcs_counts(model, mean, var, S, seed=77, offset=3, sampler="tree").cpu().numpy()  # deterministic
     assert np.array_equal(again, cnt)
 
 

@@ -394,3 +394,34 @@ def test_oracle_variance_floor_order():
     mean_b, var_b = gp_oracle.posterior_grid_batched(desc, ctx)
     torch.testing.assert_close(var_b, post.variance, rtol=1e-9, atol=0)
     assert float(var_b[0, 0]) == 1e-10
+
+
+def test_quoted_config_fixture_is_what_the_oracle_computes():
+    """tests/golden/quoted_configs_expected.json is generated by the oracle
+    (tests/golden/make_quoted_configs_golden.py); config 3 is cheap enough to regenerate here and must
+    reproduce the committed decision, margins and row digests (configs 4 / 5 take a minute: CRS_SLOW=1)."""
+    import os
+    from conftest import load_golden
+    from contextual_rs_b200.synthetic import make_config
+    fix = load_golden("quoted_configs_expected.json")
+    names = ["c3"] + (["c5", "c4"] if os.environ.get("CRS_SLOW") == "1" else [])
+    for name in names:
+        exp = fix[name]
+        desc, ctx = make_config(name)
+        mean, var = gp_oracle.posterior_grid_batched(desc, ctx, chunk=1024)
+        zeta, order = ocba_oracle.zeta_table(mean, var)
+        K = mean.shape[1]
+        flat = zeta.reshape(-1)
+        two = torch.topk(flat, 2, largest=False)
+        assert int(two.indices[0]) // (K - 1) == exp["min_context"]
+        # zeta minima are squared gaps of ~1e-5 of the mean scale: 1e-13 rounding in the means is 1e-8 of them
+        assert abs(float(two.values[0]) - exp["min_zeta"]) < 1e-6 * exp["min_zeta"]
+        assert abs(float(two.values[1]) - exp["second_zeta"]) < 1e-6 * exp["second_zeta"]
+        rows = torch.tensor(exp["rows"])
+        assert order[rows, 0].tolist() == exp["row_best_arm"]
+        want = torch.tensor([float.fromhex(h) for h in exp["row_min_zeta_hex"]], dtype=torch.float64)
+        torch.testing.assert_close(zeta[rows].min(dim=1).values, want, rtol=1e-6, atol=0)
+        model = type("M", (), {"models": [None] * K, "train_inputs": [(x,) for x in desc["train_X"]],
+                               "posterior": lambda self, X: type("P", (), {"mean": mean, "variance": var})()})()
+        arm, x = ocba_oracle.gao_modellist_ref(model, ctx)
+        assert int(arm) == exp["default"]["next_arm"] and torch.equal(x, ctx[exp["default"]["next_context"]])
