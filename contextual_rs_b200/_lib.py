@@ -85,6 +85,8 @@ _SIGNATURES = {
     "crs_ocba_scan_select_sharded": (C.c_int, [C.POINTER(GPState), vp, vp, vp, i64, i64, i32, f64, vp, vp, vp, vp, vp, vp,
                                                C.POINTER(PeerExchange), vp, vp]),
     "crs_wait_decision": (C.c_int, [vp, i32, i32]),
+    "crs_peer_sum_u64": (C.c_int, [vp, i32, vp, vp, C.POINTER(PeerExchange), vp]),
+    "crs_wait_u64": (C.c_int, [vp, u64, i32]),
     "crs_mailbox_bytes": (i64, [i32]),
     "crs_device_alloc": (C.c_int, [i64, C.POINTER(vp)]),
     "crs_device_free": (C.c_int, [vp]),

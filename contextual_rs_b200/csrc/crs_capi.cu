@@ -123,6 +123,41 @@ CRS_API int crs_wait_decision(const crs_decision* decision_host, int32_t seq, in
   return CRS_OK;
 }
 
+CRS_API int crs_peer_sum_u64(const uint64_t* values, int32_t n, uint64_t* out, uint64_t* out_host,
+                             const crs_peer_exchange* px, void* stream) {
+  uint64_t* mirror = nullptr;
+  if (out_host) {
+    void* dptr = nullptr;
+    if (cudaHostGetDevicePointer(&dptr, out_host, 0) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return CRS_ERR_INVALID_ARG;
+    }
+    mirror = reinterpret_cast<uint64_t*>(dptr);
+  }
+  return launch_peer_sum(values, n, out, mirror, px, (cudaStream_t)stream);
+}
+
+CRS_API int crs_wait_u64(const uint64_t* tag_host, uint64_t seq, int32_t timeout_ms) {
+  if (!tag_host) return CRS_ERR_INVALID_ARG;
+  const volatile uint64_t* tag = tag_host;
+  struct timespec t0;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  unsigned long long spins = 0;
+  while (*tag != seq) {
+    __builtin_ia32_pause();
+    if ((++spins & 0xfff) == 0) {
+      struct timespec t1;
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if ((t1.tv_sec - t0.tv_sec) * 1e3 + 1e-6 * (t1.tv_nsec - t0.tv_nsec) > timeout_ms) {
+        set_cuda_error(cudaErrorTimeout, "crs_wait_u64");
+        return CRS_ERR_CUDA;
+      }
+    }
+  }
+  __sync_synchronize();
+  return CRS_OK;
+}
+
 CRS_API int64_t crs_mailbox_bytes(int32_t world) { return world < 1 ? 0 : (int64_t)2 * world * 128; }
 
 CRS_API int crs_device_alloc(int64_t bytes, void** dev_ptr) {

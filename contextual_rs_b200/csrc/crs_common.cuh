@@ -167,6 +167,8 @@ int launch_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean
                        int64_t ld, int arm_offset, int p_mode, double kernel_scale,
                        crs_decision* decision, crs_decision* host_mirror, int seq, const crs_peer_exchange* px,
                        cudaStream_t s);
+int launch_peer_sum(const uint64_t* values, int n, uint64_t* out, uint64_t* host_mirror, const crs_peer_exchange* px,
+                    cudaStream_t s);
 int launch_peer_exchange_only(crs_decision* decision, crs_decision* host_mirror, int seq, const crs_peer_exchange* px,
                               cudaStream_t s);
 int launch_ocba_scan_select(const void* mean, const void* var, int64_t n_c, int K, int64_t ld,

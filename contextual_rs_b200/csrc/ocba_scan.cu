@@ -16,6 +16,7 @@
 #include <climits>
 #include <cstring>
 #include "crs_common.cuh"
+#include "peer_mailbox.cuh"
 
 namespace crs {
 namespace {
@@ -282,57 +283,23 @@ __device__ void select_block(const crs_gp_state& st, const T* __restrict__ ctx,
 }
 
 // ---- multi-GPU combine of a context-sharded decision, device side ------------------------------
-// Every rank owns a mailbox of 2 x world slots of 128 bytes in ITS memory, peer-mapped by all ranks
-// (CUDA IPC).  The rank's finishing CTA stores its 64-byte record (context made global) straight into
-// slot [seq & 1][rank] of EVERY rank's mailbox over NVLink, flags it with the exchange number
-// (release, system scope), waits until the world slots of its own mailbox carry that number
-// (acquire) and folds them with the single-GPU rule: smallest zeta, then lowest global context; tie
-// counts of the ranks that attain the minimum are added.  No NCCL launch, no host in the loop; the
-// double buffer is enough because a rank cannot post exchange s + 2 before every peer posted s + 1,
-// i.e. finished reading s.  A peer that never shows up ends the wait after ~2 s with status -2.
-constexpr int kMailSlot = 128;
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
+// The rank's finishing CTA posts its 64-byte record (context made global) to every peer's mailbox
+// (peer_mailbox.cuh), waits for the world records of this exchange in its own and folds them with the
+// single-GPU rule: smallest zeta, then lowest global context; tie counts of the ranks that attain the
+// minimum are added.  A peer that never shows up ends the wait after ~2 s with status -2.
 __device__ void peer_exchange_fold(crs_decision* dec, const crs_peer_exchange& px) {
   __shared__ int s_timeout;
   const int t = threadIdx.x;
   if (t == 0) s_timeout = 0;
   __syncthreads();  // the local decision is complete and visible to the CTA
-  const size_t half = (size_t)(px.seq & 1) * (size_t)px.world * kMailSlot;
   if (t < px.world) {
-    unsigned char* slot = reinterpret_cast<unsigned char*>(px.mailboxes[t]) + half + (size_t)px.rank * kMailSlot;
-    crs_decision rec = *dec;
+    alignas(16) crs_decision rec = *dec;
     if (rec.context >= 0) rec.context += (int32_t)px.ctx_begin;
     else rec.min_zeta = CUDART_INF;
-    const int4* src = reinterpret_cast<const int4*>(&rec);
-    int4* dst = reinterpret_cast<int4*>(slot);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = src[i];
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<int*>(slot + 64), px.seq);
-    // and wait for rank t's record in my own mailbox
-    const unsigned char* mine = reinterpret_cast<const unsigned char*>(px.mailboxes[px.rank]) + half + (size_t)t * kMailSlot;
-    const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(reinterpret_cast<const int*>(mine + 64)) != px.seq) {
-      __nanosleep(64);
-      if (global_ns() - t0 > 2000000000ull) { atomicExch(&s_timeout, 1); break; }
-    }
+    if (!mailbox::post_and_wait(px, t, reinterpret_cast<const int4*>(&rec))) atomicExch(&s_timeout, 1);
   }
   __syncthreads();
   if (t == 0) {
-    const unsigned char* base = reinterpret_cast<const unsigned char*>(px.mailboxes[px.rank]) + half;
     crs_decision out;
     out.min_zeta = CUDART_INF;
     out.tie_count = 0;
@@ -341,11 +308,8 @@ __device__ void peer_exchange_fold(crs_decision* dec, const crs_peer_exchange& p
     out.psi_best = out.psi_rest = 0.0;
     int bad = 0;
     for (int r = 0; r < px.world; ++r) {
-      const int4* src = reinterpret_cast<const int4*>(base + (size_t)r * kMailSlot);
-      crs_decision q;
-      int4* qd = reinterpret_cast<int4*>(&q);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) qd[i] = __ldcv(src + i);
+      alignas(16) crs_decision q;
+      mailbox::read_slot(px, r, reinterpret_cast<int4*>(&q));
       if (q.reserved[0] != 0 && bad == 0) bad = q.reserved[0];
       if (q.context < 0) continue;  // an empty shard
       if (q.min_zeta < out.min_zeta || (q.min_zeta == out.min_zeta && out.context < 0)) {
@@ -964,8 +928,7 @@ int launch_ocba_scan_select(const void* mean, const void* var, int64_t n_c, int 
                             const void* ctx, int p_mode, double kernel_scale,
                             crs_decision* host_mirror, int seq, const crs_peer_exchange* px, cudaStream_t s) {
   if (!mean || !var || n_c < 0 || n_c > INT_MAX || K < 1 || ld < K) return CRS_ERR_INVALID_ARG;
-  if (px && (px->world < 1 || px->rank < 0 || px->rank >= px->world || px->world > 64 || px->seq == 0 ||
-             (px->world > 1 && (!px->mailboxes || !st)))) return CRS_ERR_INVALID_ARG;
+  if (px && (!mailbox::valid(px) || (px->world > 1 && !st))) return CRS_ERR_INVALID_ARG;
   if (decision && !workspace) return CRS_ERR_INVALID_ARG;
   if (ext_best_arm && (!ext_best_mean || !ext_best_var)) return CRS_ERR_INVALID_ARG;
   if (st && (!ctx || !decision || p_mode < 0 || p_mode > 2 || st->num_arms != K)) return CRS_ERR_INVALID_ARG;
@@ -1004,9 +967,7 @@ int launch_ocba_scan_select(const void* mean, const void* var, int64_t n_c, int 
 
 int launch_peer_exchange_only(crs_decision* decision, crs_decision* host_mirror, int seq, const crs_peer_exchange* px,
                               cudaStream_t s) {
-  if (!decision || !px || px->world < 1 || px->world > 64 || px->rank < 0 || px->rank >= px->world || px->seq == 0 ||
-      (px->world > 1 && !px->mailboxes))
-    return CRS_ERR_INVALID_ARG;
+  if (!decision || !mailbox::valid(px)) return CRS_ERR_INVALID_ARG;
   peer_exchange_only_kernel<<<1, 64, 0, s>>>(decision, host_mirror, seq, *px);
   CRS_CUDA_TRY(cudaGetLastError(), "peer_exchange launch");
   return CRS_OK;

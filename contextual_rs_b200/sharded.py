@@ -111,14 +111,92 @@ def all_gather_rows(row: Tensor, group=None) -> Tensor:
     return out
 
 
+class PeerMailbox:
+    """Peer-mapped mailboxes of the ranks of ``group`` (one process per GPU of one NVLink domain):
+    the device-side exchange ``crs_ocba_scan_select_sharded`` / ``crs_peer_sum_u64`` use instead of an
+    NCCL launch + host parse (include/crs_b200.h ``crs_peer_exchange``).  Set-up (once): every rank
+    allocates its mailbox, the 64-byte CUDA IPC handles are all-gathered through ``group`` and every
+    peer's mailbox is opened.  Every rank must issue the same sequence of exchanges."""
+
+    def __init__(self, device, group=None):
+        self.lib = _lib.get()
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.seq = 0
+        self._own = C.c_void_p()
+        self._opened: List[C.c_void_p] = []
+        self._ptrs = None
+        if self.world == 1:
+            return
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crs_device_alloc(int(self.lib.crs_mailbox_bytes(self.world)), C.byref(self._own)),
+                       "crs_device_alloc")
+            handle = (C.c_ubyte * 64)()
+            _lib.check(self.lib.crs_ipc_export(self._own, handle), "crs_ipc_export")
+            mine = torch.frombuffer(bytearray(bytes(handle)), dtype=torch.uint8).to(self.device)
+            every = torch.empty(self.world, 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            every = every.cpu()
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(self._own.value)
+                    continue
+                peer = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(every[r].numpy().tobytes())
+                _lib.check(self.lib.crs_ipc_open(buf, C.byref(peer)), "crs_ipc_open")
+                self._opened.append(peer)
+                ptrs.append(peer.value)
+            self._ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+            dist.barrier(group=group)  # nobody posts before everybody has mapped everybody
+
+    def next_exchange(self, ctx_begin: int = 0) -> "_lib.PeerExchange":
+        """The descriptor of the next exchange; the sequence number advances by one on every rank."""
+        self.seq = self.seq % 0x3fffffff + 1
+        return _lib.PeerExchange(self._ptrs.data_ptr() if self._ptrs is not None else None, self.rank, self.world,
+                                 self.seq, 0, int(ctx_begin))
+
+    def close(self) -> None:
+        if self._own.value is None and not self._opened:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)  # no peer is still writing into a mailbox about to go away
+            for p in self._opened:
+                self.lib.crs_ipc_close(p)
+            self._opened = []
+            if self._own.value is not None:
+                self.lib.crs_device_free(self._own)
+                self._own = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            for p in self._opened:
+                self.lib.crs_ipc_close(p)
+            if self._own.value is not None:
+                self.lib.crs_device_free(self._own)
+        except Exception:
+            pass
+
+
 class ContextShardedDecider:
     """GP-C-OCBA decision (+ PCS) with the context set sharded over the ranks of ``group``.
 
     Every rank must construct it with the same model description and the same full
     ``context_set``; rank r keeps rows ``shard_bounds(n_c, world, r)``.
+
+    ``exchange="mailbox"`` (default on GPUs): the ranks' local minimisers are combined ON THE DEVICE by
+    the kernel that finishes the local decision (``crs_ocba_scan_select_sharded``: 64-byte stores into
+    the peers' mailboxes over NVLink, fold in the last CTA, result in mapped pinned host memory) and the
+    PCS totals by ``crs_peer_sum_u64`` — no NCCL launch, no stream synchronise, no Python parsing.
+    ``exchange="nccl"``: one 64-byte-per-rank ``all_gather`` + host-side fold (round-1 path, kept for
+    comparison and for groups without peer access).
     """
 
-    def __init__(self, model, context_set: Tensor, group=None):
+    def __init__(self, model, context_set: Tensor, group=None, exchange: str = "mailbox"):
         self.model = model
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -135,13 +213,57 @@ class ContextShardedDecider:
         # calls of any batch size passing through the same model
         self.n_loc = self.end - self.begin
         self.ws = model.private_workspace(max(self.n_loc, 1))
+        if exchange not in ("mailbox", "nccl"):
+            raise ValueError(f"unknown exchange {exchange!r}")
+        self.exchange = exchange if self.world > 1 else "nccl"
+        self.mailbox = PeerMailbox(model.device, group) if self.exchange == "mailbox" else None
+        self._sum_host = torch.zeros(10, dtype=torch.int64).pin_memory()
+        self._sum_dev = torch.zeros(8, dtype=torch.int64, device=model.device)
+        self._cdf_ws = None
+
+    def _launch_local(self, p_mode: int, kernel_scale: float, prepare_arms, grid: bool, px) -> None:
+        """prepare -> local grid -> scan / select / peer combine, all on the current stream."""
+        m, lib, ws, n_loc = self.model, _lib.get(), self.ws, self.n_loc
+        K = m.num_arms
+        stream = _lib.stream_ptr(m.device)
+        if prepare_arms is not None and prepare_arms[1] > prepare_arms[0]:
+            m.prepare(prepare_arms[0], prepare_arms[1], relearn=False)
+        st = C.byref(m.state)
+        if n_loc > 0 and grid:
+            _lib.check(lib.crs_posterior_grid(st, self.local_ctx.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
+                                              ws["var"].data_ptr(), K, 0, stream), "crs_posterior_grid")
+        _lib.check(lib.crs_ocba_scan_select_sharded(
+            st, self.local_ctx.data_ptr(), ws["mean"].data_ptr(), ws["var"].data_ptr(), n_loc, K, p_mode,
+            float(kernel_scale), ws["best_arm"].data_ptr(), ws["min_zeta"].data_ptr(), ws["min_arm"].data_ptr(),
+            ws["tie_cnt"].data_ptr(), ws["decision"].data_ptr(), ws["scan_ws"].data_ptr(), C.byref(px),
+            ws["decision_host"].data_ptr(), stream), "crs_ocba_scan_select_sharded")
+
+    def decide_struct(self, p_mode: int = _lib.CRS_P_COUNT, kernel_scale: float = 2.0,
+                      prepare_arms: Optional[Tuple[int, int]] = None, grid: bool = True) -> "_lib.Decision":
+        """Mailbox exchange: launch, then poll the mapped host copy of the GLOBAL decision (global
+        context index).  ``grid=False`` re-uses the cached local grid (sequential loop)."""
+        m = self.model
+        px = self.mailbox.next_exchange(self.begin)
+        with torch.cuda.device(m.device):
+            self._launch_local(p_mode, kernel_scale, prepare_arms, grid, px)
+            _lib.check(_lib.get().crs_wait_decision(self.ws["decision_host"].data_ptr(), px.seq, 20000), "crs_wait_decision")
+        dec = self.ws["decision_view"]
+        if dec.reserved[0] == -2:
+            raise RuntimeError("peer mailbox exchange timed out: a rank did not post its decision record")
+        if dec.reserved[0] > 0:
+            raise RuntimeError(f"arm {dec.reserved[0] - 1}: kernel matrix not positive definite")
+        return dec
 
     def decide(self, p_mode: int = _lib.CRS_P_COUNT, kernel_scale: float = 2.0,
-               prepare_arms: Optional[Tuple[int, int]] = None) -> Tensor:
+               prepare_arms: Optional[Tuple[int, int]] = None, grid: bool = True) -> Tensor:
         """Returns the combined record (``REC_*`` columns, global context index) on the host."""
         from .contextual_rs_strategies import _scan_select
         m, lib = self.model, _lib.get()
         n_loc = self.end - self.begin
+        if self.exchange == "mailbox":
+            d = self.decide_struct(p_mode, kernel_scale, prepare_arms, grid)
+            return decision_record(d.min_zeta, d.tie_count, d.context, d.zeta_arm, d.best_arm, d.next_arm,
+                                   d.psi_best, d.psi_rest)
         if n_loc > 0:
             ws = self.ws
             K = m.num_arms
@@ -150,8 +272,9 @@ class ContextShardedDecider:
                 if prepare_arms is not None and prepare_arms[1] > prepare_arms[0]:
                     m.prepare(prepare_arms[0], prepare_arms[1], relearn=False)
                 st = C.byref(m.state)
-                _lib.check(lib.crs_posterior_grid(st, self.local_ctx.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
-                                                  ws["var"].data_ptr(), K, 0, stream), "crs_posterior_grid")
+                if grid:
+                    _lib.check(lib.crs_posterior_grid(st, self.local_ctx.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
+                                                      ws["var"].data_ptr(), K, 0, stream), "crs_posterior_grid")
                 _scan_select(lib, m, ws, n_loc, p_mode, kernel_scale, stream, ctx_ptr=self.local_ctx.data_ptr())
             local = ws["decision"]
         else:
@@ -170,15 +293,41 @@ class ContextShardedDecider:
         from .generalized_pcs import pcs_counts
         n_loc = self.end - self.begin
         ws = self.ws
+        if self._cdf_ws is None:
+            nbytes = int(_lib.get().crs_pcs_cdf_workspace_bytes(max(n_loc, 1)))
+            self._cdf_ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.model.device)
         return pcs_counts(self.model, ws["mean"][:n_loc], ws["var"][:n_loc], num_samples, seed, offset,
-                          ctx_offset=self.begin, counts=ws["counts"][:n_loc], stats=ws["stats"])
+                          ctx_offset=self.begin, counts=ws["counts"][:n_loc], stats=ws["stats"], sampler="cdf",
+                          workspace=self._cdf_ws)
 
     def pcs_mean(self, num_samples: int, seed: int, offset: int = 0) -> Tensor:
-        """rho = mean over contexts: one scalar all-reduce of the summed counts."""
+        """rho = mean over contexts: the kernels accumulate the rank's total in ``stats[4]``; the ranks'
+        totals are added by ``crs_peer_sum_u64`` (mailbox) or one scalar all-reduce (nccl)."""
+        if self.exchange == "mailbox":
+            return torch.tensor([self.pcs_total(num_samples, seed, offset) / (float(num_samples) * self.n_c)],
+                                dtype=torch.float64)
         total = self.pcs_counts(num_samples, seed, offset).sum(dtype=torch.int64).to(torch.float64).reshape(1)
         if self.world > 1:
             dist.all_reduce(total, group=self.group)
         return total / (float(num_samples) * self.n_c)
+
+    def pcs_total(self, num_samples: int, seed: int, offset: int = 0) -> int:
+        """Sum over ALL contexts of all ranks of the success counts (host int), mailbox exchange."""
+        lib, m = _lib.get(), self.model
+        stats = self.ws["stats"]
+        if self.n_loc:
+            self.pcs_counts(num_samples, seed, offset)  # cdf / tree streams leave the rank's total in stats[4]
+        else:
+            stats.zero_()
+        px = self.mailbox.next_exchange(self.begin)
+        with torch.cuda.device(m.device):
+            _lib.check(lib.crs_peer_sum_u64(stats.data_ptr() + 4 * 8, 1, self._sum_dev.data_ptr(),
+                                            self._sum_host.data_ptr(), C.byref(px), _lib.stream_ptr(m.device)),
+                       "crs_peer_sum_u64")
+            _lib.check(lib.crs_wait_u64(self._sum_host.data_ptr() + 8 * 8, px.seq, 20000), "crs_wait_u64")
+        if int(self._sum_host[9]) != 0:
+            raise RuntimeError("peer mailbox exchange timed out: a rank did not post its PCS total")
+        return int(self._sum_host[0])
 
 
 def sub_description(desc: dict, a0: int, a1: int) -> dict:
@@ -321,12 +470,12 @@ class ShardedSequentialRS:
 
     def __init__(self, model, context_set: Tensor, infer_p: bool = False, use_kde: bool = False,
                  kernel_scale: float = 1.0, num_pcs_samples: int = 64, pcs_seed: int = 0, rho=None,
-                 group=None):
+                 group=None, exchange: str = "mailbox"):
         from .contextual_rs_strategies import _p_mode
         self.model = model
         self.group = group
         self.context_host = context_set.detach().cpu()
-        self.dec = ContextShardedDecider(model, context_set, group=group)
+        self.dec = ContextShardedDecider(model, context_set, group=group, exchange=exchange)
         self.world, self.rank, self.n_c = self.dec.world, self.dec.rank, self.dec.n_c
         self.n_loc = self.dec.end - self.dec.begin
         self.p_mode = _p_mode(infer_p, use_kde)
@@ -344,6 +493,11 @@ class ShardedSequentialRS:
         """Scan + step 2(b) on the cached local grid, then the 64-byte all-gather."""
         from .contextual_rs_strategies import _scan_select
         m, d = self.model, self.dec
+        if d.exchange == "mailbox":  # device-side combine, result polled from mapped host memory
+            dec = d.decide_struct(self.p_mode, self.kernel_scale, None, grid=False)
+            c = int(dec.context)
+            return {"next_arm": int(dec.next_arm), "context_index": c, "next_context": self.context_host[c],
+                    "min_zeta": float(dec.min_zeta)}
         if self.n_loc:
             ws = d.ws
             with torch.cuda.device(m.device):
@@ -364,6 +518,9 @@ class ShardedSequentialRS:
                 "min_zeta": float(rec[REC_MIN_ZETA])}
 
     def pcs(self) -> Tensor:
+        if self.rho is None and self.dec.exchange == "mailbox":  # mean over contexts: one peer sum on the device
+            total = self.dec.pcs_total(self.num_pcs_samples, self.pcs_seed, offset=self.iteration)
+            return torch.tensor(total / (float(self.num_pcs_samples) * self.n_c), dtype=torch.float64)
         counts = self.dec.pcs_counts(self.num_pcs_samples, self.pcs_seed, offset=self.iteration)
         if self.rho is None:  # mean over contexts: one scalar all-reduce
             total = counts.sum(dtype=torch.int64).to(torch.float64).reshape(1)

@@ -272,6 +272,17 @@ CRS_API int crs_ocba_scan_select_sharded(const crs_gp_state* st, const void* ctx
                                          crs_decision* decision_host, void* stream);
 /* Spin (GIL-free for ctypes callers) until decision_host->reserved[1] == seq; CRS_ERR_CUDA after timeout_ms. */
 CRS_API int crs_wait_decision(const crs_decision* decision_host, int32_t seq, int32_t timeout_ms);
+/*
+ * Sum n <= 8 counters over the ranks of a mailbox group (the "one allreduce" of the PCS success counts of
+ * a context-sharded estimate before rho, contextual_rs/generalized_pcs.py:470-479) in
+ * one single-CTA launch: `values` (device) -> `out` (device, may be NULL) and, if out_host is mapped
+ * pinned memory of 10 x uint64, out_host[0..7] = sums, [9] = 1 on a peer time-out, [8] = px->seq written
+ * LAST (poll with crs_wait_u64).  world = 1 copies.
+ */
+CRS_API int crs_peer_sum_u64(const uint64_t* values, int32_t n, uint64_t* out, uint64_t* out_host,
+                             const crs_peer_exchange* px, void* stream);
+/* Spin until *tag_host == seq (mapped pinned memory written by a kernel); CRS_ERR_CUDA after timeout_ms. */
+CRS_API int crs_wait_u64(const uint64_t* tag_host, uint64_t seq, int32_t timeout_ms);
 /* Mailbox plumbing: plain cudaMalloc'd (zeroed) memory + CUDA IPC handles (64 bytes) to map it in peers. */
 CRS_API int64_t crs_mailbox_bytes(int32_t world);
 CRS_API int crs_device_alloc(int64_t bytes, void** dev_ptr);

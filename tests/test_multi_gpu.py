@@ -29,10 +29,26 @@ def test_sharded_deciders_equal_single_gpu():
     single = pcs_counts(model, ws["mean"], ws["var"], 2048, seed=7).sum().item() / (2048 * 1000)
     c_star = int((ctx == x).all(dim=-1).nonzero()[0])
 
-    cdec = sh.ContextShardedDecider(model, ctx)
-    rec = cdec.decide(p_mode=1, kernel_scale=1.0)
-    assert (int(rec[sh.REC_NEXT_ARM]), int(rec[sh.REC_CONTEXT])) == (int(arm), c_star)
-    assert abs(float(cdec.pcs_mean(2048, seed=7)) - single) < 1e-12
+    dview = ws["decision_view"]
+    want = (dview.min_zeta, dview.tie_count, dview.context, dview.zeta_arm, dview.best_arm, dview.next_arm,
+            dview.psi_best, dview.psi_rest)
+    for exchange in ("mailbox", "nccl"):
+        cdec = sh.ContextShardedDecider(model, ctx, exchange=exchange)
+        for rep in range(3 if exchange == "nccl" else 300):  # many exchanges: the double-buffered mailbox slots
+            rec = cdec.decide(p_mode=1, kernel_scale=1.0, grid=rep == 0)
+            assert (int(rec[sh.REC_NEXT_ARM]), int(rec[sh.REC_CONTEXT])) == (int(arm), c_star)
+        assert tuple(rec.tolist()) == tuple(float(v) for v in want)  # every field of the combined record
+        assert abs(float(cdec.pcs_mean(2048, seed=7)) - single) < 1e-12
+        if cdec.mailbox is not None:
+            cdec.mailbox.close()
+    # a rank without contexts (n_c < world) takes part with an empty record
+    tiny = sh.ContextShardedDecider(model, ctx[:1])
+    a1, x1 = crs.gao_modellist(model, ctx[:1], use_kde=True, kernel_scale=1.0)
+    rec = tiny.decide(p_mode=1, kernel_scale=1.0)
+    assert (int(rec[sh.REC_NEXT_ARM]), int(rec[sh.REC_CONTEXT])) == (int(a1), 0)
+    s1 = pcs_counts(model, model.workspace(1)["mean"], model.workspace(1)["var"], 512, seed=9).sum().item() / 512
+    assert abs(float(tiny.pcs_mean(512, seed=9)) - s1) < 1e-12
+    tiny.mailbox.close()
 
     adec = sh.ArmShardedDecider(desc, ctx, dev)
     rec = adec.decide(p_mode=1, kernel_scale=1.0)
@@ -64,11 +80,15 @@ def test_sharded_loop_equals_single_gpu_loop():
                           num_pcs_samples=1024, pcs_seed=3)
     shard = sh.ShardedSequentialRS(crs.B200ModelListGP(desc, device=dev), ctx, kernel_scale=1.0,
                                    num_pcs_samples=1024, pcs_seed=3)
+    shard_nccl = sh.ShardedSequentialRS(crs.B200ModelListGP(desc, device=dev), ctx, kernel_scale=1.0,
+                                        num_pcs_samples=1024, pcs_seed=3, exchange="nccl")
     shard_min = sh.ShardedSequentialRS(crs.B200ModelListGP(desc, device=dev), ctx, kernel_scale=1.0,
                                        num_pcs_samples=1024, pcs_seed=3, rho=lambda x: x.min(dim=-2).values)
     for it in range(12):
-        a, b, c = single.step(truth), shard.step(truth), shard_min.step(truth)
+        a, b, c, e = single.step(truth), shard.step(truth), shard_min.step(truth), shard_nccl.step(truth)
         assert (a["next_arm"], a["context_index"]) == (b["next_arm"], b["context_index"]) == (c["next_arm"], c["context_index"]), it
+        assert (a["next_arm"], a["context_index"]) == (e["next_arm"], e["context_index"]), it
+        assert abs(float(a["pcs"]) - float(e["pcs"])) < 1e-12, it
         assert abs(float(a["pcs"]) - float(b["pcs"])) < 1e-12, it
         cnt = single.ws["counts"].double() / 1024
         assert abs(float(c["pcs"]) - float(cnt.min())) < 1e-12, it
