@@ -1,31 +1,34 @@
 #!/usr/bin/env python
-"""bench.py — the GP-C-OCBA decision benchmark on BASELINE.json config 2 (default workload).
+"""bench.py — the GP-C-OCBA decision hot path on BASELINE.json's headline configuration.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                  [--workload headline|c2|c3|c4|c5|loop] [--exchange mailbox|nccl] [--partition contexts|arms]
 
-A *step* is one whole GP-C-OCBA decision on a model whose caches are cold: per-arm Cholesky
-state (crs_gp_prepare, all arms), ModelListGP posterior over the arm x context grid
-(crs_posterior_grid), zeta scan + global argmin + OCBA step 2(b) fused in one launch
-(crs_ocba_scan_select) — what `gao_modellist(model, context_set)` does in the reference
-(contextual_rs/contextual_rs_strategies.py:100-202) on a freshly fitted model.
+Default workload `headline` (BASELINE.json north_star target, config 4 shapes), the same at every N:
+a *step* is one whole GP-C-OCBA decision on a model whose caches are cold — per-arm Cholesky state
+(crs_gp_prepare, all arms), ModelListGP posterior over the 1,000-arm x 65,536-context grid
+(crs_posterior_grid), zeta scan + global argmin + OCBA step 2(b) (crs_ocba_scan_select) — followed by
+one 2^16-sample generalized-PCS estimate on the same grid (crs_pcs_counts_cdf): what one iteration of the
+reference's loop does with `gao_modellist(model, context_set)` and
+`estimate_current_generalized_pcs(model, arm_set, context_set, 2**16, None, func_I, rho)`
+(contextual_rs/contextual_rs_strategies.py:100-202, contextual_rs/generalized_pcs.py:318-479,
+experiments/wsc_experiments/main.py:392-456).
 
-  value : decisions/s with every input already resident in HBM (device timed, CUDA events).
-  e2e   : decisions/s through the public drop-in `contextual_rs_b200.gao_modellist(model,
-          context_set)` with the context set in pinned HOST memory: host->device copy of the
-          contexts and device->host read of the decision inside every timed step.
-  N > 1 : default workload (c2, a 65-us decision): every rank runs its own independent replication
-          of the decision stream (own seeded problem of the same shape, no collective on the data
-          path — the way the reference's experiments use many workers) -> "weak" scaling, value =
-          decisions of all ranks / max-over-ranks time.  With --workload c3|c4|c5 (or --shard) ONE
-          decision is sharded over the ranks by contexts (NCCL: one 64-byte-per-rank all-gather per
-          decision) -> "strong" scaling.  The `pcs` (config 3) and `headline` (config 4: decision +
-          2^16-sample PCS over 1,000 arms x 65,536 contexts, target < 10 ms on 8 GPUs) sub-objects
-          are always context-sharded over all ranks.
-
-The L2 is flushed (256 MiB write) between timed steps; each step is bracketed by its own pair of
-CUDA events on the launching stream and the per-step durations are summed.
-`--impl reference` times the CPU restatement of the reference (oracle/, PyTorch on the host
-cores; BoTorch/GPyTorch are not installable here) on the same workload.
+  N > 1 : ONE step is sharded over the ranks by contexts ("strong" scaling): every rank runs prepare +
+          its slice of the grid + scan/select + PCS; the ranks' local minimisers are folded and the PCS
+          totals summed ON THE DEVICE through peer-mapped mailboxes over NVLink (one 64-byte store per
+          peer each; --exchange nccl uses one all-gather + one all-reduce instead).
+          --partition arms measures the partition the north_star describes (arms sharded, all-gather of
+          per-context bests, all-to-all re-shard for the PCS) on the same step.
+  value : decisions/s (each with its PCS estimate), every input resident in HBM, device timed.
+  e2e   : the same step through the public API with the context set in pinned HOST memory:
+          host->device copy of the contexts, device->host read of the decision and of the PCS value
+          inside every timed step.
+  The L2 is flushed (256 MiB write) between timed steps; each step is bracketed by its own pair of
+  CUDA events on the launching stream; per-step durations are summed and the max over ranks is taken.
+`--impl reference` times the CPU restatement of the reference (oracle/, PyTorch on the host cores;
+BoTorch/GPyTorch are not installable here) on the same workload, every step a bounded
+sample of it scaled linearly.
 """
 from __future__ import annotations
 
@@ -55,7 +58,10 @@ def emit(obj):
 
 import torch  # noqa: E402
 
+PCS_SAMPLES = 1 << 16
 WORKLOADS = {
+    "headline": "c4 + PCS: one GP-C-OCBA decision (cold caches) + one 2^16-sample generalized-PCS estimate, "
+                "1,000 arms x 65,536 Sobol contexts, 8-D, 18 obs/arm, Matern-5/2",
     "c2": "c2: GP-C-OCBA decision, 100 arms x 1,024 contexts, 4-D, 20 obs/arm, Matern-5/2",
     "c3": "c3: GP-C-OCBA decision, 256 arms x 8,192 contexts, 4-D, 20 obs/arm, Matern-5/2",
     "c4": "c4: GP-C-OCBA decision, 1,000 arms x 65,536 Sobol contexts, 8-D, 18 obs/arm, Matern-5/2",
@@ -63,6 +69,25 @@ WORKLOADS = {
     "loop": "c5 loop: sequential R&S, 1,000 arms x 16,384 contexts, 4-D, 20 obs/arm growing by one per iteration; "
             "every iteration = GP-C-OCBA decision on the cached grid + 2^16-sample PCS + dirty-arm update",
 }
+SHAPES = {"headline": "c4", "loop": "c5"}
+METRIC = {"loop": ("rs_loop_iterations_per_sec", "iterations/s")}
+
+
+def workload_config(name, world, args):
+    """The `config` object — identical for the GPU arm and `--impl reference` (same flags -> same dict)."""
+    from contextual_rs_b200.synthetic import CONFIGS
+    c = CONFIGS[SHAPES.get(name, name)]
+    with_pcs = name in ("headline", "loop")
+    if world == 1:
+        sharding = "none"
+    elif name == "c2" and not args.shard:
+        sharding = f"replicas x{world}: one independent decision stream per GPU, no collective on the data path"
+    else:
+        sharding = f"{args.partition}/{world}: one step sharded over the ranks"
+    cfg = {"workload": WORKLOADS[name], "arms": c["K"], "contexts": c["n_c"], "dim": c["d"], "obs_per_arm": c["n"],
+           "pcs_samples": PCS_SAMPLES if with_pcs else 0, "sharding": sharding,
+           "l2": "flushed between timed steps (256 MiB write)" if not args.no_flush else "not flushed"}
+    return cfg
 
 
 def load_peaks():
@@ -88,7 +113,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -126,12 +151,20 @@ class ClockSampler:
 
 def ncu_traffic(workload, kernel, dtype):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
-    capture of the same workload (profiles/r01d_traffic.json; fp64 captures only), else None."""
-    path = os.path.join(ROOT, "profiles", "r01d_traffic.json")
-    if dtype != "f64" or not os.path.exists(path):
-        return None
-    with open(path) as f:
-        return json.load(f).get(workload, {}).get(kernel)
+    capture of the same workload at N = 1 (profiles/r02_traffic.json, else r01d), else None."""
+    for fn in ("r02_traffic.json", "r01d_traffic.json"):
+        path = os.path.join(ROOT, "profiles", fn)
+        if os.path.exists(path):
+            with open(path) as f:
+                v = json.load(f).get(workload, {}).get(f"{kernel}:{dtype}")
+            if v is not None:
+                return v
+    if dtype == "f64":
+        path = os.path.join(ROOT, "profiles", "r01d_traffic.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                return json.load(f).get(workload, {}).get(kernel)
+    return None
 
 
 def algorithmic_flops(K, n_c, n, d):
@@ -168,11 +201,10 @@ def cpu_decision_step(desc, ctx, variant):
     return int(arm)
 
 
-def time_cpu(desc, ctx, budget_s, max_steps):
-    torch.set_num_threads(os.cpu_count() or 1)
+def pick_cpu_variant(desc, ctx):
+    """Two CPU restatements: "modellist" walks the K sub-models like the reference's ModelListGP does,
+    "batched" stacks them (bmm / batched Cholesky); the faster one (after a warm-up call) is the baseline."""
     best = None
-    # two CPU restatements: "modellist" walks the K sub-models like the reference's ModelListGP does,
-    # "batched" stacks them (bmm / batched Cholesky); the faster one (after a warm-up call) is the baseline
     for variant in ("batched", "modellist"):
         cpu_decision_step(desc, ctx, variant)
         dt = float("inf")
@@ -182,123 +214,556 @@ def time_cpu(desc, ctx, budget_s, max_steps):
             dt = min(dt, time.perf_counter() - t0)
         if best is None or dt < best[1]:
             best = (variant, dt)
-    variant, est = best
-    steps = int(max(2, min(max_steps, budget_s / max(est, 1e-6))))
-    cpu_decision_step(desc, ctx, variant)  # warm-up
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_decision_step(desc, ctx, variant)
-    dt = (time.perf_counter() - t0) / steps
-    return variant, steps, dt
+    return best
+
+
+class CpuReference:
+    """The reference's CPU path on a bounded sample of a workload: decision on the first `sub_c` contexts
+    (all arms), PCS with the marginal sampler on `pcs_c` contexts x `pcs_s` samples, both scaled linearly to
+    the full workload.  `step()` returns the scaled seconds of one full step."""
+
+    def __init__(self, name, budget_per_step_s=2.0):
+        from contextual_rs_b200.synthetic import make_config
+        from oracle import gp_oracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.name = name
+        self.cores = torch.get_num_threads()
+        self.desc, self.ctx = make_config(SHAPES.get(name, name))
+        self.K, self.n_c = len(self.desc["train_X"]), self.ctx.shape[0]
+        self.with_pcs = name in ("headline", "loop")
+        self.sub_c = self.n_c if name == "c2" else max(256, self.n_c // 128)
+        self.variant, est = pick_cpu_variant(self.desc, self.ctx[: self.sub_c])
+        while est > budget_per_step_s and self.sub_c > 128:
+            self.sub_c //= 2
+            est /= 2
+        self.ctx_s = self.ctx[: self.sub_c]
+        if self.with_pcs:
+            self.pcs_c, self.pcs_s = 32, 512
+            self.mu, self.vr = gp_oracle.posterior_grid_batched(self.desc, self.ctx[: self.pcs_c])
+            self.gen = torch.Generator().manual_seed(0)
+
+    def step(self):
+        from oracle import pcs_oracle
+        t0 = time.perf_counter()
+        cpu_decision_step(self.desc, self.ctx_s, self.variant)
+        t1 = time.perf_counter()
+        dec = (t1 - t0) * (self.n_c / self.sub_c)
+        pcs = 0.0
+        if self.with_pcs:
+            pcs_oracle.pcs_marginal_ref(self.mu, self.vr, self.pcs_s, generator=self.gen)
+            pcs = (time.perf_counter() - t1) * (self.n_c / self.pcs_c) * (PCS_SAMPLES / self.pcs_s)
+        return dec, pcs
+
+    def sample(self, steps):
+        s = (f"{steps} steps; decision: oracle '{self.variant}' variant on {self.sub_c}/{self.n_c} contexts x {self.K} arms, "
+             f"time scaled x{self.n_c / self.sub_c:.0f}")
+        if self.with_pcs:
+            s += (f"; PCS: marginal sampler (oracle.pcs_marginal_ref, fp64) on {self.pcs_c} contexts x {self.K} arms x "
+                  f"{self.pcs_s} samples, time scaled x{(self.n_c / self.pcs_c) * (PCS_SAMPLES / self.pcs_s):.0f} — the "
+                  f"reference's joint sampler is O(n_c^3) and cannot run at this size")
+        return s + f"; PyTorch CPU, {self.cores} threads"
+
+    def run(self, warmup, steps):
+        for _ in range(warmup):
+            self.step()
+        dec = pcs = 0.0
+        for _ in range(steps):
+            d, p = self.step()
+            dec += d
+            pcs += p
+        return dec / steps, pcs / steps
 
 
 def run_reference(args, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from contextual_rs_b200.synthetic import make_config
-    desc, ctx = make_config(name)
-    K, n_c = len(desc["train_X"]), ctx.shape[0]
-    full = name == "c2"
-    if not full:  # bounded sample: a slice of the contexts, scaled linearly
-        sub = max(256, n_c // 64)
-        ctx_s = ctx[:sub]
-    else:
-        sub, ctx_s = n_c, ctx
-    variant, steps, dt = time_cpu(desc, ctx_s, budget_s=min(60.0, 4.0 * max(args.steps, 1)), max_steps=max(args.steps, 2))
-    dt_full = dt * (n_c / sub)
-    cores = torch.get_num_threads()
-    sample = (f"{steps} decisions on {sub}/{n_c} contexts x {K} arms, oracle '{variant}' variant "
-              f"(PyTorch CPU, {cores} threads), time scaled x{n_c / sub:.0f}")
-    val = 1.0 / dt_full
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    ref = CpuReference(name)
+    W, steps = max(args.warmup, 0), max(args.steps, 1)
+    dec, pcs = ref.run(W, steps)
+    dt = dec + pcs
+    metric, unit = METRIC.get(name, ("gp_c_ocba_decisions_per_sec", "decisions/s"))
+    val = 1.0 / dt
+    sharded = world > 1 and not (name == "c2" and not args.shard)
     emit(({
-        "impl": "reference", "metric": "gp_c_ocba_decisions_per_sec", "value": val, "unit": "decisions/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt_full * 1e3,
-        "higher_is_better": True, "scaling": "weak" if name == "c2" else "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": WORKLOADS[name]},
-        "cpu_baseline": {"value": val, "unit": "decisions/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": metric, "value": val, "unit": unit,
+        "n_gpus": args.gpus, "steps": steps, "warmup": W, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong" if (sharded or world == 1) and name != "c2" else "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(name, world, args),
+        "breakdown_ms": {"decision": dec * 1e3, "pcs": pcs * 1e3},
+        "cpu_baseline": {"value": val, "unit": unit, "cores": ref.cores, "kind": "port", "sample": ref.sample(steps)},
+        "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
+
+# ------------------------------------------------------------------------------------------- GPU
+class Env:
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: contextual_rs_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush_buf = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)
+
+    def flush(self):
+        if self.flush_buf is not None:
+            self.flush_buf.fill_(1)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """Per-step CUDA-event pairs on the launching stream, L2 flushed in between; list of ms."""
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for i in range(steps):
+            self.flush()
+            starts[i].record()
+            fn()
+            ends[i].record()
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in zip(starts, ends)]
+
+    def max_over_ranks(self, values):
+        t = torch.tensor(values, dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def sum_over_ranks(self, values):
+        t = torch.tensor(values, dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return t.tolist()
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def expected_headline_decision():
+    """(next_arm, next_context) of the fp64 oracle on config 4, committed by
+    tests/golden/make_quoted_configs_golden.py (tests/golden/quoted_configs_expected.json)."""
+    with open(os.path.join(ROOT, "tests", "golden", "quoted_configs_expected.json")) as f:
+        exp = json.load(f)["c4"]
+    return exp["default"]["next_arm"], exp["default"]["next_context"]
+
+
+def run_headline(args, env):
+    """The default: config 4 decision + 2^16-sample PCS, contexts sharded over the ranks."""
+    import contextual_rs_b200 as crs
+    from contextual_rs_b200 import _lib
+    from contextual_rs_b200.contextual_rs_strategies import _scan, decide
+    from contextual_rs_b200.generalized_pcs import pcs_counts
+    from contextual_rs_b200.peaks import measure_fma_peak, measure_pcs_cdf_rates, pcs_cdf_roofline
+    from contextual_rs_b200.sharded import ContextShardedDecider, REC_CONTEXT, REC_NEXT_ARM
+    from contextual_rs_b200.synthetic import make_config
+    dev, world, rank = env.dev, env.world, env.rank
+    name = "headline"
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    w = 8 if dtype == torch.float64 else 4
+    desc, ctx = make_config("c4")
+    K, n_c, d = len(desc["train_X"]), ctx.shape[0], ctx.shape[1]
+    n_obs = desc["train_X"][0].shape[0]
+    S = PCS_SAMPLES
+    model = crs.B200ModelListGP(desc, device=dev, dtype=dtype)
+    model.check_status()
+    lib = _lib.get()
+    peaks, peak_src = load_peaks()
+    decider = ContextShardedDecider(model, ctx, exchange=args.exchange)
+    begin, n_loc, ws = decider.begin, decider.n_loc, decider.ws
+    ctx_dev = decider.local_ctx
+    stream = _lib.stream_ptr(dev)
+    st = C.byref(model.state)
+    stats = ws["stats"]
+    W, K_steps = max(args.warmup, 3), max(args.steps, 1)
+    it = [0]
+
+    def pcs_launch(num_samples=S):
+        if n_loc:
+            decider.pcs_counts(num_samples, seed=0, offset=it[0])
+        else:
+            stats.zero_()
+
+    def device_step():
+        """prepare -> grid -> scan/select (+ peer fold) -> PCS build + sample (+ peer sum): no host round-trip."""
+        it[0] += 1
+        if decider.exchange == "mailbox":
+            decider._launch_local(_lib.CRS_P_COUNT, 2.0, (0, K), True, decider.mailbox.next_exchange(begin))
+            pcs_launch()
+            px = decider.mailbox.next_exchange(begin)
+            _lib.check(lib.crs_peer_sum_u64(stats.data_ptr() + 32, 1, decider._sum_dev.data_ptr(), None, C.byref(px), stream))
+        else:
+            _lib.check(lib.crs_gp_prepare(st, 0, K, stream))
+            if n_loc:
+                _lib.check(lib.crs_posterior_grid(st, ctx_dev.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
+                                                  ws["var"].data_ptr(), K, 0, stream))
+                from contextual_rs_b200.contextual_rs_strategies import _scan_select
+                _scan_select(lib, model, ws, n_loc, 0, 2.0, stream, ctx_ptr=ctx_dev.data_ptr())
+            pcs_launch()
+            if world > 1:
+                env.dist.all_gather_into_tensor(decider._gather, ws["decision"] if n_loc else decider._empty)
+                env.dist.all_reduce(stats[4:5])
+
+    ctx_host = ctx.to(dtype).pin_memory()
+    arm_set = torch.arange(K, dtype=dtype).view(-1, 1)
+    func_I = lambda X: (X > 0).to(dtype)  # noqa: E731  (experiments/wsc_experiments/main.py:453)
+    rho = lambda P: P.mean(dim=-2)  # noqa: E731  (main.py:248-251 "mean")
+    last = {}
+
+    def e2e_step():
+        it[0] += 1
+        if world == 1:  # the reference-facing drop-in calls, context set on the host
+            dec = decide(model, ctx_host, True, 0, 2.0, prepare_arms=(0, K))
+            pcs = crs.estimate_current_generalized_pcs(model, arm_set, ctx_host, S, None, func_I, rho, seed=0,
+                                                       offset=it[0], reuse_grid=True)
+            last.update(next_arm=dec.next_arm, next_context=dec.context, pcs=float(pcs))
+        else:  # every rank uploads its slice of the pinned host context set; results come back to the host
+            decider.local_ctx.copy_(ctx_host[begin:begin + n_loc], non_blocking=True)
+            rec = decider.decide(prepare_arms=(0, K))
+            pcs = decider.pcs_mean(S, seed=0, offset=it[0])
+            last.update(next_arm=int(rec[REC_NEXT_ARM]), next_context=int(rec[REC_CONTEXT]), pcs=float(pcs))
+
+    for _ in range(W):
+        env.flush()
+        device_step()
+    for _ in range(W):
+        env.flush()
+        e2e_step()
+    env.barrier()
+    sampler = ClockSampler(env.local_rank)
+    if rank == 0:
+        sampler.start()
+    env.barrier()
+    dev_ms = env.timed(device_step, K_steps)
+    env.barrier()
+    e2e_ms = env.timed(e2e_step, K_steps)
+    env.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- per-kernel durations, same region style (flushed, own event pair, launching stream) ---------
+    ksteps = min(K_steps, 20)
+
+    def grid_only():
+        if n_loc:
+            lib.crs_posterior_grid(st, ctx_dev.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(), ws["var"].data_ptr(), K, 0, stream)
+
+    def scan_only():
+        if n_loc:
+            _scan(lib, model, ws, n_loc, stream)
+
+    grid_ms = env.timed(grid_only, ksteps)
+    scan_ms = env.timed(scan_only, ksteps)
+    prep_ms = env.timed(lambda: lib.crs_gp_prepare(st, 0, K, stream), ksteps)
+    build_ms = env.timed(lambda: pcs_launch(0), ksteps)
+    pcs_ms = env.timed(pcs_launch, ksteps)
+    work = stats[:2].to(torch.float64).tolist()  # {Philox calls, table terms} of this rank's last estimate
+    env.barrier()
+    avg = lambda v: sum(v) / len(v)  # noqa: E731
+    t_dev, t_e2e, grid_avg, scan_avg, prep_avg, build_avg, pcs_avg = env.max_over_ranks(
+        [sum(dev_ms) / 1e3, sum(e2e_ms) / 1e3, avg(grid_ms), avg(scan_ms), avg(prep_ms), avg(build_ms), avg(pcs_ms)])
+    calls_all, terms_all = env.sum_over_ranks(work)
+    sample_avg = max(pcs_avg - build_avg, 1e-6)
+    out = None
+    if rank == 0:
+        exp_arm, exp_ctx = expected_headline_decision()
+        got = (last["next_arm"], last["next_context"])
+        if dtype == torch.float64 and got != (exp_arm, exp_ctx):
+            raise SystemExit(f"headline decision {got} != fp64 oracle's {(exp_arm, exp_ctx)} (tests/golden/quoted_configs_expected.json)")
+        value = K_steps / t_dev
+        flops = algorithmic_flops(K, n_c, n_obs, d)
+        fma_peak = measure_fma_peak(0 if dtype == torch.float64 else 1, dev)
+        cdf_rates = measure_pcs_cdf_rates(dev)
+        roof_grid = {"kernel": "posterior_grid_kernel", "bound": "fp64_fma" if dtype == torch.float64 else "fp32_fma",
+                     "achieved": flops / world / (grid_avg * 1e-3) / 1e12, "peak": fma_peak, "unit": "TFLOP/s",
+                     "frac": flops / world / (grid_avg * 1e-3) / 1e12 / fma_peak,
+                     "traffic": ncu_traffic(name, "posterior_grid_kernel", args.dtype) if world == 1 else None,
+                     "avg_launch_ms": grid_avg, "algorithmic_flops_per_launch": flops / world,
+                     "peak_source": "measured in this run by crs_peak_probe (pure FMA micro-kernel, 16 chains/thread, CUDA "
+                                    "events); MEASURED_PEAKS.json has no fp64/fp32-FMA figure (nominal 37.2 / 74.5)"}
+        scan_bytes = (2 * K * n_c * w + n_c * (w + 12)) / world
+        roof_scan = {"kernel": "ocba_scan_kernel", "bound": "hbm", "achieved": scan_bytes / (scan_avg * 1e-3) / 1e9,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": scan_bytes / (scan_avg * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "traffic": ncu_traffic(name, "ocba_scan_kernel", args.dtype) if world == 1 else None,
+                     "avg_launch_ms": scan_avg, "peak_source": peak_src, "algorithmic_bytes_per_launch": scan_bytes}
+        roof_sample = pcs_cdf_roofline("pcs_cdf_sample_kernel", calls_all, sample_avg * 1e-3, world, cdf_rates)
+        roof_build = pcs_cdf_roofline("pcs_cdf_build_kernel", terms_all, build_avg * 1e-3, world, cdf_rates)
+        build_bytes = 2 * K * n_c * w / world
+        roof_build["hbm"] = {"algorithmic_bytes_per_launch": build_bytes, "achieved_gbs": build_bytes / (build_avg * 1e-3) / 1e9,
+                             "frac_of_hbm_peak": build_bytes / (build_avg * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        roofs = {"posterior_grid": (grid_avg, roof_grid), "pcs_cdf_sample": (sample_avg, roof_sample),
+                 "pcs_cdf_build": (build_avg, roof_build), "ocba_scan": (scan_avg, roof_scan)}
+        dominant = max(roofs, key=lambda k: roofs[k][0])
+        cfg = workload_config(name, world, args)
+        out = {
+            "metric": "gp_c_ocba_decisions_per_sec", "value": value, "unit": "decisions/s",
+            "n_gpus": world, "steps": K_steps, "warmup": W, "ms_per_step": t_dev / K_steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": cfg,
+            "step": "prepare(all arms) + posterior grid + fused zeta scan / OCBA select (+ peer fold) + PCS table build + PCS "
+                    "sampling (+ peer sum): 5 launches per rank at N = 1, 6 at N > 1; exchange = " + decider.exchange,
+            "pcs_mc_samples_per_sec": {"value": float(S) * n_c * K / (pcs_avg * 1e-3), "unit": "equivalent N(0,1) draws/s",
+                                       "ms_per_estimate": pcs_avg,
+                                       "note": "nominal S x n_c x K draws of the reference's estimator per PCS time; the cdf stream "
+                                               "executes one normal + one uniform per (sample, context): %.3g Philox calls" % calls_all},
+            "e2e": {"value": K_steps / t_e2e, "unit": "decisions/s", "ms_per_step": t_e2e / K_steps * 1e3,
+                    "h2d_bytes_per_step": int(n_c * d * w), "d2h_bytes_per_step": (64 + 80) * world if world > 1 else 64 + w,
+                    "api": ("gao_modellist's decide(model, host context_set) + estimate_current_generalized_pcs(..., reuse_grid=True)"
+                            if world == 1 else "ContextShardedDecider.decide + .pcs_mean, every rank uploading its context slice")},
+            "gpu_launches": (5 + (1 if world > 1 else 0)) * 2 * K_steps * world + 6 * ksteps * world,
+            "roofline": dict(roofs[dominant][1], dominant_of="kernel_ms"),
+            "kernel_ms": {"gp_prepare": prep_avg, "posterior_grid": grid_avg, "ocba_scan": scan_avg,
+                          "pcs_cdf_build": build_avg, "pcs_cdf_sample": sample_avg},
+            "decision": {"next_arm": got[0], "next_context": got[1], "pcs_mean": last["pcs"],
+                         "matches_fp64_oracle": got == (exp_arm, exp_ctx),
+                         "parity": "partial: decision index-exact vs the CPU oracle (a line-by-line restatement of the reference); the GP "
+                                   "arithmetic of the absent GPyTorch/BoTorch is restated, not pinned bit for bit (DESIGN.md)"},
+            "clocks": clocks,
+        }
+        for k, (_, r) in roofs.items():
+            if k != dominant:
+                out["roofline_" + k] = r
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        ref = CpuReference(name)
+        dec_s, pcs_s = ref.run(1, 6)
+        out["cpu_baseline"] = {"value": 1.0 / (dec_s + pcs_s), "unit": "decisions/s", "cores": ref.cores, "kind": "port",
+                               "sample": ref.sample(6), "breakdown_ms": {"decision": dec_s * 1e3, "pcs": pcs_s * 1e3}}
+    if world == 1 and not args.no_sub:
+        env.flush_buf = None
+        torch.cuda.empty_cache()
+        env.flush_buf = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        sub_c2 = run_decision(args, env, "c2", steps=300, sub=True)
+        sub_pcs = run_pcs(env, cpu=not args.no_cpu_baseline)
+        if rank == 0:
+            out["c2"] = sub_c2
+            out["pcs"] = sub_pcs
+            out["gpu_launches"] += sub_c2["gpu_launches"] + sub_pcs["gpu_launches"]
+    if rank == 0:
+        emit(out)
+    if decider.mailbox is not None:
+        decider.mailbox.close()
+    env.finish()
+
+
+def run_headline_arms(args, env):
+    raise SystemExit("--partition arms: not implemented yet")
+
+
+# ---------------------------------------------------------------------------------- decision only
+def run_decision(args, env, name, steps=None, sub=False):
+    """A decision-only workload (configs 2-5): prepare + grid + fused scan/select.  `sub=True` returns a
+    compact object (config 2 inside the headline line) instead of emitting."""
+    import contextual_rs_b200 as crs
+    from contextual_rs_b200 import _lib
+    from contextual_rs_b200.contextual_rs_strategies import _scan, _scan_select, decide
+    from contextual_rs_b200.peaks import measure_fma_peak
+    from contextual_rs_b200.sharded import ContextShardedDecider, REC_CONTEXT, REC_NEXT_ARM
+    from contextual_rs_b200.synthetic import make_config
+    dev, world, rank = env.dev, env.world, env.rank
+    W, K_steps = max(args.warmup, 3), steps or max(args.steps, 1)
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    w = 8 if dtype == torch.float64 else 4
+    # N > 1: c2 runs one independent replication per rank (weak scaling) unless --shard
+    sharded = world > 1 and (name != "c2" or args.shard)
+    desc, ctx = make_config(name) if (sharded or world == 1) else make_config(name, seed=rank)
+    K, n_c, d = len(desc["train_X"]), ctx.shape[0], ctx.shape[1]
+    n_obs = desc["train_X"][0].shape[0]
+    model = crs.B200ModelListGP(desc, device=dev, dtype=dtype)
+    model.check_status()
+    lib = _lib.get()
+    peaks, peak_src = load_peaks()
+    if sharded:
+        decider = ContextShardedDecider(model, ctx, exchange=args.exchange)
+        begin, n_loc, ctx_dev, ws = decider.begin, decider.n_loc, decider.local_ctx, decider.ws
+    else:
+        decider, begin, n_loc = None, 0, n_c
+        ctx_dev = ctx.to(device=dev, dtype=dtype).contiguous()
+        ws = model.workspace(n_c)
+    stream = _lib.stream_ptr(dev)
+    st = C.byref(model.state)
+
+    def device_step():
+        if sharded and decider.exchange == "mailbox":
+            decider._launch_local(_lib.CRS_P_COUNT, 2.0, (0, K), True, decider.mailbox.next_exchange(begin))
+            return
+        _lib.check(lib.crs_gp_prepare(st, 0, K, stream))
+        if n_loc:
+            _lib.check(lib.crs_posterior_grid(st, ctx_dev.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
+                                              ws["var"].data_ptr(), K, 0, stream))
+            _scan_select(lib, model, ws, n_loc, 0, 2.0, stream, ctx_ptr=ctx_dev.data_ptr())
+        if sharded:
+            env.dist.all_gather_into_tensor(decider._gather, ws["decision"] if n_loc else decider._empty)
+
+    ctx_host = ctx.to(dtype).pin_memory()
+    ctx_pageable = ctx.to(dtype).clone()
+
+    def e2e_step(host=ctx_host):
+        if not sharded:
+            dec = decide(model, host, True, 0, 2.0, prepare_arms=(0, K))
+            return dec.next_arm, dec.context
+        decider.local_ctx.copy_(host[begin:begin + n_loc], non_blocking=True)
+        rec = decider.decide(prepare_arms=(0, K))
+        return int(rec[REC_NEXT_ARM]), int(rec[REC_CONTEXT])
+
+    for _ in range(W):
+        env.flush()
+        device_step()
+    for _ in range(W):
+        env.flush()
+        e2e_step()
+        e2e_step(ctx_pageable)
+    env.barrier()
+    sampler = ClockSampler(env.local_rank)
+    if rank == 0 and not sub:
+        sampler.start()
+    env.barrier()
+    dev_ms = env.timed(device_step, K_steps)
+    env.barrier()
+    ksteps = min(K_steps, 500)
+
+    def grid_only():
+        if n_loc:
+            lib.crs_posterior_grid(st, ctx_dev.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(), ws["var"].data_ptr(), K, 0, stream)
+
+    def scan_only():
+        if n_loc:
+            _scan(lib, model, ws, n_loc, stream)
+
+    grid_ms = env.timed(grid_only, ksteps)
+    scan_ms = env.timed(scan_only, ksteps)
+    prep_ms = env.timed(lambda: lib.crs_gp_prepare(st, 0, K, stream), ksteps)
+    env.barrier()
+    e2e_ms = env.timed(e2e_step, K_steps)
+    page_ms = env.timed(lambda: e2e_step(ctx_pageable), min(K_steps, 200)) if not sharded else [0.0]
+    env.barrier()
+    clocks = sampler.stop() if (rank == 0 and not sub) else None
+    avg = lambda v: sum(v) / len(v)  # noqa: E731
+    t_dev, t_e2e, grid_avg, scan_avg, prep_avg = env.max_over_ranks(
+        [sum(dev_ms) / 1e3, sum(e2e_ms) / 1e3, avg(grid_ms), avg(scan_ms), avg(prep_ms)])
+    out = None
+    if rank == 0:
+        mult = 1 if (sharded or world == 1) else world  # replicas: every rank made K_steps decisions
+        value = mult * K_steps / t_dev
+        flops = algorithmic_flops(K, n_loc, n_obs, d)
+        fma_peak = measure_fma_peak(0 if dtype == torch.float64 else 1, dev)
+        achieved = flops / (grid_avg * 1e-3) / 1e12
+        scan_bytes = 2 * K * n_loc * w + n_loc * (w + 12)
+        # gp_prepare is a latency chain, not a throughput kernel: one CTA per arm walks the n x n Cholesky
+        # column by column; its model is n dependent column steps (sqrt + divide + rank-1 update + two
+        # substitution steps), reported as ns per dependent column step
+        out = {
+            "metric": "gp_c_ocba_decisions_per_sec", "value": value, "unit": "decisions/s",
+            "n_gpus": world, "steps": K_steps, "warmup": W, "ms_per_step": t_dev / K_steps * 1e3,
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": workload_config(name, world, args),
+            "step": "3 kernels: prepare(all arms) + posterior grid + fused zeta scan / OCBA select",
+            "e2e": {"value": mult * K_steps / t_e2e, "unit": "decisions/s", "ms_per_step": t_e2e / K_steps * 1e3,
+                    "h2d_bytes_per_step": int(n_c * d * w) * mult, "d2h_bytes_per_step": 64 * world,
+                    "pageable_contexts": ({"value": mult / (avg(page_ms) * 1e-3), "ms_per_step": avg(page_ms),
+                                           "note": "same call with the context set in ordinary (pageable) host memory, as the "
+                                                   "reference's caller holds it: plain cudaMemcpyAsync staging instead of the "
+                                                   "zero-copy read of pinned memory"} if not sharded else None)},
+            "gpu_launches": (3 * K_steps + 3 * K_steps + 3 * ksteps) * mult,
+            "roofline": {"kernel": "posterior_grid_kernel", "bound": "fp64_fma" if dtype == torch.float64 else "fp32_fma",
+                         "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
+                         "traffic": ncu_traffic(name, "posterior_grid_kernel", args.dtype) if world == 1 else None,
+                         "avg_launch_ms": grid_avg,
+                         "peak_source": "measured in this run by crs_peak_probe (pure FMA micro-kernel, 16 chains/thread, "
+                                        "CUDA events); MEASURED_PEAKS.json has no fp64/fp32-FMA figure (nominal 37.2 / 74.5)",
+                         "algorithmic_flops_per_launch": flops},
+            "roofline_scan": {"kernel": "ocba_scan_kernel", "bound": "hbm", "achieved": scan_bytes / (scan_avg * 1e-3) / 1e9,
+                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": scan_bytes / (scan_avg * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                              "traffic": ncu_traffic(name, "ocba_scan_kernel", args.dtype) if world == 1 else None,
+                              "avg_launch_ms": scan_avg, "peak_source": peak_src,
+                              "algorithmic_bytes_per_launch": scan_bytes},
+            "latency_prepare": {"kernel": "gp_prepare_kernel", "bound": "latency", "avg_launch_ms": prep_avg,
+                                "dependent_column_steps": n_obs, "ns_per_column_step": prep_avg * 1e6 / n_obs,
+                                "note": "one CTA per arm; the n x n Cholesky + two substitutions are a chain of n dependent "
+                                        "column steps (fp64 sqrt / divide ~ 100+ cycles each); K <= 148 x resident CTAs arms run "
+                                        "in one wave, so the launch time is the chain, not throughput"},
+            "kernel_ms": {"gp_prepare": prep_avg, "posterior_grid": grid_avg, "ocba_scan": scan_avg},
+            "clocks": clocks,
+        }
+        if sub:
+            for k in ("higher_is_better", "vs_baseline", "data", "clocks", "n_gpus"):
+                out.pop(k, None)
+    if sub:
+        return out
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        ref = CpuReference(name)
+        dec_s, _ = ref.run(1, 20 if name == "c2" else 6)
+        out["cpu_baseline"] = {"value": 1.0 / dec_s, "unit": "decisions/s", "cores": ref.cores, "kind": "port",
+                               "sample": ref.sample(20 if name == "c2" else 6)}
+    if rank == 0:
+        emit(out)
+    if decider is not None and decider.mailbox is not None:
+        decider.mailbox.close()
+    env.finish()
 
 
 # ------------------------------------------------------------------------------------------- PCS
 PCS_CONFIG = "c3: generalized-PCS MC estimate, 2^16 samples, 256 arms x 8,192 contexts, fp32"
 
 
-def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
-    """PCS MC samples/s on config 3 (fp32).  Contexts are sharded over ranks; counts are combined
-    with one all-reduce.  'value' counts the S*n_c*K nominal draws of the estimator ("equivalent
-    samples").  The max-tree kernel decides a sample with a root test plus a few node expansions
-    (one Philox call each) instead of K draws; the executed steps are reported beside the value
-    and are what the roofline fraction is computed from.  The flat per-arm stream is timed too."""
-    import torch.distributed as dist
+def run_pcs(env, reps=5, num_samples=PCS_SAMPLES, cpu=True):
+    """PCS MC samples/s on config 3 (fp32, one GPU): the default cdf stream (crs_pcs_counts_cdf), with the
+    max-tree stream and the flat per-arm stream on the same tables beside it.  'value' counts the S*n_c*K
+    nominal draws of the reference's estimator ("equivalent draws"); the executed work is reported beside it."""
     import contextual_rs_b200 as crs
     from contextual_rs_b200.generalized_pcs import pcs_counts
-    from contextual_rs_b200.sharded import shard_bounds
+    from contextual_rs_b200.peaks import measure_pcs_cdf_rates, pcs_cdf_roofline
     from contextual_rs_b200.synthetic import make_config
+    dev = env.dev
     desc, ctx = make_config("c3")
     K, n_c = len(desc["train_X"]), ctx.shape[0]
     model = crs.B200ModelListGP(desc, device=dev, dtype=torch.float32)
-    b, e = shard_bounds(n_c, world, rank)
-    post = model.posterior(ctx[b:e].float())
+    post = model.posterior(ctx.float().to(dev))
     mean, var = post.mean.contiguous(), post.variance.contiguous()
-    stats = torch.zeros(4, dtype=torch.int64, device=dev)
-    total = torch.zeros(1, dtype=torch.float64, device=dev)
-
-    def step(i, sampler="tree"):
-        c = pcs_counts(model, mean, var, num_samples, seed=0, offset=i, ctx_offset=b, stats=stats, sampler=sampler)
-        total[0] = c.sum(dtype=torch.int64).to(torch.float64)
-        if world > 1:
-            dist.all_reduce(total)
-
-    step(0)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = []
-    for i in range(reps):
-        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        step(1 + i)
-        t.record()
-        t.synchronize()
-        ms.append(s.elapsed_time(t))
-    t_step = sum(ms) / len(ms) * 1e-3
-    tt = torch.tensor([t_step], dtype=torch.float64, device=dev)
-    st = stats.to(torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(st)
-    t_step = float(tt)
-    roots, expansions, directs = st.tolist()[:3]
-    pcs_tree_mean = float(total) / (num_samples * n_c)
-    # the flat per-arm stream (crs_pcs_counts) on the same tables, for comparison
-    step(0, "flat")
-    torch.cuda.synchronize()
-    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    step(1, "flat")
-    t.record()
-    t.synchronize()
-    tf = torch.tensor([s.elapsed_time(t) * 1e-3], dtype=torch.float64, device=dev)
-    sf = stats.to(torch.float64)
-    if world > 1:
-        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sf)
+    stats = torch.zeros(8, dtype=torch.int64, device=dev)
+    wsb = torch.empty(int(crs._lib.get().crs_pcs_cdf_workspace_bytes(n_c)), dtype=torch.uint8, device=dev)
+    res = {}
+    launches = 0
+    for sampler in ("cdf", "cdf_build", "tree", "flat"):
+        def step(i, sampler=sampler):
+            if sampler == "cdf_build":
+                return pcs_counts(model, mean, var, 0, seed=0, offset=i, stats=stats, sampler="cdf", workspace=wsb)
+            return pcs_counts(model, mean, var, num_samples, seed=0, offset=i, stats=stats, sampler=sampler,
+                              workspace=wsb if sampler == "cdf" else None)
+        step(0)
+        torch.cuda.synchronize()
+        n = reps if sampler.startswith("cdf") else 2
+        ms = env.timed(lambda: step(1), n)
+        c = step(1)
+        launches += (n + 2) * (1 if sampler in ("tree", "flat", "cdf_build") else 2)
+        res[sampler] = {"ms": sum(ms) / len(ms), "stats": stats.cpu().tolist(),
+                        "pcs_mean": float(c.sum(dtype=torch.int64)) / (num_samples * n_c) if sampler != "cdf_build" else None}
     nominal = float(num_samples) * n_c * K
-    out = {"metric": "pcs_mc_samples_per_sec", "value": nominal / t_step, "unit": "equivalent N(0,1) draws/s",
+    t_cdf, t_build = res["cdf"]["ms"] * 1e-3, res["cdf_build"]["ms"] * 1e-3
+    rates = measure_pcs_cdf_rates(dev)
+    out = {"metric": "pcs_mc_samples_per_sec", "value": nominal / t_cdf, "unit": "equivalent N(0,1) draws/s",
            "config": {"workload": PCS_CONFIG, "samples": num_samples, "arms": K, "contexts": n_c,
-                      "sharding": f"contexts/{world}" if world > 1 else "none", "sampler": "max-tree stream (crs_pcs_counts_tree)"},
-           "ms_per_estimate": t_step * 1e3, "sample_context_pairs_per_sec": float(num_samples) * n_c / t_step,
-           "philox_calls_per_sample": (roots + expansions + directs) / (float(num_samples) * n_c),
-           "pcs_mean": pcs_tree_mean, "gpu_launches": reps + 3,
-           "flat_stream": {"ms_per_estimate": float(tf) * 1e3, "executed_draws_per_sec": float(sf[0]) / float(tf),
-                           "executed_fraction": float(sf[0]) / float(sf[0] + sf[1]),
-                           "pcs_mean": float(total) / (num_samples * n_c)}}
-    from contextual_rs_b200.peaks import measure_pcs_tree_rates, pcs_tree_roofline
-    out["roofline"] = pcs_tree_roofline(roots, expansions, t_step, world, measure_pcs_tree_rates(dev), directs)
-    if cpu and world == 1 and rank == 0:
+                      "sampler": "cdf stream (crs_pcs_counts_cdf): table build + sampling kernels"},
+           "ms_per_estimate": t_cdf * 1e3, "sample_context_pairs_per_sec": float(num_samples) * n_c / t_cdf,
+           "philox_calls_per_sample": res["cdf"]["stats"][0] / (float(num_samples) * n_c),
+           "pcs_mean": res["cdf"]["pcs_mean"], "gpu_launches": launches,
+           "kernel_ms": {"pcs_cdf_build": t_build * 1e3, "pcs_cdf_sample": (t_cdf - t_build) * 1e3},
+           "roofline": pcs_cdf_roofline("pcs_cdf_sample_kernel", res["cdf"]["stats"][0], max(t_cdf - t_build, 1e-9), 1, rates),
+           "roofline_build": pcs_cdf_roofline("pcs_cdf_build_kernel", res["cdf"]["stats"][1], t_build, 1, rates),
+           "tree_stream": {"ms_per_estimate": res["tree"]["ms"], "pcs_mean": res["tree"]["pcs_mean"],
+                           "philox_calls_per_sample": sum(res["tree"]["stats"][:3]) / (float(num_samples) * n_c)},
+           "flat_stream": {"ms_per_estimate": res["flat"]["ms"], "pcs_mean": res["flat"]["pcs_mean"],
+                           "executed_draws_per_sec": res["flat"]["stats"][0] / (res["flat"]["ms"] * 1e-3)}}
+    if cpu:
         from oracle import pcs_oracle
         torch.set_num_threads(os.cpu_count() or 1)
         sub_c, sub_s = 64, 2048
@@ -307,7 +772,7 @@ def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
         pcs_oracle.pcs_marginal_ref(mu, vr, 256, generator=g)
         t0 = time.perf_counter()
         n_rep = 0
-        while time.perf_counter() - t0 < 10.0:
+        while time.perf_counter() - t0 < 6.0:
             pcs_oracle.pcs_marginal_ref(mu, vr, sub_s, generator=g)
             n_rep += 1
         dt = (time.perf_counter() - t0) / n_rep
@@ -345,71 +810,23 @@ def run_pcs(dev, world, rank, reps=3, num_samples=1 << 16, cpu=True):
     return out
 
 
-# -------------------------------------------------------------------------------------- headline
-HEADLINE_CONFIG = ("c4: one GP-C-OCBA decision (fp64, cold caches) + one 2^16-sample generalized-PCS estimate over "
-                   "1,000 arms x 65,536 Sobol contexts, 8-D, 18 obs/arm")
-
-
-def run_headline(dev, world, rank, reps=3, num_samples=1 << 16):
-    """BASELINE.json's target: decision + 2^16-sample PCS over 1,000 arms x 65,536 contexts in
-    under 10 ms on 8 GPUs.  Contexts are sharded over the ranks; a step is prepare(all arms) +
-    grid + scan/select + 64-byte all-gather, then PCS counts + one scalar all-reduce."""
-    import torch.distributed as dist
-    import contextual_rs_b200 as crs
-    from contextual_rs_b200.sharded import ContextShardedDecider, REC_CONTEXT, REC_NEXT_ARM
-    from contextual_rs_b200.synthetic import make_config
-    desc, ctx = make_config("c4")
-    K, n_c = len(desc["train_X"]), ctx.shape[0]
-    model = crs.B200ModelListGP(desc, device=dev, dtype=torch.float64)
-    decider = ContextShardedDecider(model, ctx)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    rec = decider.decide(prepare_arms=(0, K))
-    pcs = decider.pcs_mean(num_samples, seed=0, offset=0)
-    barrier()
-    t_dec, t_pcs = [], []
-    for i in range(reps):
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record()
-        rec = decider.decide(prepare_arms=(0, K))
-        e1.record()
-        pcs = decider.pcs_mean(num_samples, seed=0, offset=1 + i)
-        e2.record()
-        e2.synchronize()
-        t_dec.append(e0.elapsed_time(e1))
-        t_pcs.append(e1.elapsed_time(e2))
-        barrier()
-    t = torch.tensor([sum(t_dec) / reps, sum(t_pcs) / reps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    d_ms, p_ms = t.tolist()
-    return {"workload": HEADLINE_CONFIG, "n_gpus": world, "sharding": f"contexts/{world}" if world > 1 else "none",
-            "ms_per_step": d_ms + p_ms, "decision_ms": d_ms, "pcs_ms": p_ms, "target_ms": 10.0, "target_gpus": 8,
-            "steps": reps, "next_arm": int(rec[REC_NEXT_ARM]), "next_context": int(rec[REC_CONTEXT]),
-            "pcs_mean": float(pcs), "pcs_equivalent_draws_per_sec": float(num_samples) * n_c * K / (p_ms * 1e-3)}
-
-
 # ------------------------------------------------------------------------------------------ loop
-def run_loop(args, dev, world, rank):
+def run_loop(args, env):
     """BASELINE config 5: the end-to-end sequential loop (experiments/wsc_experiments/main.py:345-470)
     with the context set sharded over the ranks.  One step = decide (scan + step 2(b) on the cached
-    grid, 64-byte all-gather, decision read back by the host) -> simulate -> PCS (2^16 samples, one
-    all-reduce) -> condition the sampled arm on the new observation and refresh its grid column."""
-    import torch.distributed as dist
+    grid, peer fold, decision read back by the host) -> simulate -> PCS (2^16 samples, peer sum) ->
+    condition the sampled arm on the new observation and refresh its grid column."""
     import contextual_rs_b200 as crs
-    from contextual_rs_b200.peaks import measure_pcs_tree_rates, pcs_tree_roofline
+    from contextual_rs_b200.peaks import measure_pcs_cdf_rates, pcs_cdf_roofline
     from contextual_rs_b200.sharded import ShardedSequentialRS
     from contextual_rs_b200.synthetic import make_config
+    dev, world, rank, dist = env.dev, env.world, env.rank, env.dist
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     desc, ctx = make_config("c5")
     K, n_c, d = len(desc["train_X"]), ctx.shape[0], ctx.shape[1]
-    S = 1 << 16
+    S = PCS_SAMPLES
     model = crs.B200ModelListGP(desc, device=dev, dtype=dtype)
-    loop = ShardedSequentialRS(model, ctx.to(dtype), kernel_scale=1.0, num_pcs_samples=S, pcs_seed=0)
+    loop = ShardedSequentialRS(model, ctx.to(dtype), kernel_scale=1.0, num_pcs_samples=S, pcs_seed=0, exchange=args.exchange)
     gen = torch.Generator().manual_seed(7)
     W, steps = max(args.warmup, 3), args.steps
     noise = 0.1 * torch.randn(W + steps, generator=gen, dtype=torch.float64)
@@ -419,22 +836,18 @@ def run_loop(args, dev, world, rank):
         full = torch.cat([torch.tensor([arm / (K - 1.0)], dtype=torch.float64), x.double()])
         return torch.sin(10.0 * full).sum() + noise[it_box[0]]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     stats = loop.dec.ws["stats"]
     for _ in range(W):
         loop.step(truth)
         it_box[0] += 1
-    barrier()
-    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    env.barrier()
+    sampler = ClockSampler(env.local_rank)
     if rank == 0:
         sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
-    drawn = torch.zeros(3, dtype=torch.float64)
-    barrier()
+    work = torch.zeros(2, dtype=torch.float64)
+    env.barrier()
+    t_wall = time.perf_counter()
     for i in range(steps):
         ev[i][0].record()
         out = loop.decide()
@@ -442,262 +855,67 @@ def run_loop(args, dev, world, rank):
         y = truth(out["next_arm"], out["next_context"])
         pcs = loop.pcs()
         ev[i][2].record()
-        drawn += stats[:3].cpu().to(torch.float64)  # {root tests, node expansions, direct-arm tests} of this estimate
+        work += stats[:2].cpu().to(torch.float64)  # {Philox calls, table terms} of this estimate
         loop.observe(out["next_arm"], out["next_context"].view(1, -1), y.reshape(1, 1))
         loop.iteration += 1
         it_box[0] += 1
         ev[i][3].record()
-    barrier()
+    env.barrier()
+    t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if rank == 0 else None
     parts = torch.tensor([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in ev], dtype=torch.float64).sum(dim=0)
-    t = torch.cat([parts, parts.sum().reshape(1), drawn]).to(dev)
-    if world > 1:
-        tmax = t[:4].clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dsum = t[4:].clone()
-        dist.all_reduce(dsum)
-        t = torch.cat([tmax, dsum])
-    dec_ms, pcs_ms, obs_ms, tot_ms, roots_all, exp_all, dir_all = t.tolist()
+    dec_ms, pcs_ms, obs_ms, tot_ms, wall_s = env.max_over_ranks(parts.tolist() + [float(parts.sum()), t_wall])
+    calls_all, terms_all = env.sum_over_ranks(work.tolist())
     if rank == 0:
         w = 8 if dtype == torch.float64 else 4
         val = steps / (tot_ms * 1e-3)
+        rates = measure_pcs_cdf_rates(dev)
         emit(({
-            "metric": "rs_loop_iterations_per_sec", "value": val, "unit": "iterations/s (decision + 2^16-sample PCS + update)",
+            "metric": "rs_loop_iterations_per_sec", "value": val, "unit": "iterations/s",
             "n_gpus": world, "steps": steps, "warmup": W, "ms_per_step": tot_ms / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": WORKLOADS["loop"], "arms": K, "contexts": n_c, "dim": d, "pcs_samples": S,
-                       "sharding": f"contexts/{world}" if world > 1 else "none",
-                       "l2": "no flush needed: the grid tables a step re-reads (2 x %d MB per rank) exceed the 126 MB L2" % (K * n_c * w // world // 1000000)},
+            "config": dict(workload_config("loop", world, args),
+                           l2="no flush needed: the grid tables a step re-reads (2 x %d MB per rank) exceed the 126 MB L2" % (K * n_c * w // world // 1000000)),
             "breakdown_ms": {"decide": dec_ms / steps, "pcs": pcs_ms / steps, "observe": obs_ms / steps},
-            "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": (d + 1) * 8 * world, "d2h_bytes_per_step": 64 * world,
-                    "note": "the loop is host-driven: every iteration reads the decision back and uploads the new observation"},
-            "gpu_launches": 5 * steps * world,
-            "roofline": pcs_tree_roofline(roots_all, exp_all, pcs_ms * 1e-3, world, measure_pcs_tree_rates(dev), dir_all),
+            "e2e": {"value": steps / wall_s, "unit": "iterations/s", "h2d_bytes_per_step": (d + 1) * 8 * world, "d2h_bytes_per_step": (64 + 80) * world,
+                    "note": "the loop is host-driven: every iteration reads the decision and the PCS value back and uploads the new "
+                            "observation; e2e = wall clock of the same steps"},
+            "gpu_launches": 6 * steps * world, "exchange": loop.dec.exchange,
+            "roofline": dict(pcs_cdf_roofline("pcs_cdf_sample_kernel+pcs_cdf_build_kernel", calls_all, pcs_ms / steps * 1e-3, world, rates),
+                             note="both cdf kernels + the peer sum over the bare sampling-call rate: a lower bound of the sampling kernel's fraction",
+                             table_terms=terms_all / steps),
             "pcs_last": float(pcs), "clocks": clocks}))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if loop.dec.mailbox is not None:
+        loop.dec.mailbox.close()
+    env.finish()
 
 
-# ------------------------------------------------------------------------------------------- GPU
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--exchange", default="mailbox", choices=["mailbox", "nccl"])
+    ap.add_argument("--partition", default="contexts", choices=["contexts", "arms"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush between steps (profiling only)")
-    ap.add_argument("--no-pcs", action="store_true", help="skip the PCS (config 3) and headline (config 4) sub-benchmarks")
+    ap.add_argument("--no-sub", action="store_true", help="headline: skip the config-2 and config-3 sub-objects")
     ap.add_argument("--shard", action="store_true", help="N > 1: shard ONE decision over the ranks even for c2")
     args = ap.parse_args()
     name = args.workload
     if args.impl == "reference":
         return run_reference(args, name)
-
-    import torch.distributed as dist
-    import contextual_rs_b200 as crs
-    from contextual_rs_b200 import _lib
-    from contextual_rs_b200.contextual_rs_strategies import _scan, _scan_select
-    from contextual_rs_b200.sharded import ContextShardedDecider, REC_CONTEXT, REC_NEXT_ARM, shard_bounds
-    from contextual_rs_b200.synthetic import make_config
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: contextual_rs_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    env = Env(args)
     if name == "loop":
-        if args.steps == 3000:
-            args.steps = 20
-        return run_loop(args, dev, world, rank)
-    W, K_steps = max(args.warmup, 3), args.steps
-    dtype = torch.float64 if args.dtype == "f64" else torch.float32
-    w = 8 if dtype == torch.float64 else 4
-
-    # N > 1: c2 runs one independent replication per rank (weak scaling); the larger workloads
-    # shard one decision over the ranks by contexts (strong scaling)
-    sharded = world > 1 and (name != "c2" or args.shard)
-    desc, ctx = make_config(name) if (sharded or world == 1) else make_config(name, seed=rank)
-    K, n_c, d = len(desc["train_X"]), ctx.shape[0], ctx.shape[1]
-    n_obs = desc["train_X"][0].shape[0]
-    model = crs.B200ModelListGP(desc, device=dev, dtype=dtype)
-    model.check_status()
-    lib = _lib.get()
-    peaks, peak_src = load_peaks()
-    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def flush():
-        if not args.no_flush:
-            flush_buf.fill_(1)
-
-    if sharded:
-        begin, end = shard_bounds(n_c, world, rank)
-        decider = ContextShardedDecider(model, ctx)
-        ctx_dev = decider.local_ctx
-    else:
-        begin, end = 0, n_c
-        decider = None
-        ctx_dev = ctx.to(device=dev, dtype=dtype).contiguous()
-    n_loc = end - begin
-    ws = model.workspace(max(n_loc, 1))
-    stream = _lib.stream_ptr(dev)
-    st = C.byref(model.state)
-
-    def device_step():
-        """prepare -> grid -> fused scan + select, all inputs resident, no host round-trip."""
-        _lib.check(lib.crs_gp_prepare(st, 0, K, stream))
-        if n_loc:
-            _lib.check(lib.crs_posterior_grid(st, ctx_dev.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
-                                              ws["var"].data_ptr(), K, 0, stream))
-            _scan_select(lib, model, ws, n_loc, 0, 2.0, stream, ctx_ptr=ctx_dev.data_ptr())
-        if sharded:
-            dist.all_gather_into_tensor(decider._gather, ws["decision"] if n_loc else decider._empty)
-
-    ctx_host = ctx.to(dtype).pin_memory()
-
-    def e2e_step():
-        if not sharded:
-            from contextual_rs_b200.contextual_rs_strategies import decide
-            dec = decide(model, ctx_host, True, 0, 2.0, prepare_arms=(0, K))
-            return dec.next_arm, dec.context
-        # sharded: every rank uploads its slice of the pinned host context set, then one all-gather
-        decider.local_ctx.copy_(ctx_host[begin:end], non_blocking=True)
-        rec = decider.decide(prepare_arms=(0, K))
-        return int(rec[REC_NEXT_ARM]), int(rec[REC_CONTEXT])
-
-    def timed_loop(fn, steps, per_kernel=False):
-        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        for i in range(steps):
-            flush()
-            starts[i].record()
-            fn()
-            ends[i].record()
-        torch.cuda.synchronize()
-        return [s.elapsed_time(e) for s, e in zip(starts, ends)]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- warm-up -------------------------------------------------------------------------------
-    for _ in range(W):
-        flush()
-        device_step()
-    for _ in range(W):
-        flush()
-        e2e_step()
-    barrier()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    # ---- device-resident value ---------------------------------------------------------------------
-    barrier()
-    dev_ms = timed_loop(device_step, K_steps)
-    barrier()
-    # ---- dominant-kernel duration (posterior grid), same region style -------------------------------
-    def grid_only():
-        if n_loc:
-            lib.crs_posterior_grid(st, ctx_dev.data_ptr(), n_loc, 0, K, ws["mean"].data_ptr(),
-                                   ws["var"].data_ptr(), K, 0, stream)
-    def scan_only():
-        if n_loc:
-            _scan(lib, model, ws, n_loc, stream)
-    def prep_only():
-        lib.crs_gp_prepare(st, 0, K, stream)
-    ksteps = min(K_steps, 500)
-    grid_ms = timed_loop(grid_only, ksteps)
-    scan_ms = timed_loop(scan_only, ksteps)
-    prep_ms = timed_loop(prep_only, ksteps)
-    barrier()
-    # ---- end to end through the public API -------------------------------------------------------
-    e2e_ms = timed_loop(e2e_step, K_steps)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-
-    t_dev = sum(dev_ms) / 1e3
-    t_e2e = sum(e2e_ms) / 1e3
-    if world > 1:
-        t = torch.tensor([t_dev, t_e2e, sum(grid_ms) / len(grid_ms), sum(scan_ms) / len(scan_ms)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e, grid_avg, scan_avg = t.tolist()
-    else:
-        grid_avg, scan_avg = sum(grid_ms) / len(grid_ms), sum(scan_ms) / len(scan_ms)
-    prep_avg = sum(prep_ms) / len(prep_ms)
-
-    if rank == 0:
-        mult = 1 if (sharded or world == 1) else world  # replicas: every rank made K_steps decisions
-        value = mult * K_steps / t_dev
-        flops = algorithmic_flops(K, n_loc, n_obs, d)
-        from contextual_rs_b200.peaks import measure_fma_peak
-        fp64_peak = measure_fma_peak(0 if dtype == torch.float64 else 1, dev)  # live FMA micro-kernel
-        achieved = flops / (grid_avg * 1e-3) / 1e12
-        scan_bytes = 2 * K * n_loc * w + n_loc * (w + 12)
-        out = {
-            "metric": "gp_c_ocba_decisions_per_sec", "value": value, "unit": "decisions/s",
-            "n_gpus": world, "steps": K_steps, "warmup": W, "ms_per_step": t_dev / K_steps * 1e3,
-            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": WORKLOADS[name], "arms": K, "contexts": n_c, "dim": d, "obs_per_arm": n_obs,
-                       "sharding": (f"contexts/{world}: one decision sharded over the ranks, 64-byte all-gather per decision"
-                                    if sharded else (f"replicas x{world}: one independent decision stream per GPU, no "
-                                                     "collective on the data path" if world > 1 else "none")),
-                       "l2": "flushed between timed steps (256 MiB write)" if not args.no_flush else "not flushed",
-                       "step": "3 kernels: prepare(all arms) + posterior grid + fused zeta scan / OCBA select"},
-            "e2e": {"value": mult * K_steps / t_e2e, "unit": "decisions/s", "ms_per_step": t_e2e / K_steps * 1e3,
-                    "h2d_bytes_per_step": int(n_c * d * w) * mult, "d2h_bytes_per_step": 64 * world},
-            "gpu_launches": (3 * K_steps + 3 * K_steps + 3 * ksteps) * mult,
-            "roofline": {"kernel": "posterior_grid_kernel", "bound": "fp64_fma" if dtype == torch.float64 else "fp32_fma",
-                         "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": ncu_traffic(name, "posterior_grid_kernel", args.dtype) if world == 1 else None,
-                         "avg_launch_ms": grid_avg,
-                         "peak_source": "measured in this run by crs_peak_probe (pure FMA micro-kernel, 16 chains/thread, "
-                                        "CUDA events); MEASURED_PEAKS.json has no fp64/fp32-FMA figure (nominal 37.2 / 74.5)",
-                         "algorithmic_flops_per_launch": flops},
-            "roofline_scan": {"kernel": "ocba_scan_kernel", "bound": "hbm", "achieved": scan_bytes / (scan_avg * 1e-3) / 1e9,
-                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": scan_bytes / (scan_avg * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                              "traffic": ncu_traffic(name, "ocba_scan_kernel", args.dtype) if world == 1 else None,
-                              "avg_launch_ms": scan_avg, "peak_source": peak_src,
-                              "algorithmic_bytes_per_launch": scan_bytes},
-            "kernel_ms": {"gp_prepare": prep_avg, "posterior_grid": grid_avg, "ocba_scan": scan_avg},
-            "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            if name == "c2":
-                variant, steps, dt = time_cpu(desc, ctx, budget_s=15.0, max_steps=200)
-                scale = 1.0
-                sub = n_c
-            else:
-                sub = max(256, n_c // 64)
-                variant, steps, dt = time_cpu(desc, ctx[:sub], budget_s=15.0, max_steps=50)
-                scale = n_c / sub
-            out["cpu_baseline"] = {
-                "value": 1.0 / (dt * scale), "unit": "decisions/s", "cores": torch.get_num_threads(), "kind": "port",
-                "sample": f"{steps} decisions, oracle '{variant}' variant on {sub}/{n_c} contexts x {K} arms, "
-                          f"time scaled x{scale:.0f}; PyTorch CPU, {torch.get_num_threads()} threads"}
-    pcs = headline = None
-    if not args.no_pcs and name == "c2":
-        del flush_buf
-        pcs = run_pcs(dev, world, rank, cpu=not args.no_cpu_baseline)
-        headline = run_headline(dev, world, rank)
-    if rank == 0:
-        if pcs is not None:
-            out["pcs"] = pcs
-            out["headline"] = headline
-            out["gpu_launches"] += pcs["gpu_launches"] + 4 * 4 * world  # headline: 4 kernels x (1 + 3) steps per rank
-        emit(out)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        return run_loop(args, env)
+    if name == "headline":
+        if args.partition == "arms":
+            return run_headline_arms(args, env)
+        return run_headline(args, env)
+    return run_decision(args, env, name)
 
 
 if __name__ == "__main__":

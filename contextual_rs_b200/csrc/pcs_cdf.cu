@@ -69,11 +69,23 @@ __global__ void lnphi_init_kernel() {
   g_lnphi[i] = make_float4((float)p[1], (float)c1, (float)c2, (float)c3);
 }
 
+__device__ __forceinline__ void stage_lnphi(float4* __restrict__ s_tab, int tid, int nthreads) {
+  for (int i = tid; i < kLnPhiCells; i += nthreads) s_tab[i] = g_lnphi[i];
+}
+
+// floor of 0 <= t < 2^22 without the conversion unit: t + 2^23 rounded toward zero keeps floor(t) in the
+// low mantissa bits (two FADDs and one LOP3 on the FMA / ALU pipes instead of F2I + I2F on the XU pipe)
+__device__ __forceinline__ int floor_split(float t, float& frac) {
+  const float u = __fadd_rz(t, 8388608.f);
+  frac = t - (u - 8388608.f);
+  return __float_as_int(u) & 0x3fffff;
+}
+
 __device__ __forceinline__ float lnphi(float x, const float4* __restrict__ tab) {
   float t = fmaf(x, kLnPhiScale, -kLnPhiX0 * kLnPhiScale);
   t = fminf(fmaxf(t, 0.f), (float)kLnPhiCells - 0.001f);  // x <= -9: ln Phi = -43.6 (F = 0 anyway); x >= 7: -1.3e-12
-  const int i = (int)t;
-  const float f = t - (float)i;
+  float f;
+  const int i = floor_split(t, f);
   const float4 c = tab[i];
   return fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x);
 }
@@ -101,18 +113,50 @@ __device__ __forceinline__ void competitor(const T* __restrict__ mrow, const T* 
 }
 
 // ---- build ---------------------------------------------------------------------------------------
+// The build is a stream of table terms ln Phi(a_j z_g + b_j): per term one 16-byte look-up.  A 128-bit
+// shared-memory load is served one quarter-warp (8 lanes) per wavefront, and 8 lanes reading cells an
+// irregular stride apart collide in the eight 16-byte bank groups (measured: 9 wavefronts per request,
+// the LSU pipe 96 % busy — the kernel's bound in round 2a).  So the CTA keeps EIGHT copies of the table,
+// copy k occupying bank group k only (cell i of copy k at float4 index 8 i + k), and lane l reads copy
+// l & 7: the 8 lanes of a quarter-warp never share a bank group, whatever cells they want — 4 wavefronts
+// per request, the minimum for 16 bytes per lane.  128 KB of shared memory: one 1,024-thread CTA per SM.
+constexpr int kBuildThreads = 1024;
+constexpr int kBuildWarps = kBuildThreads / 32;
+constexpr int kBuildSmem = kLnPhiCells * 8 * (int)sizeof(float4);
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// tab8_k16 = shared-window address of the interleaved table + 16 (lane & 7).  t + 2^16 rounded toward zero
+// keeps floor(128 t) in the mantissa: bits 7.. are the cell, i.e. exactly the byte offset 128 floor(t).
+__device__ __forceinline__ float lnphi8(float t, uint32_t tab8_k16) {
+  // t = (x + 9) * 64; x >= -7 for every tabulated factor on [lo - h, ...) except the sharp competitors beyond
+  // the eighth of a flagged context, x >= 7 inside a quarter that started below it: clamp both ends
+  t = fminf(fmaxf(t, 0.f), (float)kLnPhiCells - 0.001f);
+  const int u = __float_as_int(__fadd_rz(t, 65536.f));
+  const float f = t - (__int_as_float(u & ~0x7f) - 65536.f);
+  const float4 c = lds128(tab8_k16 + (uint32_t)(u & 0x1ff80));
+  return fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x);
+}
+
 template <typename T>
-__global__ void __launch_bounds__(kCdfThreads)
+__global__ void __launch_bounds__(kBuildThreads, 1)
 pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int64_t n_c, int K, int64_t ld,
                      float4* __restrict__ tables, float* __restrict__ headers, uint32_t* __restrict__ counts,
                      unsigned long long* __restrict__ ticket, unsigned long long* __restrict__ stats) {
-  __shared__ float4 s_lnphi[kLnPhiCells];
-  __shared__ float s_F[kCdfWarps][kCdfStride];
-  __shared__ float2 s_sharp[kCdfWarps][kCdfMaxSharp];
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  float4* s_tab8 = reinterpret_cast<float4*>(dyn_smem);
+  __shared__ float s_F[kBuildWarps][kCdfStride];
+  __shared__ float2 s_sharp[kBuildWarps][kCdfMaxSharp];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < kLnPhiCells; i += kCdfThreads) s_lnphi[i] = g_lnphi[i];
+  for (int i = tid; i < kLnPhiCells * 8; i += kBuildThreads) s_tab8[i] = g_lnphi[i >> 3];
   __syncthreads();
+  const uint32_t copy = smem_u32(s_tab8) + 16u * (uint32_t)(lane & 7);
   const unsigned lt_mask = (1u << lane) - 1u;
+  constexpr float kTScale = kLnPhiScale, kTShift = -kLnPhiX0 * kLnPhiScale, kTHi = (kCdfXHi - kLnPhiX0) * kLnPhiScale;
   unsigned long long n_terms = 0, n_sharp_ctx = 0, n_over_ctx = 0;
   for (;;) {
     // contexts are handed out one at a time (their cost depends on how many terms can be skipped)
@@ -164,11 +208,12 @@ pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
       z[r] = fmaf((float)(32 * r + lane - 1), h, lo);
       acc[r] = 0.f;
     }
-    float zq[4];  // lowest z of each quarter: warp-uniform skip of terms that are 0 there and above
+    float zq[4];  // lowest z of each quarter: terms that are 0 there (x >= 7) are 0 in the whole quarter and above
 #pragma unroll
     for (int r = 0; r < 4; ++r) zq[r] = fmaf((float)(32 * r - 1), h, lo);
     int n_sharp = 0;
     bool overflow = false;
+    unsigned int n_quarters = 0;  // warp-uniform count of (competitor, quarter) blocks evaluated
     for (int base = 0; base < K; base += 32) {
       const int a = base + lane;
       float aj = 0.f, bj = 1e30f, rj = 0.f;
@@ -186,28 +231,29 @@ pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
         overflow = overflow || n_sharp + __popc(sb) > kCdfMaxSharp;
         n_sharp = min(n_sharp + __popc(sb), kCdfMaxSharp);
       }
-#pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
-        const float ai = __shfl_sync(kFull, aj, i);
-        const float bb = __shfl_sync(kFull, bj, i);
-        if (fmaf(ai, zq[0], bb) < kCdfXHi) {
-          acc[0] += lnphi(fmaf(ai, z[0], bb), s_lnphi);
-          n_terms += 1;
-          if (fmaf(ai, zq[1], bb) < kCdfXHi) {
-            acc[1] += lnphi(fmaf(ai, z[1], bb), s_lnphi);
-            n_terms += 1;
-            if (fmaf(ai, zq[2], bb) < kCdfXHi) {
-              acc[2] += lnphi(fmaf(ai, z[2], bb), s_lnphi);
-              n_terms += 1;
-              if (fmaf(ai, zq[3], bb) < kCdfXHi) {
-                acc[3] += lnphi(fmaf(ai, z[3], bb), s_lnphi);
-                n_terms += 1;
-              }
-            }
-          }
+      // table coordinates t = (a_j z + b_j + 9) * 64 = at z + bt, and the number of leading quarters in
+      // which the factor is not yet 1 (a_j > 0: monotone in the quarter index), computed once per lane
+      const float at = aj * kTScale;
+      const float bt = fminf(fmaf(bj, kTScale, kTShift), 1e30f);
+      int nq = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) nq += fmaf(at, zq[r], bt) < kTHi ? 1 : 0;
+      const unsigned live = __ballot_sync(kFull, nq > 0);
+      for (unsigned m = live; m; m &= m - 1) {
+        const int i = __ffs(m) - 1;
+        const float ai = __shfl_sync(kFull, at, i);
+        const float bb = __shfl_sync(kFull, bt, i);
+        const int ni = __shfl_sync(kFull, nq, i);
+        n_quarters += ni;
+        switch (ni) {  // warp-uniform
+          case 4: acc[3] += lnphi8(fmaf(ai, z[3], bb), copy);
+          case 3: acc[2] += lnphi8(fmaf(ai, z[2], bb), copy);
+          case 2: acc[1] += lnphi8(fmaf(ai, z[1], bb), copy);
+          default: acc[0] += lnphi8(fmaf(ai, z[0], bb), copy);
         }
       }
     }
+    n_terms += n_quarters;
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < 4; ++r) s_F[warp][32 * r + lane] = exp_approx(fmaxf(acc[r], -80.f));
@@ -265,8 +311,8 @@ __device__ __forceinline__ float cdf_eval(float z, const CdfCtx& cx, const float
                                           const float2* __restrict__ sharp, const float4* __restrict__ s_lnphi) {
   const float t = (z - cx.lo) * cx.inv_h;
   const float tc = fminf(fmaxf(t, 0.f), (float)kCdfCells - 0.001f);
-  const int i = (int)tc;
-  const float f = tc - (float)i;
+  float f;
+  const int i = floor_split(tc, f);
   const float4 c = tab[i];
   float F = fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x);
   F = t < 0.f ? 0.f : (t >= (float)kCdfCells ? 1.f : F);
@@ -292,7 +338,7 @@ pcs_cdf_sample_kernel(const float4* __restrict__ tables, const float* __restrict
   __shared__ float4 s_tab[kCdfWarps][kCdfStride];
   __shared__ float2 s_sharp[kCdfWarps][kCdfMaxSharp];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < kLnPhiCells; i += kCdfThreads) s_lnphi[i] = g_lnphi[i];
+  stage_lnphi(s_lnphi, tid, kCdfThreads);
   __syncthreads();
   const int64_t ncalls = (num_samples + 1) >> 1;
   const int64_t items = n_c * splits;
@@ -346,7 +392,7 @@ pcs_cdf_sample_kernel(const float4* __restrict__ tables, const float* __restrict
 __global__ void __launch_bounds__(kCdfThreads)
 cdf_probe_kernel(int kind, int iters, const __grid_constant__ RoundKeys rk, float* out) {
   __shared__ float4 s_lnphi[kLnPhiCells];
-  for (int i = threadIdx.x; i < kLnPhiCells; i += kCdfThreads) s_lnphi[i] = g_lnphi[i];
+  stage_lnphi(s_lnphi, threadIdx.x, kCdfThreads);
   __syncthreads();
   const uint32_t smp = blockIdx.x * kCdfThreads + threadIdx.x;
   unsigned int hits = 0;
@@ -361,25 +407,38 @@ cdf_probe_kernel(int kind, int iters, const __grid_constant__ RoundKeys rk, floa
       for (int k = 0; k < 2; ++k) {
         const float t = ((k ? z2 : z1) + 5.f) * 12.5f;
         const float tc = fminf(fmaxf(t, 0.f), 124.999f);
-        const int i = (int)tc;
-        const float f = tc - (float)i;
-        const float v = fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x + 1e-3f * (float)i);
+        float f;
+        const int i = floor_split(tc, f);
+        const float v = fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x + __int_as_float(i));
         F[k] = t < 0.f ? 0.f : (t >= 125.f ? 1.f : v);
       }
       hits += w.z < prob_to_u32(F[0]) ? 1u : 0u;
       hits += w.w < prob_to_u32(F[1]) ? 1u : 0u;
     }
-  } else {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float a = 1.f + 1e-3f * (float)(smp & 31), b = 0.5f;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] += lnphi(fmaf(a, -2.f + 1.3f * (float)r, b), s_lnphi);
-      b += 1e-3f;
-    }
-    hits = (acc[0] + acc[1] + acc[2] + acc[3]) < -1e30f ? 1u : 0u;
   }
   if (hits == 0xffffffffu) out[0] = 1.f;  // keep the loop alive
+}
+
+// kind 9: the bare table term of the build on the 8-way bank-interleaved table (one FMA, one clamp, the
+// index split, one 16-byte look-up, three FMAs, one add), four independent accumulators per thread
+__global__ void __launch_bounds__(kBuildThreads, 1)
+cdf_build_probe_kernel(int iters, float* out) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  float4* s_tab8 = reinterpret_cast<float4*>(dyn_smem);
+  for (int i = threadIdx.x; i < kLnPhiCells * 8; i += kBuildThreads) s_tab8[i] = g_lnphi[i >> 3];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t copy = smem_u32(s_tab8) + 16u * (uint32_t)(lane & 7);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float a = 64.f * (1.f + 1e-3f * (float)lane);
+  float b = 576.f + 32.f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] += lnphi8(fmaf(a, -2.f + 1.3f * (float)r + 0.09f * (float)lane, b), copy);
+    b += 0.05f;
+    b = b > 700.f ? 576.f : b;
+  }
+  if (__float_as_uint(acc[0] + acc[1] + acc[2] + acc[3]) == 0xffffffffu) out[0] = 1.f;  // keep the loop alive
 }
 
 struct CdfDevInfo { bool ready = false; int sms = 0; int build_ctas[2] = {0, 0}; int sample_ctas = 0; };
@@ -403,10 +462,9 @@ int cdf_device_ready(CdfDevInfo& info) {
     CRS_CUDA_TRY(cudaDeviceGetAttribute(&g_cdf_info[dev].sms, cudaDevAttrMultiProcessorCount, dev), "pcs_cdf sm count");
     // resident CTAs of each kernel: the grids are sized to exactly one wave
     int per_sm = 0;
-    CRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcs_cdf_build_kernel<double>, kCdfThreads, 0), "pcs_cdf occupancy");
-    g_cdf_info[dev].build_ctas[0] = g_cdf_info[dev].sms * (per_sm > 0 ? per_sm : 1);
-    CRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcs_cdf_build_kernel<float>, kCdfThreads, 0), "pcs_cdf occupancy");
-    g_cdf_info[dev].build_ctas[1] = g_cdf_info[dev].sms * (per_sm > 0 ? per_sm : 1);
+    CRS_CUDA_TRY(cudaFuncSetAttribute(pcs_cdf_build_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBuildSmem), "pcs_cdf smem attr");
+    CRS_CUDA_TRY(cudaFuncSetAttribute(pcs_cdf_build_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBuildSmem), "pcs_cdf smem attr");
+    g_cdf_info[dev].build_ctas[0] = g_cdf_info[dev].build_ctas[1] = g_cdf_info[dev].sms;  // 128 KB table: one CTA per SM
     CRS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcs_cdf_sample_kernel, kCdfThreads, 0), "pcs_cdf occupancy");
     g_cdf_info[dev].sample_ctas = g_cdf_info[dev].sms * (per_sm > 0 ? per_sm : 1);
     g_cdf_info[dev].ready = true;
@@ -436,14 +494,14 @@ int launch_pcs_counts_cdf(const void* mean, const void* var, int64_t n_c, int K,
   float* headers = reinterpret_cast<float*>(tables + n_c * kCdfStride);
   unsigned long long* ticket = reinterpret_cast<unsigned long long*>(headers + n_c * kCdfHdr);
   CRS_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s), "pcs_cdf memset ticket");
-  const int64_t want_b = (n_c + kCdfWarps - 1) / kCdfWarps;
+  const int64_t want_b = (n_c + kBuildWarps - 1) / kBuildWarps;
   const int64_t res_b = info.build_ctas[dtype == CRS_F64 ? 0 : 1];
   const int blocks_b = (int)(want_b < res_b ? want_b : res_b);
   if (dtype == CRS_F64)
-    pcs_cdf_build_kernel<double><<<blocks_b, kCdfThreads, 0, s>>>((const double*)mean, (const double*)var, n_c, K, ld, tables,
+    pcs_cdf_build_kernel<double><<<blocks_b, kBuildThreads, kBuildSmem, s>>>((const double*)mean, (const double*)var, n_c, K, ld, tables,
                                                                   headers, counts, ticket, (unsigned long long*)stats);
   else if (dtype == CRS_F32)
-    pcs_cdf_build_kernel<float><<<blocks_b, kCdfThreads, 0, s>>>((const float*)mean, (const float*)var, n_c, K, ld, tables,
+    pcs_cdf_build_kernel<float><<<blocks_b, kBuildThreads, kBuildSmem, s>>>((const float*)mean, (const float*)var, n_c, K, ld, tables,
                                                                  headers, counts, ticket, (unsigned long long*)stats);
   else
     return CRS_ERR_INVALID_ARG;
@@ -471,7 +529,12 @@ int launch_cdf_probe(int kind, int iters, int blocks, void* out, cudaStream_t s)
   CdfDevInfo info;
   int rc;
   if ((rc = cdf_device_ready(info)) != CRS_OK) return rc;
-  cdf_probe_kernel<<<blocks, kCdfThreads, 0, s>>>(kind, iters, round_keys(1u, 2u), (float*)out);
+  if (kind == 9) {
+    CRS_CUDA_TRY(cudaFuncSetAttribute(cdf_build_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBuildSmem), "cdf_probe attr");
+    cdf_build_probe_kernel<<<info.sms, kBuildThreads, kBuildSmem, s>>>(iters, (float*)out);  // one CTA per SM, like the build
+  } else {
+    cdf_probe_kernel<<<blocks, kCdfThreads, 0, s>>>(kind, iters, round_keys(1u, 2u), (float*)out);
+  }
   CRS_CUDA_TRY(cudaGetLastError(), "cdf_probe launch");
   return CRS_OK;
 }
