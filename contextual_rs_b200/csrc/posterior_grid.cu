@@ -272,8 +272,12 @@ __device__ __forceinline__ double chunk_sqnorm(const double* __restrict__ s_pane
 
 template <typename T> struct CStride { static constexpr int value = sizeof(T) == 8 ? kGridThreads + 8 : kGridThreads; };
 
-template <typename T, int D, int VB>
-__global__ void __launch_bounds__(kGridThreads, kMinBlocks)
+// DIRECT = true: results go straight to the tables (no [2][arm_tile][128] staging buffer), which takes the
+// CTA under 45 KB of shared memory at n <= 24 and, with <= 96 registers, lets FIVE CTAs share an SM
+// instead of four (20 warps: the FP64 pipe was 50 % busy at 16).  The 8-byte stores of one context's
+// arm tile fill the same two 32-byte sectors within microseconds and merge in L2.
+template <typename T, int D, int VB, bool DIRECT>
+__global__ void __launch_bounds__(kGridThreads, DIRECT ? kMinBlocks + 1 : kMinBlocks)
 posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, int arm_begin,
                       int arm_end, int arm_tile, int n_rows, T* __restrict__ mean,
                       T* __restrict__ var, int64_t ld, int col_offset) {
@@ -403,8 +407,16 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
     const T mu = fma(ysd, m + macc_sum, ybar);
     T vr = (ysd * ysd) * (o - q);
     vr = vr > variance_floor<T>() ? vr : variance_floor<T>();  // also maps NaN to the floor
-    s_out[t * kGridThreads + tid] = mu;
-    s_out[(arm_tile + t) * kGridThreads + tid] = vr;
+    if constexpr (DIRECT) {
+      if (live) {
+        const int64_t o_idx = c * ld + col_offset + (k - arm_begin);
+        mean[o_idx] = mu;
+        var[o_idx] = vr;
+      }
+    } else {
+      s_out[t * kGridThreads + tid] = mu;
+      s_out[(arm_tile + t) * kGridThreads + tid] = vr;
+    }
 
     __syncthreads();  // every thread is done with this stage buffer
     if (tid == 0 && t + 2 < na) {
@@ -413,7 +425,7 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
     }
   }
 
-  if (live) {
+  if (!DIRECT && live) {
     T* mrow = mean + c * ld + col_offset + (a0 - arm_begin);
     T* vrow = var + c * ld + col_offset + (a0 - arm_begin);
     for (int a = 0; a < na; ++a) {
@@ -423,7 +435,7 @@ posterior_grid_kernel(crs_gp_state st, const T* __restrict__ ctx, int64_t n_c, i
   }
 }
 
-template <typename T, int D, int VB>
+template <typename T, int D, int VB, bool DIRECT>
 int launch_variant(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm_begin,
                    int arm_end, int n_rows, void* mean, void* var, int64_t ld, int col_offset,
                    cudaStream_t s) {
@@ -440,14 +452,14 @@ int launch_variant(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm
   auto smem_for = [&](int at) {
     const size_t stage = kHeadElems + (size_t)n_rows + (size_t)n_rows * D + (size_t)n_rows * PanelLd<T>::value;
     return 32 + sizeof(T) * (64 + kGridThreads + 2 * stage + (size_t)n_rows * CStride<T>::value +
-                             2 * (size_t)at * kGridThreads);
+                             (DIRECT ? 0 : 2 * (size_t)at * kGridThreads));
   };
   while (arm_tile > 1 && smem_for(arm_tile) > 227 * 1024) arm_tile >>= 1;
   const size_t smem = smem_for(arm_tile);
   if (smem > 227 * 1024) return CRS_ERR_UNSUPPORTED;
   const int arm_tiles = (narms + arm_tile - 1) / arm_tile;
   if (arm_tiles > 65535) return CRS_ERR_UNSUPPORTED;
-  auto kern = posterior_grid_kernel<T, D, VB>;
+  auto kern = posterior_grid_kernel<T, D, VB, DIRECT>;
   if (smem > 40 * 1024)
     CRS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "grid attr");
   dim3 grid((unsigned)ctx_tiles, (unsigned)arm_tiles);
@@ -460,12 +472,26 @@ int launch_variant(const crs_gp_state* st, const void* ctx, int64_t n_c, int arm
 template <typename T, int VB>
 int dispatch_dim(const crs_gp_state* st, const void* ctx, int64_t n_c, int a0, int a1, int n_rows,
                  void* mean, void* var, int64_t ld, int col, cudaStream_t s) {
+  // fp64, n <= 24, large grids: the 5-CTA/SM variant without output staging (see the kernel's comment)
+  static const int direct_mode = [] {
+    const char* e = getenv("CRS_GRID_DIRECT");  // tuning hook: 0 = never, 1 = always (where instantiated)
+    return e ? atoi(e) : -1;
+  }();
+  if constexpr (sizeof(T) == 8 && VB <= 24) {
+    const bool big = n_c * (int64_t)(a1 - a0) >= (int64_t)1 << 20;  // >= ~1 wave of 5 CTAs x 148 SMs x 8 arms x 128 contexts
+    if (direct_mode == 1 || (direct_mode < 0 && big)) {
+      switch (st->dim_pad) {
+        case 4: return launch_variant<T, 4, VB, true>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
+        case 8: return launch_variant<T, 8, VB, true>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
+      }
+    }
+  }
   switch (st->dim_pad) {
-    case 1: return launch_variant<T, 1, VB>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
-    case 2: return launch_variant<T, 2, VB>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
-    case 4: return launch_variant<T, 4, VB>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
-    case 8: return launch_variant<T, 8, VB>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
-    case 16: return launch_variant<T, 16, VB>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
+    case 1: return launch_variant<T, 1, VB, false>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
+    case 2: return launch_variant<T, 2, VB, false>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
+    case 4: return launch_variant<T, 4, VB, false>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
+    case 8: return launch_variant<T, 8, VB, false>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
+    case 16: return launch_variant<T, 16, VB, false>(st, ctx, n_c, a0, a1, n_rows, mean, var, ld, col, s);
   }
   return CRS_ERR_UNSUPPORTED;
 }
