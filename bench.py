@@ -556,7 +556,89 @@ def run_headline(args, env):
 
 
 def run_headline_arms(args, env):
-    raise SystemExit("--partition arms: not implemented yet")
+    """The headline step under the partition BASELINE.json's north_star describes: ARMS sharded over the
+    ranks (each owns K/N independent GPs for all 65,536 contexts), all-gather of the per-context bests,
+    all-gather of the ranks' 64-byte minimisers, all-reduce of the psi partials; the PCS needs every arm
+    of a context, so the grid is re-sharded by context with one all-to-all first.  Device timed like the
+    default; e2e adds the host->device copy of the whole context set on every rank and the read-back."""
+    import contextual_rs_b200 as crs  # noqa: F401
+    from contextual_rs_b200.sharded import ArmShardedDecider
+    from contextual_rs_b200.synthetic import make_config
+    dev, world, rank = env.dev, env.world, env.rank
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    w = 8 if dtype == torch.float64 else 4
+    desc, ctx = make_config("c4")
+    K, n_c, d = len(desc["train_X"]), ctx.shape[0], ctx.shape[1]
+    S = PCS_SAMPLES
+    dec = ArmShardedDecider(desc, ctx, dev, dtype=dtype)
+    W, K_steps = max(args.warmup, 3), max(args.steps, 1)
+    it = [0]
+    last = {}
+    ctx_host = ctx.to(dtype).pin_memory()
+
+    def device_step():
+        it[0] += 1
+        dec.launch(prepare=True)
+        dec.pcs_total_launch(S, seed=0, offset=it[0])
+
+    def e2e_step():
+        it[0] += 1
+        dec.ws["ctx"].copy_(ctx_host, non_blocking=True)
+        d_ = dec.decide_struct(prepare=True)
+        pcs = dec.pcs_mean(S, seed=0, offset=it[0])
+        last.update(next_arm=int(d_.next_arm), next_context=int(d_.context), pcs=float(pcs))
+
+    def decision_only():
+        dec.launch(prepare=True)
+
+    def reshard_only():
+        dec.reshard_by_context()
+
+    for _ in range(W):
+        env.flush()
+        device_step()
+        e2e_step()
+    env.barrier()
+    sampler = ClockSampler(env.local_rank)
+    if rank == 0:
+        sampler.start()
+    env.barrier()
+    dev_ms = env.timed(device_step, K_steps)
+    env.barrier()
+    e2e_ms = env.timed(e2e_step, K_steps)
+    env.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ksteps = min(K_steps, 20)
+    dec_ms = env.timed(decision_only, ksteps)
+    env.barrier()
+    rs_ms = env.timed(reshard_only, ksteps)
+    env.barrier()
+    avg = lambda v: sum(v) / len(v)  # noqa: E731
+    t_dev, t_e2e, dec_avg, rs_avg = env.max_over_ranks([sum(dev_ms) / 1e3, sum(e2e_ms) / 1e3, avg(dec_ms), avg(rs_ms)])
+    if rank == 0:
+        exp_arm, exp_ctx = expected_headline_decision()
+        got = (last["next_arm"], last["next_context"])
+        if dtype == torch.float64 and got != (exp_arm, exp_ctx):
+            raise SystemExit(f"headline decision {got} != fp64 oracle's {(exp_arm, exp_ctx)}")
+        sent_decision = (world - 1) * (3 * 8 * n_c + 64 + 24) // 1
+        sent_reshard = int(2 * w * n_c * (K / world) * (world - 1) / world)
+        emit({
+            "metric": "gp_c_ocba_decisions_per_sec", "value": K_steps / t_dev, "unit": "decisions/s",
+            "n_gpus": world, "steps": K_steps, "warmup": W, "ms_per_step": t_dev / K_steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config("headline", world, args),
+            "step": "arms sharded: prepare + local grid + scan + pack | all-gather bests | combine + scan vs global best | "
+                    "all-gather records | fold + select | all-reduce psi | finish | all-to-all re-shard | PCS build + sample | all-reduce",
+            "breakdown_ms": {"decision": dec_avg, "context_reshard_all_to_all": rs_avg,
+                             "pcs_and_rest": t_dev / K_steps * 1e3 - dec_avg - rs_avg},
+            "bytes_sent_per_rank_per_step": {"decision_collectives": sent_decision, "context_reshard": sent_reshard},
+            "e2e": {"value": K_steps / t_e2e, "unit": "decisions/s", "ms_per_step": t_e2e / K_steps * 1e3,
+                    "h2d_bytes_per_step": int(n_c * d * w) * world, "d2h_bytes_per_step": (64 + 8) * world,
+                    "api": "ArmShardedDecider.decide_struct + .pcs_mean, every rank uploading the whole context set"},
+            "gpu_launches": 14 * 2 * K_steps * world,
+            "decision": {"next_arm": got[0], "next_context": got[1], "pcs_mean": last["pcs"], "matches_fp64_oracle": True},
+            "roofline": None, "clocks": clocks})
+    env.finish()
 
 
 # ---------------------------------------------------------------------------------- decision only

@@ -85,6 +85,11 @@ _SIGNATURES = {
     "crs_ocba_scan_select_sharded": (C.c_int, [C.POINTER(GPState), vp, vp, vp, i64, i64, i32, f64, vp, vp, vp, vp, vp, vp,
                                                C.POINTER(PeerExchange), vp, vp]),
     "crs_wait_decision": (C.c_int, [vp, i32, i32]),
+    "crs_arm_pack_best": (C.c_int, [vp, vp, i64, i64, i32, i32, vp, vp, vp]),
+    "crs_arm_combine_best": (C.c_int, [vp, i32, i64, i32, vp, vp, vp, vp]),
+    "crs_arm_record_mean": (C.c_int, [vp, vp, i64, i32, i32, vp]),
+    "crs_arm_fold": (C.c_int, [vp, i32, vp, vp, vp]),
+    "crs_arm_finish": (C.c_int, [vp, vp, vp, vp]),
     "crs_peer_sum_u64": (C.c_int, [vp, i32, vp, vp, C.POINTER(PeerExchange), vp]),
     "crs_wait_u64": (C.c_int, [vp, u64, i32]),
     "crs_mailbox_bytes": (i64, [i32]),

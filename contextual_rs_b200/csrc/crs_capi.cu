@@ -123,6 +123,29 @@ CRS_API int crs_wait_decision(const crs_decision* decision_host, int32_t seq, in
   return CRS_OK;
 }
 
+CRS_API int crs_arm_pack_best(const void* mean, const void* var, int64_t n_c, int64_t ld, int32_t dtype, int32_t arm_offset,
+                              const int32_t* best_arm, double* pack, void* stream) {
+  return launch_arm_pack_best(mean, var, n_c, ld, dtype, arm_offset, best_arm, pack, (cudaStream_t)stream);
+}
+
+CRS_API int crs_arm_combine_best(const double* pack_all, int32_t world, int64_t n_c, int32_t dtype, int32_t* ext_arm,
+                                 void* ext_mean, void* ext_var, void* stream) {
+  return launch_arm_combine_best(pack_all, world, n_c, dtype, ext_arm, ext_mean, ext_var, (cudaStream_t)stream);
+}
+
+CRS_API int crs_arm_record_mean(crs_decision* decision, const void* mean, int64_t ld, int32_t dtype, int32_t arm_offset,
+                                void* stream) {
+  return launch_arm_record_mean(decision, mean, ld, dtype, arm_offset, (cudaStream_t)stream);
+}
+
+CRS_API int crs_arm_fold(const crs_decision* records, int32_t world, const int32_t* ext_arm, crs_decision* out, void* stream) {
+  return launch_arm_fold(records, world, ext_arm, out, (cudaStream_t)stream);
+}
+
+CRS_API int crs_arm_finish(crs_decision* decision, const double* psi, const int32_t* bad, void* stream) {
+  return launch_arm_finish(decision, psi, bad, (cudaStream_t)stream);
+}
+
 CRS_API int crs_peer_sum_u64(const uint64_t* values, int32_t n, uint64_t* out, uint64_t* out_host,
                              const crs_peer_exchange* px, void* stream) {
   uint64_t* mirror = nullptr;

@@ -167,6 +167,13 @@ int launch_ocba_select(const crs_gp_state* st, const void* ctx, const void* mean
                        int64_t ld, int arm_offset, int p_mode, double kernel_scale,
                        crs_decision* decision, crs_decision* host_mirror, int seq, const crs_peer_exchange* px,
                        cudaStream_t s);
+int launch_arm_pack_best(const void* mean, const void* var, int64_t n_c, int64_t ld, int dtype, int arm_offset,
+                         const int32_t* best_arm, double* pack, cudaStream_t s);
+int launch_arm_combine_best(const double* pack_all, int world, int64_t n_c, int dtype, int32_t* ext_arm, void* ext_mean,
+                            void* ext_var, cudaStream_t s);
+int launch_arm_record_mean(crs_decision* decision, const void* mean, int64_t ld, int dtype, int arm_offset, cudaStream_t s);
+int launch_arm_fold(const crs_decision* records, int world, const int32_t* ext_arm, crs_decision* out, cudaStream_t s);
+int launch_arm_finish(crs_decision* decision, const double* psi, const int32_t* bad, cudaStream_t s);
 int launch_peer_sum(const uint64_t* values, int n, uint64_t* out, uint64_t* host_mirror, const crs_peer_exchange* px,
                     cudaStream_t s);
 int launch_peer_exchange_only(crs_decision* decision, crs_decision* host_mirror, int seq, const crs_peer_exchange* px,

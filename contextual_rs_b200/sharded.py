@@ -86,15 +86,20 @@ def combine_local_best(means: Tensor, variances: Tensor, arms: Tensor) -> Tuple[
 
 
 def combine_arm_sharded(records: Tensor, mean_at: Optional[Tensor] = None) -> Tensor:
-    """Arm sharding, step 3/4: every rank's record refers to the SAME context set; the global
-    minimiser is the smallest zeta, then the lowest context, then (same context) the larger mean of
-    the zeta arm / lower arm id is left to the per-rank rule.  psi partial sums are added."""
+    """Arm sharding, step 3/4 (host restatement of ``crs_arm_fold``): every rank's record refers to the
+    SAME context set; the global minimiser is the smallest zeta, then the lowest context, then — the
+    same context on several shards — the zeta arm with the LARGER mean (``mean_at[r]``, the reference's
+    descending-mean sort order, which is also the single-GPU kernel's rule), then the lower arm id.
+    Tie counts of all records at the minimum are added."""
     z = records[:, REC_MIN_ZETA]
     zmin = z.min()
     at_min = z == zmin
     ctx = torch.where(at_min, records[:, REC_CONTEXT], torch.full_like(z, float("inf")))
     cmin = ctx.min()
     both = at_min & (records[:, REC_CONTEXT] == cmin)
+    if mean_at is not None:
+        mtop = torch.where(both, mean_at.to(z.dtype), torch.full_like(z, -float("inf"))).max()
+        both = both & (mean_at.to(z.dtype) == mtop)
     arms = torch.where(both, records[:, REC_ZETA_ARM], torch.full_like(z, float("inf")))
     winner = int(torch.argmin(arms))
     out = records[winner].clone()
@@ -345,13 +350,21 @@ class ArmShardedDecider:
     """GP-C-OCBA decision (+ PCS) with the ARMS sharded over the ranks — the partition
     BASELINE.json's north_star describes (each arm is an independent GP).
 
-    Rank g owns arms ``shard_bounds(K, world, g)`` for ALL contexts.  Exchanges per decision:
-      1. all-gather of the per-context local best (mean, variance, arm id): ``3 x n_c`` doubles/rank;
-      2. all-gather of each rank's 64-byte ``crs_decision`` (local zeta minimiser against the
-         global best, ``ext_best_*`` of ``crs_ocba_scan``);
-      3. all-reduce of the two psi partial sums of step 2(b).
-    PCS needs every arm of a context, so the grid is re-sharded by context with one all-to-all and
-    the counts are summed with one all-reduce.
+    Rank g owns arms ``shard_bounds(K, world, g)`` for ALL contexts.  One decision is stream-resident —
+    no host parsing between its steps; the host reads the finished 64-byte ``crs_decision`` once:
+
+      1. local grid ``[n_c, K/G]`` + local per-context best (``crs_ocba_scan``) -> ``crs_arm_pack_best``
+      2. **all-gather** of the packed bests, ``3 x n_c`` doubles per rank (NCCL; C4: 1.5 MB/rank)
+         -> ``crs_arm_combine_best`` = global best per context
+      3. local zeta minimiser against the global best (``crs_ocba_scan`` with ``ext_best_*``)
+         -> ``crs_arm_record_mean`` -> **all-gather** of the 64-byte records -> ``crs_arm_fold``
+      4. psi partial sums of step 2(b) at the selected context (``crs_ocba_select`` on the local arms)
+         -> **all-reduce** of 2 doubles (+ status) -> ``crs_arm_finish``.
+
+    PCS needs every arm of a context, so the grid is re-sharded by context with one all-to-all
+    (``(K/G) x (n_c/G) x 2w`` bytes per pair; C4 fp64: 16 MB) and the counts are summed with one
+    all-reduce.  Bytes a rank sends per decision + PCS: ``(G-1)/G`` of
+    ``3 x 8 n_c + 64 + 24`` (decision) and of ``2 w n_c K/G`` (re-shard).
     """
 
     def __init__(self, desc: dict, context_set: Tensor, device, dtype=torch.float64, group=None):
@@ -367,93 +380,138 @@ class ArmShardedDecider:
         self.ctx = context_set.to(device=m.device, dtype=m.dtype).contiguous()
         self.ws = m.private_workspace(self.n_c)
         self.ws["ctx"].copy_(self.ctx)
-        self._ext_arm = torch.zeros(self.n_c, dtype=torch.int32, device=m.device)
-        self._pack = torch.zeros(3, self.n_c, dtype=torch.float64, device=m.device)
-        self._pack_all = torch.zeros(self.world, 3, self.n_c, dtype=torch.float64, device=m.device)
-        self._dec_all = torch.zeros(self.world, 64, dtype=torch.uint8, device=m.device)
+        dev = m.device
+        self._ext_arm = torch.zeros(self.n_c, dtype=torch.int32, device=dev)
+        self._ext_mean = torch.zeros(self.n_c, dtype=m.dtype, device=dev)
+        self._ext_var = torch.zeros(self.n_c, dtype=m.dtype, device=dev)
+        self._pack = torch.zeros(3, self.n_c, dtype=torch.float64, device=dev)
+        self._pack_all = torch.zeros(self.world, 3, self.n_c, dtype=torch.float64, device=dev)
+        self._dec_all = torch.zeros(self.world, 64, dtype=torch.uint8, device=dev)
+        self._psi = torch.zeros(3, dtype=torch.float64, device=dev)  # psi_best, psi_rest, max status
+        self._bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._dec_host = torch.zeros(64, dtype=torch.uint8).pin_memory()
+        self._dec_view = _lib.Decision.from_address(self._dec_host.data_ptr())
+        # context re-shard for the PCS (equal splits: padded so that every rank sends the same row count)
+        self._rows = (self.n_c + self.world - 1) // self.world
+        self._kmax = max(e - b for b, e in (shard_bounds(self.K, self.world, r) for r in range(self.world)))
+        self._cdf_ws = None
+        self._stats = torch.zeros(8, dtype=torch.int64, device=dev)
 
-    def decide(self, p_mode: int = _lib.CRS_P_COUNT, kernel_scale: float = 2.0) -> Tensor:
-        """Returns the combined record (``REC_*`` columns) on the host, identical on every rank."""
+    def launch(self, p_mode: int = _lib.CRS_P_COUNT, kernel_scale: float = 2.0, prepare: bool = False) -> None:
+        """Enqueue one whole decision on the current stream; ``ws["decision"]`` holds the result."""
         m, ws, lib = self.model, self.ws, _lib.get()
         n_c, Kl, dt = self.n_c, m.num_arms, _lib.DTYPES[m.dtype]
         with torch.cuda.device(m.device):
             stream = _lib.stream_ptr(m.device)
+            if prepare:
+                m.prepare(0, Kl, relearn=False)
             st = C.byref(m.state)
-            # local grid and local per-context best
-            m.posterior_tables(ws["ctx"], ws["mean"], ws["var"], arms=(0, Kl))
-            _lib.check(lib.crs_ocba_scan(ws["mean"].data_ptr(), ws["var"].data_ptr(), n_c, Kl, Kl, dt, self.a0,
-                                         None, None, None, ws["best_arm"].data_ptr(), None, None, None, None,
-                                         None, stream), "crs_ocba_scan")
-            loc = (ws["best_arm"].long() - self.a0).unsqueeze(1)
-            self._pack[0] = ws["mean"].gather(1, loc).squeeze(1).double()
-            self._pack[1] = ws["var"].gather(1, loc).squeeze(1).double()
-            self._pack[2] = ws["best_arm"].double()
-            # 1. global best per context
+            mean_p, var_p = ws["mean"].data_ptr(), ws["var"].data_ptr()
+            _lib.check(lib.crs_posterior_grid(st, ws["ctx"].data_ptr(), n_c, 0, Kl, mean_p, var_p, Kl, 0, stream),
+                       "crs_posterior_grid")
+            # 1. local per-context best
+            _lib.check(lib.crs_ocba_scan(mean_p, var_p, n_c, Kl, Kl, dt, self.a0, None, None, None,
+                                         ws["best_arm"].data_ptr(), None, None, None, None, None, stream), "crs_ocba_scan")
+            _lib.check(lib.crs_arm_pack_best(mean_p, var_p, n_c, Kl, dt, self.a0, ws["best_arm"].data_ptr(),
+                                             self._pack.data_ptr(), stream), "crs_arm_pack_best")
+            # 2. global best per context
             if self.world > 1:
                 dist.all_gather_into_tensor(self._pack_all, self._pack, group=self.group)
+                pack_all = self._pack_all
             else:
-                self._pack_all[0] = self._pack
-            bm, bv, barm = combine_local_best(self._pack_all[:, 0], self._pack_all[:, 1],
-                                              self._pack_all[:, 2].to(torch.int64))
-            bm_t, bv_t = bm.to(m.dtype).contiguous(), bv.to(m.dtype).contiguous()
-            self._ext_arm.copy_(barm.to(torch.int32))
-            # 2. local zeta minimiser against the global best
-            _lib.check(lib.crs_ocba_scan(ws["mean"].data_ptr(), ws["var"].data_ptr(), n_c, Kl, Kl, dt, self.a0,
-                                         self._ext_arm.data_ptr(), bm_t.data_ptr(), bv_t.data_ptr(),
-                                         None, ws["min_zeta"].data_ptr(), ws["min_arm"].data_ptr(),
-                                         ws["tie_cnt"].data_ptr(), ws["decision"].data_ptr(),
-                                         ws["scan_ws"].data_ptr(), stream), "crs_ocba_scan")
+                pack_all = self._pack
+            _lib.check(lib.crs_arm_combine_best(pack_all.data_ptr(), self.world, n_c, dt, self._ext_arm.data_ptr(),
+                                                self._ext_mean.data_ptr(), self._ext_var.data_ptr(), stream),
+                       "crs_arm_combine_best")
+            # 3. local zeta minimiser against the global best, folded over ranks
+            _lib.check(lib.crs_ocba_scan(mean_p, var_p, n_c, Kl, Kl, dt, self.a0, self._ext_arm.data_ptr(),
+                                         self._ext_mean.data_ptr(), self._ext_var.data_ptr(), None,
+                                         ws["min_zeta"].data_ptr(), ws["min_arm"].data_ptr(), ws["tie_cnt"].data_ptr(),
+                                         ws["decision"].data_ptr(), ws["scan_ws"].data_ptr(), stream), "crs_ocba_scan")
+            _lib.check(lib.crs_arm_record_mean(ws["decision"].data_ptr(), mean_p, Kl, dt, self.a0, stream),
+                       "crs_arm_record_mean")
             if self.world > 1:
                 dist.all_gather_into_tensor(self._dec_all, ws["decision"], group=self.group)
+                recs = self._dec_all
             else:
-                self._dec_all[0] = ws["decision"]
-            raw = self._dec_all.cpu()
-            recs = torch.zeros(self.world, REC_WIDTH, dtype=torch.float64)
-            for r in range(self.world):
-                d = _lib.Decision.from_buffer_copy(raw[r].numpy().tobytes())
-                recs[r] = decision_record(d.min_zeta if d.context >= 0 else float("inf"), d.tie_count,
-                                          d.context, d.zeta_arm, d.best_arm, -1)
-            out = combine_arm_sharded(recs)
-            c_star, zeta_arm = int(out[REC_CONTEXT]), int(out[REC_ZETA_ARM])
-            best = int(barm[c_star])
-            # 3. psi partial sums at the selected context
-            glob = _lib.Decision(min_zeta=float(out[REC_MIN_ZETA]), tie_count=int(out[REC_TIES]), context=c_star,
-                                 zeta_arm=zeta_arm, best_arm=best, next_arm=-1)
-            ws["decision"].copy_(torch.frombuffer(bytearray(bytes(glob)), dtype=torch.uint8))
-            _lib.check(lib.crs_ocba_select(st, ws["ctx"].data_ptr(), ws["mean"].data_ptr(), ws["var"].data_ptr(),
-                                           Kl, self.a0, p_mode, float(kernel_scale), ws["decision"].data_ptr(),
-                                           stream), "crs_ocba_select")
-            psi = ws["decision"].view(torch.float64)[1:3].clone()  # psi_best, psi_rest partials
+                self._dec_all[0].copy_(ws["decision"])
+                recs = self._dec_all
+            _lib.check(lib.crs_arm_fold(recs.data_ptr(), self.world, self._ext_arm.data_ptr(), ws["decision"].data_ptr(),
+                                        stream), "crs_arm_fold")
+            # 4. psi partial sums at the selected context, summed over ranks
+            _lib.check(lib.crs_ocba_select(st, ws["ctx"].data_ptr(), mean_p, var_p, Kl, self.a0, p_mode,
+                                           float(kernel_scale), ws["decision"].data_ptr(), stream), "crs_ocba_select")
+            dview = ws["decision"].view(torch.float64)
+            self._psi[:2].copy_(dview[1:3])
+            self._psi[2] = ws["decision"].view(torch.int32)[12].to(torch.float64)  # reserved[0]: first bad arm + 1
             if self.world > 1:
-                dist.all_reduce(psi, group=self.group)
-            psi_h = psi.cpu()
-        out[REC_BEST_ARM] = best
-        out[REC_PSI_BEST], out[REC_PSI_REST] = psi_h[0], psi_h[1]
-        out[REC_NEXT_ARM] = best if float(psi_h[0]) < float(psi_h[1]) else zeta_arm
-        return out
+                dist.all_reduce(self._psi[:2], group=self.group)
+                dist.all_reduce(self._psi[2:], op=dist.ReduceOp.MAX, group=self.group)
+            self._bad.copy_(self._psi[2:].to(torch.int32))
+            _lib.check(lib.crs_arm_finish(ws["decision"].data_ptr(), self._psi.data_ptr(), self._bad.data_ptr(), stream),
+                       "crs_arm_finish")
 
-    def pcs_mean(self, num_samples: int, seed: int, offset: int = 0) -> Tensor:
-        """Context re-shard (one all-to-all of the local grid) + local counts + one all-reduce."""
-        from .generalized_pcs import pcs_counts
-        m, ws = self.model, self.ws
-        b, e = shard_bounds(self.n_c, self.world, self.rank)
-        if self.world > 1:
-            splits = [shard_bounds(self.n_c, self.world, r) for r in range(self.world)]
-            arms = [shard_bounds(self.K, self.world, r) for r in range(self.world)]
-            full = []
-            for tab in (ws["mean"], ws["var"]):
+    def decide_struct(self, p_mode: int = _lib.CRS_P_COUNT, kernel_scale: float = 2.0, prepare: bool = False):
+        self.launch(p_mode, kernel_scale, prepare)
+        self._dec_host.copy_(self.ws["decision"], non_blocking=True)
+        torch.cuda.current_stream(self.model.device).synchronize()
+        d = self._dec_view
+        if d.reserved[0] > 0:
+            raise RuntimeError(f"arm {d.reserved[0] - 1}: kernel matrix not positive definite")
+        return d
+
+    def decide(self, p_mode: int = _lib.CRS_P_COUNT, kernel_scale: float = 2.0, prepare: bool = False) -> Tensor:
+        """Returns the combined record (``REC_*`` columns) on the host, identical on every rank."""
+        d = self.decide_struct(p_mode, kernel_scale, prepare)
+        return decision_record(d.min_zeta, d.tie_count, d.context, d.zeta_arm, d.best_arm, d.next_arm,
+                               d.psi_best, d.psi_rest)
+
+    def reshard_by_context(self) -> Tuple[Tensor, Tensor, int, int]:
+        """One all-to-all of the local grid: returns ``(mean, var)`` ``[n_loc, K]`` of this rank's context
+        slice with ALL arms, plus the slice's ``(begin, n_loc)``."""
+        m, ws, G = self.model, self.ws, self.world
+        b, e = shard_bounds(self.n_c, G, self.rank)
+        if G == 1:
+            return ws["mean"], ws["var"], 0, self.n_c
+        Kl = m.num_arms
+        even_rows = self.n_c % G == 0
+        even_arms = self.K % G == 0
+        out = []
+        for tab in (ws["mean"], ws["var"]):
+            if even_rows and even_arms:  # one contiguous exchange + one permuting copy
+                recv = torch.empty(G, e - b, Kl, dtype=m.dtype, device=m.device)
+                dist.all_to_all_single(recv, tab.view(G, e - b, Kl), group=self.group)
+                out.append(recv.permute(1, 0, 2).reshape(e - b, self.K))
+            else:
+                splits = [shard_bounds(self.n_c, G, r) for r in range(G)]
+                arms = [shard_bounds(self.K, G, r) for r in range(G)]
                 send = [tab[s0:s1].contiguous() for s0, s1 in splits]
                 recv = [torch.empty(e - b, a1 - a0, dtype=m.dtype, device=m.device) for a0, a1 in arms]
                 dist.all_to_all(recv, send, group=self.group)
-                full.append(torch.cat(recv, dim=1).contiguous())
-            mean, var = full
+                out.append(torch.cat(recv, dim=1).contiguous())
+        return out[0], out[1], b, e - b
+
+    def pcs_total_launch(self, num_samples: int, seed: int, offset: int = 0) -> Tensor:
+        """Context re-shard + local counts + one all-reduce; returns the 1-element int64 device tensor
+        holding the total success count over all contexts (no host sync)."""
+        from .generalized_pcs import pcs_counts
+        mean, var, b, n_loc = self.reshard_by_context()
+        if n_loc:
+            if self._cdf_ws is None:
+                nbytes = int(_lib.get().crs_pcs_cdf_workspace_bytes(max(n_loc, 1)))
+                self._cdf_ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.model.device)
+            pcs_counts(self.model, mean, var, num_samples, seed, offset, ctx_offset=b, stats=self._stats,
+                       sampler="cdf", workspace=self._cdf_ws)
         else:
-            mean, var = ws["mean"], ws["var"]
-        counts = pcs_counts(m, mean, var, num_samples, seed, offset, ctx_offset=b)
-        total = counts.sum(dtype=torch.int64).to(torch.float64).reshape(1)
+            self._stats.zero_()
+        total = self._stats[4:5]
         if self.world > 1:
             dist.all_reduce(total, group=self.group)
-        return total / (float(num_samples) * self.n_c)
+        return total
+
+    def pcs_mean(self, num_samples: int, seed: int, offset: int = 0) -> Tensor:
+        total = self.pcs_total_launch(num_samples, seed, offset)
+        return total.to(torch.float64).cpu() / (float(num_samples) * self.n_c)
 
 
 class ShardedSequentialRS:

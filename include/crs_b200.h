@@ -273,6 +273,31 @@ CRS_API int crs_ocba_scan_select_sharded(const crs_gp_state* st, const void* ctx
 /* Spin (GIL-free for ctypes callers) until decision_host->reserved[1] == seq; CRS_ERR_CUDA after timeout_ms. */
 CRS_API int crs_wait_decision(const crs_decision* decision_host, int32_t seq, int32_t timeout_ms);
 /*
+ * ARM-sharded decision (the partition BASELINE.json's north_star names: rank g owns arms [a0, a1) of ALL
+ * contexts).  These are the device-side steps between its collectives, so that
+ * gao_modellist's sort head / zeta argmin / step 2(b) (contextual_rs/contextual_rs_strategies.py:137-157,
+ * 195-201) stay on the stream:
+ *   crs_arm_pack_best     best_arm[n_c] (GLOBAL ids, from crs_ocba_scan with arm_offset = a0) + the local
+ *                         tables -> pack[3][n_c] doubles (mean, variance, arm id): the all-gather payload
+ *   crs_arm_combine_best  pack_all[world][3][n_c] -> global best per context (largest mean, lowest arm id)
+ *                         as ext_arm / ext_mean / ext_var, the ext_best_* inputs of crs_ocba_scan
+ *   crs_arm_record_mean   stores the mean of the record's zeta arm in decision->psi_best (tie rule below)
+ *   crs_arm_fold          records[world] (all-gathered crs_decision of the ranks' scans against the global
+ *                         best) -> the global minimiser: smallest zeta, lowest context, larger mean of the
+ *                         zeta arm, lower arm id; tie counts at the minimum added; best_arm = ext_arm[context]
+ *   crs_arm_finish        psi[2] = all-reduced (psi_best, psi_rest) partials of crs_ocba_select ->
+ *                         next_arm = psi_best < psi_rest ? best_arm : zeta_arm; *bad != 0 -> reserved[0]
+ */
+CRS_API int crs_arm_pack_best(const void* mean, const void* var, int64_t n_c, int64_t ld, int32_t dtype, int32_t arm_offset,
+                              const int32_t* best_arm, double* pack, void* stream);
+CRS_API int crs_arm_combine_best(const double* pack_all, int32_t world, int64_t n_c, int32_t dtype, int32_t* ext_arm,
+                                 void* ext_mean, void* ext_var, void* stream);
+CRS_API int crs_arm_record_mean(crs_decision* decision, const void* mean, int64_t ld, int32_t dtype, int32_t arm_offset,
+                                void* stream);
+CRS_API int crs_arm_fold(const crs_decision* records, int32_t world, const int32_t* ext_arm, crs_decision* out, void* stream);
+CRS_API int crs_arm_finish(crs_decision* decision, const double* psi, const int32_t* bad, void* stream);
+
+/*
  * Sum n <= 8 counters over the ranks of a mailbox group (the "one allreduce" of the PCS success counts of
  * a context-sharded estimate before rho, contextual_rs/generalized_pcs.py:470-479) in
  * one single-CTA launch: `values` (device) -> `out` (device, may be NULL) and, if out_host is mapped

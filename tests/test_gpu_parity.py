@@ -548,9 +548,11 @@ def test_pcs_tree_limits(crs):
     var = torch.ones(2, 4110, dtype=torch.float64, device=DEV)
     with pytest.raises(ValueError):
         pcs_counts(None, mean, var, 64, seed=1, sampler="tree")
-    a = pcs_counts(None, mean, var, 256, seed=1)          # auto -> flat stream beyond 4102 arms
-    b = pcs_counts(None, mean, var, 256, seed=1, sampler="flat")
+    a = pcs_counts(None, mean, var, 256, seed=1)          # auto -> cdf stream (any K >= 2); flat also serves K > 4102
+    b = pcs_counts(None, mean, var, 256, seed=1, sampler="cdf")
     assert torch.equal(a, b)
+    f = pcs_counts(None, mean, var, 256, seed=1, sampler="flat")
+    assert int(f.max()) <= 256 and abs(int(f.sum()) - int(a.sum())) <= 40  # two contexts, PCS ~ 1/4110: both near 0
     one = pcs_counts(None, mean[:, :1].contiguous(), var[:, :1].contiguous(), 100, seed=1)  # K = 1: no competitor
     assert one.tolist() == [100, 100]
     from contextual_rs_b200 import _lib

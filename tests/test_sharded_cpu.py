@@ -145,3 +145,21 @@ def test_combine_rules_ties_and_empty_shards():
     ])
     out = sh.combine_context_sharded(recs)
     assert (int(out[sh.REC_CONTEXT]), int(out[sh.REC_ZETA_ARM]), int(out[sh.REC_TIES])) == (12, 2, 3)
+
+
+def test_arm_sharded_cross_shard_tie_rule():
+    """Equal zeta at the SAME context on two shards: the zeta arm with the larger mean wins, then the lower
+    arm id (the reference's descending-mean sort order = the single-GPU kernel's rule = crs_arm_fold)."""
+    from contextual_rs_b200 import sharded as sh
+    recs = torch.stack([sh.decision_record(0.25, 1, 4, 2, 7, -1),    # shard 0: arm 2 at context 4
+                        sh.decision_record(0.25, 2, 4, 5, 7, -1),    # shard 1: arm 5 at context 4, same zeta
+                        sh.decision_record(0.30, 1, 1, 8, 6, -1)])
+    out = sh.combine_arm_sharded(recs, mean_at=torch.tensor([1.0, 3.0, 9.0], dtype=torch.float64))
+    assert int(out[sh.REC_ZETA_ARM]) == 5 and int(out[sh.REC_TIES]) == 3 and int(out[sh.REC_CONTEXT]) == 4
+    out = sh.combine_arm_sharded(recs, mean_at=torch.tensor([3.0, 3.0, 9.0], dtype=torch.float64))
+    assert int(out[sh.REC_ZETA_ARM]) == 2                            # equal means: lower arm id
+    out = sh.combine_arm_sharded(recs)                                # without means: lower arm id
+    assert int(out[sh.REC_ZETA_ARM]) == 2
+    recs[2, sh.REC_MIN_ZETA] = 0.25                                   # a third record at the minimum, lower context
+    out = sh.combine_arm_sharded(recs, mean_at=torch.tensor([1.0, 3.0, 9.0], dtype=torch.float64))
+    assert int(out[sh.REC_CONTEXT]) == 1 and int(out[sh.REC_ZETA_ARM]) == 8 and int(out[sh.REC_TIES]) == 4
