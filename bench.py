@@ -609,7 +609,13 @@ def run_headline_arms(args, env):
     env.barrier()
     clocks = sampler.stop() if rank == 0 else None
     ksteps = min(K_steps, 20)
+    for _ in range(2):
+        decision_only()
+    env.barrier()
     dec_ms = env.timed(decision_only, ksteps)
+    env.barrier()
+    for _ in range(2):
+        reshard_only()
     env.barrier()
     rs_ms = env.timed(reshard_only, ksteps)
     env.barrier()

@@ -10,9 +10,10 @@ from .continuous_context import MinZeta, find_next_arm_given_context
 from .generalized_pcs import (estimate_current_generalized_pcs, estimate_lookahead_generalized_pcs_modellist,
                               empirical_best_arms)
 from .levi import PredictiveEI, discrete_levi
+from .optimize import optimize_acqf
 
 __all__ = [
     "B200ModelListGP", "B200Posterior", "from_botorch", "gao_modellist", "MinZeta",
     "find_next_arm_given_context", "estimate_current_generalized_pcs", "empirical_best_arms",
-    "PredictiveEI", "discrete_levi", "estimate_lookahead_generalized_pcs_modellist",
+    "PredictiveEI", "discrete_levi", "estimate_lookahead_generalized_pcs_modellist", "optimize_acqf",
 ]

@@ -107,12 +107,18 @@ def _projected_gradient(raw: Tensor, g: Tensor, d: int) -> Tensor:
     return pg
 
 
-def batched_lbfgs(obj: _Objective, raw0: Tensor, active: Optional[Tensor] = None, maxiter: int = 500,
-                  history: int = 10, gtol: float = 1e-6, ftol: float = 1e-12, max_backtracks: int = 25):
+def batched_lbfgs(obj, raw0: Tensor, active: Optional[Tensor] = None, maxiter: int = 500,
+                  history: int = 10, gtol: float = 1e-6, ftol: float = 1e-12, max_backtracks: int = 25,
+                  project=None, projected_gradient=None):
     """K independent L-BFGS minimisations advanced in lockstep.  Stopping rules are scipy
     L-BFGS-B's (projected-gradient sup-norm, relative decrease) with 10x / 2000x tighter
-    tolerances than its defaults (1e-5, 2.2e-9): an objective launch costs < 1 ms for all arms."""
+    tolerances than its defaults (1e-5, 2.2e-9): an objective launch costs < 1 ms for all arms.
+    ``obj(x) -> (f [K], g [K, P])``; ``project(x, d)`` / ``projected_gradient(x, g, d)`` encode the
+    feasible set (default: the noise bound of the hyper-parameter fit; ``contextual_rs_b200.optimize``
+    passes box bounds) — ``d`` is ``obj.d``."""
     d = obj.d
+    _project = project if project is not None else globals()["_project"]
+    _projected_gradient = projected_gradient if projected_gradient is not None else globals()["_projected_gradient"]
     x = _project(raw0.clone(), d)
     f, g = obj(x)
     K = x.shape[0]
@@ -120,6 +126,7 @@ def batched_lbfgs(obj: _Objective, raw0: Tensor, active: Optional[Tensor] = None
     live &= torch.isfinite(f)
     hist: List = []
     iters = torch.zeros(K, dtype=torch.int32, device=x.device)
+    retry = torch.zeros(K, dtype=torch.bool, device=x.device)  # line search failed: next step is steepest descent
     for _ in range(maxiter):
         pg = _projected_gradient(x, g, d)
         live &= pg.abs().amax(dim=-1) > gtol
@@ -144,7 +151,7 @@ def batched_lbfgs(obj: _Objective, raw0: Tensor, active: Optional[Tensor] = None
             r += s * (a - b).unsqueeze(-1)
         dirn = -r
         gd = (pg * dirn).sum(-1)
-        reset = ~(gd < 0)
+        reset = ~(gd < 0) | retry
         dirn = torch.where(reset.unsqueeze(-1), -pg, dirn)
         gd = torch.where(reset, -(pg * pg).sum(-1), gd)
         # Armijo back-tracking with a per-arm step
@@ -163,6 +170,14 @@ def batched_lbfgs(obj: _Objective, raw0: Tensor, active: Optional[Tensor] = None
                 break
             t = torch.where(pending, t * 0.5, t)
         moved = live & ~pending
+        # a failed quasi-Newton line search (kinks of a min over arms, stale curvature) gets ONE steepest-descent
+        # retry with its curvature pairs dropped before the problem is declared finished
+        failed = live & pending
+        second = failed & retry
+        retry = failed & ~retry
+        if bool(retry.any()):
+            keep = (~retry).unsqueeze(-1)
+            hist = [(s_ * keep, y_ * keep, rho_ * (~retry)) for s_, y_, rho_ in hist]
         s, y = x_new - x, g_new - g
         sy = (s * y).sum(-1)
         good = moved & (sy > 1e-10 * (y * y).sum(-1).clamp_min(1e-300))
@@ -174,7 +189,8 @@ def batched_lbfgs(obj: _Objective, raw0: Tensor, active: Optional[Tensor] = None
         small = (f - f_new) <= ftol * torch.maximum(torch.maximum(f.abs(), f_new.abs()), torch.ones_like(f))
         iters += moved.to(torch.int32)
         x, f, g = x_new, f_new, g_new
-        live &= moved & ~small  # an arm whose line search failed, or that stopped improving, is done
+        live &= (moved & ~small) | retry  # failed twice in a row, or stopped improving: done
+        live &= ~second
     return x, f, g, iters
 
 
