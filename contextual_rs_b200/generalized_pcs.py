@@ -230,33 +230,41 @@ def estimate_lookahead_generalized_pcs_modellist(
         seed = int(torch.randint(2 ** 62, (1,)))
     if model_sampler is not None and fantasy_base is None:
         fantasy_base = torch.randn(n, num_fantasies, dtype=torch.float64)
-    noise_orig = (m.noise * m.y_std * m.y_std).cpu()
-    out = torch.zeros(n, dtype=torch.float64)
-    for i in range(n):
-        arm = int(candidate[i, 0, 0])
+    # Everything below is enqueued without a host round-trip per candidate: the candidates' own posterior
+    # (one [n, K] launch), the fantasy values (device arithmetic), then per (candidate, fantasy) one arm's
+    # prepare + one grid column + the PCS kernels + rho — the host reads the n results once at the end.
+    arms = [int(a) for a in candidate[:, 0, 0].tolist()]
+    for i, arm in enumerate(arms):
         if not 0 <= arm < K:
             raise ValueError(f"candidate {i}: arm index {arm} out of range")
-        x = candidate[i, :, 1:].to(torch.float64)
-        at_x = m.posterior(x.to(m.dtype), arms=(arm, arm + 1))
-        mu_x, var_x = float(at_x.mean), float(at_x.variance)
-        if model_sampler is None:
-            ys = [mu_x]
-        else:  # fantasize(): noisy posterior draw, in the outcome's original units
-            sd = (var_x + float(noise_orig[arm])) ** 0.5
-            ys = [mu_x + sd * float(z) for z in fantasy_base[i]]
-        keep_m, keep_v = ws["mean"][:, arm].clone(), ws["var"][:, arm].clone()
-        vals = []
-        for f, y in enumerate(ys):
-            m.condition_on_observations(arm, x, torch.tensor([[y]], dtype=torch.float64))
+    xs = candidate[:, 0, 1:].to(device=m.device, dtype=torch.float64)
+    at_mu, at_var = m.posterior_tables(xs.to(m.dtype).contiguous())
+    pick = torch.tensor(arms, dtype=torch.long, device=m.device).unsqueeze(-1)
+    mu_x = at_mu.gather(1, pick).squeeze(-1).to(torch.float64)
+    var_x = at_var.gather(1, pick).squeeze(-1).to(torch.float64)
+    if model_sampler is None:
+        ys = mu_x.unsqueeze(-1)  # certainty equivalent, :262-265
+    else:  # fantasize(): noisy posterior draws, in the outcome's original units, :259-260
+        noise_orig = (m.noise * m.y_std * m.y_std).to(torch.float64)
+        sd = (var_x + noise_orig[pick.squeeze(-1)]).sqrt()
+        ys = mu_x.unsqueeze(-1) + sd.unsqueeze(-1) * fantasy_base.to(device=m.device, dtype=torch.float64)
+    keep_m, keep_v = ws["mean"].clone(), ws["var"].clone()
+    vals = []
+    for i, arm in enumerate(arms):
+        x = xs[i:i + 1]
+        for f in range(num_fantasies):
+            m.condition_on_observations(arm, x, ys[i, f].reshape(1, 1))
             m.posterior_tables(ws["ctx"], ws["mean"], ws["var"], arms=(arm, arm + 1))
             counts = pcs_counts(m, ws["mean"], ws["var"], num_samples, seed, offset=i * num_fantasies + f,
                                 counts=ws["counts"], stats=ws["stats"])
             pcs_c_est = (counts.to(m.dtype) / float(num_samples)).unsqueeze(-1)
-            vals.append(rho(pcs_c_est).squeeze(-1).double().cpu())  # :309
-            m.pop_observations(arm, 1)
-        ws["mean"][:, arm] = keep_m
-        ws["var"][:, arm] = keep_v
-        out[i] = torch.stack(vals).mean()  # :311
+            vals.append(rho(pcs_c_est).squeeze(-1).double().reshape(()))  # :309, stays on the device
+            m.pop_observations(arm, 1, prepare=False)  # the next append (or the final restore) re-prepares the arm
+        ws["mean"][:, arm] = keep_m[:, arm]
+        ws["var"][:, arm] = keep_v[:, arm]
+    for arm in sorted(set(arms)):
+        m.prepare(arm, arm + 1, relearn=False)  # back to the un-fantasised state
+    out = torch.stack(vals).reshape(n, num_fantasies).mean(dim=-1)  # :311
     return out.to(device=candidate.device, dtype=candidate.dtype)
 
 

@@ -243,15 +243,17 @@ class B200ModelListGP:
         if need > self.n_cap:
             self._grow(_round_up(need + 8, 8))
 
-    def pop_observations(self, arm: int, count: int = 1) -> "B200ModelListGP":
-        """Undo the last ``count`` appends to one arm (fantasy roll-back) and rebuild its state."""
+    def pop_observations(self, arm: int, count: int = 1, prepare: bool = True) -> "B200ModelListGP":
+        """Undo the last ``count`` appends to one arm (fantasy roll-back) and rebuild its state
+        (``prepare=False``: the caller re-prepares the arm itself, e.g. with the next fantasy append)."""
         n = self._n_host[arm]
         if count < 0 or count > n:
             raise ValueError("cannot remove more observations than the arm holds")
         self._n_host[arm] = n - count
         self.n_obs[arm] = n - count
         self._state.n_max = self._state_frozen.n_max = max(self._n_host)
-        self.prepare(arm, arm + 1, relearn=False)
+        if prepare:
+            self.prepare(arm, arm + 1, relearn=False)
         return self
 
     def _grow(self, new_cap: int) -> None:
