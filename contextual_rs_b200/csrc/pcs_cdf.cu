@@ -258,24 +258,27 @@ pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
 #pragma unroll
     for (int r = 0; r < 4; ++r) s_F[warp][32 * r + lane] = exp_approx(fmaxf(acc[r], -80.f));
     __syncwarp();
+    // slot 0 = "below lo" (F = 0), slots 1 .. 125 = the cells, slot 126 = "above hi" (F = 1): the sampler
+    // clamps its table coordinate t' = (z - lo) / h + 1 to [0, 127) and needs no range selects
     float4* tab = tables + c * kCdfStride;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int i = 32 * r + lane;
-      float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < kCdfCells) {
+      const int slot = 32 * r + lane, i = slot - 1;
+      float4 cf = make_float4(slot == kCdfCells + 1 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+      if (i >= 0 && i < kCdfCells) {
         const float p0 = s_F[warp][i], p1 = s_F[warp][i + 1], p2 = s_F[warp][i + 2], p3 = s_F[warp][i + 3];
         cf.x = p1;
         cf.y = fmaf(-1.f / 3.f, p0, fmaf(-0.5f, p1, fmaf(-1.f / 6.f, p3, p2)));
         cf.z = fmaf(0.5f, p0 + p2, -p1);
         cf.w = fmaf(1.f / 6.f, p3 - p0, 0.5f * (p1 - p2));
       }
-      tab[i] = cf;
+      tab[slot] = cf;
     }
     float* hdr = headers + c * kCdfHdr;
     if (lane == 0) {
       hdr[0] = lo;
       hdr[1] = inv_h;
+      hdr[4] = fmaf(-lo, inv_h, 1.f);  // t' = z inv_h + hdr[4]
       hdr[2] = __int_as_float(n_sharp);
       hdr[3] = __int_as_float(overflow ? 1 : 0);
       counts[c] = 0u;  // the sampling kernel adds to it
@@ -303,20 +306,24 @@ pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
 
 // ---- sample --------------------------------------------------------------------------------------
 struct CdfCtx {
-  float lo, inv_h;
-  int n_sharp;
+  float inv_h, t0;   // table coordinate t' = z inv_h + t0 (slot 0: below the range, slot 126: above)
+  uint32_t tab;      // shared-window address of this warp's staged table (2 KB aligned)
 };
 
-__device__ __forceinline__ float cdf_eval(float z, const CdfCtx& cx, const float4* __restrict__ tab,
-                                          const float2* __restrict__ sharp, const float4* __restrict__ s_lnphi) {
-  const float t = (z - cx.lo) * cx.inv_h;
-  const float tc = fminf(fmaxf(t, 0.f), (float)kCdfCells - 0.001f);
-  float f;
-  const int i = floor_split(tc, f);
-  const float4 c = tab[i];
-  float F = fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x);
-  F = t < 0.f ? 0.f : (t >= (float)kCdfCells ? 1.f : F);
-  for (int k = 0; k < cx.n_sharp; ++k) {  // warp-uniform trip count
+// F(z) from the staged table: t' + 2^19 rounded toward zero keeps floor(16 t') in the mantissa, i.e. bits
+// 4.. are the slot = exactly its byte offset 16 floor(t'); no conversion unit, no range selects.
+__device__ __forceinline__ float cdf_eval(float z, const CdfCtx& cx) {
+  const float t = fminf(fmaxf(fmaf(z, cx.inv_h, cx.t0), 0.f), (float)(kCdfCells + 2) - 0.001f);
+  const int u = __float_as_int(__fadd_rz(t, 524288.f));
+  const float f = t - (__int_as_float(u & ~0xf) - 524288.f);
+  const float4 c = lds128(cx.tab | (uint32_t)(u & 0x7f0));
+  return fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x);
+}
+
+__device__ __forceinline__ float sharp_factor(float z, int n_sharp, const float2* __restrict__ sharp,
+                                              const float4* __restrict__ s_lnphi) {
+  float F = 1.f;
+  for (int k = 0; k < n_sharp; ++k) {  // warp-uniform trip count
     const float2 ab = sharp[k];
     F *= exp_approx(lnphi(fmaf(ab.x, z, ab.y), s_lnphi));
   }
@@ -335,42 +342,59 @@ pcs_cdf_sample_kernel(const float4* __restrict__ tables, const float* __restrict
                       int64_t ctx_offset, int splits, uint32_t* __restrict__ counts,
                       unsigned long long* __restrict__ stats) {
   __shared__ float4 s_lnphi[kLnPhiCells];
-  __shared__ float4 s_tab[kCdfWarps][kCdfStride];
+  // the warps' 2 KB tables start on a 2 KB boundary of the shared window (the slot's byte offset is OR-ed
+  // into the base): one spare table of slack, aligned by hand
+  __shared__ __align__(16) float4 s_tab_raw[(kCdfWarps + 1) * kCdfStride];
   __shared__ float2 s_sharp[kCdfWarps][kCdfMaxSharp];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   stage_lnphi(s_lnphi, tid, kCdfThreads);
   __syncthreads();
+  const uint32_t tab_base = ((smem_u32(s_tab_raw) + 2047u) & ~2047u) + 2048u * (uint32_t)warp;
+  float4* const my_tab = s_tab_raw + (tab_base - smem_u32(s_tab_raw)) / 16u;
   const int64_t ncalls = (num_samples + 1) >> 1;
+  const uint32_t odd_call = (num_samples & 1) ? (uint32_t)(ncalls - 1) : 0xffffffffu;  // its second sample does not exist
   const int64_t items = n_c * splits;
   const int64_t gw = (int64_t)blockIdx.x * kCdfWarps + warp, nw = (int64_t)gridDim.x * kCdfWarps;
   unsigned long long total = 0, calls = 0;
+  CdfCtx cx;
+  cx.tab = tab_base;
+  const float2* sharp = s_sharp[warp];
   for (int64_t item = gw; item < items; item += nw) {
     const int64_t c = item / splits;
     const int sp = (int)(item - c * splits);
-    const int64_t i_lo = ncalls * sp / splits, i_hi = ncalls * (sp + 1) / splits;
+    const uint32_t i_lo = (uint32_t)(ncalls * sp / splits), i_hi = (uint32_t)(ncalls * (sp + 1) / splits);
     const float* hdr = headers + c * kCdfHdr;
-    CdfCtx cx;
-    cx.lo = hdr[0];
     cx.inv_h = hdr[1];
-    cx.n_sharp = __float_as_int(hdr[2]);
+    cx.t0 = hdr[4];
+    const int n_sharp = __float_as_int(hdr[2]);
     const float4* gt = tables + c * kCdfStride;
     __syncwarp();  // the previous item's reads of this warp's stage are done
 #pragma unroll
-    for (int r = 0; r < 4; ++r) s_tab[warp][32 * r + lane] = gt[32 * r + lane];
+    for (int r = 0; r < 4; ++r) my_tab[32 * r + lane] = gt[32 * r + lane];
     if (lane < kCdfMaxSharp) s_sharp[warp][lane] = make_float2(hdr[8 + 2 * lane], hdr[9 + 2 * lane]);
     __syncwarp();
     const uint32_t cw = (uint32_t)(c + ctx_offset);
-    const float4* tab = s_tab[warp];
-    const float2* sharp = s_sharp[warp];
     unsigned int hits = 0;
-    for (int64_t i = i_lo + lane; i < i_hi; i += 32) {
-      const Words w = philox4x32_10((uint32_t)i, cw, kCdfTag, offset, rk);
-      float z1, z2;
-      box_muller(w.x, w.y, z1, z2);
-      const float F1 = cdf_eval(z1, cx, tab, sharp, s_lnphi);
-      const float F2 = cdf_eval(z2, cx, tab, sharp, s_lnphi);
-      hits += w.z < prob_to_u32(F1) ? 1u : 0u;
-      hits += (w.w < prob_to_u32(F2) && 2 * i + 1 < num_samples) ? 1u : 0u;
+    if (n_sharp == 0) {  // the common case: everything is in the table
+      for (uint32_t i = i_lo + lane; i < i_hi; i += 32) {
+        const Words w = philox4x32_10(i, cw, kCdfTag, offset, rk);
+        float z1, z2;
+        box_muller(w.x, w.y, z1, z2);
+        const uint32_t p1 = prob_to_u32(cdf_eval(z1, cx));
+        const uint32_t p2 = prob_to_u32(cdf_eval(z2, cx));
+        hits += w.z < p1 ? 1u : 0u;
+        hits += (w.w < p2 && i != odd_call) ? 1u : 0u;
+      }
+    } else {
+      for (uint32_t i = i_lo + lane; i < i_hi; i += 32) {
+        const Words w = philox4x32_10(i, cw, kCdfTag, offset, rk);
+        float z1, z2;
+        box_muller(w.x, w.y, z1, z2);
+        const uint32_t p1 = prob_to_u32(cdf_eval(z1, cx) * sharp_factor(z1, n_sharp, sharp, s_lnphi));
+        const uint32_t p2 = prob_to_u32(cdf_eval(z2, cx) * sharp_factor(z2, n_sharp, sharp, s_lnphi));
+        hits += w.z < p1 ? 1u : 0u;
+        hits += (w.w < p2 && i != odd_call) ? 1u : 0u;
+      }
     }
     calls += lane == 0 ? (unsigned long long)(i_hi - i_lo) : 0ull;
     hits = warp_sum(hits);
@@ -397,23 +421,25 @@ cdf_probe_kernel(int kind, int iters, const __grid_constant__ RoundKeys rk, floa
   const uint32_t smp = blockIdx.x * kCdfThreads + threadIdx.x;
   unsigned int hits = 0;
   if (kind == 8) {
-    const float4 c = make_float4(0.3f, 0.2f, -0.05f, 0.01f);
+    // a 2 KB table per warp in shared memory, like the sampler's stage
+    __shared__ __align__(16) float4 s_tab_raw[(kCdfWarps + 1) * kCdfStride];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tab_base = ((smem_u32(s_tab_raw) + 2047u) & ~2047u) + 2048u * (uint32_t)warp;
+    float4* const my_tab = s_tab_raw + (tab_base - smem_u32(s_tab_raw)) / 16u;
+    for (int r = 0; r < 4; ++r) my_tab[32 * r + lane] = make_float4(0.3f + 1e-3f * (float)(32 * r + lane), 0.2f, -0.05f, 0.01f);
+    __syncwarp();
+    CdfCtx cx;
+    cx.tab = tab_base;
+    cx.inv_h = 10.5f;
+    cx.t0 = 63.f;
     for (int it = 0; it < iters; ++it) {
       const Words w = philox4x32_10(smp, 7u, (uint32_t)it, 0u, rk);
       float z1, z2;
       box_muller(w.x, w.y, z1, z2);
-      float F[2];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const float t = ((k ? z2 : z1) + 5.f) * 12.5f;
-        const float tc = fminf(fmaxf(t, 0.f), 124.999f);
-        float f;
-        const int i = floor_split(tc, f);
-        const float v = fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x + __int_as_float(i));
-        F[k] = t < 0.f ? 0.f : (t >= 125.f ? 1.f : v);
-      }
-      hits += w.z < prob_to_u32(F[0]) ? 1u : 0u;
-      hits += w.w < prob_to_u32(F[1]) ? 1u : 0u;
+      const uint32_t p1 = prob_to_u32(cdf_eval(z1, cx));
+      const uint32_t p2 = prob_to_u32(cdf_eval(z2, cx));
+      hits += w.z < p1 ? 1u : 0u;
+      hits += (w.w < p2 && (uint32_t)it != 0xffffffffu) ? 1u : 0u;
     }
   }
   if (hits == 0xffffffffu) out[0] = 1.f;  // keep the loop alive

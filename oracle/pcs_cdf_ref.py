@@ -87,17 +87,21 @@ def context_plan(mean_row: np.ndarray, var_row: np.ndarray) -> dict:
 
 
 def success_probability(plan: dict, z: np.ndarray) -> np.ndarray:
-    """The kernel's F(z): cubic of the cell (fp32 Horner), 0 / 1 outside the range, times the sharp
-    competitors' exact factors."""
+    """The kernel's F(z): table coordinate ``t' = fma(z, inv_h, t0)`` with ``t0 = fma(-lo, inv_h, 1)``,
+    clamped to [0, 127); slot 0 is the guard below the range (F = 0), slots 1..125 the cubic cells (fp32
+    Horner), slot 126 the guard above it (F = 1); times the sharp competitors' exact factors."""
     z = z.astype(F32)
-    t = ((z - plan["lo"]).astype(F32) * plan["inv_h"]).astype(F32)
-    tc = np.minimum(np.maximum(t, F32(0.0)), F32(G_CELLS - 0.001))
+    lo64, ih64 = np.float64(plan["lo"]), np.float64(plan["inv_h"])
+    t0 = F32(1.0 - lo64 * ih64)                                  # one rounding, like the kernel's fma
+    t = (z.astype(np.float64) * ih64 + np.float64(t0)).astype(F32)
+    tc = np.minimum(np.maximum(t, F32(0.0)), F32(G_CELLS + 2 - 0.001))
     i = tc.astype(np.int32)
     f = (tc - i.astype(F32)).astype(F32)
-    c = plan["coef"][i]
+    guard_lo = np.zeros((1, 4), dtype=F32)
+    guard_hi = np.array([[1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]], dtype=F32)
+    c = np.concatenate([guard_lo, plan["coef"], guard_hi], axis=0)[i]
     F = ((c[:, 3] * f + c[:, 2]).astype(F32) * f + c[:, 1]).astype(F32)
-    F = (F * f + c[:, 0]).astype(F32)
-    F = np.where(t < 0, F32(0.0), np.where(t >= G_CELLS, F32(1.0), F)).astype(np.float64)
+    F = (F * f + c[:, 0]).astype(F32).astype(np.float64)
     for a, b in zip(plan["sharp_a"], plan["sharp_b"]):
         F = F * np.exp(log_ndtr(np.float64(a) * z.astype(np.float64) + np.float64(b)))
     return F
