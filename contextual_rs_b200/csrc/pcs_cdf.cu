@@ -23,7 +23,7 @@
 //           independent of K, with no divergence and no queues.
 // Philox counters (call, global context, 0xCDF00001, offset): counts do not depend on how contexts are
 // sharded.  Stream definition and CPU restatement: oracle/pcs_cdf_ref.py.  Interpolation bias of F,
-// integrated against the normal density: < 2e-7 on all BASELINE configurations (tests/tools/cdf_design.py),
+// integrated against the normal density: < 3e-7 on all BASELINE configurations (tests/tools/cdf_design.py),
 // three orders of magnitude below the Monte-Carlo standard error of a 2^16-sample estimate.
 #include <math_constants.h>
 #include <atomic>

@@ -69,3 +69,21 @@ def test_degenerate_ranges_and_shard_invariance():
     full, _ = pcs_cdf_ref.pcs_counts_cdf_ref(mu2, var2, 1001, seed=9, offset=3)
     part, _ = pcs_cdf_ref.pcs_counts_cdf_ref(mu2[4:], var2[4:], 1001, seed=9, offset=3, ctx_offset=4)
     assert np.array_equal(full[4:], part)
+
+
+def test_cdf_table_bias_is_far_below_mc_error():
+    """tests/tools/cdf_design.py on a few config-2 contexts: the tabulated F_c integrated against the normal
+    density differs from the exact product by < 1e-6 (measured <= 3e-7 on every BASELINE configuration) — three
+    orders below the 4e-4 .. 2e-3 standard error of a 2^16-sample estimate."""
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+    import cdf_design
+    from contextual_rs_b200.synthetic import make_config
+    from oracle import gp_oracle
+    desc, ctx = make_config("c2")
+    mu, var = gp_oracle.posterior_grid_batched(desc, ctx[::171])
+    for i in range(mu.shape[0]):
+        bias, pcs, _ = cdf_design.context_bias(mu[i].numpy(), var[i].numpy(), nodes=20001)
+        assert 0.0 <= pcs <= 1.0 and abs(bias) < 1e-6
