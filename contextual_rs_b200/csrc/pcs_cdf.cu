@@ -26,6 +26,7 @@
 // integrated against the normal density: < 3e-7 on all BASELINE configurations (tests/tools/cdf_design.py),
 // three orders of magnitude below the Monte-Carlo standard error of a 2^16-sample estimate.
 #include <math_constants.h>
+#include <type_traits>
 #include <atomic>
 #include <climits>
 #include <mutex>
@@ -39,7 +40,11 @@ using namespace rng;
 
 constexpr int kCdfThreads = 256;
 constexpr int kCdfWarps = kCdfThreads / 32;
-constexpr int kCdfCells = 125;          // cells of the F table (grid points -1 .. 126: 4 per lane)
+constexpr int kCdfCells = 125;          // most cells an F table has (grid points -1 .. 126: 4 per lane)
+constexpr int kCdfMinCells = 29;        // fewest: one quarter of the grid
+constexpr float kCdfH0 = 11.6f / 125.f; // design spacing: a full-range table, z in [-5.8, 5.8]
+constexpr float kCdfLnDead = -23.f;     // ln F below this (F < 1e-10): F = 0 below the live range
+constexpr float kCdfLnFull = -2e-8f;    // ln F above this: F = 1 above the live range
 constexpr int kCdfStride = 128;         // float4 per context in the workspace
 constexpr int kCdfHdr = 24;             // floats per context header: lo, inv_h, n_sharp, flags, pad[4], sharp[8] (a, b)
 constexpr int kCdfMaxSharp = 8;
@@ -196,11 +201,71 @@ pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
       zlo = fmaxf(zlo, __shfl_xor_sync(kFull, zlo, o));
       zhi = fmaxf(zhi, __shfl_xor_sync(kFull, zhi, o));
     }
-    const float lo = fmaxf(zlo, -kCdfZMax);
+    float lo = fmaxf(zlo, -kCdfZMax);
     float hi = fminf(zhi, kCdfZMax);
     if (!(hi > lo + 1e-3f)) hi = lo + 1e-3f;  // F is 0 (or 1) over the whole sampled range
-    const float h = __fdiv_rn(hi - lo, (float)kCdfCells);
-    const float inv_h = __fdiv_rn((float)kCdfCells, hi - lo);
+    unsigned int n_search = 0;
+    // ---- live range.  [lo, hi] is where ONE factor leaves 0 / the last one reaches 1; with many competitors
+    // the product F is below 1e-10 on most of it.  ln F is non-decreasing in z, so the live part [lo', hi']
+    // (ln F > -23 ... ln F < -2e-8) is bracketed by two 8-point evaluations of ln F over ALL competitors
+    // (lanes over competitors here, approximate (a, b): only the bracket depends on them) and only that
+    // part is tabulated: K x 16 look-ups buy back up to three quarters of the K x 128 of the table.
+    if (hi - lo > (float)kCdfMinCells * kCdfH0) {
+      float zp[8], lf[8];
+      auto eval8 = [&]() {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) lf[p] = 0.f;
+        for (int a = lane; a < K; a += 32) {
+          if (a == bi) continue;
+          const float rs = rsqrtf((float)vrow[a]);
+          const float at = sd_b * rs * kTScale;
+          const float bt = fmaf((float)(mu_b - mrow[a]) * rs, kTScale, kTShift);
+#pragma unroll
+          for (int p = 0; p < 8; ++p) lf[p] += lnphi8(fmaf(at, zp[p], bt), copy);
+          n_search += 8;
+        }
+#pragma unroll
+        for (int p = 0; p < 8; ++p) lf[p] = warp_sum(lf[p]);
+      };
+      const float d1 = (hi - lo) * (1.f / 9.f);
+#pragma unroll
+      for (int p = 0; p < 8; ++p) zp[p] = fmaf((float)(p + 1), d1, lo);
+      eval8();
+      int nlo = 0, nhi = 0;  // leading points still dead / leading points not yet saturated
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        nlo += (lf[p] < kCdfLnDead && nlo == p) ? 1 : 0;
+        nhi += (lf[p] < kCdfLnFull && nhi == p) ? 1 : 0;
+      }
+      const float l0 = fmaf((float)nlo, d1, lo);                     // dead at l0 (or l0 = lo), alive at l0 + d1
+      const float u1 = nhi == 8 ? hi : fmaf((float)(nhi + 1), d1, lo);  // saturated at u1 (or u1 = hi)
+      const float u0 = u1 - d1 < lo ? lo : (nhi == 8 ? fmaf(8.f, d1, lo) : u1 - d1);
+      const float d2l = d1 * 0.2f, d2u = (u1 - u0) * 0.2f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        zp[p] = fmaf((float)(p + 1), d2l, l0);
+        zp[4 + p] = fmaf((float)(p + 1), d2u, u0);
+      }
+      eval8();
+      int mlo = 0, mhi = 0;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        mlo += (lf[p] < kCdfLnDead && mlo == p) ? 1 : 0;
+        mhi += (lf[4 + p] < kCdfLnFull && mhi == p) ? 1 : 0;
+      }
+      const float lo2 = fmaf((float)mlo, d2l, l0);
+      const float hi2 = mhi == 4 ? u1 : fmaf((float)(mhi + 1), d2u, u0);
+      lo = fmaxf(lo, lo2);
+      hi = fminf(hi, fmaxf(hi2, lo + 1e-3f));
+    }
+    n_terms += n_search;
+    // cells: as many as the live range needs at the design spacing h0 (the spacing of a full-range table),
+    // in whole quarters of 32 grid points: 29 / 61 / 93 / 125
+    int R = ((int)ceilf((hi - lo) * (1.f / kCdfH0)) + 3 + 31) >> 5;
+    R = R < 1 ? 1 : (R > 4 ? 4 : R);
+    const int cells = 32 * R - 3;
+    const float h = __fdiv_rn(hi - lo, (float)cells);
+    const float inv_h = __fdiv_rn((float)cells, hi - lo);
     // grid points g = 32 r + lane <-> z = lo + (g - 1) h
     float z[4], acc[4];
 #pragma unroll
@@ -210,7 +275,7 @@ pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
     }
     float zq[4];  // lowest z of each quarter: terms that are 0 there (x >= 7) are 0 in the whole quarter and above
 #pragma unroll
-    for (int r = 0; r < 4; ++r) zq[r] = fmaf((float)(32 * r - 1), h, lo);
+    for (int r = 0; r < 4; ++r) zq[r] = r < R ? fmaf((float)(32 * r - 1), h, lo) : CUDART_INF_F;  // quarters beyond R: never live
     int n_sharp = 0;
     bool overflow = false;
     unsigned int n_quarters = 0;  // warp-uniform count of (competitor, quarter) blocks evaluated
@@ -238,20 +303,28 @@ pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
       int nq = 0;
 #pragma unroll
       for (int r = 0; r < 4; ++r) nq += fmaf(at, zq[r], bt) < kTHi ? 1 : 0;
-      const unsigned live = __ballot_sync(kFull, nq > 0);
-      for (unsigned m = live; m; m &= m - 1) {
-        const int i = __ffs(m) - 1;
-        const float ai = __shfl_sync(kFull, at, i);
-        const float bb = __shfl_sync(kFull, bt, i);
-        const int ni = __shfl_sync(kFull, nq, i);
-        n_quarters += ni;
-        switch (ni) {  // warp-uniform
-          case 4: acc[3] += lnphi8(fmaf(ai, z[3], bb), copy);
-          case 3: acc[2] += lnphi8(fmaf(ai, z[2], bb), copy);
-          case 2: acc[1] += lnphi8(fmaf(ai, z[1], bb), copy);
-          default: acc[0] += lnphi8(fmaf(ai, z[0], bb), copy);
+      // one loop per class "live in the first q quarters": the body is straight-line code with exactly q
+      // look-ups (a per-competitor switch on q costs ~15 instructions of branch bookkeeping: the compiler
+      // cannot see that q is warp-uniform)
+      auto run_class = [&](auto q_tag, unsigned mask) {
+        constexpr int Q = decltype(q_tag)::value;
+        for (unsigned m = mask; m; m &= m - 1) {
+          const int i = __ffs(m) - 1;
+          const float ai = __shfl_sync(kFull, at, i);
+          const float bb = __shfl_sync(kFull, bt, i);
+          if constexpr (Q >= 4) acc[3] += lnphi8(fmaf(ai, z[3], bb), copy);
+          if constexpr (Q >= 3) acc[2] += lnphi8(fmaf(ai, z[2], bb), copy);
+          if constexpr (Q >= 2) acc[1] += lnphi8(fmaf(ai, z[1], bb), copy);
+          acc[0] += lnphi8(fmaf(ai, z[0], bb), copy);
         }
-      }
+      };
+      const unsigned m4 = __ballot_sync(kFull, nq == 4), m3 = __ballot_sync(kFull, nq == 3);
+      const unsigned m2 = __ballot_sync(kFull, nq == 2), m1 = __ballot_sync(kFull, nq == 1);
+      n_quarters += 4 * __popc(m4) + 3 * __popc(m3) + 2 * __popc(m2) + __popc(m1);
+      if (m4) run_class(std::integral_constant<int, 4>{}, m4);
+      if (m3) run_class(std::integral_constant<int, 3>{}, m3);
+      if (m2) run_class(std::integral_constant<int, 2>{}, m2);
+      if (m1) run_class(std::integral_constant<int, 1>{}, m1);
     }
     n_terms += n_quarters;
     __syncwarp();
@@ -264,8 +337,8 @@ pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int slot = 32 * r + lane, i = slot - 1;
-      float4 cf = make_float4(slot == kCdfCells + 1 ? 1.f : 0.f, 0.f, 0.f, 0.f);
-      if (i >= 0 && i < kCdfCells) {
+      float4 cf = make_float4(slot == cells + 1 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+      if (i >= 0 && i < cells) {
         const float p0 = s_F[warp][i], p1 = s_F[warp][i + 1], p2 = s_F[warp][i + 2], p3 = s_F[warp][i + 3];
         cf.x = p1;
         cf.y = fmaf(-1.f / 3.f, p0, fmaf(-0.5f, p1, fmaf(-1.f / 6.f, p3, p2)));
@@ -279,6 +352,7 @@ pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
       hdr[0] = lo;
       hdr[1] = inv_h;
       hdr[4] = fmaf(-lo, inv_h, 1.f);  // t' = z inv_h + hdr[4]
+      hdr[5] = (float)(cells + 2) - 0.001f;  // clamp of t': slot cells + 1 is the guard above the range
       hdr[2] = __int_as_float(n_sharp);
       hdr[3] = __int_as_float(overflow ? 1 : 0);
       counts[c] = 0u;  // the sampling kernel adds to it
@@ -306,14 +380,15 @@ pcs_cdf_build_kernel(const T* __restrict__ mean, const T* __restrict__ var, int6
 
 // ---- sample --------------------------------------------------------------------------------------
 struct CdfCtx {
-  float inv_h, t0;   // table coordinate t' = z inv_h + t0 (slot 0: below the range, slot 126: above)
+  float inv_h, t0;   // table coordinate t' = z inv_h + t0 (slot 0: below the range, slot cells + 1: above)
+  float tmax;        // cells + 2 - 0.001
   uint32_t tab;      // shared-window address of this warp's staged table (2 KB aligned)
 };
 
 // F(z) from the staged table: t' + 2^19 rounded toward zero keeps floor(16 t') in the mantissa, i.e. bits
 // 4.. are the slot = exactly its byte offset 16 floor(t'); no conversion unit, no range selects.
 __device__ __forceinline__ float cdf_eval(float z, const CdfCtx& cx) {
-  const float t = fminf(fmaxf(fmaf(z, cx.inv_h, cx.t0), 0.f), (float)(kCdfCells + 2) - 0.001f);
+  const float t = fminf(fmaxf(fmaf(z, cx.inv_h, cx.t0), 0.f), cx.tmax);
   const int u = __float_as_int(__fadd_rz(t, 524288.f));
   const float f = t - (__int_as_float(u & ~0xf) - 524288.f);
   const float4 c = lds128(cx.tab | (uint32_t)(u & 0x7f0));
@@ -366,6 +441,7 @@ pcs_cdf_sample_kernel(const float4* __restrict__ tables, const float* __restrict
     const float* hdr = headers + c * kCdfHdr;
     cx.inv_h = hdr[1];
     cx.t0 = hdr[4];
+    cx.tmax = hdr[5];
     const int n_sharp = __float_as_int(hdr[2]);
     const float4* gt = tables + c * kCdfStride;
     __syncwarp();  // the previous item's reads of this warp's stage are done
@@ -432,6 +508,7 @@ cdf_probe_kernel(int kind, int iters, const __grid_constant__ RoundKeys rk, floa
     cx.tab = tab_base;
     cx.inv_h = 10.5f;
     cx.t0 = 63.f;
+    cx.tmax = 126.999f;
     for (int it = 0; it < iters; ++it) {
       const Words w = philox4x32_10(smp, 7u, (uint32_t)it, 0u, rk);
       float z1, z2;

@@ -17,10 +17,15 @@ indicator (a Bernoulli(PCS(c)) draw): ``counts[c] ~ Binomial(S, PCS(c))`` either
   * range: ``lo = max(max_j (-6 - b_j) / a_j, -5.8)``, ``hi = min(max_j (7 - b_j) / a_j, 5.8)`` (fp32, the
     kernel's operation order); ``F = 0`` below ``lo`` (one factor is below Phi(-6)), ``F = 1`` above
     ``hi`` (every factor is above Phi(7)); ``hi = lo + 1e-3`` if the range is empty.
-  * table: ``G = 125`` cells of width ``h = (hi - lo) / G``; competitors with ``a_j h > 1`` whose factor
+  * live range: ``ln F`` summed over ALL competitors is non-decreasing in z; two 8-point evaluations (nine
+    equal parts of ``[lo, hi]``, then five equal parts of the two bracketing intervals) move ``lo`` up to the
+    last point with ``ln F < -23`` and ``hi`` down to the first with ``ln F > -2e-8`` (skipped when
+    ``hi - lo <= 29 h0``).  ``F = 0`` / ``F = 1`` outside the live range to 1e-10 / 2e-8.
+  * table: ``G = 32 R - 3`` cells (``R = 1..4`` quarters of the grid: 29 / 61 / 93 / 125), the fewest with
+    ``h = (hi - lo) / G <= h0 = 11.6 / 125``; competitors with ``a_j h > 1`` whose factor
     is not yet 1 at ``lo`` (``a_j lo + b_j < 7``) are SHARP: they stay out of the table (at most 8 per
     context, in arm order) and are evaluated exactly per sample.  The other factors are multiplied at
-    the grid points ``z_g = lo + (g - 1) h``, ``g = 0..127``, and each cell carries the 4-point Lagrange
+    the grid points ``z_g = lo + (g - 1) h``, ``g = 0..G+2``, and each cell carries the 4-point Lagrange
     cubic through its four surrounding grid values.
   * Philox4x32-10 (``philox_ref``), key = seed, counter ``(call, context, 0xCDF00001, offset)``:
     ``(w0, w1)`` -> Box-Muller pair ``(z1, z2)`` = the best arm's normals of samples ``2 call`` and
@@ -39,7 +44,11 @@ from scipy.special import log_ndtr
 from .philox_ref import philox4x32_10, box_muller
 
 F32 = np.float32
-G_CELLS = 125
+G_CELLS = 125                      # most cells of a table
+MIN_CELLS = 29                     # fewest (one quarter of the grid points)
+H0 = F32(11.6 / 125.0)             # design spacing (a full-range table)
+LN_DEAD = -23.0                    # ln F below this: F = 0 below the live range
+LN_FULL = -2e-8                    # ln F above this: F = 1 above it
 Z_MAX = F32(5.8)
 X_LO = F32(6.0)
 X_HI = F32(7.0)
@@ -67,22 +76,59 @@ def context_plan(mean_row: np.ndarray, var_row: np.ndarray) -> dict:
     if not hi > F32(lo + F32(1e-3)):
         hi = F32(lo + F32(1e-3))
     lo, hi = F32(lo), F32(hi)
-    h = F32(F32(hi - lo) / F32(G_CELLS))
-    inv_h = F32(F32(G_CELLS) / F32(hi - lo))
+    # live range: ln F (all competitors) is non-decreasing; two 8-point evaluations bracket where it leaves
+    # LN_DEAD (F = 0 below) and reaches LN_FULL (F = 1 above) — the kernel's search, with exact ln Phi
+    if F32(hi - lo) > F32(MIN_CELLS * H0):
+        a64, b64 = a.astype(np.float64), bb.astype(np.float64)
+
+        def ln_f(zs):
+            x = a64[None, :] * np.asarray(zs, dtype=np.float64)[:, None] + b64[None, :]
+            return log_ndtr(np.clip(x, -9.0, 40.0)).sum(axis=1)
+
+        def leading(flags):
+            n = 0
+            for f in flags:
+                if not f:
+                    break
+                n += 1
+            return n
+
+        d1 = F32(F32(hi - lo) * F32(1.0 / 9.0))
+        z1 = [F32(np.float64(p + 1) * np.float64(d1) + np.float64(lo)) for p in range(8)]
+        lf = ln_f(z1)
+        nlo, nhi = leading(lf < LN_DEAD), leading(lf < LN_FULL)
+        l0 = F32(np.float64(nlo) * np.float64(d1) + np.float64(lo))
+        u1 = hi if nhi == 8 else F32(np.float64(nhi + 1) * np.float64(d1) + np.float64(lo))
+        u0 = lo if F32(u1 - d1) < lo else (F32(8.0 * np.float64(d1) + np.float64(lo)) if nhi == 8 else F32(u1 - d1))
+        d2l, d2u = F32(d1 * F32(0.2)), F32(F32(u1 - u0) * F32(0.2))
+        z2 = [F32(np.float64(p + 1) * np.float64(d2l) + np.float64(l0)) for p in range(4)] + \
+             [F32(np.float64(p + 1) * np.float64(d2u) + np.float64(u0)) for p in range(4)]
+        lf2 = ln_f(z2)
+        mlo, mhi = leading(lf2[:4] < LN_DEAD), leading(lf2[4:] < LN_FULL)
+        lo2 = F32(np.float64(mlo) * np.float64(d2l) + np.float64(l0))
+        hi2 = u1 if mhi == 4 else F32(np.float64(mhi + 1) * np.float64(d2u) + np.float64(u0))
+        lo = max(lo, lo2)
+        hi = min(hi, max(hi2, F32(lo + F32(1e-3))))
+        lo, hi = F32(lo), F32(hi)
+    R = (int(np.ceil(F32(F32(hi - lo) * F32(1.0 / H0)))) + 3 + 31) >> 5
+    R = min(max(R, 1), 4)
+    cells = 32 * R - 3
+    h = F32(F32(hi - lo) / F32(cells))
+    inv_h = F32(F32(cells) / F32(hi - lo))
     alive = (a * lo + bb).astype(F32) < X_HI                     # (the kernel's fma differs in the last ulp only)
     sharp_idx = np.nonzero(((a * h).astype(F32) > SHARP) & alive)[0]
     overflow = len(sharp_idx) > MAX_SHARP
     sharp_idx = sharp_idx[:MAX_SHARP]
     smooth = np.ones(len(a), dtype=bool)
     smooth[sharp_idx] = False
-    g = np.arange(128, dtype=np.float64)
+    g = np.arange(cells + 3, dtype=np.float64)
     z = (np.float64(lo) + (g - 1.0) * np.float64(h)).astype(F32).astype(np.float64)
     x = a[smooth].astype(np.float64)[None, :] * z[:, None] + bb[smooth].astype(np.float64)[None, :]
     lnF = np.where(x < float(X_HI), log_ndtr(np.minimum(x, 40.0)), 0.0).sum(axis=1)
     Fg = np.exp(np.maximum(lnF, -80.0)).astype(F32).astype(np.float64)
-    p0, p1, p2, p3 = Fg[0:G_CELLS], Fg[1:G_CELLS + 1], Fg[2:G_CELLS + 2], Fg[3:G_CELLS + 3]
+    p0, p1, p2, p3 = Fg[0:cells], Fg[1:cells + 1], Fg[2:cells + 2], Fg[3:cells + 3]
     coef = np.stack([p1, -p0 / 3 - p1 / 2 + p2 - p3 / 6, (p0 + p2) / 2 - p1, (p3 - p0) / 6 + (p1 - p2) / 2], axis=1)
-    return {"best": b, "lo": lo, "hi": hi, "h": h, "inv_h": inv_h, "coef": coef.astype(F32),
+    return {"best": b, "lo": lo, "hi": hi, "h": h, "inv_h": inv_h, "cells": cells, "coef": coef.astype(F32),
             "sharp_a": a[sharp_idx], "sharp_b": bb[sharp_idx], "overflow": overflow, "a": a, "b": bb}
 
 
@@ -94,7 +140,7 @@ def success_probability(plan: dict, z: np.ndarray) -> np.ndarray:
     lo64, ih64 = np.float64(plan["lo"]), np.float64(plan["inv_h"])
     t0 = F32(1.0 - lo64 * ih64)                                  # one rounding, like the kernel's fma
     t = (z.astype(np.float64) * ih64 + np.float64(t0)).astype(F32)
-    tc = np.minimum(np.maximum(t, F32(0.0)), F32(G_CELLS + 2 - 0.001))
+    tc = np.minimum(np.maximum(t, F32(0.0)), F32(plan["cells"] + 2 - 0.001))
     i = tc.astype(np.int32)
     f = (tc - i.astype(F32)).astype(F32)
     guard_lo = np.zeros((1, 4), dtype=F32)
