@@ -195,7 +195,7 @@ def batched_lbfgs(obj, raw0: Tensor, active: Optional[Tensor] = None, maxiter: i
 
 
 def fit_hyperparameters(model: B200ModelListGP, arms: Optional[Sequence[int]] = None, raw0: Optional[Tensor] = None,
-                        maxiter: int = 500) -> Dict:
+                        maxiter: int = 500, max_retries: int = 3) -> Dict:
     """Maximise every (selected) arm's exact MLL + priors in place and re-prepare the model.
 
     Returns ``{"objective": [K] final -(MLL + priors)/n, "iterations": [K], "evaluations": int,
@@ -213,6 +213,35 @@ def fit_hyperparameters(model: B200ModelListGP, arms: Optional[Sequence[int]] = 
         cur = torch.cat([sp_inv(keep[0]), sp_inv(keep[1]).unsqueeze(-1), keep[2].unsqueeze(-1), keep[3].unsqueeze(-1)], dim=-1)
         raw = torch.where(active.unsqueeze(-1), raw, cur)
     raw, f, g, iters = batched_lbfgs(obj, raw, active=active, maxiter=maxiter)
+    # experiment_utils.py:107-113: a fit that fails (NotPSDError in the reference; here a non-finite
+    # objective, i.e. the arm's Cholesky broke down at its starting point or along the way) is retried
+    # from hyper-parameters sampled from the priors (`sample_all_priors`), a few times, arm by arm
+    retried: List[int] = []
+    for attempt in range(max_retries):
+        bad = active & ~torch.isfinite(f)
+        if not bool(bad.any()):
+            break
+        retried = sorted(set(retried) | set(torch.nonzero(bad).flatten().tolist()))
+        gen = torch.Generator().manual_seed(1234 + attempt)
+        sp_inv = lambda v: torch.where(v > 20, v, torch.log(torch.expm1(v.clamp_max(20.0))))  # noqa: E731
+        gamma = lambda conc, rate, shape: torch.distributions.Gamma(conc, rate).sample(shape)  # noqa: E731
+        with torch.random.fork_rng():
+            torch.manual_seed(int(gen.initial_seed()))
+            ls0 = gamma(LENGTHSCALE_PRIOR[0], LENGTHSCALE_PRIOR[1], (K, d)).to(torch.float64)
+            os0 = gamma(OUTPUTSCALE_PRIOR[0], OUTPUTSCALE_PRIOR[1], (K,)).to(torch.float64)
+            nz0 = gamma(NOISE_PRIOR[0], NOISE_PRIOR[1], (K,)).to(torch.float64).clamp_min(10 * MIN_NOISE)
+        fresh = torch.cat([sp_inv(ls0), sp_inv(os0).unsqueeze(-1), nz0.unsqueeze(-1), torch.zeros(K, 1, dtype=torch.float64)],
+                          dim=-1).to(model.device)
+        start = torch.where(bad.unsqueeze(-1), fresh, raw)
+        raw2, f2, g2, it2 = batched_lbfgs(obj, start, active=bad, maxiter=maxiter)
+        better = bad & torch.isfinite(f2)
+        raw = torch.where(better.unsqueeze(-1), raw2, raw)
+        f = torch.where(better, f2, f)
+        iters = torch.where(better, it2, iters)
+    still = active & ~torch.isfinite(f)
+    if bool(still.any()):
+        raise RuntimeError("hyper-parameter fit failed (kernel matrix not positive definite at every start) for arms "
+                           f"{torch.nonzero(still).flatten().tolist()}")
     ls, osc, noise, mean = obj.natural(raw)
     sel = active
     model.lengthscale.copy_(torch.where(sel.unsqueeze(-1), ls, keep[0]))
@@ -221,7 +250,8 @@ def fit_hyperparameters(model: B200ModelListGP, arms: Optional[Sequence[int]] = 
     model.mean_const.copy_(torch.where(sel, mean, keep[3]))
     model.prepare(relearn=False)
     model.check_status()
-    return {"objective": f.cpu(), "iterations": iters.cpu(), "evaluations": obj.evaluations, "raw": raw.cpu()}
+    return {"objective": f.cpu(), "iterations": iters.cpu(), "evaluations": obj.evaluations, "raw": raw.cpu(),
+            "retried_arms": retried}
 
 
 def _transforms(Xk: Tensor, Yk: Tensor):

@@ -472,3 +472,22 @@ def test_optimize_acqf_minzeta_against_scipy_on_the_oracle(crs):
     arm = crs.find_next_arm_given_context(cand, model, kernel_scale=2.0, randomize_ties=False)
     rarm = ocba_oracle.find_next_arm_given_context_ref(cand, ref, kernel_scale=2.0, randomize_ties=False)
     assert int(arm) == int(rarm)
+
+
+def test_fit_retries_a_failed_arm_from_prior_samples(crs):
+    """experiment_utils.py:107-113: a failed fit (NotPSDError there, a non-finite objective here) is retried
+    from prior-sampled hyper-parameters instead of silently keeping the defaults / failing the whole model."""
+    from contextual_rs_b200 import fit
+    from contextual_rs_b200.synthetic import make_problem
+    desc, _ = make_problem(K=5, n_c=32, d=2, n=12, seed=9)
+    model = crs.B200ModelListGP(desc, device=DEV)
+    raw0 = fit.default_raw_parameters(5, 2, DEV)
+    raw0[1, 0] = float("nan")  # arm 1 cannot even be evaluated at its starting point
+    info = fit.fit_hyperparameters(model, raw0=raw0)
+    assert info["retried_arms"] == [1] and bool(torch.isfinite(info["objective"]).all())
+    base = fit.fit_hyperparameters(crs.B200ModelListGP(desc, device=DEV))
+    assert base["retried_arms"] == []
+    # the retried arm ends at an optimum of the same objective (possibly another local one): never worse than the
+    # objective at the default starting point, and the other arms are untouched by the retry
+    torch.testing.assert_close(info["objective"][[0, 2, 3, 4]], base["objective"][[0, 2, 3, 4]], rtol=1e-9, atol=1e-12)
+    assert float(info["objective"][1]) <= float(base["objective"][1]) + 0.05 * abs(float(base["objective"][1])) + 0.05
