@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcrs_b200.so")
+LIB_PATH = os.environ.get("CRS_B200_LIB") or os.path.join(_HERE, "libcrs_b200.so")  # env: A/B runs of two builds
 
 CRS_OK, CRS_ERR_INVALID_ARG, CRS_ERR_UNSUPPORTED, CRS_ERR_CUDA, CRS_ERR_NOT_PSD, CRS_TIES_PENDING = range(6)
 CRS_F64, CRS_F32 = 0, 1

@@ -9,6 +9,7 @@
 //     alpha[i]     = o * (K^^-1 (y~ - m))[i]
 // which give  mu~ = m + c* . alpha  and  ||L^-1 k*||^2 = || sum_j linv_t[j][:] c*_j ||^2  for the
 // unscaled correlation vector c* = c(x~*, X~).
+#include <cstdio>
 #include "crs_common.cuh"
 
 namespace crs {
@@ -247,6 +248,13 @@ gp_prepare_kernel(crs_gp_state st, int arm_begin, int arm_end) {
 //   Cholesky     left-looking, lane i owns row i:  s_i = A[i][j] - sum_{k<j} L[i][k] L[j][k]
 //   alpha        column-oriented forward / backward substitution, r_i in a register per lane
 //   L^-1         lane c solves L x = e_c for column c (no synchronisation at all)
+#ifdef CRS_PREP_TIMING
+__device__ long long g_prep_clk[8];
+__device__ long long g_prep_start;
+#define CRS_PREP_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_prep_clk[i] = clock64(); } while (0)
+#else
+#define CRS_PREP_MARK(i) do { } while (0)
+#endif
 constexpr int kSmallThreads = 128;
 constexpr int kSmallCap = 32;
 
@@ -255,6 +263,9 @@ __global__ void __launch_bounds__(kSmallThreads)
 gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end, const uint4* __restrict__ cp_src,
                         uint4* __restrict__ cp_dst, int cp_n16) {
   griddep_launch_dependents();  // the grid kernel may become resident now; it waits for this grid before reading
+#ifdef CRS_PREP_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_prep_start = clock64();
+#endif
   const int k = arm_begin + blockIdx.x;
   if (k >= arm_end) {
     // extra CTAs (crs_gao_decide_host): bring the caller's context set from mapped pinned host memory
@@ -290,6 +301,7 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end, const uint4
   __shared__ double s_ls[CRS_MAX_DIM];
   if (tid < d) s_ls[tid] = ls;
   __syncthreads();
+  CRS_PREP_MARK(0);
 
   // ---- Normalize bounds (warp 0: lane = dimension) and Standardize constants (warp 1) ---------
   if (warp == 0 && lane < d) {
@@ -341,6 +353,7 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end, const uint4
     }
   }
   __syncthreads();
+  CRS_PREP_MARK(1);
   const double ybar = s_stat[0], ysd = s_stat[1];
 
   // ---- transformed inputs ----------------------------------------------------------------
@@ -363,6 +376,7 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end, const uint4
   if (tid < n) rhs[tid] = (s_y[tid] - ybar) / ysd - m;
   for (int idx = tid; idx < kSmallCap * lda; idx += nt) B[idx] = 0.0;
   __syncthreads();
+  CRS_PREP_MARK(2);
 
   // ---- K^ (lower triangle), all warps --------------------------------------------------------
   for (int idx = tid; idx < n * n; idx += nt) {
@@ -379,6 +393,7 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end, const uint4
     }
   }
   __syncthreads();
+  CRS_PREP_MARK(3);
 
   // ---- factorisation: warp 0 alone -----------------------------------------------------------
   if (warp == 0) {
@@ -410,6 +425,7 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end, const uint4
     s_dinv[lane] = dinv;
   }
   __syncthreads();
+  CRS_PREP_MARK(4);
   if (fail) {
     if (tid == 0) st.status[k] = fail;
     return;
@@ -431,23 +447,30 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end, const uint4
     }
     if (row) rhs[lane] = r;
   } else if (warp == 0) {
-    const bool row = lane < n;
-    // column `lane` of X = L^-1 by forward substitution (entries above the diagonal stay 0)
-    for (int i = 0; i < n; ++i) {
-      const double di = s_dinv[i];
-      if (row && i >= lane) {
-        double a0 = i == lane ? 1.0 : 0.0, a1 = 0.0;
-        int c = lane;
-        for (; c + 1 < i; c += 2) {
-          a0 = fma(-A[i * lda + c], B[c * lda + lane], a0);
-          a1 = fma(-A[i * lda + c + 1], B[(c + 1) * lda + lane], a1);
+    // column `lane` of X = L^-1 by forward substitution, the column in registers: x[c] = 0 for c < lane
+    // (above the diagonal), so the sums need no lane-dependent bounds; L[i][c] is a broadcast load.
+    // (clock64, n = 20: 615 cycles per row with the column re-read from shared memory -> see above.)
+    double x[kSmallCap];
+#pragma unroll
+    for (int i = 0; i < kSmallCap; ++i) {
+      x[i] = 0.0;
+      if (i < n) {  // uniform
+        double a0 = i == lane ? 1.0 : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int c = 0; c < i; ++c) {
+          const double l = A[i * lda + c];
+          if ((c & 3) == 0) a0 = fma(-l, x[c], a0);
+          else if ((c & 3) == 1) a1 = fma(-l, x[c], a1);
+          else if ((c & 3) == 2) a2 = fma(-l, x[c], a2);
+          else a3 = fma(-l, x[c], a3);
         }
-        if (c < i) a0 = fma(-A[i * lda + c], B[c * lda + lane], a0);
-        B[i * lda + lane] = (a0 + a1) * di;
+        x[i] = ((a0 + a1) + (a2 + a3)) * s_dinv[i];
+        if (lane < n) B[i * lda + lane] = x[i];
       }
     }
   }
   __syncthreads();
+  CRS_PREP_MARK(5);
   if (fail) {
     if (tid == 0) st.status[k] = fail;
     return;
@@ -478,6 +501,14 @@ gp_prepare_small_kernel(crs_gp_state st, int arm_begin, int arm_end, const uint4
     head[kHeadScal + 2] = T(ybar);
     head[kHeadScal + 3] = T(ysd);
     st.status[k] = 0;
+#ifdef CRS_PREP_TIMING
+    if (blockIdx.x == 0) {
+      const long long t6 = clock64();
+      printf("prepare phases (cycles): load %lld | bounds %lld | transforms %lld | Khat %lld | cholesky %lld | alpha+Linv %lld | write %lld\n",
+             g_prep_clk[0] - g_prep_start, g_prep_clk[1] - g_prep_clk[0], g_prep_clk[2] - g_prep_clk[1], g_prep_clk[3] - g_prep_clk[2],
+             g_prep_clk[4] - g_prep_clk[3], g_prep_clk[5] - g_prep_clk[4], t6 - g_prep_clk[5]);
+    }
+#endif
   }
 }
 
