@@ -498,6 +498,9 @@ def run_headline(args, env):
                      "avg_launch_ms": scan_avg, "peak_source": peak_src, "algorithmic_bytes_per_launch": scan_bytes}
         roof_sample = pcs_cdf_roofline("pcs_cdf_sample_kernel", calls_all, sample_avg * 1e-3, world, cdf_rates)
         roof_build = pcs_cdf_roofline("pcs_cdf_build_kernel", terms_all, build_avg * 1e-3, world, cdf_rates)
+        if world == 1:
+            roof_sample["traffic"] = ncu_traffic(name, "pcs_cdf_sample_kernel", args.dtype)
+            roof_build["traffic"] = ncu_traffic(name, "pcs_cdf_build_kernel", args.dtype)
         build_bytes = 2 * K * n_c * w / world
         roof_build["hbm"] = {"algorithmic_bytes_per_launch": build_bytes, "achieved_gbs": build_bytes / (build_avg * 1e-3) / 1e9,
                              "frac_of_hbm_peak": build_bytes / (build_avg * 1e-3) / 1e9 / peaks["hbm_gbs"]}
