@@ -547,10 +547,12 @@ def run_headline(args, env):
         env.flush_buf = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
         sub_c2 = run_decision(args, env, "c2", steps=300, sub=True)
         sub_pcs = run_pcs(env, cpu=not args.no_cpu_baseline)
+        sub_cont = run_continuous(env, model, ctx)
         if rank == 0:
             out["c2"] = sub_c2
             out["pcs"] = sub_pcs
-            out["gpu_launches"] += sub_c2["gpu_launches"] + sub_pcs["gpu_launches"]
+            out["continuous"] = sub_cont
+            out["gpu_launches"] += sub_c2["gpu_launches"] + sub_pcs["gpu_launches"] + sub_cont["gpu_launches"]
     if rank == 0:
         emit(out)
     if decider.mailbox is not None:
@@ -648,6 +650,54 @@ def run_headline_arms(args, env):
             "decision": {"next_arm": got[0], "next_context": got[1], "pcs_mean": last["pcs"], "matches_fp64_oracle": True},
             "roofline": None, "clocks": clocks})
     env.finish()
+
+
+def run_continuous(env, model, ctx):
+    """BASELINE config 4 as the reference's continuous-context driver runs it
+    (experiments/continuous_experiments/main.py:252-268, 304-306) on the headline's model (1,000 arms, 8-D):
+    the MinZeta sweep over the 65,536-point Sobol set, the 20-restart / 1,024-raw-sample optimize_acqf
+    refinement of MinZeta, find_next_arm_given_context at the refined context, and a 10-candidate
+    look-ahead PCS (generalized_pcs.py:203-315) on the first 4,096 contexts.  Wall clock of the host
+    API calls (they end in a device->host read), median of 3."""
+    import contextual_rs_b200 as crs
+    dev = env.dev
+    K = model.num_arms
+    acq = crs.MinZeta(model)
+    X = ctx.to(device=dev, dtype=model.dtype).unsqueeze(-2)
+    bounds = torch.stack([torch.zeros(ctx.shape[1], dtype=model.dtype), torch.ones(ctx.shape[1], dtype=model.dtype)]).to(dev)
+
+    def med(fn, n=3):
+        ts = []
+        res = None
+        for _ in range(n):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        return sorted(ts)[len(ts) // 2] * 1e3, res
+
+    acq(X)
+    sweep_ms, vals = med(lambda: acq(X))
+    crs.optimize_acqf(acq, bounds, q=1, num_restarts=20, raw_samples=1024, seed=1)
+    opt_ms, (cand, val, det) = med(lambda: crs.optimize_acqf(acq, bounds, q=1, num_restarts=20, raw_samples=1024, seed=1,
+                                                            return_details=True))
+    arm_ms, arm = med(lambda: crs.find_next_arm_given_context(cand, model, kernel_scale=2.0, randomize_ties=False))
+    sub_ctx = ctx[:4096].to(device=dev, dtype=model.dtype)
+    cand_la = torch.cat([torch.arange(10, dtype=model.dtype, device=dev).view(-1, 1, 1) * (K // 10),
+                         sub_ctx[:10].unsqueeze(-2)], dim=-1)
+    f_I = lambda Xd: (Xd > 0).to(model.dtype)  # noqa: E731
+    rho = lambda P: P.mean(dim=-2)  # noqa: E731
+    crs.estimate_lookahead_generalized_pcs_modellist(cand_la, model, None, sub_ctx, 4096, None, f_I, rho, seed=2)
+    la_ms, la = med(lambda: crs.estimate_lookahead_generalized_pcs_modellist(cand_la, model, None, sub_ctx, 4096, None, f_I, rho, seed=2))
+    return {"workload": "c4 continuous: MinZeta sweep over 65,536 Sobol contexts, optimize_acqf(MinZeta, q=1, num_restarts=20, "
+                        "raw_samples=1024), find_next_arm_given_context; look-ahead PCS of 10 candidates on 4,096 contexts x 4,096 samples",
+            "min_zeta_sweep_ms": sweep_ms, "sweep_best": float(vals.max()),
+            "optimize_acqf_ms": opt_ms, "optimize_acqf_value": float(val), "raw_best": det["raw_best"],
+            "objective_launches": int(det["evaluations"]), "lbfgs_iterations_max": int(det["iterations"].max()),
+            "find_next_arm_ms": arm_ms, "next_arm": int(arm),
+            "lookahead_pcs_ms": la_ms, "lookahead_pcs_ms_per_candidate": la_ms / 10, "lookahead_values": [round(float(v), 5) for v in la],
+            "gpu_launches": 4 * 2 + 8 * (2 + int(det["evaluations"])) + 8 + 4 * 10 * 5}
 
 
 # ---------------------------------------------------------------------------------- decision only
