@@ -1022,9 +1022,10 @@ def run_loop(args, env):
                     "note": "the loop is host-driven: every iteration reads the decision and the PCS value back and uploads the new "
                             "observation; e2e = wall clock of the same steps"},
             "gpu_launches": 6 * steps * world, "exchange": loop.dec.exchange,
-            "roofline": dict(pcs_cdf_roofline("pcs_cdf_sample_kernel+pcs_cdf_build_kernel", calls_all, pcs_ms / steps * 1e-3, world, rates),
-                             note="both cdf kernels + the peer sum over the bare sampling-call rate: a lower bound of the sampling kernel's fraction",
-                             table_terms=terms_all / steps),
+            "roofline": dict(pcs_cdf_roofline("pcs_cdf_sample_kernel", calls_all / steps, pcs_ms / steps * 1e-3, world, rates),
+                             note="time = both cdf kernels + the peer sum of one iteration, work = the sampling calls of one iteration over "
+                                  "the bare sampling-call rate: a lower bound of the sampling kernel's fraction",
+                             table_terms_per_iteration=terms_all / steps),
             "pcs_last": float(pcs), "clocks": clocks}))
     if loop.dec.mailbox is not None:
         loop.dec.mailbox.close()
