@@ -143,6 +143,7 @@ void set_cuda_error(cudaError_t e, const char* where);
   do {                                            \
     cudaError_t _e = (expr);                      \
     if (_e != cudaSuccess) {                      \
+      (void)cudaGetLastError(); /* reported here: must not resurface as the next launch's error */ \
       crs::set_cuda_error(_e, where);             \
       return CRS_ERR_CUDA;                        \
     }                                             \

@@ -135,27 +135,53 @@ class PeerMailbox:
         self._ptrs = None
         if self.world == 1:
             return
+        # Every rank runs the SAME sequence of collectives whatever fails locally (no rank may be left waiting
+        # in a barrier); the outcome is agreed on with one all-reduce, and on failure every rank raises.
+        err = None
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.crs_device_alloc(int(self.lib.crs_mailbox_bytes(self.world)), C.byref(self._own)),
-                       "crs_device_alloc")
             handle = (C.c_ubyte * 64)()
-            _lib.check(self.lib.crs_ipc_export(self._own, handle), "crs_ipc_export")
+            try:
+                import os
+                if os.environ.get("CRS_DISABLE_IPC") == "1":  # test hook: this rank cannot map peer memory
+                    raise RuntimeError("CUDA IPC disabled by CRS_DISABLE_IPC")
+                _lib.check(self.lib.crs_device_alloc(int(self.lib.crs_mailbox_bytes(self.world)), C.byref(self._own)),
+                           "crs_device_alloc")
+                _lib.check(self.lib.crs_ipc_export(self._own, handle), "crs_ipc_export")
+            except Exception as e:  # noqa: BLE001
+                err = e
             mine = torch.frombuffer(bytearray(bytes(handle)), dtype=torch.uint8).to(self.device)
             every = torch.empty(self.world, 64, dtype=torch.uint8, device=self.device)
             dist.all_gather_into_tensor(every, mine, group=group)
             every = every.cpu()
             ptrs = []
-            for r in range(self.world):
-                if r == self.rank:
-                    ptrs.append(self._own.value)
-                    continue
-                peer = C.c_void_p()
-                buf = (C.c_ubyte * 64).from_buffer_copy(every[r].numpy().tobytes())
-                _lib.check(self.lib.crs_ipc_open(buf, C.byref(peer)), "crs_ipc_open")
-                self._opened.append(peer)
-                ptrs.append(peer.value)
+            if err is None:
+                try:
+                    for r in range(self.world):
+                        if r == self.rank:
+                            ptrs.append(self._own.value)
+                            continue
+                        peer = C.c_void_p()
+                        buf = (C.c_ubyte * 64).from_buffer_copy(every[r].numpy().tobytes())
+                        _lib.check(self.lib.crs_ipc_open(buf, C.byref(peer)), "crs_ipc_open")
+                        self._opened.append(peer)
+                        ptrs.append(peer.value)
+                except Exception as e:  # noqa: BLE001
+                    err = e
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # also: nobody posts before everybody has mapped everybody
+            if int(ok) == 0:
+                self._release()
+                raise RuntimeError("peer mailboxes unavailable (CUDA IPC / peer access failed on at least one rank"
+                                   + (f"; here: {err}" if err is not None else "") + ")")
             self._ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
-            dist.barrier(group=group)  # nobody posts before everybody has mapped everybody
+
+    def _release(self) -> None:
+        for p in self._opened:
+            self.lib.crs_ipc_close(p)
+        self._opened = []
+        if self._own.value is not None:
+            self.lib.crs_device_free(self._own)
+            self._own = C.c_void_p()
 
     def next_exchange(self, ctx_begin: int = 0) -> "_lib.PeerExchange":
         """The descriptor of the next exchange; the sequence number advances by one on every rank."""
@@ -170,12 +196,7 @@ class PeerMailbox:
             torch.cuda.synchronize(self.device)
             if self.world > 1 and dist.is_initialized():
                 dist.barrier(group=self.group)  # no peer is still writing into a mailbox about to go away
-            for p in self._opened:
-                self.lib.crs_ipc_close(p)
-            self._opened = []
-            if self._own.value is not None:
-                self.lib.crs_device_free(self._own)
-                self._own = C.c_void_p()
+            self._release()
 
     def __del__(self):  # pragma: no cover
         try:
@@ -221,7 +242,14 @@ class ContextShardedDecider:
         if exchange not in ("mailbox", "nccl"):
             raise ValueError(f"unknown exchange {exchange!r}")
         self.exchange = exchange if self.world > 1 else "nccl"
-        self.mailbox = PeerMailbox(model.device, group) if self.exchange == "mailbox" else None
+        self.mailbox = None
+        if self.exchange == "mailbox":
+            try:
+                self.mailbox = PeerMailbox(model.device, group)
+            except RuntimeError as e:  # raised on EVERY rank (the outcome is agreed on collectively): fall back together
+                import sys
+                print(f"contextual_rs_b200: {e}; falling back to exchange='nccl'", file=sys.stderr)
+                self.exchange = "nccl"
         self._sum_host = torch.zeros(10, dtype=torch.int64).pin_memory()
         self._sum_dev = torch.zeros(8, dtype=torch.int64, device=model.device)
         self._cdf_ws = None

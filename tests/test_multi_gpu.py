@@ -93,3 +93,33 @@ def test_sharded_loop_equals_single_gpu_loop():
         cnt = single.ws["counts"].double() / 1024
         assert abs(float(c["pcs"]) - float(cnt.min())) < 1e-12, it
     dist.barrier()
+
+
+@pytest.mark.skipif(WORLD < 2, reason="needs torchrun with >= 2 ranks")
+def test_mailbox_failure_on_one_rank_falls_back_to_nccl_on_all():
+    """Peer mailboxes need CUDA IPC between the ranks' processes; where ONE rank cannot set them up, every
+    rank must agree to use the NCCL exchange instead (no rank left waiting in a barrier), with equal results."""
+    import torch.distributed as dist
+    import contextual_rs_b200 as crs
+    from contextual_rs_b200 import sharded as sh
+    from contextual_rs_b200.synthetic import make_problem
+    rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    desc, ctx = make_problem(K=9, n_c=130, d=2, n=8, seed=2)
+    model = crs.B200ModelListGP(desc, device=dev)
+    arm, x = crs.gao_modellist(model, ctx)
+    c_star = int((ctx == x).all(dim=-1).nonzero()[0])
+    if rank == 1:
+        os.environ["CRS_DISABLE_IPC"] = "1"
+    try:
+        dec = sh.ContextShardedDecider(model, ctx)
+    finally:
+        os.environ.pop("CRS_DISABLE_IPC", None)
+    assert dec.exchange == "nccl" and dec.mailbox is None
+    rec = dec.decide()
+    assert (int(rec[sh.REC_NEXT_ARM]), int(rec[sh.REC_CONTEXT])) == (int(arm), c_star)
+    assert 0.0 <= float(dec.pcs_mean(1024, seed=3)) <= 1.0
+    dist.barrier()
