@@ -387,6 +387,14 @@ struct CdfCtx {
 
 // F(z) from the staged table: t' + 2^19 rounded toward zero keeps floor(16 t') in the mantissa, i.e. bits
 // 4.. are the slot = exactly its byte offset 16 floor(t'); no conversion unit, no range selects.
+__device__ __forceinline__ float cdf_eval_t(float tp, const CdfCtx& cx) {
+  const float t = fminf(fmaxf(tp, 0.f), cx.tmax);
+  const int u = __float_as_int(__fadd_rz(t, 524288.f));
+  const float f = t - (__int_as_float(u & ~0xf) - 524288.f);
+  const float4 c = lds128(cx.tab | (uint32_t)(u & 0x7f0));
+  return fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x);
+}
+
 __device__ __forceinline__ float cdf_eval(float z, const CdfCtx& cx) {
   const float t = fminf(fmaxf(fmaf(z, cx.inv_h, cx.t0), 0.f), cx.tmax);
   const int u = __float_as_int(__fadd_rz(t, 524288.f));
@@ -452,12 +460,14 @@ pcs_cdf_sample_kernel(const float4* __restrict__ tables, const float* __restrict
     const uint32_t cw = (uint32_t)(c + ctx_offset);
     unsigned int hits = 0;
     if (n_sharp == 0) {  // the common case: everything is in the table
+#pragma unroll 2
       for (uint32_t i = i_lo + lane; i < i_hi; i += 32) {
         const Words w = philox4x32_10(i, cw, kCdfTag, offset, rk);
-        float z1, z2;
-        box_muller(w.x, w.y, z1, z2);
-        const uint32_t p1 = prob_to_u32(cdf_eval(z1, cx));
-        const uint32_t p2 = prob_to_u32(cdf_eval(z2, cx));
+        float rad, cs, sn;
+        box_muller_parts(w.x, w.y, rad, cs, sn);
+        const float rs = rad * cx.inv_h;  // t' = z inv_h + t0 with z = rad cs | rad sn: one multiply less per call
+        const uint32_t p1 = prob_to_u32(cdf_eval_t(fmaf(rs, cs, cx.t0), cx));
+        const uint32_t p2 = prob_to_u32(cdf_eval_t(fmaf(rs, sn, cx.t0), cx));
         hits += w.z < p1 ? 1u : 0u;
         hits += (w.w < p2 && i != odd_call) ? 1u : 0u;
       }
@@ -509,12 +519,14 @@ cdf_probe_kernel(int kind, int iters, const __grid_constant__ RoundKeys rk, floa
     cx.inv_h = 10.5f;
     cx.t0 = 63.f;
     cx.tmax = 126.999f;
+#pragma unroll 2
     for (int it = 0; it < iters; ++it) {
       const Words w = philox4x32_10(smp, 7u, (uint32_t)it, 0u, rk);
-      float z1, z2;
-      box_muller(w.x, w.y, z1, z2);
-      const uint32_t p1 = prob_to_u32(cdf_eval(z1, cx));
-      const uint32_t p2 = prob_to_u32(cdf_eval(z2, cx));
+      float rad, cs, sn;
+      box_muller_parts(w.x, w.y, rad, cs, sn);
+      const float rs = rad * cx.inv_h;
+      const uint32_t p1 = prob_to_u32(cdf_eval_t(fmaf(rs, cs, cx.t0), cx));
+      const uint32_t p2 = prob_to_u32(cdf_eval_t(fmaf(rs, sn, cx.t0), cx));
       hits += w.z < p1 ? 1u : 0u;
       hits += (w.w < p2 && (uint32_t)it != 0xffffffffu) ? 1u : 0u;
     }

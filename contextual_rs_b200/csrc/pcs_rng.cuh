@@ -72,6 +72,14 @@ __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, 
   z1 = rad * sn;
 }
 
+// the same pair in parts: z0 = rad * cs, z1 = rad * sn (lets a caller fold a scale into the radius)
+__device__ __forceinline__ void box_muller_parts(uint32_t wa, uint32_t wb, float& rad, float& cs, float& sn) {
+  const float a = __uint_as_float(mantissa_bits(wa)) - 0.99999994039535522f;
+  const float b = __uint_as_float(mantissa_bits(wb)) - 1.0f;
+  rad = approx_sqrt(-1.3862943611198906f * approx_log2(a));
+  __sincosf(6.2831853071795865f * b, &sn, &cs);
+}
+
 // log2 of the open-interval uniform u(w) = ((w >> 9) + 1/2) 2^-23; -ln 2 times this is an Exp(1) variate
 __device__ __forceinline__ float log2_unit_open(uint32_t w) {
   return approx_log2(__uint_as_float(mantissa_bits(w)) - 0.99999994039535522f);
