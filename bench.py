@@ -491,6 +491,23 @@ def run_headline(args, env):
                      "avg_launch_ms": grid_avg, "algorithmic_flops_per_launch": flops / world,
                      "peak_source": "measured in this run by crs_peak_probe (pure FMA micro-kernel, 16 chains/thread, CUDA "
                                     "events); MEASURED_PEAKS.json has no fp64/fp32-FMA figure (nominal 37.2 / 74.5)"}
+        if dtype == torch.float64:
+            # what the kernel actually has to issue on the FP64 pipe (SASS count; ncu profiles/r02c):
+            # per observation and (context, arm) pair 2d distance + 7 sqrt + 10 exp + 2 polynomial + 3 product /
+            # accumulation DFMA-class instructions, plus the DMMA tiles of the triangular contraction at 8
+            # DFMA-equivalents each (config 4: 44 tiles per warp and arm) -- software exp / sqrt count as 17 here,
+            # as 2 in F1
+            n4 = (n_obs + 3) // 4 * 4
+            dmma = None
+            if n4 <= 32:  # one 32-column panel: k-steps 2 sg, 2 sg + 1 reach the row tiles mt >= sg (posterior_grid.cu)
+                mt_tiles, ksteps = (8 if n_obs <= 8 else 16 if n_obs <= 16 else 24 if n_obs <= 24 else 32) // 8, n4 // 4
+                dmma = 4 * sum((mt_tiles - sg) * sum(1 for ks in (2 * sg, 2 * sg + 1) if ks < ksteps) for sg in range(mt_tiles))
+            if dmma is not None:
+                exec_flops = (n4 * (2 * d + 22) + dmma * 8) * 2.0 * K * n_c / world
+                roof_grid["instruction_floor"] = {"fp64_flops_issued_per_launch": exec_flops,
+                                                  "frac": exec_flops / (grid_avg * 1e-3) / 1e12 / fma_peak,
+                                                  "note": "issued FP64 work (DFMA-class instructions + DMMA at 8 DFMA-equivalents) over the "
+                                                          "measured FMA peak: the FP64 pipe's busy fraction (ncu: 75 %)"}
         scan_bytes = (2 * K * n_c * w + n_c * (w + 12)) / world
         roof_scan = {"kernel": "ocba_scan_kernel", "bound": "hbm", "achieved": scan_bytes / (scan_avg * 1e-3) / 1e9,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": scan_bytes / (scan_avg * 1e-3) / 1e9 / peaks["hbm_gbs"],

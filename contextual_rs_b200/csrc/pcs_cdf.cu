@@ -460,7 +460,7 @@ pcs_cdf_sample_kernel(const float4* __restrict__ tables, const float* __restrict
     const uint32_t cw = (uint32_t)(c + ctx_offset);
     unsigned int hits = 0;
     if (n_sharp == 0) {  // the common case: everything is in the table
-#pragma unroll 2
+#pragma unroll 4
       for (uint32_t i = i_lo + lane; i < i_hi; i += 32) {
         const Words w = philox4x32_10(i, cw, kCdfTag, offset, rk);
         float rad, cs, sn;
@@ -519,7 +519,7 @@ cdf_probe_kernel(int kind, int iters, const __grid_constant__ RoundKeys rk, floa
     cx.inv_h = 10.5f;
     cx.t0 = 63.f;
     cx.tmax = 126.999f;
-#pragma unroll 2
+#pragma unroll 4
     for (int it = 0; it < iters; ++it) {
       const Words w = philox4x32_10(smp, 7u, (uint32_t)it, 0u, rk);
       float rad, cs, sn;
