@@ -623,11 +623,11 @@ int launch_pcs_counts_cdf(const void* mean, const void* var, int64_t n_c, int K,
   CRS_CUDA_TRY(cudaGetLastError(), "pcs_cdf build launch");
   if (num_samples == 0) return CRS_OK;
   // sampling: every (context, range) item costs the same, so a static round-robin over warps is
-  // balanced as soon as each warp holds a few items; contexts are split only when they are few
+  // balanced as soon as each warp holds many items; contexts are split when they are too few for that
   const int64_t ncalls = (num_samples + 1) >> 1;
   const int64_t warps = (int64_t)info.sample_ctas * kCdfWarps;
   int64_t splits = 1;
-  if (n_c < 4 * warps) splits = (4 * warps + n_c - 1) / n_c;
+  if (n_c < 16 * warps) splits = (16 * warps + n_c - 1) / n_c;  // >= 16 items per warp: the last round is <= 6 % of the work
   const int64_t max_splits = ncalls / 64 > 0 ? ncalls / 64 : 1;  // >= 2 calls per lane and item
   if (splits > max_splits) splits = max_splits;
   const int64_t items = n_c * splits;

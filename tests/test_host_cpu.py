@@ -223,3 +223,42 @@ def test_description_from_botorch_attribute_paths(transformed_in_eval, condition
     subs[0].train_targets = subs[0].train_targets[:-1]
     with pytest.raises(ValueError):
         description_from_botorch(fake)
+
+
+def test_initialize_q_batch_keeps_the_best_and_samples_without_replacement():
+    """contextual_rs_b200.optimize.initialize_q_batch (BoTorch's heuristic): the arg-max is always among the
+    starts, starts are distinct raw candidates, equal values fall back to a random subset, n >= n_raw returns all."""
+    from contextual_rs_b200.optimize import initialize_q_batch
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(64, 3, dtype=torch.float64, generator=g)
+    Y = torch.randn(64, dtype=torch.float64, generator=g)
+    for seed in range(5):
+        x0 = initialize_q_batch(X, Y, 8, eta=2.0, generator=torch.Generator().manual_seed(seed))
+        assert x0.shape == (8, 3)
+        rows = [int((X == r).all(dim=-1).nonzero()[0]) for r in x0]
+        assert len(set(rows)) == 8 and int(torch.argmax(Y)) in rows
+    x0 = initialize_q_batch(X, torch.zeros(64, dtype=torch.float64), 8, generator=torch.Generator().manual_seed(1))
+    assert x0.shape == (8, 3)
+    assert initialize_q_batch(X[:5], Y[:5], 8).shape == (5, 3)
+
+
+def test_batched_lbfgs_box_constraints_on_cpu():
+    """fit.batched_lbfgs with the box projection of optimize.py on a CPU objective: independent quadratics whose
+    unconstrained minima lie inside / outside the unit box end at the projected minima."""
+    from contextual_rs_b200.fit import batched_lbfgs
+    target = torch.tensor([[0.3, 0.7], [1.5, -0.4], [0.5, 2.0]], dtype=torch.float64)
+    scale = torch.tensor([[1.0, 10.0], [3.0, 0.5], [2.0, 2.0]], dtype=torch.float64)
+
+    class Obj:
+        d = 2
+
+        def __call__(self, x):
+            r = x - target
+            return 0.5 * (scale * r * r).sum(-1), scale * r
+
+    lo, up = torch.zeros(2, dtype=torch.float64), torch.ones(2, dtype=torch.float64)
+    project = lambda x, _d: torch.minimum(torch.maximum(x, lo), up)  # noqa: E731
+    pg = lambda x, g, _d: torch.where(((x <= lo) & (g > 0)) | ((x >= up) & (g < 0)), torch.zeros_like(g), g)  # noqa: E731
+    x, f, g, it = batched_lbfgs(Obj(), torch.full((3, 2), 0.5, dtype=torch.float64), project=project, projected_gradient=pg,
+                                gtol=1e-10, ftol=1e-15)
+    torch.testing.assert_close(x, target.clamp(0.0, 1.0), rtol=0, atol=1e-7)
