@@ -422,11 +422,14 @@ def run_headline(args, env):
     rho = lambda P: P.mean(dim=-2)  # noqa: E731  (main.py:248-251 "mean")
     last = {}
 
-    def e2e_step():
+    ctx_pageable = ctx.to(dtype).clone()  # ordinary host memory, as the reference's caller holds the context set
+
+    def e2e_step(host=None):
         it[0] += 1
+        host = ctx_host if host is None else host
         if world == 1:  # the reference-facing drop-in calls, context set on the host
-            dec = decide(model, ctx_host, True, 0, 2.0, prepare_arms=(0, K))
-            pcs = crs.estimate_current_generalized_pcs(model, arm_set, ctx_host, S, None, func_I, rho, seed=0,
+            dec = decide(model, host, True, 0, 2.0, prepare_arms=(0, K))
+            pcs = crs.estimate_current_generalized_pcs(model, arm_set, host, S, None, func_I, rho, seed=0,
                                                        offset=it[0], reuse_grid=True)
             last.update(next_arm=dec.next_arm, next_context=dec.context, pcs=float(pcs))
         else:  # every rank uploads its slice of the pinned host context set; results come back to the host
@@ -450,6 +453,10 @@ def run_headline(args, env):
     env.barrier()
     e2e_ms = env.timed(e2e_step, K_steps)
     env.barrier()
+    page_ms = None
+    if world == 1:
+        e2e_step(ctx_pageable)
+        page_ms = env.timed(lambda: e2e_step(ctx_pageable), min(K_steps, 10))
     clocks = sampler.stop() if rank == 0 else None
     # ---- per-kernel durations, same region style (flushed, own event pair, launching stream) ---------
     ksteps = min(K_steps, 20)
@@ -539,7 +546,10 @@ def run_headline(args, env):
             "e2e": {"value": K_steps / t_e2e, "unit": "decisions/s", "ms_per_step": t_e2e / K_steps * 1e3,
                     "h2d_bytes_per_step": int(n_c * d * w), "d2h_bytes_per_step": (64 + 80) * world if world > 1 else 64 + w,
                     "api": ("gao_modellist's decide(model, host context_set) + estimate_current_generalized_pcs(..., reuse_grid=True)"
-                            if world == 1 else "ContextShardedDecider.decide + .pcs_mean, every rank uploading its context slice")},
+                            if world == 1 else "ContextShardedDecider.decide + .pcs_mean, every rank uploading its context slice"),
+                    "pageable_contexts": ({"ms_per_step": sum(page_ms) / len(page_ms), "value": len(page_ms) / (sum(page_ms) * 1e-3),
+                                           "note": "same calls with the context set in ordinary (pageable) host memory"}
+                                          if page_ms else None)},
             "gpu_launches": (5 + (1 if world > 1 else 0)) * 2 * K_steps * world + 6 * ksteps * world,
             "roofline": dict(roofs[dominant][1], dominant_of="kernel_ms"),
             "kernel_ms": {"gp_prepare": prep_avg, "posterior_grid": grid_avg, "ocba_scan": scan_avg,
