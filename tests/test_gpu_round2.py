@@ -491,3 +491,25 @@ def test_fit_retries_a_failed_arm_from_prior_samples(crs):
     # objective at the default starting point, and the other arms are untouched by the retry
     torch.testing.assert_close(info["objective"][[0, 2, 3, 4]], base["objective"][[0, 2, 3, 4]], rtol=1e-9, atol=1e-12)
     assert float(info["objective"][1]) <= float(base["objective"][1]) + 0.05 * abs(float(base["objective"][1])) + 0.05
+
+
+def test_posterior_against_50_digit_arithmetic(crs):
+    """The CUDA posterior (fp64) against tests/hp_reference.py — an independent 50-digit evaluation of the exact-GP
+    equations — on an ill-conditioned arm (two inputs 1e-3 apart, cond(K^) > 1e4, a query on a training input):
+    within 1e-10 of scale, the tolerance BASELINE.json states for fp64."""
+    import hp_reference
+    X, Y, ls, osc, noise, mconst, Xq = hp_reference.ill_conditioned_problem()
+    mean, var, cond, scale = hp_reference.mp_posterior(X, Y, ls, osc, noise, mconst, Xq)
+    desc = {"train_X": [X, X], "train_Y": [Y, Y + 1.0], "lengthscale": torch.stack([ls, ls]),
+            "outputscale": torch.tensor([osc, osc], dtype=torch.float64), "noise": torch.tensor([noise, noise], dtype=torch.float64),
+            "mean_const": torch.tensor([mconst, mconst], dtype=torch.float64), "kernel": "matern52", "normalize": True,
+            "standardize": True}
+    model = crs.B200ModelListGP(desc, device=DEV)
+    p = model.posterior(Xq)
+    got_m, got_v = p.mean[:, 0].cpu(), p.variance[:, 0].cpu()
+    em, ev = float((got_m - mean).abs().max() / mean.abs().max()), float((got_v - var).abs().max() / scale)
+    print(f"cond(K^) = {cond:.2e}: mean error {em:.2e}, variance error {ev:.2e} of scale (50-digit reference)")
+    assert em <= 1e-10 and ev <= 1e-10
+    # the second arm has the same inputs and targets shifted by a constant: same variance, mean shifted by 1
+    torch.testing.assert_close(p.variance[:, 1].cpu(), got_v, rtol=0, atol=1e-12 * scale)
+    torch.testing.assert_close(p.mean[:, 1].cpu(), got_m + 1.0, rtol=0, atol=1e-10)

@@ -425,3 +425,18 @@ def test_quoted_config_fixture_is_what_the_oracle_computes():
                                "posterior": lambda self, X: type("P", (), {"mean": mean, "variance": var})()})()
         arm, x = ocba_oracle.gao_modellist_ref(model, ctx)
         assert int(arm) == exp["default"]["next_arm"] and torch.equal(x, ctx[exp["default"]["next_context"]])
+
+
+def test_oracle_gp_equations_against_50_digit_arithmetic():
+    """The fp64 oracle (and through it the 1e-10 claims of the GPU tests) against an INDEPENDENT evaluation of the
+    same exact-GP equations in 50-digit arithmetic (tests/hp_reference.py: mpmath, dense inverse by LU instead of
+    Cholesky, the Matern-5/2 correlation from the general Bessel-K formula instead of its closed form): posterior
+    mean and variance agree to 1e-11 of their scale even at cond(K^) > 1e4, with a query on top of a training input."""
+    import hp_reference
+    X, Y, ls, osc, noise, mconst, Xq = hp_reference.ill_conditioned_problem()
+    m = gp_oracle.OracleSingleTaskGP(X, Y, ls, osc, noise, mconst, kernel="matern52")
+    post = m.posterior(Xq)
+    mean, var, cond, scale = hp_reference.mp_posterior(X, Y, ls, osc, noise, mconst, Xq)
+    assert cond > 1e4
+    assert float((post.mean[:, 0] - mean).abs().max()) <= 1e-11 * float(mean.abs().max())
+    assert float((post.variance[:, 0] - var).abs().max()) <= 1e-11 * scale
