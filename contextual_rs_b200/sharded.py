@@ -185,7 +185,7 @@ class PeerMailbox:
 
     def next_exchange(self, ctx_begin: int = 0) -> "_lib.PeerExchange":
         """The descriptor of the next exchange; the sequence number advances by one on every rank."""
-        self.seq = self.seq % 0x3fffffff + 1
+        self.seq = self.seq % 0x3ffffffe + 1  # 1 .. 0x3ffffffe: the slot parity (seq & 1) keeps alternating across the wrap
         return _lib.PeerExchange(self._ptrs.data_ptr() if self._ptrs is not None else None, self.rank, self.world,
                                  self.seq, 0, int(ctx_begin))
 
