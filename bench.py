@@ -438,16 +438,17 @@ def run_headline(args, env):
             pcs = decider.pcs_mean(S, seed=0, offset=it[0])
             last.update(next_arm=int(rec[REC_NEXT_ARM]), next_context=int(rec[REC_CONTEXT]), pcs=float(pcs))
 
+    # nvidia-smi needs ~0.1 s before its first sample: it is started ahead of the warm-up steps (same kernels, same
+    # load) so that it is already sampling, every 20 ms, when the timed region begins
+    sampler = ClockSampler(env.local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(W):
         env.flush()
         device_step()
     for _ in range(W):
         env.flush()
         e2e_step()
-    env.barrier()
-    sampler = ClockSampler(env.local_rank)
-    if rank == 0:
-        sampler.start()
     env.barrier()
     dev_ms = env.timed(device_step, K_steps)
     env.barrier()
