@@ -1014,7 +1014,7 @@ def run_loop(args, env):
     if rank == 0:
         sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
-    work = torch.zeros(2, dtype=torch.float64, device=dev)  # accumulated on the device: no host sync inside an iteration
+    work = torch.zeros(2, dtype=torch.float64)
     env.barrier()
     t_wall = time.perf_counter()
     for i in range(steps):
@@ -1024,7 +1024,7 @@ def run_loop(args, env):
         y = truth(out["next_arm"], out["next_context"])
         pcs = loop.pcs()
         ev[i][2].record()
-        work += stats[:2].to(torch.float64)  # {Philox calls, table terms} of this estimate (stream-ordered after it)
+        work += stats[:2].cpu().to(torch.float64)  # {Philox calls, table terms} of this estimate
         loop.observe(out["next_arm"], out["next_context"].view(1, -1), y.reshape(1, 1))
         loop.iteration += 1
         it_box[0] += 1
@@ -1034,7 +1034,7 @@ def run_loop(args, env):
     clocks = sampler.stop() if rank == 0 else None
     parts = torch.tensor([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in ev], dtype=torch.float64).sum(dim=0)
     dec_ms, pcs_ms, obs_ms, tot_ms, wall_s = env.max_over_ranks(parts.tolist() + [float(parts.sum()), t_wall])
-    calls_all, terms_all = env.sum_over_ranks(work.cpu().tolist())
+    calls_all, terms_all = env.sum_over_ranks(work.tolist())
     if rank == 0:
         w = 8 if dtype == torch.float64 else 4
         val = steps / (tot_ms * 1e-3)
