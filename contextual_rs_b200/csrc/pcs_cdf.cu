@@ -10,17 +10,21 @@
 // Bernoulli law as drawing all K normals and comparing (counts[c] ~ Binomial(S, PCS(c)) either way), at
 // the cost of one normal and one uniform instead of K normals.  Two kernels:
 //   build   one warp per context: arg-max, the range [lo, hi] of z outside which F is 0 / 1 to 1e-9
-//           (lo = max_j (-6 - b_j) / a_j, hi = max_j (7 - b_j) / a_j, clipped to the Box-Muller range),
-//           ln F at 128 grid points (ln Phi from a 1,024-cell cubic table in shared memory: 13
-//           instructions per term, terms with a_j z + b_j > 7 skipped warp-uniformly), then the 4-point
-//           Lagrange cubic of F on each of the G = 125 cells as one float4 -> workspace.  Competitors
-//           whose factor is too sharp for the grid (a_j h > 1: the best arm's posterior is much wider
-//           than theirs) are kept OUT of the table, listed in the context's header and evaluated exactly
-//           per sample (up to 8 per context; beyond that the context is flagged in stats).
+//           (lo = max_j (-6 - b_j) / a_j, hi = max_j (7 - b_j) / a_j, clipped to the Box-Muller range), narrowed
+//           to the LIVE range (two 8-point evaluations of ln F over all competitors bracket ln F = -23 and
+//           ln F = -2e-8: with many competitors the product is dead on most of [lo, hi]); ln F at 32 R grid
+//           points, R = 1..4 (ln Phi from a 1,024-cell cubic table kept in EIGHT bank-interleaved copies in
+//           shared memory — 128-bit look-ups without bank conflicts for any access pattern; 14 instructions per
+//           term; competitors grouped by the number of leading quarters in which their factor is not yet 1),
+//           then the 4-point Lagrange cubic of F on each of the G = 32 R - 3 cells as one float4 -> workspace,
+//           with a guard slot below (F = 0) and above (F = 1).  Competitors whose factor is too sharp for the
+//           grid (a_j h > 1: the best arm's posterior is much wider than theirs) are kept OUT of the table,
+//           listed in the context's header and evaluated exactly per sample (up to 8 per context; beyond that
+//           the context is flagged in stats).
 //   sample  one warp per (context, sample range): the 2 KB table goes to shared memory; one
 //           Philox4x32-10 call per TWO samples — Box-Muller pair (z1, z2) from words 0, 1, the uniforms
-//           are words 2, 3 compared as integers with F * 2^32 — so a sample costs ~45 instructions,
-//           independent of K, with no divergence and no queues.
+//           are words 2, 3 compared as integers with F * 2^32 — ~24 instructions per sample,
+//           independent of K, with no divergence and no queues; four calls in flight per lane.
 // Philox counters (call, global context, 0xCDF00001, offset): counts do not depend on how contexts are
 // sharded.  Stream definition and CPU restatement: oracle/pcs_cdf_ref.py.  Interpolation bias of F,
 // integrated against the normal density: < 3e-7 on all BASELINE configurations (tests/tools/cdf_design.py),
