@@ -323,8 +323,8 @@ CRS_API int crs_ipc_close(void* dev_ptr);
  * best arm's draw y_b = mu_b + sd_b z the sample succeeds with probability
  * F_c(z) = prod_{j != b} Phi((y_b - mu_j) / sd_j); one sample is z ~ N(0,1), u ~ U(0,1), success iff
  * u < F_c(z) — the same Bernoulli law as drawing all K normals, for one normal and one uniform.  A
- * build kernel tabulates F_c per context (cubic on 125 cells, competitors too sharp for the grid kept
- * exact), a sampling kernel spends one Philox4x32-10 call per two samples.  Stream definition and CPU
+ * build kernel tabulates F_c per context over its live range (cubic on 29 / 61 / 93 / 125 cells, competitors too
+ * sharp for the grid kept exact), a sampling kernel spends one Philox4x32-10 call per two samples.  Stream definition and CPU
  * restatement: oracle/pcs_cdf_ref.py.  Counters (call, context + ctx_offset, 0xCDF00001, offset):
  * counts do not depend on how contexts are sharded.  Any K >= 2.
  * workspace: crs_pcs_cdf_workspace_bytes(n_c) bytes of device memory, 16-byte aligned, no
