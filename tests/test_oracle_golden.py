@@ -440,3 +440,30 @@ def test_oracle_gp_equations_against_50_digit_arithmetic():
     assert cond > 1e4
     assert float((post.mean[:, 0] - mean).abs().max()) <= 1e-11 * float(mean.abs().max())
     assert float((post.variance[:, 0] - var).abs().max()) <= 1e-11 * scale
+
+
+def test_pcs_quadrature_against_30_digit_integration():
+    """The exact PCS(c) every Monte-Carlo stream is judged against (oracle.pcs_exact_quadrature) against an
+    independent 30-digit adaptive integration (mpmath) of the same integral
+    int phi(z) prod_{j != b} Phi((mu_b + sd_b z - mu_j) / sd_j) dz — including a near-step factor (sd_j << sd_b)."""
+    import mpmath as mp
+    mp.mp.dps = 30
+    mean = np.array([[1.0, 0.4, 0.9, -0.3], [0.2, 0.25, 0.1, 0.249], [2.0, 1.9, -1.0, 1.95]])
+    var = np.array([[0.5, 0.3, 0.8, 1.0], [0.04, 0.09, 0.01, 0.0001], [1e-2, 1.0, 1.0, 1e-4]])
+    got = pcs_oracle.pcs_exact_quadrature(mean, var)
+    for c in range(mean.shape[0]):
+        b = int(np.argmax(mean[c]))
+        others = [j for j in range(mean.shape[1]) if j != b]
+
+        def f(z, c=c, b=b, others=others):
+            yb = mp.mpf(mean[c, b]) + mp.sqrt(mp.mpf(var[c, b])) * z
+            p = mp.npdf(z)
+            for j in others:
+                p *= mp.ncdf((yb - mp.mpf(mean[c, j])) / mp.sqrt(mp.mpf(var[c, j])))
+            return p
+
+        # split the range at the near-steps of the sharp factors so that the adaptive rule sees them
+        sd_b = np.sqrt(var[c, b])
+        cuts = sorted({float(np.clip((mean[c, j] - mean[c, b]) / sd_b, -11, 11)) for j in others} | {-12.0, 12.0})
+        want = float(mp.quad(f, cuts))
+        assert abs(got[c] - want) < 2e-9, (c, got[c], want)
