@@ -12,7 +12,9 @@ What BoTorch does for ``q = 1`` and what is mirrored here:
 3. the restarts are refined by L-BFGS under the box constraints (BoTorch: scipy L-BFGS-B on the
    stacked restarts; here the restarts are independent box-constrained L-BFGS problems advanced in
    lockstep by ``fit.batched_lbfgs`` — every iteration is ONE objective launch for all restarts, with
-   the analytic gradient of ``crs_min_zeta_grad`` when the acquisition function is ``MinZeta``);
+   the analytic gradient of ``crs_min_zeta_grad`` when the acquisition function is ``MinZeta``; an
+   acquisition function without a backward, e.g. ``PredictiveEI``, gets central differences from one
+   more launch);
 4. the best refined point and its value are returned as ``(candidate [1, d], value)``.
 
 The optimiser trajectory is not scipy's (its More-Thuente line search is not replicated); the
@@ -32,16 +34,31 @@ class _BoxObjective:
     """f = -acq(X) and its gradient for a batch of restarts ``[R, d]`` (autograd through the
     acquisition function: ``MinZeta`` carries the analytic backward of ``crs_min_zeta_grad``)."""
 
-    def __init__(self, acq: Callable[[Tensor], Tensor], d: int):
+    def __init__(self, acq: Callable[[Tensor], Tensor], d: int, fd_step: Optional[Tensor] = None):
         self.acq, self.d = acq, d
+        self.fd_step = fd_step if fd_step is not None else torch.full((d,), 1e-6, dtype=torch.float64)
         self.evaluations = 0
 
     def __call__(self, x: Tensor):
         X = x.detach().clone().unsqueeze(-2).requires_grad_(True)
         with torch.enable_grad():
             val = self.acq(X)
-            (g,) = torch.autograd.grad(val.sum(), X)
+            differentiable = val.requires_grad
+            if differentiable:
+                (g,) = torch.autograd.grad(val.sum(), X)
         self.evaluations += 1
+        if not differentiable:
+            # an acquisition function without a backward (``PredictiveEI``: the LEVI branch of the continuous
+            # driver, experiments/continuous_experiments/main.py:269-281): central differences, all 2 d
+            # perturbations of all restarts in ONE further launch
+            R, d = x.shape
+            h = self.fd_step.to(device=x.device, dtype=x.dtype)
+            eye = torch.eye(d, dtype=x.dtype, device=x.device) * h
+            pts = torch.cat([x.unsqueeze(1) + eye, x.unsqueeze(1) - eye], dim=1).reshape(R * 2 * d, 1, d)
+            with torch.no_grad():
+                v = self.acq(pts).reshape(R, 2, d).to(torch.float64)
+            g = ((v[:, 0] - v[:, 1]) / (2.0 * h.to(torch.float64))).unsqueeze(-2)
+            self.evaluations += 1
         f = -val.detach().to(torch.float64)
         g = -g.squeeze(-2).to(torch.float64)
         bad = ~torch.isfinite(f)
@@ -105,7 +122,7 @@ def optimize_acqf(acq_function: Callable[[Tensor], Tensor], bounds: Tensor, q: i
         blocked = ((x <= lo) & (g > 0)) | ((x >= up) & (g < 0))  # descent direction -g leaves the box
         return torch.where(blocked, torch.zeros_like(g), g)
 
-    obj = _BoxObjective(lambda X: acq_function(X.to(bounds.dtype)), d)
+    obj = _BoxObjective(lambda X: acq_function(X.to(bounds.dtype)), d, fd_step=1e-6 * (upper - lower).clamp_min(1e-12))
     x, f, g, iters = batched_lbfgs(obj, x0.to(torch.float64), maxiter=int(options.get("maxiter", 200)),
                                    gtol=float(options.get("gtol", 1e-5)), ftol=float(options.get("ftol", 2.2e-9)),
                                    project=project, projected_gradient=projected_gradient)

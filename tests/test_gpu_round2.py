@@ -513,3 +513,25 @@ def test_posterior_against_50_digit_arithmetic(crs):
     # the second arm has the same inputs and targets shifted by a constant: same variance, mean shifted by 1
     torch.testing.assert_close(p.variance[:, 1].cpu(), got_v, rtol=0, atol=1e-12 * scale)
     torch.testing.assert_close(p.mean[:, 1].cpu(), got_m + 1.0, rtol=0, atol=1e-10)
+
+
+def test_optimize_acqf_predictive_ei_continuous_levi_step(crs):
+    """The LEVI branch of the continuous driver (experiments/continuous_experiments/main.py:269-284):
+    optimize_acqf(PredictiveEI(model), bounds, q=1, ...) -> next_context, then discrete_levi at it.  PredictiveEI has
+    no backward: the refinement runs on central differences; the oracle reproduces the reported value at the
+    refined point, which is at least as good as every raw candidate, and the arm choice there equals the oracle's."""
+    from oracle import levi_oracle
+    from contextual_rs_b200.optimize import optimize_acqf
+    from contextual_rs_b200.synthetic import make_problem
+    desc, _ = make_problem(K=5, n_c=16, d=2, n=8, seed=6, train="rand")
+    model = crs.B200ModelListGP(desc, device=DEV)
+    ref = gp_oracle.model_from_description(desc)
+    acq = crs.PredictiveEI(model)
+    bounds = torch.tensor([[0.0, 0.0], [1.0, 1.0]], dtype=torch.float64)
+    cand, val, det = optimize_acqf(acq, bounds, q=1, num_restarts=6, raw_samples=128, seed=2, return_details=True)
+    assert float(val) >= det["raw_best"] - 1e-12 and bool(((cand >= 0) & (cand <= 1)).all())
+    want = levi_oracle.predictive_ei(cand.unsqueeze(-2), ref)
+    assert abs(float(want) - float(val)) <= 1e-9 * max(abs(float(val)), 1e-3)
+    arm, x = crs.discrete_levi(model, context_set=cand)
+    rarm, rx = levi_oracle.discrete_levi_ref(ref, context_set=cand)
+    assert int(arm) == int(rarm) and torch.equal(x, rx)

@@ -262,3 +262,27 @@ def test_batched_lbfgs_box_constraints_on_cpu():
     x, f, g, it = batched_lbfgs(Obj(), torch.full((3, 2), 0.5, dtype=torch.float64), project=project, projected_gradient=pg,
                                 gtol=1e-10, ftol=1e-15)
     torch.testing.assert_close(x, target.clamp(0.0, 1.0), rtol=0, atol=1e-7)
+
+
+def test_optimize_acqf_without_a_backward_uses_central_differences():
+    """An acquisition function that returns values without a graph (like PredictiveEI) is refined with
+    central differences: a smooth bump inside the box is found; one on the boundary ends on the boundary."""
+    from contextual_rs_b200.optimize import optimize_acqf
+    bounds = torch.tensor([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0]], dtype=torch.float64)
+    peak = torch.tensor([0.3, 0.8, 0.55], dtype=torch.float64)
+
+    def acq(X):  # batch x 1 x d -> batch, deliberately detached
+        with torch.no_grad():
+            return torch.exp(-4.0 * ((X.squeeze(-2) - peak) ** 2).sum(-1))
+
+    cand, val, det = optimize_acqf(acq, bounds, q=1, num_restarts=6, raw_samples=64, seed=3, return_details=True)
+    torch.testing.assert_close(cand.reshape(-1), peak, rtol=0, atol=1e-4)
+    assert abs(float(val) - 1.0) < 1e-7 and float(val) >= det["raw_best"]
+    peak2 = torch.tensor([1.4, 0.2, -0.3], dtype=torch.float64)  # outside the box
+
+    def acq2(X):
+        with torch.no_grad():
+            return -((X.squeeze(-2) - peak2) ** 2).sum(-1)
+
+    cand2, _ = optimize_acqf(acq2, bounds, q=1, num_restarts=4, raw_samples=32, seed=1)
+    torch.testing.assert_close(cand2.reshape(-1), torch.tensor([1.0, 0.2, 0.0], dtype=torch.float64), rtol=0, atol=1e-5)
