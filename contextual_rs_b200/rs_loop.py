@@ -44,6 +44,8 @@ class SequentialRS:
         self.ws = model.private_workspace(self.n_c)  # owned: not shared with the stateless entry points
         self.ws["ctx"].copy_(self.ctx)
         self._dirty: Optional[int] = None
+        if getattr(model, "n_at_fit", None) is None:  # observation counts at the last fit: refit() re-fits arms that grew since
+            model.n_at_fit = model.num_observations()
         # full grid once; afterwards only dirty columns
         model.posterior_tables(self.ws["ctx"], self.ws["mean"], self.ws["var"], arms=(0, model.num_arms))
 
@@ -57,6 +59,25 @@ class SequentialRS:
             m.posterior_tables(self.ws["ctx"], self.ws["mean"], self.ws["var"], arms=(0, m.num_arms))
         else:
             m.posterior_tables(self.ws["ctx"], self.ws["mean"], self.ws["var"], arms=(int(arm), int(arm) + 1))
+
+    def refit(self) -> None:
+        """Re-fit the hyper-parameters of every arm that received observations since its last fit and rebuild
+        the grid — what the reference's loop does every ``fit_frequency`` iterations with
+        ``fit_modellist_with_reuse(X, Y, num_arms, old_model)`` (``experiments/wsc_experiments/main.py:345-370``,
+        ``contextual_rs/experiment_utils.py:68-121``): a re-fitted arm gets fresh Normalize / Standardize constants
+        and L-BFGS-fitted hyper-parameters, the others keep theirs."""
+        from .fit import fit_modellist_with_reuse
+        old = self.model
+        desc = old.description()
+        K = old.num_arms
+        X = torch.cat([torch.cat([torch.full((x.shape[0], 1), float(k), dtype=torch.float64), x.to(torch.float64)], dim=-1)
+                       for k, x in enumerate(desc["train_X"])])
+        Y = torch.cat([y.to(torch.float64).reshape(-1, 1) for y in desc["train_Y"]])
+        new = fit_modellist_with_reuse(X, Y, K, old_model=old, device=old.device, dtype=old.dtype, kernel=old.kernel)
+        self.model = new
+        self.ws = new.private_workspace(self.n_c)
+        self.ws["ctx"].copy_(self.ctx)
+        new.posterior_tables(self.ws["ctx"], self.ws["mean"], self.ws["var"], arms=(0, K))
 
     # -- one iteration -----------------------------------------------------------------------------
     def decide(self) -> Dict:
@@ -97,8 +118,12 @@ class SequentialRS:
         """Predicted best arm per context: a by-product of the scan (``main.py:459-468``)."""
         return self.ws["best_arm"].to(torch.long)
 
-    def step(self, evaluate: Callable[[int, Tensor], Tensor]) -> Dict:
-        """decide -> simulate -> update -> PCS, the order of ``main.py:392-468``."""
+    def step(self, evaluate: Callable[[int, Tensor], Tensor], fit_frequency: Optional[int] = None) -> Dict:
+        """decide -> simulate -> update -> PCS, the order of ``main.py:392-468``; with ``fit_frequency`` the
+        model is re-fitted (:meth:`refit`) at the top of every ``fit_frequency``-th iteration instead of being
+        conditioned only (``main.py:352-370``)."""
+        if fit_frequency and self.iteration > 0 and self.iteration % int(fit_frequency) == 0:
+            self.refit()
         out = self.decide()
         y = evaluate(out["next_arm"], out["next_context"])
         pcs = self.pcs()               # PCS of the model that made the decision (:447-455)

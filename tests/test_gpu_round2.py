@@ -535,3 +535,35 @@ def test_optimize_acqf_predictive_ei_continuous_levi_step(crs):
     arm, x = crs.discrete_levi(model, context_set=cand)
     rarm, rx = levi_oracle.discrete_levi_ref(ref, context_set=cand)
     assert int(arm) == int(rarm) and torch.equal(x, rx)
+
+
+def test_sequential_loop_with_periodic_refit_equals_the_manual_sequence(crs):
+    """experiments/wsc_experiments/main.py:345-370: every fit_frequency-th iteration re-fits (arms with new data only,
+    fit_modellist_with_reuse), the others condition the sampled arm.  SequentialRS.step(evaluate, fit_frequency=3)
+    must make the decisions of that sequence written out by hand with the stateless drop-ins."""
+    from contextual_rs_b200 import fit
+    from contextual_rs_b200.rs_loop import SequentialRS
+    g = torch.Generator().manual_seed(4)
+    K, n_c, d, n0 = 4, 12, 1, 6
+    ctx = torch.rand(n_c, d, dtype=torch.float64, generator=g)
+
+    def truth(arm, x):
+        return torch.sin(6.0 * x.double().sum() + arm) + 0.3 * arm
+
+    X = torch.cat([torch.cat([torch.full((n0, 1), float(k), dtype=torch.float64), ctx[torch.randperm(n_c, generator=g)[:n0]]], dim=-1)
+                   for k in range(K)])
+    Y = torch.stack([truth(int(r[0]), r[1:]) for r in X]).reshape(-1, 1)
+    loop = SequentialRS(fit.fit_modellist(X, Y, K, device=DEV), ctx, randomize_ties=False, kernel_scale=1.0, num_pcs_samples=256)
+    manual = fit.fit_modellist(X, Y, K, device=DEV)
+    Xm, Ym = X.clone(), Y.clone()
+    for i in range(8):
+        if i > 0 and i % 3 == 0:
+            manual = fit.fit_modellist_with_reuse(Xm, Ym, K, old_model=manual, device=DEV)
+        arm, x = crs.gao_modellist(manual, ctx, randomize_ties=False, kernel_scale=1.0)
+        out = loop.step(truth, fit_frequency=3)
+        assert (out["next_arm"], out["next_context"].tolist()) == (int(arm), x.tolist()), i
+        y = truth(int(arm), x)
+        manual.condition_on_observations(int(arm), x.view(1, -1), y.reshape(1, 1))
+        Xm = torch.cat([Xm, torch.cat([torch.tensor([[float(arm)]], dtype=torch.float64), x.view(1, -1)], dim=-1)])
+        Ym = torch.cat([Ym, y.reshape(1, 1)])
+    assert loop.model.n_at_fit != [n0] * K  # at least one arm was re-fitted with its new observations
