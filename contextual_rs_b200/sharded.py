@@ -275,7 +275,9 @@ class ContextShardedDecider:
     def decide_struct(self, p_mode: int = _lib.CRS_P_COUNT, kernel_scale: float = 2.0,
                       prepare_arms: Optional[Tuple[int, int]] = None, grid: bool = True) -> "_lib.Decision":
         """Mailbox exchange: launch, then poll the mapped host copy of the GLOBAL decision (global
-        context index).  ``grid=False`` re-uses the cached local grid (sequential loop)."""
+        context index).  ``grid=False`` re-uses the cached local grid (sequential loop).  The returned
+        struct is a VIEW of this decider's pinned host buffer: read it before the next decision overwrites it
+        (:meth:`decide` returns a copy)."""
         m = self.model
         px = self.mailbox.next_exchange(self.begin)
         with torch.cuda.device(m.device):
